@@ -1,0 +1,177 @@
+/*
+ * spx.h -- C ABI of libspx.so: the B200 (sm_100a) batched self-play engine.
+ *
+ * This is the drop-in boundary for ONE hot path of reubenvanammers/self_play_reinforcement_learning:
+ * many concurrent AlphaZero MCTS searches (games/algos/mcts.py) driven by the self-play workers
+ * (games/algos/selfplayworker.py, games/algos/self_play_parallel.py).  Every entry point names the
+ * reference interface it replaces (file:line relative to the reference tree).
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "dev" is a CUDA device pointer owned by the caller
+ *     (e.g. torch tensor .data_ptr()); "host" pointers are ordinary host memory.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it unless stated.
+ *   - return value: 0 = OK, <0 = error (SPX_E_*); spx_last_error() gives a thread-local message.
+ *   - one engine per device; an engine is not thread-safe (the host serialises calls), exactly like
+ *     one reference InferenceWorker/SelfPlayWorker pair.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns SPX_E_CUDA.
+ *
+ * Bitboards: Connect4 bit = col*7 + row (row 0 = bottom, bit 6 of each column never set);
+ * TicTacToe bit = x*3 + y (== action index).  "own" = cells equal to +1, "opp" = cells equal to -1
+ * in whichever frame the call documents (see oracle/spec.py board_to_bits for the test-side twin).
+ */
+#ifndef SPX_H
+#define SPX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPX_GAME_CONNECT4 0  /* games/connect4/connect4env.py, default 7x6 only      */
+#define SPX_GAME_TICTACTOE 1 /* games/tictactoe/tictactoe_env.py, default 3x3x3 only */
+
+#define SPX_MAX_ACTIONS 9
+
+#define SPX_E_ARG (-1)      /* bad argument                       */
+#define SPX_E_CUDA (-2)     /* CUDA runtime error / no device      */
+#define SPX_E_STATE (-3)    /* call made in the wrong engine state */
+#define SPX_E_OVERFLOW (-4) /* node pool / record ring overflow    */
+
+/* status codes written per game by spx_env_step (the reference raises instead) */
+#define SPX_ENV_OK 0
+#define SPX_ENV_GAME_OVER (-1)   /* GameOver    connect4env.py:30-31, tictactoe_env.py:24-25 */
+#define SPX_ENV_VALUE_ERROR (-2) /* ValueError  connect4env.py:36-37 (full column)           */
+#define SPX_ENV_SKIPPED (-3)     /* action < 0: slot not stepped                             */
+
+typedef struct spx_engine spx_engine;
+
+/* Mirrors MCTreeSearch.__init__ kwargs (mcts.py:119-136), MCNode constants x=0.25, cpuct=4
+ * (mcts.py:24-26) are fixed.  thread_count is always 1 (sequential search: the parity target). */
+typedef struct spx_config {
+    int32_t game;              /* SPX_GAME_*                                                        */
+    int32_t n_games;           /* concurrent game slots on this device (two trees per game)         */
+    int32_t sims;              /* `iterations`                                     mcts.py:125,333  */
+    int32_t evaluate;          /* MCTreeSearch.evaluate(True): temp/20             mcts.py:273-274  */
+    int32_t strong_play;       /* mcts.py:133,307-311                                               */
+    int32_t tie_mode;          /* 0: tie noise == 0, 1: counter stream             mcts.py:355      */
+    int32_t noise_mode;        /* 0: Dirichlet == 1/A, 1: injected table, 2: generated on device    */
+    int32_t emit_records;      /* play_episode(update=...)                 selfplayworker.py:186-190 */
+    int32_t max_sims_per_tick; /* terminal re-visits resolved inside one advance call (>=1)         */
+    int32_t nodes_per_tree;    /* 0: worst-case bound (sims+1)*ceil(max_moves/2)+max_moves+2        */
+    int32_t move_log;          /* 1: keep per-move root statistics for spx_read_move_log (debug)    */
+    int32_t two_nets;          /* 1: tree 1 is evaluated by net 1 (compare_models / elo.py:73-91)   */
+    double alpha;              /* Dirichlet alpha                                   mcts.py:135      */
+    uint64_t seed;             /* counter-stream seed (oracle/spec.py)                              */
+    int64_t slot_offset;       /* global index of this device's slot 0 (multi-GPU sharding)         */
+    int64_t slot_stride;       /* total slots over all devices; game index = slot + k*stride        */
+    int64_t games_target;      /* games with index < target are played, then the slot idles         */
+    int64_t record_capacity;   /* Move records buffered on device between drains                    */
+    int64_t result_capacity;   /* game results buffered on device between drains                    */
+} spx_config;
+
+/* One Move record (mcts.py:17,282-289 + :230): state in the tree's own frame, tree_probs, q, and
+ * actual_val stamped at game end (+r for the policy, -r for the opponent). 80 bytes. */
+typedef struct spx_record {
+    uint64_t own, opp;
+    uint64_t game_index;
+    float tree_probs[SPX_MAX_ACTIONS];
+    float q;
+    float actual_val;
+    uint8_t tree; /* 0 = policy, 1 = opposing policy (selfplayworker.py:67-90) */
+    uint8_t ply;  /* pieces on the board when the move was searched             */
+    uint16_t pad0;
+    uint64_t pad1;
+} spx_record;
+
+/* One result_queue entry {"reward": r, "swap_sides": b} (selfplayworker.py:185). 16 bytes. */
+typedef struct spx_result {
+    uint64_t game_index;
+    int8_t reward;
+    uint8_t swap_sides;
+    uint8_t plies;
+    uint8_t pad[5];
+} spx_result;
+
+/* Per-move root statistics (debug / parity): what MCTreeSearch._play sees (mcts.py:272-299). */
+typedef struct spx_move_log {
+    int32_t tree, ply, action, root_n;
+    double root_w;
+    int32_t n[SPX_MAX_ACTIONS];
+    int32_t pad;
+    double w[SPX_MAX_ACTIONS];
+    double noise[SPX_MAX_ACTIONS];
+} spx_move_log;
+
+typedef struct spx_counters {
+    uint64_t sims;          /* completed search_node iterations (mcts.py:333-334)      */
+    uint64_t leaf_evals;    /* network evaluations requested (all kinds)               */
+    uint64_t terminal_sims; /* sims that ended on a terminal child (no evaluation)     */
+    uint64_t path_len_sum;  /* sum over sims of select-path length L                   */
+    uint64_t moves;         /* _play calls == Move records produced                    */
+    uint64_t games_finished;
+    uint64_t nodes_allocated;
+    uint64_t ticks;
+    uint64_t records_dropped; /* ring overflow (host drained too rarely)               */
+    uint64_t errors;          /* node-pool overflow etc.; must stay 0                  */
+} spx_counters;
+
+const char* spx_last_error(void);
+int spx_version(void);
+/* number of CUDA kernels launched by this library since load (bench.py "gpu_launches") */
+uint64_t spx_launch_count(void);
+
+/* ---------------------------------------------------------------- environment (batched)
+ * Replaces Connect4Env.step/get_reward/valid_moves (connect4env.py:29-48,72-92) and
+ * TicTacToeEnv.step/get_reward/valid_moves (tictactoe_env.py:23-45,62-82) for n independent boards.
+ * state: dev ulonglong2[n] = {own, opp}; done: dev u8[n] in/out (episode_over); action: dev i32[n]
+ * (<0 = skip); player: dev i8[n] (+1/-1); reward: dev i8[n] out; valid: dev u16[n] out, bit a set iff
+ * action a is legal AFTER the step; status: dev i8[n] out (SPX_ENV_*). */
+int spx_env_step(int32_t game, int64_t n, void* state, uint8_t* done, const int32_t* action, const int8_t* player,
+                 int8_t* reward, uint16_t* valid, int8_t* status, void* stream);
+/* valid_moves() only (connect4env.py:47-48, tictactoe_env.py:42-43) */
+int spx_env_valid_moves(int32_t game, int64_t n, const void* state, uint16_t* valid, void* stream);
+
+/* ---------------------------------------------------------------- synthetic network (tests / search-only bench)
+ * The oracle/spec.py hash net evaluated on device: policy dev f32[n,A], value dev f32[n]. */
+int spx_hashnet_forward(int32_t game, int64_t n, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval,
+                        const uint8_t* net_id, uint64_t net_seed0, uint64_t net_seed1, float* policy, float* value,
+                        void* stream);
+
+/* ---------------------------------------------------------------- search engine
+ * Replaces, for n_games concurrent games with two trees each: MCTreeSearch.reset/search/search_node/
+ * _expand_node/_play/play_action/_set_node/push_to_queue (mcts.py:166-232,272-367) and
+ * SelfPlayer.play_episode (selfplayworker.py:172-224); the InferenceProxy/InferenceWorker queue round
+ * trip (inference_proxy.py:21-24, inference_worker.py:89-119) becomes the dense leaf batch below. */
+int spx_create(const spx_config* cfg, spx_engine** out);
+int spx_destroy(spx_engine* e);
+/* (re)start: every slot begins game index slot_offset+slot (generation 0) */
+int spx_reset(spx_engine* e, void* stream);
+/* injected Dirichlet noise (noise_mode 1): dev f64 [n_table_games][2][table_moves][A], row for game
+ * index i is i - first_game_index */
+int spx_set_noise_table(spx_engine* e, const double* table, int64_t first_game_index, int64_t n_table_games,
+                        int32_t table_moves);
+/* One tick: consume the previous tick's network outputs (policy dev f32[n_games,A], value dev
+ * f32[n_games]; ignored for slots that did not request an evaluation; may be NULL on the first
+ * tick), run every game's state machine until it needs the network again, and fill the leaf batch. */
+int spx_advance(spx_engine* e, const float* policy, const float* value, void* stream);
+/* engine-owned leaf batch of the last tick, indexed by slot: own/opp in the NET frame
+ * (general/modules.py:109-112: the side that just moved is +1), needs_eval u8, net_id u8 */
+int spx_leaf_batch(spx_engine* e, uint64_t** own, uint64_t** opp, uint8_t** needs_eval, uint8_t** net_id);
+/* root statistics of one tree per slot (root.children[a].n / .w, root.n, root.w): dev outputs */
+int spx_root_stats(spx_engine* e, int32_t tree, int32_t* n, double* w, int32_t* root_n, double* root_w,
+                   uint16_t* valid, void* stream);
+/* copy out and clear buffered records / results (synchronises the stream) */
+int spx_drain_records(spx_engine* e, spx_record* host_out, int64_t capacity, int64_t* n_out, void* stream);
+int spx_drain_results(spx_engine* e, spx_result* host_out, int64_t capacity, int64_t* n_out, void* stream);
+int spx_read_move_log(spx_engine* e, int32_t slot, spx_move_log* host_out, int32_t capacity, int32_t* n_out,
+                      void* stream);
+int spx_counters_read(spx_engine* e, spx_counters* host_out, void* stream);
+/* 1 when every slot is idle (games_target reached) */
+int spx_all_idle(spx_engine* e, int32_t* idle_out, void* stream);
+int64_t spx_device_bytes(spx_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPX_H */

@@ -129,10 +129,11 @@ def main():
         alpha = 1.0 if i % 3 else 0.15
         table = rng.dirichlet([alpha] * A, size=(2, 22))
         opp_seed = 77 if ev else None
-        r = rh.run_episode(game, sims, seed=40 + i, game_uid=1000 + i, swap_sides=swap, evaluate=ev,
+        uid = 1000 + 2 * i + int(swap)  # engine convention: swap_sides == game index odd (self_play_parallel.py:252)
+        r = rh.run_episode(game, sims, seed=40 + i, game_uid=uid, swap_sides=swap, evaluate=ev,
                            noise_table=table, net_seed=i, net_seed_opp=opp_seed, strong_play=strong)
         eps.append(dict(game=game, sims=sims, swap=swap, evaluate=ev, strong_play=strong, seed=40 + i,
-                        game_uid=1000 + i, net_seed=i, net_seed_opp=opp_seed,
+                        game_uid=uid, net_seed=i, net_seed_opp=opp_seed,
                         noise_table=[[[float(x).hex() for x in row] for row in t] for t in table],
                         reward=r["reward"],
                         moves=[dict(tree=m["tree"], ply=m["ply"], action=m["action"], n=m["n"],

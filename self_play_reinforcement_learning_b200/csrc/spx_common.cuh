@@ -1,0 +1,136 @@
+// spx_common.cuh -- device-side building blocks shared by the env and search kernels.
+//   * counter-based RNG stream (twin of oracle/spec.py; integer-only, so CPU == GPU bit for bit)
+//   * bitboard game rules for Connect4 (7x6) and TicTacToe (3x3), following
+//     games/connect4/connect4env.py:29-48,72-92 and games/tictactoe/tictactoe_env.py:23-45,62-82
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/spx.h"
+
+typedef unsigned long long u64;
+
+namespace spx {
+
+enum { PURPOSE_TIE = 0, PURPOSE_GAMMA = 1, PURPOSE_ACTION = 2 };
+
+__host__ __device__ __forceinline__ u64 sm64(u64 x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    u64 z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+// prefix of the key that does not depend on (sim, depth, idx): hoisted out of the select loop
+__host__ __device__ __forceinline__ u64 rng_prefix(u64 seed, u64 game_uid, int tree, int purpose, int ply) {
+    u64 h = sm64(seed);
+    h = sm64(h ^ game_uid);
+    h = sm64(h ^ ((u64)(tree & 0xFF) | ((u64)(purpose & 0xFF) << 8) | ((u64)(ply & 0xFFFF) << 16)));
+    return h;
+}
+__host__ __device__ __forceinline__ double rng_uniform_from(u64 prefix, uint32_t sim, uint32_t depth, u64 idx) {
+    u64 h = sm64(prefix ^ ((u64)sim | ((u64)depth << 32)));
+    h = sm64(h ^ idx);
+    return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int GAME> struct Rules;
+
+template <> struct Rules<SPX_GAME_CONNECT4> {
+    static constexpr int W = 7, H = 6, A = 7, STRIDE = 7, WIN = 4, CELLS = 42;
+    static constexpr u64 BOARD = 0x0000FDFBF7EFDFBFULL;  // 6 playable bits in each of 7 columns
+    __host__ __device__ static __forceinline__ int height(u64 occ, int c) { return __builtin_popcountll((occ >> (7 * c)) & 0x3FULL); }
+};
+template <> struct Rules<SPX_GAME_TICTACTOE> {
+    static constexpr int W = 3, H = 3, A = 9, STRIDE = 3, WIN = 3, CELLS = 9;
+    static constexpr u64 BOARD = 0x1FFULL;
+};
+
+#ifdef __CUDA_ARCH__
+#define SPX_POPC(x) __popcll(x)
+#else
+#define SPX_POPC(x) __builtin_popcountll(x)
+#endif
+
+// Does `b` hold a run of >= WIN along the full line through cell (x,y) in direction (dx,dy)?
+// This is functools.reduce(_calc_win_in_a_row, line*player, 0) == WIN (connect4env.py:80-92): the
+// fold saturates once any run of WIN appears anywhere on that line, not only through (x,y).
+template <int GAME>
+__host__ __device__ __forceinline__ bool line_has_run(u64 b, int x, int y, int dx, int dy) {
+    typedef Rules<GAME> R;
+    // walk back to the first cell of the line
+    int back = 0;
+    {
+        int bx = dx > 0 ? x : (dx < 0 ? R::W - 1 - x : 99);
+        int by = dy > 0 ? y : (dy < 0 ? R::H - 1 - y : 99);
+        back = bx < by ? bx : by;
+    }
+    int cx = x - back * dx, cy = y - back * dy;
+    unsigned bits = 0;
+    int len = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        if (cx >= 0 && cx < R::W && cy >= 0 && cy < R::H) {
+            bits |= (unsigned)((b >> (cx * R::STRIDE + cy)) & 1ULL) << len;
+            ++len;
+            cx += dx;
+            cy += dy;
+        }
+    }
+    unsigned m = bits & (bits >> 1) & (bits >> 2);
+    if (R::WIN == 4) m &= (bits >> 3);
+    return m != 0;
+}
+
+// get_reward(action, player): 1 iff one of the four lines through the last cell holds a run of WIN
+// of the mover's pieces (connect4env.py:72-83, tictactoe_env.py:62-74)
+template <int GAME>
+__host__ __device__ __forceinline__ int reward_at(u64 mover_bits, int x, int y) {
+    return (line_has_run<GAME>(mover_bits, x, y, 1, 0) ||   // board[:, y]
+            line_has_run<GAME>(mover_bits, x, y, 0, 1) ||   // board[x, :]
+            line_has_run<GAME>(mover_bits, x, y, 1, 1) ||   // np.diagonal(board, y - x)
+            line_has_run<GAME>(mover_bits, x, y, -1, 1))    // np.diagonal(np.flipud(board), ...)
+               ? 1 : 0;
+}
+
+template <int GAME>
+__host__ __device__ __forceinline__ unsigned valid_mask(u64 own, u64 opp) {
+    typedef Rules<GAME> R;
+    u64 occ = own | opp;
+    if (GAME == SPX_GAME_CONNECT4) {
+        unsigned m = 0;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) m |= (unsigned)(((occ >> (7 * c + 5)) & 1ULL) ^ 1ULL) << c;  // heights < 6
+        return m;
+    }
+    return (unsigned)(~occ & R::BOARD);  // board.reshape(-1) == 0
+}
+
+// One env.step.  `own`/`opp` are the +1 / -1 cells of the env's frame; `player` is +1 or -1.
+// Returns SPX_ENV_OK / SPX_ENV_VALUE_ERROR; reward in {0,1}; done = reward != 0 or board full.
+template <int GAME>
+__host__ __device__ __forceinline__ int env_step(u64& own, u64& opp, int action, int player, int& reward, int& done) {
+    typedef Rules<GAME> R;
+    u64 occ = own | opp;
+    int x, y;
+    if (GAME == SPX_GAME_CONNECT4) {
+        x = action;
+        y = SPX_POPC((occ >> (7 * action)) & 0x3FULL);  // heights[action]
+        if (y >= R::H) { reward = 0; done = 0; return SPX_ENV_VALUE_ERROR; }
+        u64 bit = 1ULL << (x * 7 + y);
+        if (player > 0) own |= bit; else opp |= bit;
+    } else {
+        x = action / 3;  // np.unravel_index(action, (3,3))
+        y = action % 3;
+        u64 bit = 1ULL << action;
+        if (!(occ & bit)) { if (player > 0) own |= bit; else opp |= bit; }  // occupied: silent no-op
+    }
+    u64 mover = player > 0 ? own : opp;
+    reward = reward_at<GAME>(mover, x, y);
+    done = (reward != 0) || (SPX_POPC(own | opp) == R::CELLS);
+    return SPX_ENV_OK;
+}
+
+}  // namespace spx

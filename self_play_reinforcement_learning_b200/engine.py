@@ -1,0 +1,197 @@
+"""SelfPlayEngine: host-side driver of one spx_engine (one per GPU).
+
+One ``tick`` = spx_advance (every game's state machine runs until it needs the network) followed by
+one batched network evaluation of the dense leaf batch.  This replaces the reference's
+SelfPlayWorker threads + InferenceProxy queues + InferenceWorker batching
+(selfplayworker.py:95-142, inference_proxy.py:21-24, inference_worker.py:61-119).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Config, Counters, MoveLog, Record, Result, check, lib
+
+RECORD_DTYPE = np.dtype([("own", "<u8"), ("opp", "<u8"), ("game_index", "<u8"), ("tree_probs", "<f4", (9,)),
+                         ("q", "<f4"), ("actual_val", "<f4"), ("tree", "u1"), ("ply", "u1"), ("pad0", "<u2"),
+                         ("pad1", "<u8")])
+RESULT_DTYPE = np.dtype([("game_index", "<u8"), ("reward", "i1"), ("swap_sides", "u1"), ("plies", "u1"),
+                         ("pad", "u1", (5,))])
+assert RECORD_DTYPE.itemsize == C.sizeof(Record) == 80
+assert RESULT_DTYPE.itemsize == C.sizeof(Result) == 16
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ carrier so torch can view engine-owned device memory."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr,
+                                         "version": 2}
+
+
+def _view(ptr, shape, typestr, device):
+    return torch.as_tensor(_DevArray(ptr, shape, typestr), device=device)
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class HashNetEvaluator:
+    """The synthetic oracle/spec.py hash network evaluated by a libspx kernel (tests, search-only bench)."""
+
+    def __init__(self, game, net_seed=0, net_seed_opp=None):
+        self.game = game
+        self.seed0 = int(net_seed)
+        self.seed1 = int(net_seed if net_seed_opp is None else net_seed_opp)
+
+    def bind(self, engine):
+        self.engine = engine
+
+    def __call__(self, engine):
+        check(lib().spx_hashnet_forward(self.game, engine.n_games, engine.leaf_own.data_ptr(), engine.leaf_opp.data_ptr(),
+                                        engine.needs_eval.data_ptr(), engine.net_id.data_ptr(), self.seed0, self.seed1,
+                                        engine.policy.data_ptr(), engine.value.data_ptr(), _stream_ptr()),
+              "spx_hashnet_forward")
+
+
+class SelfPlayEngine:
+    """n_games concurrent self-play games (two MCTS trees each) on the current CUDA device."""
+
+    def __init__(self, game, n_games, sims, evaluator, *, evaluate=False, strong_play=False, alpha=1.0, seed=0,
+                 tie_mode=1, noise_mode=2, emit_records=True, max_sims_per_tick=8, nodes_per_tree=0, move_log=False,
+                 two_nets=False, slot_offset=0, slot_stride=None, games_target=None, record_capacity=None,
+                 result_capacity=None):
+        if not torch.cuda.is_available():
+            raise _lib.SpxError("SelfPlayEngine needs a CUDA device (B200); there is no CPU fallback")
+        self.game, self.n_games, self.sims = game, int(n_games), int(sims)
+        self.W, self.H, self.A = _lib.GAME_DIMS[game]
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        cfg = Config()
+        cfg.game, cfg.n_games, cfg.sims = game, n_games, sims
+        cfg.evaluate, cfg.strong_play, cfg.tie_mode, cfg.noise_mode = int(evaluate), int(strong_play), tie_mode, noise_mode
+        cfg.emit_records, cfg.max_sims_per_tick, cfg.nodes_per_tree = int(emit_records), max_sims_per_tick, nodes_per_tree
+        cfg.move_log, cfg.two_nets, cfg.alpha, cfg.seed = int(move_log), int(two_nets), float(alpha), int(seed)
+        cfg.slot_offset = slot_offset
+        cfg.slot_stride = n_games if slot_stride is None else slot_stride
+        cfg.games_target = (1 << 62) if games_target is None else games_target
+        max_moves = self.W * self.H
+        cfg.record_capacity = record_capacity or max(4 * n_games * max_moves, 1024)
+        cfg.result_capacity = result_capacity or max(8 * n_games, 1024)
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        check(lib().spx_create(C.byref(cfg), C.byref(self._h)), "spx_create")
+        own, opp, need, nid = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().spx_leaf_batch(self._h, C.byref(own), C.byref(opp), C.byref(need), C.byref(nid)), "spx_leaf_batch")
+        self.leaf_own = _view(own.value, (n_games,), "<i8", self.device)
+        self.leaf_opp = _view(opp.value, (n_games,), "<i8", self.device)
+        self.needs_eval = _view(need.value, (n_games,), "|u1", self.device)
+        self.net_id = _view(nid.value, (n_games,), "|u1", self.device)
+        self.policy = torch.zeros(n_games, self.A, dtype=torch.float32, device=self.device)
+        self.value = torch.zeros(n_games, dtype=torch.float32, device=self.device)
+        self._noise_table = None
+        self._first = True
+        self.evaluator = evaluator
+        if hasattr(evaluator, "bind"):
+            evaluator.bind(self)
+        self._rec_host = np.zeros(cfg.record_capacity, RECORD_DTYPE)
+        self._res_host = np.zeros(cfg.result_capacity, RESULT_DTYPE)
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            torch.cuda.synchronize()
+            lib().spx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        check(lib().spx_reset(self._h, _stream_ptr()), "spx_reset")
+        self._first = True
+
+    def set_noise_table(self, table, first_game_index=0):
+        """table: float64 [n_table_games, 2, table_moves, A] (host array or device tensor)."""
+        t = torch.as_tensor(np.ascontiguousarray(table, dtype=np.float64) if not torch.is_tensor(table) else table)
+        t = t.to(self.device, torch.float64).contiguous()
+        assert t.dim() == 4 and t.shape[1] == 2 and t.shape[3] == self.A
+        self._noise_table = t
+        check(lib().spx_set_noise_table(self._h, t.data_ptr(), first_game_index, t.shape[0], t.shape[2]), "spx_set_noise_table")
+
+    # ------------------------------------------------------------------ the hot loop
+    def advance(self):
+        """spx_advance only (consume last outputs, fill the leaf batch)."""
+        p = None if self._first else self.policy.data_ptr()
+        v = None if self._first else self.value.data_ptr()
+        check(lib().spx_advance(self._h, p, v, _stream_ptr()), "spx_advance")
+        self._first = False
+
+    def tick(self):
+        self.advance()
+        self.evaluator(self)
+
+    def run_ticks(self, n):
+        for _ in range(n):
+            self.tick()
+
+    def run_until_idle(self, max_ticks=10_000_000, poll_every=64):
+        t = 0
+        while t < max_ticks:
+            self.run_ticks(poll_every)
+            t += poll_every
+            if self.all_idle():
+                return t
+        raise _lib.SpxError("run_until_idle: max_ticks reached")
+
+    # ------------------------------------------------------------------ readouts
+    def all_idle(self):
+        out = C.c_int32()
+        check(lib().spx_all_idle(self._h, C.byref(out), _stream_ptr()), "spx_all_idle")
+        return bool(out.value)
+
+    def counters(self):
+        c = Counters()
+        check(lib().spx_counters_read(self._h, C.byref(c), _stream_ptr()), "spx_counters_read")
+        return {k: int(getattr(c, k)) for k, _ in Counters._fields_}
+
+    def drain_records(self):
+        n = C.c_int64()
+        check(lib().spx_drain_records(self._h, self._rec_host.ctypes.data, len(self._rec_host), C.byref(n), _stream_ptr()),
+              "spx_drain_records")
+        return self._rec_host[:n.value].copy()
+
+    def drain_results(self):
+        n = C.c_int64()
+        check(lib().spx_drain_results(self._h, self._res_host.ctypes.data, len(self._res_host), C.byref(n), _stream_ptr()),
+              "spx_drain_results")
+        return self._res_host[:n.value].copy()
+
+    def root_stats(self, tree):
+        G, A = self.n_games, self.A
+        n = torch.zeros(G, A, dtype=torch.int32, device=self.device)
+        w = torch.zeros(G, A, dtype=torch.float64, device=self.device)
+        rn = torch.zeros(G, dtype=torch.int32, device=self.device)
+        rw = torch.zeros(G, dtype=torch.float64, device=self.device)
+        valid = torch.zeros(G, dtype=torch.int16, device=self.device)
+        check(lib().spx_root_stats(self._h, tree, n.data_ptr(), w.data_ptr(), rn.data_ptr(), rw.data_ptr(), valid.data_ptr(),
+                                   _stream_ptr()), "spx_root_stats")
+        torch.cuda.synchronize()
+        vm = valid.cpu().numpy().astype(np.uint16)
+        return dict(n=n.cpu().numpy(), w=w.cpu().numpy(), root_n=rn.cpu().numpy(), root_w=rw.cpu().numpy(),
+                    valid=((vm[:, None] >> np.arange(A)) & 1).astype(bool))
+
+    def move_log(self, slot):
+        buf = (MoveLog * 44)()
+        n = C.c_int32()
+        check(lib().spx_read_move_log(self._h, slot, buf, 44, C.byref(n), _stream_ptr()), "spx_read_move_log")
+        A = self.A
+        return [dict(tree=m.tree, ply=m.ply, action=m.action, root_n=m.root_n, root_w=m.root_w, n=list(m.n[:A]),
+                     w=list(m.w[:A]), noise=list(m.noise[:A])) for m in buf[:n.value]]
+
+    def device_bytes(self):
+        return int(lib().spx_device_bytes(self._h))
