@@ -170,6 +170,24 @@ int spx_counters_read(spx_engine* e, spx_counters* host_out, void* stream);
 /* 1 when every slot is idle (games_target reached) */
 int spx_all_idle(spx_engine* e, int32_t* idle_out, void* stream);
 int64_t spx_device_bytes(spx_engine* e);
+/* dev i32[n_games]: the tree (0/1) whose evaluation each slot is waiting for, -1 if none (replay logging) */
+int spx_pending_tree(spx_engine* e, int32_t* tree_out, void* stream);
+
+/* ---------------------------------------------------------------- network tower (tcgen05)
+ * Replaces InferenceWorker.calculate (inference_worker.py:114-119) -> ResidualTower.forward
+ * (general/modules.py:88-107, BN in eval mode folded into the convolutions) for the 7x6 Connect4
+ * ResidualTower with 128 trunk channels (filter_factor 32) and `num_blocks` residual blocks.
+ * Weights arrive as one packed device blob (layout: nets.pack_tower_blob, size spx_tower_blob_bytes), so a
+ * weight refresh is a single device-to-device copy (or the receive buffer of an NCCL broadcast). */
+typedef struct spx_tower spx_tower;
+int64_t spx_tower_blob_bytes(int32_t game, int32_t num_blocks);
+int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out);
+int spx_tower_destroy(spx_tower* t);
+int spx_tower_load(spx_tower* t, const void* dev_blob, int64_t bytes, void* stream);
+/* own/opp: dev u64[n] bitboards in the NET frame; needs_eval: dev u8[n] or NULL (all); policy dev f32[n,A]
+ * (softmax), value dev f32[n] (tanh).  Rows whose needs_eval is 0 may be left untouched. */
+int spx_tower_forward(spx_tower* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n,
+                      float* policy, float* value, void* stream);
 
 #ifdef __cplusplus
 }

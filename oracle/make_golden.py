@@ -146,6 +146,29 @@ def main():
         print("episode", i, game, sims, swap, ev, "reward", r["reward"], "plies", len(r["moves"]))
     with open(os.path.join(OUT, "episodes.json"), "w") as f:
         json.dump(eps, f)
+    # ---- network fixtures: the reference's own classes, random init under a fixed seed, fp32 CPU
+    import torch
+    rh._import_reference()
+    from games.general.modules import ResidualTower
+    from games.tictactoe.modules import ConvNetTicTacToe
+    nets = {}
+    torch.set_num_threads(1)
+    for name, ctor, seed, (W, Hh) in [("tower20", lambda: ResidualTower(7, 6, 7, num_blocks=20), 0, (7, 6)),
+                                      ("tower2", lambda: ResidualTower(7, 6, 7, num_blocks=2), 3, (7, 6)),
+                                      ("tower_ttt", lambda: ResidualTower(3, 3, 9, num_blocks=3), 4, (3, 3)),
+                                      ("convttt", lambda: ConvNetTicTacToe(3, 3, 9), 1, (3, 3))]:
+        torch.manual_seed(seed)
+        net = ctor().eval()
+        x = torch.from_numpy(rng.integers(-1, 2, size=(24, W, Hh)).astype(np.int64))
+        x[0] = 0
+        with torch.no_grad():
+            p, v = net.forward(x)
+        nets[name + "_x"] = x.numpy().astype(np.int8)
+        nets[name + "_policy"] = p.numpy()
+        nets[name + "_value"] = v.numpy()
+        nets[name + "_wsum"] = np.array([sum(float(t.double().abs().sum()) for t in net.state_dict().values())])
+        nets[name + "_seed"] = np.array([seed])
+    np.savez_compressed(os.path.join(OUT, "nets.npz"), **nets)
     print("golden fixtures written to", OUT)
 
 

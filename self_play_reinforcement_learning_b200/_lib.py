@@ -50,7 +50,8 @@ class Counters(C.Structure):
 EXPORTS = ["spx_last_error", "spx_version", "spx_launch_count", "spx_env_step", "spx_env_valid_moves",
            "spx_hashnet_forward", "spx_create", "spx_destroy", "spx_reset", "spx_set_noise_table", "spx_advance",
            "spx_leaf_batch", "spx_root_stats", "spx_drain_records", "spx_drain_results", "spx_read_move_log",
-           "spx_counters_read", "spx_all_idle", "spx_device_bytes"]
+           "spx_counters_read", "spx_all_idle", "spx_device_bytes", "spx_pending_tree", "spx_tower_blob_bytes",
+           "spx_tower_create", "spx_tower_destroy", "spx_tower_load", "spx_tower_forward"]
 
 _lib = None
 
@@ -83,6 +84,13 @@ def lib():
         L.spx_read_move_log.argtypes = [vp, i32, vp, i32, C.POINTER(i32), vp]
         L.spx_counters_read.argtypes = [vp, C.POINTER(Counters), vp]
         L.spx_all_idle.argtypes = [vp, C.POINTER(i32), vp]
+        L.spx_pending_tree.argtypes = [vp, vp, vp]
+        L.spx_tower_blob_bytes.restype = C.c_int64
+        L.spx_tower_blob_bytes.argtypes = [i32, i32]
+        L.spx_tower_create.argtypes = [i32, i32, C.POINTER(vp)]
+        L.spx_tower_destroy.argtypes = [vp]
+        L.spx_tower_load.argtypes = [vp, vp, i64, vp]
+        L.spx_tower_forward.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
         _lib = L
     return _lib
 

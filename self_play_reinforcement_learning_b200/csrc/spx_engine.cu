@@ -608,6 +608,11 @@ __global__ void counters_kernel(EngineDev E, spx_counters* out) {
     }
 }
 
+__global__ void pending_tree_kernel(EngineDev E, int* out) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < E.cfg.n_games) out[g] = E.games[g].pend_kind != PK_NONE ? E.games[g].pend_tree : -1;
+}
+
 __global__ void idle_kernel(EngineDev E, int* out) {
     __shared__ int any;
     if (threadIdx.x == 0) any = 0;
@@ -898,5 +903,13 @@ int spx_all_idle(spx_engine* e, int32_t* idle_out, void* stream) {
 }
 
 int64_t spx_device_bytes(spx_engine* e) { return e ? e->bytes : 0; }
+
+int spx_pending_tree(spx_engine* e, int32_t* tree_out, void* stream) {
+    if (!e || !tree_out) return set_err(SPX_E_ARG, "spx_pending_tree: bad argument%s", "");
+    pending_tree_kernel<<<(e->d.cfg.n_games + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e->d, tree_out);
+    count_launch();
+    SPX_CUDA(cudaGetLastError());
+    return 0;
+}
 
 }  // extern "C"

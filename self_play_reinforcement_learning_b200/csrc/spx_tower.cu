@@ -1,0 +1,497 @@
+// spx_tower.cu -- the policy/value network evaluated at the MCTS leaves, hand-written for sm_100a.
+//
+// Replaces InferenceWorker.calculate (inference_worker.py:114-119) + ResidualTower.forward
+// (games/general/modules.py:27-40,88-107): preprocess -> conv3x3 stem -> N residual blocks @128 ch ->
+// 1x1 policy/value head convs (BN folded, eval mode) in ONE persistent kernel, then the small fully
+// connected heads in a second kernel.
+//
+// Design (B200-first):
+//   * One CTA owns 7 boards for the whole tower.  Activations never leave shared memory: two bf16
+//     ping-pong buffers of 400 rows x 128 channels (row = padded board cell, index col*7+row, 56 rows
+//     per board incl. zero guard cells, so a 3x3 tap is a constant row shift and needs no im2col).
+//   * Every conv is 9 (taps) x 8 (K slices of 16 channels) tcgen05.mma steps of M=128 rows x N=128
+//     out-channels x K=16, for 3 row tiles; A = activations read in place through a shifted
+//     no-swizzle K-major shared-memory descriptor, B = the 4 KB weight slice of that (tap, K slice),
+//     D = fp32 accumulators in TMEM (3 x 128 columns).
+//   * Weights (12.6 MB bf16 for 20 blocks, L2 resident) are pre-packed on the host in exactly the
+//     order the MMA consumes them and streamed by one producer thread with cp.async.bulk (TMA) through
+//     a 6-stage mbarrier ring; each slice is loaded once per layer and reused by the 3 row tiles.
+//   * 8 epilogue warps read TMEM (tcgen05.ld 32x32b), add the folded-BN bias, the residual, apply ReLU,
+//     zero the padding rows and write bf16 rows back into the other activation buffer.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 4..11 = epilogue.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "spx_common.cuh"
+
+namespace spx {
+int set_err(int code, const char* fmt, const char* detail);
+void count_launch();
+}  // namespace spx
+
+#define SPX_CUDA_T(expr)                                                                  \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) return spx::set_err(SPX_E_CUDA, #expr ": %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+namespace spx {
+namespace tower {
+
+// ------------------------------------------------------------------------------------------------ geometry
+constexpr int CH = 128;          // trunk channels (filter_factor * 4)
+constexpr int HEAD_CH = 64;      // 32 policy + 32 value head channels, one fused 1x1 conv
+constexpr int BOARD_W = 7, BOARD_H = 6, CELLS = 42;
+constexpr int PAD_STRIDE = 7;    // padded column stride (== the bitboard bit index)
+constexpr int BOARD_ROWS = 56;   // rows per board incl. the shared zero guard column
+constexpr int NB = 7;            // boards per CTA
+constexpr int MT = 3;            // 128-row MMA tiles per CTA
+constexpr int ROWS = MT * 128;   // 384 >= 6*56 + 48
+constexpr int GUARD = 8;         // zero rows before/after (largest tap shift is +-8)
+constexpr int ROWS_TOT = ROWS + 2 * GUARD;
+constexpr int CHUNK_BYTES = ROWS_TOT * 16;   // one 8-channel chunk of every row
+constexpr int ACT_BYTES = CHUNK_BYTES * (CH / 8);
+constexpr int NSTAGE = 6;
+constexpr int STAGE_BYTES = 2 * CH * 16;     // [2 k-chunks][128 out][8 in] bf16 = 4 KB
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARP0 = 4, EPI_THREADS = 256;
+constexpr int FLAT = 32 * CELLS;             // 1344 inputs of each head's first Linear
+constexpr int FC_HIDDEN = 256;
+
+struct Smem {
+    unsigned char act[2][ACT_BYTES];
+    unsigned char wstage[NSTAGE][STAGE_BYTES];
+    unsigned long long full[NSTAGE], empty[NSTAGE], acc_full, epi_done;
+    unsigned long long own[NB], opp[NB];
+    unsigned tmem_base;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(void* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(unsigned taddr, unsigned (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor: core matrix = 8 rows x 16 bytes (contiguous 128 B);
+// SBO = byte stride between 8-row groups, LBO = byte stride between the two 16-byte K chunks of one MMA.
+__device__ __forceinline__ unsigned long long make_desc(unsigned saddr, unsigned lbo, unsigned sbo) {
+    return (unsigned long long)((saddr >> 4) & 0x3FFFu) | ((unsigned long long)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((unsigned long long)((sbo >> 4) & 0x3FFFu) << 32) | (1ULL << 46);
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr unsigned make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ bool row_is_cell(int row, int& board, int& cell) {
+    board = row / BOARD_ROWS;
+    const int p = row - board * BOARD_ROWS;
+    const int col = p / PAD_STRIDE, r = p - col * PAD_STRIDE;
+    cell = col * BOARD_H + r;
+    return p < BOARD_W * PAD_STRIDE && r < BOARD_H;
+}
+
+struct LayerInfo { int taps, kslices, n, in_buf, out_buf, residual; };
+__device__ __forceinline__ LayerInfo layer_info(int l, int n_layers) {
+    LayerInfo li;
+    if (l == 0) { li.taps = 9; li.kslices = 1; li.n = CH; li.in_buf = 0; li.out_buf = 1; li.residual = 0; }
+    else if (l == n_layers - 1) { li.taps = 1; li.kslices = CH / 16; li.n = HEAD_CH; li.in_buf = 1; li.out_buf = -1; li.residual = 0; }
+    else { const int second = ((l - 1) & 1); li.taps = 9; li.kslices = CH / 16; li.n = CH; li.in_buf = second ? 0 : 1; li.out_buf = second ? 1 : 0; li.residual = second; }
+    return li;
+}
+__device__ __forceinline__ int tap_shift(int tap) { return (tap / 3 - 1) * PAD_STRIDE + (tap % 3 - 1); }  // (kh-1)*7 + (kw-1)
+
+// ------------------------------------------------------------------------------------------------ the tower kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long long* __restrict__ opp_g,
+             const unsigned char* __restrict__ needs, long long n_boards, int n_layers,
+             const unsigned char* __restrict__ wconv, const float* __restrict__ bias_all, float* __restrict__ head_out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long n_groups = (n_boards + NB - 1) / NB;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+        mbar_init(&S.acc_full, 1);
+        mbar_init(&S.epi_done, EPI_THREADS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // zero both activation buffers once: guard rows and padding cells must read as zero forever
+    for (int i = tid; i < 2 * ACT_BYTES / 16; i += NUM_THREADS) reinterpret_cast<uint4*>(S.act[0])[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = S.tmem_base;
+
+    unsigned stage = 0, sphase = 0;   // weight ring position (producer and MMA walk the same sequence)
+    unsigned lphase = 0;              // per-layer barrier parity (acc_full / epi_done)
+
+    for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        // CTA-uniform skip when none of the boards of this group asked for an evaluation
+        bool any = needs == nullptr;
+        if (!any) for (int b = 0; b < NB; ++b) { long long gb = grp * NB + b; if (gb < n_boards && needs[gb]) any = true; }
+        if (!any) continue;
+
+        if (warp == 0) {
+            // ===================== TMA producer: stream the pre-packed weight slices in consumption order
+            if (lane == 0) {
+                const unsigned char* wp = wconv;
+                for (int l = 0; l < n_layers; ++l) {
+                    const LayerInfo li = layer_info(l, n_layers);
+                    const unsigned bytes = 2u * (unsigned)li.n * 16u;
+                    for (int it = 0; it < li.taps * li.kslices; ++it) {
+                        mbar_wait(&S.empty[stage], sphase ^ 1u);
+                        mbar_expect_tx(&S.full[stage], bytes);
+                        tma_bulk_g2s(S.wstage[stage], wp, bytes, &S.full[stage]);
+                        wp += bytes;
+                        if (++stage == NSTAGE) { stage = 0; sphase ^= 1u; }
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ===================== MMA issuer (one thread)
+            if (lane == 0) {
+                for (int l = 0; l < n_layers; ++l) {
+                    const LayerInfo li = layer_info(l, n_layers);
+                    const unsigned idesc = make_idesc(128, li.n);
+                    const unsigned a_base = smem_u32(S.act[li.in_buf]) + GUARD * 16;
+                    mbar_wait(&S.epi_done, lphase);   // inputs of this layer written, accumulators drained
+                    tc_fence_after();
+                    int it = 0;
+                    for (int tap = 0; tap < li.taps; ++tap) {
+                        const int shift = li.taps == 9 ? tap_shift(tap) : 0;
+                        for (int ks = 0; ks < li.kslices; ++ks, ++it) {
+                            mbar_wait(&S.full[stage], sphase);
+                            tc_fence_after();
+                            const unsigned long long bdesc = make_desc(smem_u32(S.wstage[stage]), (unsigned)li.n * 16u, 128u);
+#pragma unroll
+                            for (int t = 0; t < MT; ++t) {
+                                const unsigned a_addr = a_base + (unsigned)(2 * ks) * CHUNK_BYTES + (unsigned)((t * 128 + shift) * 16);
+                                tc_mma(tmem_base + (unsigned)(t * 128), make_desc(a_addr, CHUNK_BYTES, 128u), bdesc, idesc, it > 0 ? 1u : 0u);
+                            }
+                            tc_commit(&S.empty[stage]);   // frees the weight slot once these MMAs retire
+                            if (++stage == NSTAGE) { stage = 0; sphase ^= 1u; }
+                        }
+                    }
+                    tc_commit(&S.acc_full);
+                    lphase ^= 1u;
+                }
+            }
+        } else if (warp >= EPI_WARP0) {
+            // ===================== epilogue warps (also write the stem input)
+            const int et = tid - EPI_WARP0 * 32;          // 0..255
+            const int quarter = warp & 3, half = (warp - EPI_WARP0) >> 2;
+            if (et < NB) {
+                const long long gb = grp * NB + et;
+                S.own[et] = gb < n_boards ? own_g[gb] : 0ULL;
+                S.opp[et] = gb < n_boards ? opp_g[gb] : 0ULL;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+            // preprocess (modules.py:115-125): planes (empty, own, enemy) -> channels 0..2 of buffer 0, channels 3..15 zero
+            for (int row = et; row < ROWS; row += EPI_THREADS) {
+                int board, cell;
+                const bool real = row_is_cell(row, board, cell);
+                const int p = row - board * BOARD_ROWS;
+                unsigned o = 0, e = 0;
+                if (real) { o = (unsigned)((S.own[board] >> p) & 1ULL); e = (unsigned)((S.opp[board] >> p) & 1ULL); }
+                const unsigned emp = real ? (1u - o - e) : 0u;
+                const unsigned one = 0x3F80u;  // bf16(1.0)
+                uint4 v0 = make_uint4((emp ? one : 0u) | ((o ? one : 0u) << 16), e ? one : 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(S.act[0] + (GUARD + row) * 16) = v0;
+                *reinterpret_cast<uint4*>(S.act[0] + CHUNK_BYTES + (GUARD + row) * 16) = make_uint4(0, 0, 0, 0);
+            }
+            fence_proxy_async();
+            mbar_arrive(&S.epi_done);
+            for (int l = 0; l < n_layers; ++l) {
+                const LayerInfo li = layer_info(l, n_layers);
+                const float* bias = bias_all + (size_t)l * CH;
+                const int ncol = li.n / 2;   // columns handled by this half
+                mbar_wait(&S.acc_full, lphase);
+                tc_fence_after();
+                for (int t = 0; t < MT; ++t) {
+                    const int row = t * 128 + quarter * 32 + lane;
+                    int board, cell;
+                    const bool real = row_is_cell(row, board, cell);
+                    const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(t * 128 + half * ncol);
+                    for (int c0 = 0; c0 < ncol; c0 += 32) {
+                        unsigned v[32];
+                        tc_ld32(taddr + (unsigned)c0, v);
+                        const int ch0 = half * ncol + c0;
+                        if (li.out_buf >= 0) {
+                            unsigned char* obase = S.act[li.out_buf] + (GUARD + row) * 16;
+#pragma unroll
+                            for (int g8 = 0; g8 < 4; ++g8) {
+                                const int ch = ch0 + g8 * 8;
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + ch));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + ch + 4));
+                                float y[8] = {__uint_as_float(v[g8 * 8 + 0]) + b0.x, __uint_as_float(v[g8 * 8 + 1]) + b0.y,
+                                              __uint_as_float(v[g8 * 8 + 2]) + b0.z, __uint_as_float(v[g8 * 8 + 3]) + b0.w,
+                                              __uint_as_float(v[g8 * 8 + 4]) + b1.x, __uint_as_float(v[g8 * 8 + 5]) + b1.y,
+                                              __uint_as_float(v[g8 * 8 + 6]) + b1.z, __uint_as_float(v[g8 * 8 + 7]) + b1.w};
+                                uint4* dst = reinterpret_cast<uint4*>(obase + (ch >> 3) * CHUNK_BYTES);
+                                if (li.residual) {  // out += identity (modules.py:37), identity lives in the output buffer
+                                    const uint4 idv = *dst;
+                                    const unsigned iw[4] = {idv.x, idv.y, idv.z, idv.w};
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        y[2 * k] += __uint_as_float(iw[k] << 16);
+                                        y[2 * k + 1] += __uint_as_float(iw[k] & 0xFFFF0000u);
+                                    }
+                                }
+                                unsigned pk[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const float lo = real ? fmaxf(y[2 * k], 0.f) : 0.f, hi = real ? fmaxf(y[2 * k + 1], 0.f) : 0.f;
+                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+                                    pk[k] = *reinterpret_cast<unsigned*>(&h2);
+                                }
+                                *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                        } else if (real) {
+                            // fused policy/value 1x1 head conv + BN + ReLU (modules.py:97,102) -> fp32 [board][ch*42 + cell]
+                            const long long gb = grp * NB + board;
+                            if (gb < n_boards) {
+                                float* ob = head_out + (size_t)gb * (HEAD_CH * CELLS) + cell;
+#pragma unroll
+                                for (int k = 0; k < 32; ++k) {
+                                    const int ch = ch0 + k;
+                                    ob[(size_t)ch * CELLS] = fmaxf(__uint_as_float(v[k]) + __ldg(bias + ch), 0.f);
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                lphase ^= 1u;
+                if (l + 1 < n_layers) mbar_arrive(&S.epi_done);
+            }
+        }
+        // non-elected lanes of warps 0-1 and warps 2-3 fall through; ring/phase state persists in the elected lanes
+        __syncthreads();   // group boundary: accumulators drained, buffers reusable
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ fully connected heads
+// policy: Linear(1344 -> A) + softmax (modules.py:99-100); value: Linear(1344 -> 256) + ReLU + Linear(256 -> 1) + tanh
+// (modules.py:104-105).  One CTA = 8 boards, thread j = hidden unit j; fp32 accumulation.
+constexpr int HB = 8;
+__global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ head_in, const unsigned char* __restrict__ needs,
+                                                    long long n_boards, int A, const float* __restrict__ pol_w,
+                                                    const float* __restrict__ pol_b, const __nv_bfloat16* __restrict__ w1t,
+                                                    const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                                                    float* __restrict__ policy, float* __restrict__ value) {
+    extern __shared__ float hs[];            // [FLAT][HB] value-head inputs, then [HB][256] hidden
+    float* vin = hs;
+    float* hid = hs + FLAT * HB;
+    const long long b0 = (long long)blockIdx.x * HB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    bool any = needs == nullptr;
+    if (!any) for (int b = 0; b < HB; ++b) if (b0 + b < n_boards && needs[b0 + b]) any = true;
+    if (!any) return;
+    for (int i = tid; i < FLAT * HB; i += 256) {
+        const int b = i / FLAT, k = i - b * FLAT;
+        vin[k * HB + b] = (b0 + b < n_boards) ? head_in[(size_t)(b0 + b) * (HEAD_CH * CELLS) + FLAT + k] : 0.f;
+    }
+    __syncthreads();
+    float acc[HB];
+#pragma unroll
+    for (int b = 0; b < HB; ++b) acc[b] = 0.f;
+    for (int k = 0; k < FLAT; ++k) {
+        const float w = __bfloat162float(w1t[(size_t)k * FC_HIDDEN + tid]);
+        const float4 x0 = *reinterpret_cast<const float4*>(vin + k * HB), x1 = *reinterpret_cast<const float4*>(vin + k * HB + 4);
+        acc[0] = fmaf(w, x0.x, acc[0]); acc[1] = fmaf(w, x0.y, acc[1]); acc[2] = fmaf(w, x0.z, acc[2]); acc[3] = fmaf(w, x0.w, acc[3]);
+        acc[4] = fmaf(w, x1.x, acc[4]); acc[5] = fmaf(w, x1.y, acc[5]); acc[6] = fmaf(w, x1.z, acc[6]); acc[7] = fmaf(w, x1.w, acc[7]);
+    }
+    const float bb = b1[tid];
+#pragma unroll
+    for (int b = 0; b < HB; ++b) hid[b * FC_HIDDEN + tid] = fmaxf(acc[b] + bb, 0.f);
+    __syncthreads();
+    // warp w finishes board w: value = tanh(hid . w2 + b2); policy = softmax(W_p x + b_p)
+    const long long gb = b0 + warp;
+    if (gb >= n_boards) return;
+    float s = 0.f;
+    for (int j = lane; j < FC_HIDDEN; j += 32) s = fmaf(hid[warp * FC_HIDDEN + j], w2[j], s);
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) value[gb] = tanhf(s + b2[0]);
+    const float* pin = head_in + (size_t)gb * (HEAD_CH * CELLS);
+    float logit[SPX_MAX_ACTIONS];
+    for (int a = 0; a < A; ++a) {
+        float d = 0.f;
+        for (int k = lane; k < FLAT; k += 32) d = fmaf(pin[k], pol_w[(size_t)a * FLAT + k], d);
+        for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+        logit[a] = d + pol_b[a];
+    }
+    if (lane == 0) {
+        float m = logit[0];
+        for (int a = 1; a < A; ++a) m = fmaxf(m, logit[a]);
+        float z = 0.f;
+        for (int a = 0; a < A; ++a) { logit[a] = expf(logit[a] - m); z += logit[a]; }
+        for (int a = 0; a < A; ++a) policy[gb * A + a] = logit[a] / z;
+    }
+}
+
+}  // namespace tower
+}  // namespace spx
+
+// ================================================================================================== C ABI
+struct spx_tower {
+    int game, num_blocks, n_layers, A;
+    size_t off_bias, off_polw, off_polb, off_w1t, off_b1, off_w2, off_b2, blob_bytes;
+    unsigned char* blob;    // device copy of the packed weights
+    float* head_buf;        // [capacity][64*42] fp32 head-conv activations
+    long long capacity;
+    int sm_count;
+};
+
+using namespace spx::tower;
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" {
+
+int64_t spx_tower_blob_bytes(int32_t game, int32_t num_blocks) {
+    if (game != SPX_GAME_CONNECT4 || num_blocks < 0) return -1;
+    const int A = 7, n_layers = 2 * num_blocks + 2;
+    size_t conv = (size_t)9 * 1 * STAGE_BYTES + (size_t)num_blocks * 2 * 9 * 8 * STAGE_BYTES + (size_t)8 * (2 * HEAD_CH * 16);
+    size_t off = align_up(conv, 256);
+    off = align_up(off + (size_t)n_layers * CH * 4, 256);      // biases
+    off = align_up(off + (size_t)A * FLAT * 4, 256);           // policy weight
+    off = align_up(off + 16 * 4, 256);                         // policy bias (padded)
+    off = align_up(off + (size_t)FLAT * FC_HIDDEN * 2, 256);   // value fc1, transposed bf16
+    off = align_up(off + FC_HIDDEN * 4, 256);                  // b1
+    off = align_up(off + FC_HIDDEN * 4, 256);                  // w2
+    off = align_up(off + 16, 256);                             // b2
+    return (int64_t)off;
+}
+
+int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
+    if (!out) return spx::set_err(SPX_E_ARG, "spx_tower_create: null out%s", "");
+    if (game != SPX_GAME_CONNECT4) return spx::set_err(SPX_E_ARG, "spx_tower_create: the native tower is built for the 7x6 connect4 ResidualTower%s", "");
+    if (num_blocks < 1 || num_blocks > 64) return spx::set_err(SPX_E_ARG, "spx_tower_create: num_blocks out of range%s", "");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return spx::set_err(SPX_E_CUDA, "spx_tower_create: no CUDA device (there is no CPU fallback)%s", "");
+    spx_tower* t = new (std::nothrow) spx_tower();
+    if (!t) return spx::set_err(SPX_E_ARG, "spx_tower_create: out of host memory%s", "");
+    memset(t, 0, sizeof(*t));
+    t->game = game; t->num_blocks = num_blocks; t->n_layers = 2 * num_blocks + 2; t->A = 7;
+    size_t conv = (size_t)9 * STAGE_BYTES + (size_t)num_blocks * 2 * 72 * STAGE_BYTES + (size_t)8 * (2 * HEAD_CH * 16);
+    size_t off = align_up(conv, 256);
+    t->off_bias = off; off = align_up(off + (size_t)t->n_layers * CH * 4, 256);
+    t->off_polw = off; off = align_up(off + (size_t)t->A * FLAT * 4, 256);
+    t->off_polb = off; off = align_up(off + 16 * 4, 256);
+    t->off_w1t = off; off = align_up(off + (size_t)FLAT * FC_HIDDEN * 2, 256);
+    t->off_b1 = off; off = align_up(off + FC_HIDDEN * 4, 256);
+    t->off_w2 = off; off = align_up(off + FC_HIDDEN * 4, 256);
+    t->off_b2 = off; off = align_up(off + 16, 256);
+    t->blob_bytes = off;
+    SPX_CUDA_T(cudaMalloc((void**)&t->blob, t->blob_bytes));
+    int dev = 0;
+    SPX_CUDA_T(cudaGetDevice(&dev));
+    SPX_CUDA_T(cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024));
+    SPX_CUDA_T(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((FLAT * HB + HB * FC_HIDDEN) * 4)));
+    *out = t;
+    return 0;
+}
+
+int spx_tower_destroy(spx_tower* t) {
+    if (!t) return 0;
+    if (t->blob) cudaFree(t->blob);
+    if (t->head_buf) cudaFree(t->head_buf);
+    delete t;
+    return 0;
+}
+
+/* copies a packed weight blob (device pointer, layout of nets.pack_tower_blob / spx_tower_blob_bytes) */
+int spx_tower_load(spx_tower* t, const void* dev_blob, int64_t bytes, void* stream) {
+    if (!t || !dev_blob) return spx::set_err(SPX_E_ARG, "spx_tower_load: null argument%s", "");
+    if ((size_t)bytes != t->blob_bytes) return spx::set_err(SPX_E_ARG, "spx_tower_load: blob size mismatch%s", "");
+    SPX_CUDA_T(cudaMemcpyAsync(t->blob, dev_blob, t->blob_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int spx_tower_forward(spx_tower* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n,
+                      float* policy, float* value, void* stream) {
+    if (!t || !own || !opp || !policy || !value) return spx::set_err(SPX_E_ARG, "spx_tower_forward: null argument%s", "");
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n > t->capacity) {
+        if (t->head_buf) { SPX_CUDA_T(cudaStreamSynchronize(st)); SPX_CUDA_T(cudaFree(t->head_buf)); t->head_buf = nullptr; }
+        SPX_CUDA_T(cudaMalloc((void**)&t->head_buf, (size_t)n * HEAD_CH * CELLS * sizeof(float)));
+        t->capacity = n;
+    }
+    const long long groups = (n + NB - 1) / NB;
+    const int grid = (int)(groups < t->sm_count ? groups : t->sm_count);
+    tower_kernel<<<grid, NUM_THREADS, sizeof(Smem) + 1024, st>>>((const unsigned long long*)own, (const unsigned long long*)opp, needs_eval, n,
+                                                              t->n_layers, t->blob, (const float*)(t->blob + t->off_bias), t->head_buf);
+    spx::count_launch();
+    SPX_CUDA_T(cudaGetLastError());
+    heads_kernel<<<(int)((n + HB - 1) / HB), 256, (FLAT * HB + HB * FC_HIDDEN) * 4, st>>>(
+        t->head_buf, needs_eval, n, t->A, (const float*)(t->blob + t->off_polw), (const float*)(t->blob + t->off_polb),
+        (const __nv_bfloat16*)(t->blob + t->off_w1t), (const float*)(t->blob + t->off_b1), (const float*)(t->blob + t->off_w2),
+        (const float*)(t->blob + t->off_b2), policy, value);
+    spx::count_launch();
+    SPX_CUDA_T(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"
