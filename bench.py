@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- MCTS sims/sec (and self-play positions/sec) for Connect4 self-play, 800 sims/move.
+
+Contract (see DESIGN.md "Measurement"):
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
+  python bench.py --impl reference ...                     (the CPU arm: oracle port on the host cores)
+
+Workload at N=1 = BASELINE.json configs[1]: Connect4 6x7 self-play, the repo's connect4 net
+ResidualTower(7,6,7,num_blocks=20) with random init (torch.manual_seed(0)), 1024 concurrent games per GPU,
+800 sims/move, Dirichlet alpha=1 generated on device, tie noise on, finished games replaced at once.
+A "step" = 800 engine ticks (one tick = one spx_advance over all games + one batched network evaluation),
+i.e. about one searched move per game.  `value` = completed MCTS simulations per second over all ranks, device
+timed with everything resident in HBM.  `e2e` = the same metric through the package's public API with HOST
+buffers: every step uploads the packed network weights from pinned host memory (the weight refresh the
+reference does through checkpoint files) and downloads that step's Move records, game results and counters.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_LEAF_20 = 497_138_048  # ResidualTower-20, SURVEY.md 6 / 8(d)
+TICKS_PER_STEP = 800
+
+
+def flop_per_leaf(blocks):
+    conv = 2 * 42 * (9 * 3 * 128 + blocks * 2 * 9 * 128 * 128 + 128 * 64)
+    fc = 2 * (1344 * 7 + 1344 * 256 + 256)
+    return conv + fc
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--games", type=int, default=1024, help="concurrent games per GPU")
+    ap.add_argument("--sims", type=int, default=800)
+    ap.add_argument("--blocks", type=int, default=20)
+    ap.add_argument("--net", default="tower", choices=["tower", "torch", "hash"])
+    ap.add_argument("--ticks-per-step", type=int, default=TICKS_PER_STEP)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bounded CPU-baseline sample per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- CPU arm
+def _cpu_worker(idx, counters_addr_holder, blocks, sims, seed):
+    """One host core: the oracle port (C tree/env restatement + fp32 torch net, batch 1, one thread), i.e. the
+    reference's direct mode (BASELINE.md 4 mode (i)): SelfPlayer.play_episode over two MCTreeSearch."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    from oracle import oracle as ox
+    from self_play_reinforcement_learning_b200 import nets
+    torch.manual_seed(0)
+    net = nets.ResidualTower(7, 6, 7, num_blocks=blocks).eval()
+    shared = counters_addr_holder
+    ox.lib().ox_set_live_counters(C.addressof(shared))
+
+    def fn(state, tree):
+        with torch.no_grad():
+            p, v = net.forward(torch.from_numpy(np.ascontiguousarray(state).astype(np.int64)))
+        return p[0].tolist(), float(v.item())
+    pynet = ox.PyNet(0, fn)
+    g = idx
+    while True:
+        cfg = ox.make_cfg(0, sims, seed=seed, game_uid=g, noise_mode=2, alpha=1.0)
+        ox.play_episode(cfg, bool(g & 1), nets=((pynet.addr, None), (pynet.addr, None)))
+        g += 1 << 20
+
+
+def cpu_baseline(seconds, blocks, sims, procs=None):
+    """Time-boxed: `procs` processes play self-play games for `seconds`; sims and moves counted live."""
+    import multiprocessing as mp
+    import ctypes as C
+    ctx = mp.get_context("fork")
+    procs = procs or len(os.sched_getaffinity(0))
+
+    class Pair(C.Structure):
+        _fields_ = [("sims", C.c_long), ("moves", C.c_long)]
+    shared = [ctx.RawValue(Pair) for _ in range(procs)]
+    ps = [ctx.Process(target=_cpu_worker, args=(i, shared[i], blocks, sims, 0), daemon=True) for i in range(procs)]
+    for p in ps:
+        p.start()
+    # wait until every worker is past start-up (first simulation done), then measure a clean window
+    t_dead = time.time() + 120
+    while time.time() < t_dead and not all(s.sims > 0 for s in shared):
+        time.sleep(0.2)
+    s0 = sum(s.sims for s in shared); m0 = sum(s.moves for s in shared); t0 = time.time()
+    time.sleep(seconds)
+    s1 = sum(s.sims for s in shared); m1 = sum(s.moves for s in shared); t1 = time.time()
+    for p in ps:
+        p.terminate()
+    for p in ps:
+        p.join(timeout=5)
+    dt = t1 - t0
+    return {"sims_per_s": (s1 - s0) / dt, "positions_per_s": (m1 - m0) / dt, "cores": procs, "seconds": dt, "sims": s1 - s0}
+
+
+def run_reference(args, workload):
+    """--impl reference: the reference's CPU implementation of the path (oracle port, kind 'port': the reference is
+    pure Python and does not exist on the GPU box) on all host cores; each 'step' is a bounded time-boxed sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, cores = [], None
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_baseline(min(args.cpu_seconds, 5.0), args.blocks, args.sims)
+    t0 = time.time()
+    for _ in range(args.steps):
+        r = cpu_baseline(args.cpu_seconds, args.blocks, args.sims)
+        vals.append(r)
+        cores = r["cores"]
+    tot_sims = sum(v["sims"] for v in vals); tot_t = sum(v["seconds"] for v in vals)
+    value = tot_sims / tot_t
+    sample = (f"{args.steps} x {args.cpu_seconds:.0f}s windows, {cores} processes x 1 thread, each playing Connect4 self-play "
+              f"episodes (two trees, {args.sims} sims/move) with the C oracle tree + fp32 torch ResidualTower-{args.blocks} at batch 1")
+    line = {"impl": "reference", "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot_t / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload,
+            "cpu_baseline": {"value": value, "unit": "sims/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "positions_per_sec": sum(v["positions_per_s"] * v["seconds"] for v in vals) / tot_t,
+            "wall_s": time.time() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = {"workload": f"connect4 6x7 self-play, ResidualTower-{args.blocks} random init (seed 0), {args.games} concurrent games/GPU, "
+                            f"{args.sims} sims/move, two trees per game, finished games replaced immediately",
+                "games_per_gpu": args.games, "sims_per_move": args.sims, "net": args.net, "ticks_per_step": args.ticks_per_step,
+                "l2_policy": "node pools (5.4 GB/GPU) and weights (12.6 MB) are the inputs; the touched working set per step "
+                             "exceeds L2 (126 MB), no flush needed", "parallelism": f"games sharded over {max(world, args.gpus)} GPU(s), no data-path collective"}
+    if args.impl == "reference":
+        return run_reference(args, workload)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from self_play_reinforcement_learning_b200 import _lib, nets
+    from self_play_reinforcement_learning_b200.engine import HashNetEvaluator, SelfPlayEngine
+    from self_play_reinforcement_learning_b200.selfplay import BatchedSelfPlay
+
+    torch.manual_seed(0)
+    module = nets.ResidualTower(7, 6, 7, num_blocks=args.blocks).eval()
+    G, T = args.games, args.ticks_per_step
+
+    # ---- public-API object (also used for the resident-data measurement through its engine)
+    sp = BatchedSelfPlay(module, game=0, n_games=G, sims=args.sims, net=args.net, seed=0, rank=rank, world=world)
+    eng, ev = sp.engine, sp.evaluator
+    blob_host = sp.packed_weights_pinned() if args.net == "tower" else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (untimed)
+    for _ in range(max(args.warmup, 3)):
+        eng.run_ticks(T)
+    barrier()
+    c0 = eng.counters()
+    launches0 = _lib.lib().spx_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---- timed region 1: everything resident (value); events around the dominant kernel every 8th tick
+    tower_ev, adv_ev = [], []
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for s in range(args.steps):
+        for t in range(T):
+            if args.net == "tower" and t % 8 == 0:
+                a = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                n3 = tuple(torch.cuda.Event(enable_timing=True) for _ in range(3))
+                eng.tick(advance_events=a, net_events=n3)
+                adv_ev.append(a); tower_ev.append(n3)
+            else:
+                eng.tick()
+    end.record()
+    barrier()
+    ms = start.elapsed_time(end)
+    c1 = eng.counters()
+    launches1 = _lib.lib().spx_launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    sims = c1["sims"] - c0["sims"]
+    moves = c1["moves"] - c0["moves"]
+    evals = c1["leaf_evals"] - c0["leaf_evals"]
+    ticks = c1["ticks"] - c0["ticks"]
+    path = (c1["path_len_sum"] - c0["path_len_sum"]) / max(sims, 1)
+    stat = torch.tensor([ms, float(sims), float(moves), float(evals)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stat.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stat.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, sims_all, moves_all, evals_all = mx[0].item(), sm[1].item(), sm[2].item(), sm[3].item()
+    else:
+        sims_all, moves_all, evals_all = float(sims), float(moves), float(evals)
+    value = sims_all / (ms / 1e3)
+
+    tower_ms = heads_ms = adv_ms = None
+    if tower_ev:
+        tower_ms = sum(e[0].elapsed_time(e[1]) for e in tower_ev) / len(tower_ev)
+        heads_ms = sum(e[1].elapsed_time(e[2]) for e in tower_ev) / len(tower_ev)
+        adv_ms = sum(a[0].elapsed_time(a[1]) for a in adv_ev) / len(adv_ev)
+
+    # ---- timed region 2: end to end through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        t_sims0 = eng.counters()["sims"]
+        h2d = d2h = 0
+        start2, end2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start2.record()
+        for s in range(args.steps):
+            out = sp.play_step(T, weights_host=blob_host)   # H2D weights, T ticks, D2H records/results/counters
+            h2d += out["h2d_bytes"]; d2h += out["d2h_bytes"]
+        end2.record()
+        barrier()
+        ms2 = start2.elapsed_time(end2)
+        s2 = eng.counters()["sims"] - t_sims0
+        st2 = torch.tensor([ms2, float(s2)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            mx2 = st2.clone(); dist.all_reduce(mx2, op=dist.ReduceOp.MAX)
+            sm2 = st2.clone(); dist.all_reduce(sm2, op=dist.ReduceOp.SUM)
+            ms2, s2 = mx2[0].item(), sm2[1].item()
+        e2e = {"value": s2 / (ms2 / 1e3), "unit": "sims/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
+               "ms_per_step": ms2 / args.steps}
+
+    # ---- search-only leg (hash net): HBM roofline of the search/env kernel
+    search = None
+    if rank == 0 and args.net == "tower":
+        sp.close()
+        e2 = SelfPlayEngine(game=0, n_games=G, sims=args.sims, evaluator=HashNetEvaluator(0, 1), seed=1, noise_mode=2)
+        e2.run_ticks(3 * T)
+        torch.cuda.synchronize()
+        k0 = e2.counters()
+        evs = []
+        for t in range(2 * T):
+            a = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            e2.tick(advance_events=a)
+            evs.append(a)
+        torch.cuda.synchronize()
+        k1 = e2.counters()
+        a_ms = sum(a[0].elapsed_time(a[1]) for a in evs)
+        s_ = k1["sims"] - k0["sims"]
+        L = (k1["path_len_sum"] - k0["path_len_sum"]) / max(s_, 1)
+        bytes_per_sim = 136.0 * L + 212.0
+        peaks_s = _peaks()
+        search = {"sims_per_s_kernel_only": s_ / (a_ms / 1e3), "mean_path_len": L, "bytes_per_sim": bytes_per_sim,
+                  "achieved_GBps": s_ * bytes_per_sim / (a_ms / 1e3) / 1e9, "peak_GBps": peaks_s["hbm_gbs"],
+                  "frac": s_ * bytes_per_sim / (a_ms / 1e3) / 1e9 / peaks_s["hbm_gbs"], "advance_ms_per_launch": a_ms / len(evs)}
+        e2.close()
+
+    if rank == 0:
+        peaks = _peaks()
+        fl = flop_per_leaf(args.blocks)
+        roof = None
+        if tower_ms:
+            leaves_per_launch = evals / max(ticks, 1)
+            achieved = leaves_per_launch * fl / (tower_ms / 1e3) / 1e12
+            roof = {"bound": "tensor", "kernel": "spx::tower::tower_kernel", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
+                    "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": _ncu_traffic(),
+                    "peak_source": peaks["source"], "flop_per_leaf": fl, "leaves_per_launch": leaves_per_launch,
+                    "kernel_ms": tower_ms, "heads_kernel_ms": heads_ms, "advance_kernel_ms": adv_ms,
+                    "kernel_share_of_step": tower_ms * ticks / max(ms, 1e-9) if world == 1 else None}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            r = cpu_baseline(args.cpu_seconds, args.blocks, args.sims)
+            cpu = {"value": r["sims_per_s"], "unit": "sims/s", "cores": r["cores"], "kind": "port",
+                   "sample": f"{r['seconds']:.0f}s window, {r['cores']} processes x 1 thread: C oracle tree/env + fp32 torch "
+                             f"ResidualTower-{args.blocks} at batch 1 (the reference's direct mode), {args.sims} sims/move",
+                   "positions_per_s": r["positions_per_s"]}
+        line = {"metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": workload, "positions_per_sec": moves_all / (ms / 1e3), "leaf_evals_per_sec": evals_all / (ms / 1e3),
+                "mean_select_path_len": path, "e2e": e2e, "gpu_launches": int(launches1 - launches0), "clocks": clocks,
+                "roofline": roof, "search_roofline": search, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def _ncu_traffic():
+    """dram bytes per launch of the tower kernel from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "tower_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))["dram_bytes_per_launch"]
+        except Exception:
+            return None
+    return None
+
+
+if __name__ == "__main__":
+    main()

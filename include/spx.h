@@ -188,6 +188,12 @@ int spx_tower_load(spx_tower* t, const void* dev_blob, int64_t bytes, void* stre
  * (softmax), value dev f32[n] (tanh).  Rows whose needs_eval is 0 may be left untouched. */
 int spx_tower_forward(spx_tower* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n,
                       float* policy, float* value, void* stream);
+/* same, recording caller-owned cudaEvent_t handles (void*) around the conv tower and the heads kernel: bench.py
+ * times the dominant kernel on the launching stream with these */
+int spx_tower_forward_timed(spx_tower* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n,
+                            float* policy, float* value, void* stream, void* ev_start, void* ev_tower_done, void* ev_end);
+/* spx_advance with events before/after (HBM roofline of the search kernel) */
+int spx_advance_timed(spx_engine* e, const float* policy, const float* value, void* stream, void* ev_start, void* ev_end);
 
 #ifdef __cplusplus
 }

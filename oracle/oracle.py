@@ -79,6 +79,7 @@ def lib():
         L.ox_tree_counter.restype = C.c_long
         L.ox_play_episode.argtypes = [C.POINTER(Cfg), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Episode)]
         L.ox_hashnet_bits.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.ox_set_live_counters.argtypes = [C.c_void_p]
         L.ox_env_playout.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
         _lib = L
     return _lib

@@ -389,6 +389,10 @@ static void remove_noise(ox_tree* t) { /* mcts.py:55-57 */
     for (int i = 0; i < t->A; ++i) t->nodes[root->first_child + i].noise_active = 0;
 }
 
+/* live counters for the time-boxed CPU baseline (bench.py): [0] sims, [1] moves; may point into shared memory */
+static volatile long* g_live = 0;
+void ox_set_live_counters(long* p) { g_live = p; }
+
 /* mcts.py:340-367 (sequential mode: thread_count == 1) */
 static void search_node(ox_tree* t, int ply, uint32_t sim) {
     int node = t->root;
@@ -426,7 +430,7 @@ static void search_node(ox_tree* t, int ply, uint32_t sim) {
 void ox_tree_search(ox_tree* t) { /* mcts.py:323-338 */
     add_noise(t);
     int ply = root_ply(t);
-    for (int i = 0; i < t->cfg.sims; ++i) { search_node(t, ply, (uint32_t)i); t->sims_done++; }
+    for (int i = 0; i < t->cfg.sims; ++i) { search_node(t, ply, (uint32_t)i); t->sims_done++; if (g_live) g_live[0]++; }
     remove_noise(t);
 }
 
@@ -468,6 +472,7 @@ int ox_tree_play(ox_tree* t, ox_move* log) {
         rec->q = (float)node_q(root);
     }
     if (log) log->action = action;
+    if (g_live) g_live[1]++;
     t->moves_played += 1;
     return action;
 }

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspx.so")
+LIB_PATH = os.environ.get("SPX_LIB_PATH") or os.path.join(_HERE, "libspx.so")  # override: experiment builds only
 
 MAX_ACTIONS = 9
 GAME_CONNECT4, GAME_TICTACTOE = 0, 1
@@ -51,7 +51,8 @@ EXPORTS = ["spx_last_error", "spx_version", "spx_launch_count", "spx_env_step", 
            "spx_hashnet_forward", "spx_create", "spx_destroy", "spx_reset", "spx_set_noise_table", "spx_advance",
            "spx_leaf_batch", "spx_root_stats", "spx_drain_records", "spx_drain_results", "spx_read_move_log",
            "spx_counters_read", "spx_all_idle", "spx_device_bytes", "spx_pending_tree", "spx_tower_blob_bytes",
-           "spx_tower_create", "spx_tower_destroy", "spx_tower_load", "spx_tower_forward"]
+           "spx_tower_create", "spx_tower_destroy", "spx_tower_load", "spx_tower_forward", "spx_tower_forward_timed",
+           "spx_advance_timed"]
 
 _lib = None
 
@@ -91,6 +92,8 @@ def lib():
         L.spx_tower_destroy.argtypes = [vp]
         L.spx_tower_load.argtypes = [vp, vp, i64, vp]
         L.spx_tower_forward.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
+        L.spx_tower_forward_timed.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+        L.spx_advance_timed.argtypes = [vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 

@@ -835,6 +835,14 @@ int spx_advance(spx_engine* e, const float* policy, const float* value, void* st
     return 0;
 }
 
+int spx_advance_timed(spx_engine* e, const float* policy, const float* value, void* stream, void* ev_start, void* ev_end) {
+    if (ev_start) SPX_CUDA(cudaEventRecord((cudaEvent_t)ev_start, (cudaStream_t)stream));
+    int rc = spx_advance(e, policy, value, stream);
+    if (rc) return rc;
+    if (ev_end) SPX_CUDA(cudaEventRecord((cudaEvent_t)ev_end, (cudaStream_t)stream));
+    return 0;
+}
+
 int spx_leaf_batch(spx_engine* e, uint64_t** own, uint64_t** opp, uint8_t** needs_eval, uint8_t** net_id) {
     if (!e) return set_err(SPX_E_ARG, "spx_leaf_batch: null engine%s", "");
     if (own) *own = (uint64_t*)e->d.leaf_own;

@@ -15,7 +15,7 @@
 //     D = fp32 accumulators in TMEM (3 x 128 columns).
 //   * Weights (12.6 MB bf16 for 20 blocks, L2 resident) are pre-packed on the host in exactly the
 //     order the MMA consumes them and streamed by one producer thread with cp.async.bulk (TMA) through
-//     a 6-stage mbarrier ring; each slice is loaded once per layer and reused by the 3 row tiles.
+//     a 3-stage (8 KB each) mbarrier ring; each slice is loaded once per layer and reused by the 3 row tiles.
 //   * 8 epilogue warps read TMEM (tcgen05.ld 32x32b), add the folded-BN bias, the residual, apply ReLU,
 //     zero the padding rows and write bf16 rows back into the other activation buffer.
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 4..11 = epilogue.
@@ -56,8 +56,12 @@ constexpr int GUARD = 8;         // zero rows before/after (largest tap shift is
 constexpr int ROWS_TOT = ROWS + 2 * GUARD;
 constexpr int CHUNK_BYTES = ROWS_TOT * 16;   // one 8-channel chunk of every row
 constexpr int ACT_BYTES = CHUNK_BYTES * (CH / 8);
-constexpr int NSTAGE = 6;
-constexpr int STAGE_BYTES = 2 * CH * 16;     // [2 k-chunks][128 out][8 in] bf16 = 4 KB
+#ifndef SPX_NSTAGE
+#define SPX_NSTAGE 3
+#endif
+constexpr int NSTAGE = SPX_NSTAGE;
+constexpr int KSTEP_BYTES = 2 * CH * 16;     // one K=16 weight slice: [2 k-chunks][128 out][8 in] bf16 = 4 KB
+constexpr int STAGE_BYTES = 2 * KSTEP_BYTES; // a ring stage carries two K steps (K = 32)
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4, EPI_THREADS = 256;
 constexpr int FLAT = 32 * CELLS;             // 1344 inputs of each head's first Linear
@@ -94,6 +98,11 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -187,49 +196,67 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
         if (!any) continue;
 
         if (warp == 0) {
-            // ===================== TMA producer: stream the pre-packed weight slices in consumption order
-            if (lane == 0) {
-                const unsigned char* wp = wconv;
-                for (int l = 0; l < n_layers; ++l) {
-                    const LayerInfo li = layer_info(l, n_layers);
-                    const unsigned bytes = 2u * (unsigned)li.n * 16u;
-                    for (int it = 0; it < li.taps * li.kslices; ++it) {
-                        mbar_wait(&S.empty[stage], sphase ^ 1u);
+            // ===================== TMA producer: stream the pre-packed weight slices in consumption order.
+            // The whole warp walks the loop (warp-uniform control flow keeps addresses in uniform registers);
+            // one elected lane issues the copies.
+            const bool leader = elect_one();
+            const unsigned char* wp = wconv;
+            for (int l = 0; l < n_layers; ++l) {
+                const LayerInfo li = layer_info(l, n_layers);
+                const int ksteps = li.kslices >= 2 ? 2 : 1;                  // K steps (of 16 channels) per ring stage
+                const unsigned bytes = 2u * (unsigned)li.n * 16u * (unsigned)ksteps;
+                const int iters = li.taps * (li.kslices / ksteps);
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(&S.empty[stage], sphase ^ 1u);
+                    if (leader) {
                         mbar_expect_tx(&S.full[stage], bytes);
                         tma_bulk_g2s(S.wstage[stage], wp, bytes, &S.full[stage]);
-                        wp += bytes;
-                        if (++stage == NSTAGE) { stage = 0; sphase ^= 1u; }
                     }
+                    __syncwarp();
+                    wp += bytes;
+                    if (++stage == NSTAGE) { stage = 0; sphase ^= 1u; }
                 }
             }
         } else if (warp == 1) {
-            // ===================== MMA issuer (one thread)
-            if (lane == 0) {
-                for (int l = 0; l < n_layers; ++l) {
-                    const LayerInfo li = layer_info(l, n_layers);
-                    const unsigned idesc = make_idesc(128, li.n);
-                    const unsigned a_base = smem_u32(S.act[li.in_buf]) + GUARD * 16;
-                    mbar_wait(&S.epi_done, lphase);   // inputs of this layer written, accumulators drained
-                    tc_fence_after();
-                    int it = 0;
-                    for (int tap = 0; tap < li.taps; ++tap) {
-                        const int shift = li.taps == 9 ? tap_shift(tap) : 0;
-                        for (int ks = 0; ks < li.kslices; ++ks, ++it) {
-                            mbar_wait(&S.full[stage], sphase);
-                            tc_fence_after();
-                            const unsigned long long bdesc = make_desc(smem_u32(S.wstage[stage]), (unsigned)li.n * 16u, 128u);
+            // ===================== MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit
+            const bool leader = elect_one();
+            for (int l = 0; l < n_layers; ++l) {
+                const LayerInfo li = layer_info(l, n_layers);
+                const unsigned idesc = make_idesc(128, li.n);
+                const int ksteps = li.kslices >= 2 ? 2 : 1;
+                const int kpairs = li.kslices / ksteps;
+                const unsigned kstep_bytes = 2u * (unsigned)li.n * 16u;
+                const unsigned a_base = smem_u32(S.act[li.in_buf]) + GUARD * 16;
+                mbar_wait(&S.epi_done, lphase);   // inputs of this layer written, accumulators drained
+                tc_fence_after();
+                unsigned acc = 0;
+                for (int tap = 0; tap < li.taps; ++tap) {
+                    const int shift = li.taps == 9 ? tap_shift(tap) : 0;
+                    for (int kp = 0; kp < kpairs; ++kp) {
+                        mbar_wait(&S.full[stage], sphase);
+                        tc_fence_after();
+                        const unsigned b_addr = smem_u32(S.wstage[stage]);
+                        const unsigned a_addr0 = a_base + (unsigned)(2 * ksteps * kp) * CHUNK_BYTES + (unsigned)(shift * 16);
+                        if (leader) {
+                            for (int j = 0; j < ksteps; ++j) {
+                                const unsigned long long bdesc = make_desc(b_addr + (unsigned)j * kstep_bytes, (unsigned)li.n * 16u, 128u);
 #pragma unroll
-                            for (int t = 0; t < MT; ++t) {
-                                const unsigned a_addr = a_base + (unsigned)(2 * ks) * CHUNK_BYTES + (unsigned)((t * 128 + shift) * 16);
-                                tc_mma(tmem_base + (unsigned)(t * 128), make_desc(a_addr, CHUNK_BYTES, 128u), bdesc, idesc, it > 0 ? 1u : 0u);
+                                for (int t = 0; t < MT; ++t) {
+                                    const unsigned a_addr = a_addr0 + (unsigned)(2 * j) * CHUNK_BYTES + (unsigned)(t * 128 * 16);
+                                    tc_mma(tmem_base + (unsigned)(t * 128), make_desc(a_addr, CHUNK_BYTES, 128u), bdesc, idesc, acc);
+                                }
+                                acc = 1u;
                             }
                             tc_commit(&S.empty[stage]);   // frees the weight slot once these MMAs retire
-                            if (++stage == NSTAGE) { stage = 0; sphase ^= 1u; }
                         }
+                        acc = 1u;
+                        __syncwarp();
+                        if (++stage == NSTAGE) { stage = 0; sphase ^= 1u; }
                     }
-                    tc_commit(&S.acc_full);
-                    lphase ^= 1u;
                 }
+                if (leader) tc_commit(&S.acc_full);
+                __syncwarp();
+                lphase ^= 1u;
             }
         } else if (warp >= EPI_WARP0) {
             // ===================== epilogue warps (also write the stem input)
@@ -263,6 +290,9 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 mbar_wait(&S.acc_full, lphase);
                 tc_fence_after();
                 for (int t = 0; t < MT; ++t) {
+#ifdef SPX_DBG_SKIP_EPI
+                    if (li.out_buf >= 0) continue;
+#endif
                     const int row = t * 128 + quarter * 32 + lane;
                     int board, cell;
                     const bool real = row_is_cell(row, board, cell);
@@ -411,7 +441,7 @@ extern "C" {
 int64_t spx_tower_blob_bytes(int32_t game, int32_t num_blocks) {
     if (game != SPX_GAME_CONNECT4 || num_blocks < 0) return -1;
     const int A = 7, n_layers = 2 * num_blocks + 2;
-    size_t conv = (size_t)9 * 1 * STAGE_BYTES + (size_t)num_blocks * 2 * 9 * 8 * STAGE_BYTES + (size_t)8 * (2 * HEAD_CH * 16);
+    size_t conv = (size_t)9 * 1 * KSTEP_BYTES + (size_t)num_blocks * 2 * 9 * 8 * KSTEP_BYTES + (size_t)8 * (2 * HEAD_CH * 16);
     size_t off = align_up(conv, 256);
     off = align_up(off + (size_t)n_layers * CH * 4, 256);      // biases
     off = align_up(off + (size_t)A * FLAT * 4, 256);           // policy weight
@@ -433,7 +463,7 @@ int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
     if (!t) return spx::set_err(SPX_E_ARG, "spx_tower_create: out of host memory%s", "");
     memset(t, 0, sizeof(*t));
     t->game = game; t->num_blocks = num_blocks; t->n_layers = 2 * num_blocks + 2; t->A = 7;
-    size_t conv = (size_t)9 * STAGE_BYTES + (size_t)num_blocks * 2 * 72 * STAGE_BYTES + (size_t)8 * (2 * HEAD_CH * 16);
+    size_t conv = (size_t)9 * KSTEP_BYTES + (size_t)num_blocks * 2 * 72 * KSTEP_BYTES + (size_t)8 * (2 * HEAD_CH * 16);
     size_t off = align_up(conv, 256);
     t->off_bias = off; off = align_up(off + (size_t)t->n_layers * CH * 4, 256);
     t->off_polw = off; off = align_up(off + (size_t)t->A * FLAT * 4, 256);
@@ -469,11 +499,10 @@ int spx_tower_load(spx_tower* t, const void* dev_blob, int64_t bytes, void* stre
     return 0;
 }
 
-int spx_tower_forward(spx_tower* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n,
-                      float* policy, float* value, void* stream) {
+static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n,
+                              float* policy, float* value, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2) {
     if (!t || !own || !opp || !policy || !value) return spx::set_err(SPX_E_ARG, "spx_tower_forward: null argument%s", "");
     if (n <= 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
     if (n > t->capacity) {
         if (t->head_buf) { SPX_CUDA_T(cudaStreamSynchronize(st)); SPX_CUDA_T(cudaFree(t->head_buf)); t->head_buf = nullptr; }
         SPX_CUDA_T(cudaMalloc((void**)&t->head_buf, (size_t)n * HEAD_CH * CELLS * sizeof(float)));
@@ -481,17 +510,32 @@ int spx_tower_forward(spx_tower* t, const uint64_t* own, const uint64_t* opp, co
     }
     const long long groups = (n + NB - 1) / NB;
     const int grid = (int)(groups < t->sm_count ? groups : t->sm_count);
+    if (e0) SPX_CUDA_T(cudaEventRecord(e0, st));
     tower_kernel<<<grid, NUM_THREADS, sizeof(Smem) + 1024, st>>>((const unsigned long long*)own, (const unsigned long long*)opp, needs_eval, n,
                                                               t->n_layers, t->blob, (const float*)(t->blob + t->off_bias), t->head_buf);
     spx::count_launch();
     SPX_CUDA_T(cudaGetLastError());
+    if (e1) SPX_CUDA_T(cudaEventRecord(e1, st));
     heads_kernel<<<(int)((n + HB - 1) / HB), 256, (FLAT * HB + HB * FC_HIDDEN) * 4, st>>>(
         t->head_buf, needs_eval, n, t->A, (const float*)(t->blob + t->off_polw), (const float*)(t->blob + t->off_polb),
         (const __nv_bfloat16*)(t->blob + t->off_w1t), (const float*)(t->blob + t->off_b1), (const float*)(t->blob + t->off_w2),
         (const float*)(t->blob + t->off_b2), policy, value);
     spx::count_launch();
     SPX_CUDA_T(cudaGetLastError());
+    if (e2) SPX_CUDA_T(cudaEventRecord(e2, st));
     return 0;
+}
+
+int spx_tower_forward(spx_tower* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n,
+                      float* policy, float* value, void* stream) {
+    return tower_forward_impl(t, own, opp, needs_eval, n, policy, value, (cudaStream_t)stream, nullptr, nullptr, nullptr);
+}
+
+/* same, recording caller-owned cudaEvent_t handles before the conv tower, between tower and heads, and after */
+int spx_tower_forward_timed(spx_tower* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n,
+                            float* policy, float* value, void* stream, void* ev_start, void* ev_tower_done, void* ev_end) {
+    return tower_forward_impl(t, own, opp, needs_eval, n, policy, value, (cudaStream_t)stream, (cudaEvent_t)ev_start,
+                              (cudaEvent_t)ev_tower_done, (cudaEvent_t)ev_end);
 }
 
 }  // extern "C"

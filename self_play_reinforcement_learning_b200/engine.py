@@ -49,7 +49,7 @@ class HashNetEvaluator:
     def bind(self, engine):
         self.engine = engine
 
-    def __call__(self, engine):
+    def __call__(self, engine, events=None):
         check(lib().spx_hashnet_forward(self.game, engine.n_games, engine.leaf_own.data_ptr(), engine.leaf_opp.data_ptr(),
                                         engine.needs_eval.data_ptr(), engine.net_id.data_ptr(), self.seed0, self.seed1,
                                         engine.policy.data_ptr(), engine.value.data_ptr(), _stream_ptr()),
@@ -124,16 +124,24 @@ class SelfPlayEngine:
         check(lib().spx_set_noise_table(self._h, t.data_ptr(), first_game_index, t.shape[0], t.shape[2]), "spx_set_noise_table")
 
     # ------------------------------------------------------------------ the hot loop
-    def advance(self):
-        """spx_advance only (consume last outputs, fill the leaf batch)."""
+    def advance(self, events=None):
+        """spx_advance only (consume last outputs, fill the leaf batch).  ``events``: optional pair of
+        torch.cuda.Event recorded right before/after the launch on the launching stream."""
         p = None if self._first else self.policy.data_ptr()
         v = None if self._first else self.value.data_ptr()
-        check(lib().spx_advance(self._h, p, v, _stream_ptr()), "spx_advance")
+        if events is None:
+            check(lib().spx_advance(self._h, p, v, _stream_ptr()), "spx_advance")
+        else:
+            check(lib().spx_advance_timed(self._h, p, v, _stream_ptr(), C.c_void_p(events[0].cuda_event),
+                                          C.c_void_p(events[1].cuda_event)), "spx_advance_timed")
         self._first = False
 
-    def tick(self):
-        self.advance()
-        self.evaluator(self)
+    def tick(self, advance_events=None, net_events=None):
+        self.advance(advance_events)
+        if net_events is None:
+            self.evaluator(self)
+        else:
+            self.evaluator(self, events=net_events)
 
     def run_ticks(self, n):
         for _ in range(n):

@@ -287,13 +287,20 @@ class NativeTower:
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         check(lib().spx_tower_load(self._h, self.blob_dev.data_ptr(), self.blob_dev.numel(), stream), "spx_tower_load")
 
-    def forward_bits(self, own, opp, needs_eval=None, policy=None, value=None):
+    def forward_bits(self, own, opp, needs_eval=None, policy=None, value=None, events=None):
+        """events: optional (start, tower_done, end) torch.cuda.Event triple recorded around the two kernels."""
         n = own.numel()
         policy = torch.empty(n, self.A, dtype=torch.float32, device=own.device) if policy is None else policy
         value = torch.empty(n, dtype=torch.float32, device=own.device) if value is None else value
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        check(lib().spx_tower_forward(self._h, own.data_ptr(), opp.data_ptr(), None if needs_eval is None else needs_eval.data_ptr(),
-                                      n, policy.data_ptr(), value.data_ptr(), stream), "spx_tower_forward")
+        need = None if needs_eval is None else needs_eval.data_ptr()
+        if events is None:
+            check(lib().spx_tower_forward(self._h, own.data_ptr(), opp.data_ptr(), need, n, policy.data_ptr(), value.data_ptr(),
+                                          stream), "spx_tower_forward")
+        else:
+            ev = [C.c_void_p(e.cuda_event) for e in events]
+            check(lib().spx_tower_forward_timed(self._h, own.data_ptr(), opp.data_ptr(), need, n, policy.data_ptr(),
+                                                value.data_ptr(), stream, ev[0], ev[1], ev[2]), "spx_tower_forward_timed")
         return policy, value
 
     def close(self):
@@ -321,8 +328,8 @@ class TowerEvaluator:
     def load(self, module_or_blob):
         self.tower.load(module_or_blob)
 
-    def __call__(self, engine):
-        self.tower.forward_bits(engine.leaf_own, engine.leaf_opp, engine.needs_eval, engine.policy, engine.value)
+    def __call__(self, engine, events=None):
+        self.tower.forward_bits(engine.leaf_own, engine.leaf_opp, engine.needs_eval, engine.policy, engine.value, events)
 
 
 def smoke_check():
