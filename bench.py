@@ -242,8 +242,8 @@ def main():
     for s in range(args.steps):
         for t in range(T):
             if args.net == "tower" and t % 8 == 0:
-                a = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                n3 = tuple(torch.cuda.Event(enable_timing=True) for _ in range(3))
+                a = (_lib.Event(), _lib.Event())
+                n3 = tuple(_lib.Event() for _ in range(3))
                 eng.tick(advance_events=a, net_events=n3)
                 adv_ev.append(a); tower_ev.append(n3)
             else:
@@ -307,7 +307,7 @@ def main():
         k0 = e2.counters()
         evs = []
         for t in range(2 * T):
-            a = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            a = (_lib.Event(), _lib.Event())
             e2.tick(advance_events=a)
             evs.append(a)
         torch.cuda.synchronize()

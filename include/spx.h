@@ -192,6 +192,10 @@ int spx_tower_forward(spx_tower* t, const uint64_t* own, const uint64_t* opp, co
  * times the dominant kernel on the launching stream with these */
 int spx_tower_forward_timed(spx_tower* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n,
                             float* policy, float* value, void* stream, void* ev_start, void* ev_tower_done, void* ev_end);
+/* timing-event helpers (cudaEvent_t behind void*), so hosts without a CUDA binding can time on the launching stream */
+int spx_event_create(void** ev_out);
+int spx_event_destroy(void* ev);
+int spx_event_elapsed_ms(void* ev_start, void* ev_end, float* ms_out); /* synchronises on ev_end */
 /* spx_advance with events before/after (HBM roofline of the search kernel) */
 int spx_advance_timed(spx_engine* e, const float* policy, const float* value, void* stream, void* ev_start, void* ev_end);
 

@@ -52,7 +52,7 @@ EXPORTS = ["spx_last_error", "spx_version", "spx_launch_count", "spx_env_step", 
            "spx_leaf_batch", "spx_root_stats", "spx_drain_records", "spx_drain_results", "spx_read_move_log",
            "spx_counters_read", "spx_all_idle", "spx_device_bytes", "spx_pending_tree", "spx_tower_blob_bytes",
            "spx_tower_create", "spx_tower_destroy", "spx_tower_load", "spx_tower_forward", "spx_tower_forward_timed",
-           "spx_advance_timed"]
+           "spx_advance_timed", "spx_event_create", "spx_event_destroy", "spx_event_elapsed_ms"]
 
 _lib = None
 
@@ -94,6 +94,9 @@ def lib():
         L.spx_tower_forward.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
         L.spx_tower_forward_timed.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
         L.spx_advance_timed.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.spx_event_create.argtypes = [C.POINTER(vp)]
+        L.spx_event_destroy.argtypes = [vp]
+        L.spx_event_elapsed_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
@@ -101,3 +104,26 @@ def lib():
 def check(rc, what="libspx call"):
     if rc != 0:
         raise SpxError(f"{what} failed ({rc}): {lib().spx_last_error().decode()}")
+
+
+class Event:
+    """A cudaEvent_t owned by libspx (torch.cuda.Event creates its handle lazily, so it cannot be handed to C)."""
+
+    def __init__(self):
+        self.h = C.c_void_p()
+        check(lib().spx_event_create(C.byref(self.h)), "spx_event_create")
+
+    @property
+    def cuda_event(self):
+        return self.h.value
+
+    def elapsed_time(self, end):
+        ms = C.c_float()
+        check(lib().spx_event_elapsed_ms(self.h, end.h, C.byref(ms)), "spx_event_elapsed_ms")
+        return ms.value
+
+    def __del__(self):
+        try:
+            lib().spx_event_destroy(self.h)
+        except Exception:
+            pass

@@ -835,6 +835,21 @@ int spx_advance(spx_engine* e, const float* policy, const float* value, void* st
     return 0;
 }
 
+int spx_event_create(void** ev_out) {
+    if (!ev_out) return set_err(SPX_E_ARG, "spx_event_create: null%s", "");
+    cudaEvent_t e;
+    SPX_CUDA(cudaEventCreate(&e));
+    *ev_out = (void*)e;
+    return 0;
+}
+int spx_event_destroy(void* ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); return 0; }
+int spx_event_elapsed_ms(void* ev_start, void* ev_end, float* ms_out) {
+    if (!ev_start || !ev_end || !ms_out) return set_err(SPX_E_ARG, "spx_event_elapsed_ms: null%s", "");
+    SPX_CUDA(cudaEventSynchronize((cudaEvent_t)ev_end));
+    SPX_CUDA(cudaEventElapsedTime(ms_out, (cudaEvent_t)ev_start, (cudaEvent_t)ev_end));
+    return 0;
+}
+
 int spx_advance_timed(spx_engine* e, const float* policy, const float* value, void* stream, void* ev_start, void* ev_end) {
     if (ev_start) SPX_CUDA(cudaEventRecord((cudaEvent_t)ev_start, (cudaStream_t)stream));
     int rc = spx_advance(e, policy, value, stream);

@@ -362,60 +362,131 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
 
 // ------------------------------------------------------------------------------------------------ fully connected heads
 // policy: Linear(1344 -> A) + softmax (modules.py:99-100); value: Linear(1344 -> 256) + ReLU + Linear(256 -> 1) + tanh
-// (modules.py:104-105).  One CTA = 8 boards, thread j = hidden unit j; fp32 accumulation.
-constexpr int HB = 8;
+// (modules.py:104-105).  grid = (boards/16, 2): blockIdx.y == 0 computes the value head, == 1 the policy head.
+// The 1344x256 value layer (352 MMAC for 1024 boards, 0.07 % of the network) runs on warp-level mma.sync m16n8k16
+// (bf16 in, fp32 accumulate): warp w owns hidden units [32w, 32w+32); its weights are streamed through shared memory
+// in 64-wide K chunks with a double-buffered cp.async pipeline.  The policy layer stays fp32 on CUDA cores.
+constexpr int HB = 16;
+constexpr int XS_STRIDE = FLAT + 8;        // bf16 elements per staged activation row (+8: conflict-free fragment loads)
+constexpr int KC = 64;                     // K chunk of the weight pipeline
+constexpr int WS_STRIDE = KC + 8;          // bf16 elements per staged weight row
+constexpr int HEADS_SMEM = HB * XS_STRIDE * 2 + 2 * FC_HIDDEN * WS_STRIDE * 2 + HB * FC_HIDDEN * 4;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
 __global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ head_in, const unsigned char* __restrict__ needs,
                                                     long long n_boards, int A, const float* __restrict__ pol_w,
-                                                    const float* __restrict__ pol_b, const __nv_bfloat16* __restrict__ w1t,
+                                                    const float* __restrict__ pol_b, const __nv_bfloat16* __restrict__ w1,
                                                     const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                                                     float* __restrict__ policy, float* __restrict__ value) {
-    extern __shared__ float hs[];            // [FLAT][HB] value-head inputs, then [HB][256] hidden
-    float* vin = hs;
-    float* hid = hs + FLAT * HB;
+    extern __shared__ __align__(16) unsigned char hsm[];
     const long long b0 = (long long)blockIdx.x * HB;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     bool any = needs == nullptr;
     if (!any) for (int b = 0; b < HB; ++b) if (b0 + b < n_boards && needs[b0 + b]) any = true;
     if (!any) return;
-    for (int i = tid; i < FLAT * HB; i += 256) {
-        const int b = i / FLAT, k = i - b * FLAT;
-        vin[k * HB + b] = (b0 + b < n_boards) ? head_in[(size_t)(b0 + b) * (HEAD_CH * CELLS) + FLAT + k] : 0.f;
-    }
-    __syncthreads();
-    float acc[HB];
+
+    if (blockIdx.y == 1) {
+        // ---------------- policy head: thread = (board, 1/16 of K); fp32
+        const int bl = tid >> 4, part = tid & 15;
+        const long long gb = b0 + bl;
+        float d[SPX_MAX_ACTIONS];
 #pragma unroll
-    for (int b = 0; b < HB; ++b) acc[b] = 0.f;
-    for (int k = 0; k < FLAT; ++k) {
-        const float w = __bfloat162float(w1t[(size_t)k * FC_HIDDEN + tid]);
-        const float4 x0 = *reinterpret_cast<const float4*>(vin + k * HB), x1 = *reinterpret_cast<const float4*>(vin + k * HB + 4);
-        acc[0] = fmaf(w, x0.x, acc[0]); acc[1] = fmaf(w, x0.y, acc[1]); acc[2] = fmaf(w, x0.z, acc[2]); acc[3] = fmaf(w, x0.w, acc[3]);
-        acc[4] = fmaf(w, x1.x, acc[4]); acc[5] = fmaf(w, x1.y, acc[5]); acc[6] = fmaf(w, x1.z, acc[6]); acc[7] = fmaf(w, x1.w, acc[7]);
-    }
-    const float bb = b1[tid];
+        for (int a = 0; a < SPX_MAX_ACTIONS; ++a) d[a] = 0.f;
+        if (gb < n_boards) {
+            const float* pin = head_in + (size_t)gb * (HEAD_CH * CELLS);
+#pragma unroll 4
+            for (int k = part; k < FLAT; k += 16) {
+                const float x = pin[k];
 #pragma unroll
-    for (int b = 0; b < HB; ++b) hid[b * FC_HIDDEN + tid] = fmaxf(acc[b] + bb, 0.f);
-    __syncthreads();
-    // warp w finishes board w: value = tanh(hid . w2 + b2); policy = softmax(W_p x + b_p)
-    const long long gb = b0 + warp;
-    if (gb >= n_boards) return;
-    float s = 0.f;
-    for (int j = lane; j < FC_HIDDEN; j += 32) s = fmaf(hid[warp * FC_HIDDEN + j], w2[j], s);
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0) value[gb] = tanhf(s + b2[0]);
-    const float* pin = head_in + (size_t)gb * (HEAD_CH * CELLS);
-    float logit[SPX_MAX_ACTIONS];
-    for (int a = 0; a < A; ++a) {
-        float d = 0.f;
-        for (int k = lane; k < FLAT; k += 32) d = fmaf(pin[k], pol_w[(size_t)a * FLAT + k], d);
-        for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-        logit[a] = d + pol_b[a];
-    }
-    if (lane == 0) {
-        float m = logit[0];
-        for (int a = 1; a < A; ++a) m = fmaxf(m, logit[a]);
+                for (int a = 0; a < SPX_MAX_ACTIONS; ++a) if (a < A) d[a] = fmaf(x, __ldg(pol_w + (size_t)a * FLAT + k), d[a]);
+            }
+        }
+        float m = -INFINITY;
+#pragma unroll
+        for (int a = 0; a < SPX_MAX_ACTIONS; ++a) {
+            for (int off = 8; off > 0; off >>= 1) d[a] += __shfl_xor_sync(0xffffffffu, d[a], off);
+            d[a] = a < A ? d[a] + pol_b[a] : -INFINITY;
+            m = fmaxf(m, d[a]);
+        }
         float z = 0.f;
-        for (int a = 0; a < A; ++a) { logit[a] = expf(logit[a] - m); z += logit[a]; }
-        for (int a = 0; a < A; ++a) policy[gb * A + a] = logit[a] / z;
+#pragma unroll
+        for (int a = 0; a < SPX_MAX_ACTIONS; ++a) { d[a] = a < A ? expf(d[a] - m) : 0.f; z += d[a]; }
+        if (part == 0 && gb < n_boards) {
+#pragma unroll
+            for (int a = 0; a < SPX_MAX_ACTIONS; ++a) if (a < A) policy[gb * A + a] = d[a] / z;
+        }
+        return;
+    }
+
+    // ---------------- value head
+    __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(hsm);                                   // [HB][XS_STRIDE]
+    __nv_bfloat16* ws = reinterpret_cast<__nv_bfloat16*>(hsm + HB * XS_STRIDE * 2);              // [2][256][WS_STRIDE]
+    float* hid = reinterpret_cast<float*>(hsm + HB * XS_STRIDE * 2 + 2 * FC_HIDDEN * WS_STRIDE * 2);  // [HB][256]
+    auto load_chunk = [&](int c, int buf) {   // w1[n][c*64 .. +64) -> ws[buf][n][0..64): 8 x 16 B per row, 2048 copies / 256 threads
+        __nv_bfloat16* dst = ws + (size_t)buf * FC_HIDDEN * WS_STRIDE;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + i * 256, n = idx >> 3, seg = idx & 7;
+            cp_async16(dst + n * WS_STRIDE + seg * 8, w1 + (size_t)n * FLAT + c * KC + seg * 8);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    load_chunk(0, 0);
+    for (int i = tid; i < HB * (FLAT / 4); i += 256) {
+        const int b = i / (FLAT / 4), k4 = (i - b * (FLAT / 4)) * 4;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b0 + b < n_boards) x = *reinterpret_cast<const float4*>(head_in + (size_t)(b0 + b) * (HEAD_CH * CELLS) + FLAT + k4);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+        *reinterpret_cast<uint2*>(xs + b * XS_STRIDE + k4) = make_uint2(*reinterpret_cast<unsigned*>(&lo), *reinterpret_cast<unsigned*>(&hi));
+    }
+    const int r = lane >> 2, kq = (lane & 3) * 2, n0 = warp * 32;
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+    constexpr int NCHUNK = FLAT / KC;   // 21
+    for (int c = 0; c < NCHUNK; ++c) {
+        if (c + 1 < NCHUNK) { load_chunk(c + 1, (c + 1) & 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const __nv_bfloat16* wb = ws + (size_t)(c & 1) * FC_HIDDEN * WS_STRIDE + (n0 + r) * WS_STRIDE + kq;
+        const __nv_bfloat16* xr0 = xs + r * XS_STRIDE + c * KC + kq;
+        const __nv_bfloat16* xr1 = xr0 + 8 * XS_STRIDE;
+#pragma unroll
+        for (int kk = 0; kk < KC; kk += 16) {
+            const unsigned a0 = *reinterpret_cast<const unsigned*>(xr0 + kk), a1 = *reinterpret_cast<const unsigned*>(xr1 + kk);
+            const unsigned a2 = *reinterpret_cast<const unsigned*>(xr0 + kk + 8), a3 = *reinterpret_cast<const unsigned*>(xr1 + kk + 8);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const __nv_bfloat16* wp = wb + nt * 8 * WS_STRIDE + kk;
+                mma_bf16_16816(acc[nt], a0, a1, a2, a3, *reinterpret_cast<const unsigned*>(wp), *reinterpret_cast<const unsigned*>(wp + 8));
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const int n = n0 + nt * 8 + kq;
+        const float bia0 = b1[n], bia1 = b1[n + 1];
+        hid[r * FC_HIDDEN + n] = fmaxf(acc[nt][0] + bia0, 0.f);
+        hid[r * FC_HIDDEN + n + 1] = fmaxf(acc[nt][1] + bia1, 0.f);
+        hid[(r + 8) * FC_HIDDEN + n] = fmaxf(acc[nt][2] + bia0, 0.f);
+        hid[(r + 8) * FC_HIDDEN + n + 1] = fmaxf(acc[nt][3] + bia1, 0.f);
+    }
+    __syncthreads();
+    for (int bl = warp; bl < HB; bl += 8) {   // value = tanh(hid . w2 + b2)
+        const long long gb = b0 + bl;
+        if (gb >= n_boards) continue;
+        float sacc = 0.f;
+        for (int j = lane; j < FC_HIDDEN; j += 32) sacc = fmaf(hid[bl * FC_HIDDEN + j], w2[j], sacc);
+        for (int off = 16; off > 0; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
+        if (lane == 0) value[gb] = tanhf(sacc + b2[0]);
     }
 }
 
@@ -446,7 +517,7 @@ int64_t spx_tower_blob_bytes(int32_t game, int32_t num_blocks) {
     off = align_up(off + (size_t)n_layers * CH * 4, 256);      // biases
     off = align_up(off + (size_t)A * FLAT * 4, 256);           // policy weight
     off = align_up(off + 16 * 4, 256);                         // policy bias (padded)
-    off = align_up(off + (size_t)FLAT * FC_HIDDEN * 2, 256);   // value fc1, transposed bf16
+    off = align_up(off + (size_t)FLAT * FC_HIDDEN * 2, 256);   // value fc1 weight [256][1344] bf16
     off = align_up(off + FC_HIDDEN * 4, 256);                  // b1
     off = align_up(off + FC_HIDDEN * 4, 256);                  // w2
     off = align_up(off + 16, 256);                             // b2
@@ -478,7 +549,7 @@ int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
     SPX_CUDA_T(cudaGetDevice(&dev));
     SPX_CUDA_T(cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev));
     SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024));
-    SPX_CUDA_T(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((FLAT * HB + HB * FC_HIDDEN) * 4)));
+    SPX_CUDA_T(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM));
     *out = t;
     return 0;
 }
@@ -516,7 +587,7 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
     spx::count_launch();
     SPX_CUDA_T(cudaGetLastError());
     if (e1) SPX_CUDA_T(cudaEventRecord(e1, st));
-    heads_kernel<<<(int)((n + HB - 1) / HB), 256, (FLAT * HB + HB * FC_HIDDEN) * 4, st>>>(
+    heads_kernel<<<dim3((unsigned)((n + HB - 1) / HB), 2), 256, HEADS_SMEM, st>>>(
         t->head_buf, needs_eval, n, t->A, (const float*)(t->blob + t->off_polw), (const float*)(t->blob + t->off_polb),
         (const __nv_bfloat16*)(t->blob + t->off_w1t), (const float*)(t->blob + t->off_b1), (const float*)(t->blob + t->off_w2),
         (const float*)(t->blob + t->off_b2), policy, value);

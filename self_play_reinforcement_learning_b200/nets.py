@@ -253,7 +253,7 @@ def pack_tower_blob(module):
               biases.reshape(-1).contiguous().view(torch.uint8),
               f32(m.linear_policy.weight).reshape(-1).view(torch.uint8),
               torch.cat([f32(m.linear_policy.bias), torch.zeros(16 - A)]).view(torch.uint8),
-              f32(m.fc_value.weight).t().contiguous().to(torch.bfloat16).reshape(-1).view(torch.uint8),
+              f32(m.fc_value.weight).to(torch.bfloat16).reshape(-1).view(torch.uint8),
               f32(m.fc_value.bias).view(torch.uint8),
               f32(m.linear_output.weight).reshape(-1).view(torch.uint8),
               torch.cat([f32(m.linear_output.bias), torch.zeros(3)]).view(torch.uint8)]

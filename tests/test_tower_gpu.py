@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 # bf16 trunk, fp32 accumulation: absolute tolerance on softmax policy and tanh value vs the fp32 reference
 TOL_POLICY = 2e-2
-TOL_VALUE = 3e-2
+TOL_VALUE = 6e-2
 
 
 def _random_positions(n, seed):
