@@ -16,9 +16,9 @@
 //   * Weights (12.6 MB bf16 for 20 blocks, L2 resident) are pre-packed on the host in exactly the
 //     order the MMA consumes them and streamed by one producer thread with cp.async.bulk (TMA) through
 //     a 3-stage (8 KB each) mbarrier ring; each slice is loaded once per layer and reused by the 3 row tiles.
-//   * 8 epilogue warps read TMEM (tcgen05.ld 32x32b), add the folded-BN bias, the residual, apply ReLU,
+//   * 16 epilogue warps read TMEM (tcgen05.ld 32x32b), add the folded-BN bias, the residual, apply ReLU,
 //     zero the padding rows and write bf16 rows back into the other activation buffer.
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 4..11 = epilogue.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 4..19 = epilogue.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -62,8 +62,12 @@ constexpr int ACT_BYTES = CHUNK_BYTES * (CH / 8);
 constexpr int NSTAGE = SPX_NSTAGE;
 constexpr int KSTEP_BYTES = 2 * CH * 16;     // one K=16 weight slice: [2 k-chunks][128 out][8 in] bf16 = 4 KB
 constexpr int STAGE_BYTES = 2 * KSTEP_BYTES; // a ring stage carries two K steps (K = 32)
-constexpr int NUM_THREADS = 384;
-constexpr int EPI_WARP0 = 4, EPI_THREADS = 256;
+#ifndef SPX_EPI_WARPS
+#define SPX_EPI_WARPS 16
+#endif
+constexpr int EPI_WARP0 = 4, EPI_WARPS = SPX_EPI_WARPS, EPI_THREADS = EPI_WARPS * 32, EPI_SPLIT = EPI_WARPS / 4;
+constexpr int NUM_THREADS = EPI_WARP0 * 32 + EPI_THREADS;
+static_assert(EPI_SPLIT == 4, "epilogue column split is written for 4 parts of 32 (trunk) / 16 (head) columns");
 constexpr int FLAT = 32 * CELLS;             // 1344 inputs of each head's first Linear
 constexpr int FC_HIDDEN = 256;
 
@@ -72,6 +76,7 @@ struct Smem {
     unsigned char wstage[NSTAGE][STAGE_BYTES];
     unsigned long long full[NSTAGE], empty[NSTAGE], acc_full, epi_done;
     unsigned long long own[NB], opp[NB];
+    float bias[2][CH];
     unsigned tmem_base;
 };
 
@@ -125,6 +130,25 @@ __device__ __forceinline__ void tc_ld32(unsigned taddr, unsigned (&v)[32]) {
           "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
           "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld32_nowait(unsigned taddr, unsigned (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld16(unsigned taddr, unsigned (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -260,13 +284,14 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
             }
         } else if (warp >= EPI_WARP0) {
             // ===================== epilogue warps (also write the stem input)
-            const int et = tid - EPI_WARP0 * 32;          // 0..255
-            const int quarter = warp & 3, half = (warp - EPI_WARP0) >> 2;
+            const int et = tid - EPI_WARP0 * 32;          // 0..EPI_THREADS-1
+            const int quarter = warp & 3, part = (warp - EPI_WARP0) >> 2;   // TMEM lane quarter, column part
             if (et < NB) {
                 const long long gb = grp * NB + et;
                 S.own[et] = gb < n_boards ? own_g[gb] : 0ULL;
                 S.opp[et] = gb < n_boards ? opp_g[gb] : 0ULL;
             }
+            if (et < CH) S.bias[0][et] = __ldg(bias_all + et);
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
             // preprocess (modules.py:115-125): planes (empty, own, enemy) -> channels 0..2 of buffer 0, channels 3..15 zero
             for (int row = et; row < ROWS; row += EPI_THREADS) {
@@ -283,71 +308,85 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
             }
             fence_proxy_async();
             mbar_arrive(&S.epi_done);
+            // per-tile row bookkeeping is layer independent
+            bool real_t[MT]; int board_t[MT], cell_t[MT];
+#pragma unroll
+            for (int t = 0; t < MT; ++t) real_t[t] = row_is_cell(t * 128 + quarter * 32 + lane, board_t[t], cell_t[t]);
             for (int l = 0; l < n_layers; ++l) {
                 const LayerInfo li = layer_info(l, n_layers);
-                const float* bias = bias_all + (size_t)l * CH;
-                const int ncol = li.n / 2;   // columns handled by this half
+                const float* bias_s = S.bias[l & 1];
+                // stage the NEXT layer's folded-BN bias while this layer's MMAs are still running
+                if (l + 1 < n_layers && et < CH) S.bias[(l + 1) & 1][et] = __ldg(bias_all + (size_t)(l + 1) * CH + et);
                 mbar_wait(&S.acc_full, lphase);
                 tc_fence_after();
-                for (int t = 0; t < MT; ++t) {
+                if (li.out_buf >= 0) {
+                    // trunk layer: this warp owns 128/EPI_SPLIT = 32 columns of its 32 rows, for each of the 3 row tiles
+                    const int ch0 = part * (CH / EPI_SPLIT);
+                    const unsigned tcol = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)ch0;
+                    unsigned v[2][32];
+                    tc_ld32_nowait(tcol, v[0]);
+#pragma unroll
+                    for (int t = 0; t < MT; ++t) {
+                        tc_wait_ld();
+                        if (t + 1 < MT) tc_ld32_nowait(tcol + (unsigned)((t + 1) * 128), v[(t + 1) & 1]);
 #ifdef SPX_DBG_SKIP_EPI
-                    if (li.out_buf >= 0) continue;
+                        continue;
 #endif
-                    const int row = t * 128 + quarter * 32 + lane;
-                    int board, cell;
-                    const bool real = row_is_cell(row, board, cell);
-                    const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(t * 128 + half * ncol);
-                    for (int c0 = 0; c0 < ncol; c0 += 32) {
-                        unsigned v[32];
-                        tc_ld32(taddr + (unsigned)c0, v);
-                        const int ch0 = half * ncol + c0;
-                        if (li.out_buf >= 0) {
-                            unsigned char* obase = S.act[li.out_buf] + (GUARD + row) * 16;
+                        const int row = t * 128 + quarter * 32 + lane;
+                        unsigned char* obase = S.act[li.out_buf] + (GUARD + row) * 16 + (ch0 >> 3) * CHUNK_BYTES;
+                        if (!real_t[t]) {   // padding / guard cell: must read as zero in the next layer
 #pragma unroll
-                            for (int g8 = 0; g8 < 4; ++g8) {
-                                const int ch = ch0 + g8 * 8;
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + ch));
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + ch + 4));
-                                float y[8] = {__uint_as_float(v[g8 * 8 + 0]) + b0.x, __uint_as_float(v[g8 * 8 + 1]) + b0.y,
-                                              __uint_as_float(v[g8 * 8 + 2]) + b0.z, __uint_as_float(v[g8 * 8 + 3]) + b0.w,
-                                              __uint_as_float(v[g8 * 8 + 4]) + b1.x, __uint_as_float(v[g8 * 8 + 5]) + b1.y,
-                                              __uint_as_float(v[g8 * 8 + 6]) + b1.z, __uint_as_float(v[g8 * 8 + 7]) + b1.w};
-                                uint4* dst = reinterpret_cast<uint4*>(obase + (ch >> 3) * CHUNK_BYTES);
-                                if (li.residual) {  // out += identity (modules.py:37), identity lives in the output buffer
-                                    const uint4 idv = *dst;
-                                    const unsigned iw[4] = {idv.x, idv.y, idv.z, idv.w};
+                            for (int g8 = 0; g8 < 4; ++g8) *reinterpret_cast<uint4*>(obase + g8 * CHUNK_BYTES) = make_uint4(0, 0, 0, 0);
+                            continue;
+                        }
+                        const unsigned* vv = v[t & 1];
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        y[2 * k] += __uint_as_float(iw[k] << 16);
-                                        y[2 * k + 1] += __uint_as_float(iw[k] & 0xFFFF0000u);
-                                    }
-                                }
-                                unsigned pk[4];
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch0 + g8 * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch0 + g8 * 8 + 4);
+                            float y[8] = {__uint_as_float(vv[g8 * 8 + 0]) + b0.x, __uint_as_float(vv[g8 * 8 + 1]) + b0.y,
+                                          __uint_as_float(vv[g8 * 8 + 2]) + b0.z, __uint_as_float(vv[g8 * 8 + 3]) + b0.w,
+                                          __uint_as_float(vv[g8 * 8 + 4]) + b1.x, __uint_as_float(vv[g8 * 8 + 5]) + b1.y,
+                                          __uint_as_float(vv[g8 * 8 + 6]) + b1.z, __uint_as_float(vv[g8 * 8 + 7]) + b1.w};
+                            uint4* dst = reinterpret_cast<uint4*>(obase + g8 * CHUNK_BYTES);
+                            if (li.residual) {  // out += identity (modules.py:37), identity lives in the output buffer
+                                const uint4 idv = *dst;
+                                const unsigned iw[4] = {idv.x, idv.y, idv.z, idv.w};
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    const float lo = real ? fmaxf(y[2 * k], 0.f) : 0.f, hi = real ? fmaxf(y[2 * k + 1], 0.f) : 0.f;
-                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-                                    pk[k] = *reinterpret_cast<unsigned*>(&h2);
+                                    y[2 * k] += __uint_as_float(iw[k] << 16);
+                                    y[2 * k + 1] += __uint_as_float(iw[k] & 0xFFFF0000u);
                                 }
-                                *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             }
-                        } else if (real) {
-                            // fused policy/value 1x1 head conv + BN + ReLU (modules.py:97,102) -> fp32 [board][ch*42 + cell]
-                            const long long gb = grp * NB + board;
-                            if (gb < n_boards) {
-                                float* ob = head_out + (size_t)gb * (HEAD_CH * CELLS) + cell;
+                            unsigned pk[4];
 #pragma unroll
-                                for (int k = 0; k < 32; ++k) {
-                                    const int ch = ch0 + k;
-                                    ob[(size_t)ch * CELLS] = fmaxf(__uint_as_float(v[k]) + __ldg(bias + ch), 0.f);
-                                }
+                            for (int k = 0; k < 4; ++k) {
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(y[2 * k], 0.f), fmaxf(y[2 * k + 1], 0.f));
+                                pk[k] = *reinterpret_cast<unsigned*>(&h2);
                             }
+                            *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                } else {
+                    // fused policy/value 1x1 head conv + BN + ReLU (modules.py:97,102) -> fp32 [board][ch*42 + cell];
+                    // 64 columns: each warp owns 64/EPI_SPLIT = 16 of them
+                    const int ch0 = part * (HEAD_CH / EPI_SPLIT);
+#pragma unroll
+                    for (int t = 0; t < MT; ++t) {
+                        unsigned v[16];
+                        tc_ld16(tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(t * 128 + ch0), v);
+                        const long long gb = grp * NB + board_t[t];
+                        if (real_t[t] && gb < n_boards) {
+                            float* ob = head_out + (size_t)gb * (HEAD_CH * CELLS) + cell_t[t];
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) ob[(size_t)(ch0 + k) * CELLS] = fmaxf(__uint_as_float(v[k]) + bias_s[ch0 + k], 0.f);
                         }
                     }
                 }
                 tc_fence_before();
                 fence_proxy_async();
                 lphase ^= 1u;
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));   // next layer's bias visible to every epilogue warp
                 if (l + 1 < n_layers) mbar_arrive(&S.epi_done);
             }
         }
@@ -548,7 +587,7 @@ int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
     int dev = 0;
     SPX_CUDA_T(cudaGetDevice(&dev));
     SPX_CUDA_T(cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev));
-    SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024));
+    SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
     SPX_CUDA_T(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM));
     *out = t;
     return 0;
@@ -582,7 +621,7 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
     const long long groups = (n + NB - 1) / NB;
     const int grid = (int)(groups < t->sm_count ? groups : t->sm_count);
     if (e0) SPX_CUDA_T(cudaEventRecord(e0, st));
-    tower_kernel<<<grid, NUM_THREADS, sizeof(Smem) + 1024, st>>>((const unsigned long long*)own, (const unsigned long long*)opp, needs_eval, n,
+    tower_kernel<<<grid, NUM_THREADS, sizeof(Smem), st>>>((const unsigned long long*)own, (const unsigned long long*)opp, needs_eval, n,
                                                               t->n_layers, t->blob, (const float*)(t->blob + t->off_bias), t->head_buf);
     spx::count_launch();
     SPX_CUDA_T(cudaGetLastError());
