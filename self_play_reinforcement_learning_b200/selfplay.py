@@ -53,10 +53,10 @@ def results_to_dicts(results):
 class BatchedSelfPlay:
     def __init__(self, network, game=None, env=None, n_games=1024, sims=800, net="tower", evaluation_network=None,
                  evaluate=False, update=True, alpha=1.0, strong_play=False, seed=0, rank=0, world=1, games_target=None,
-                 max_sims_per_tick=8, noise_mode=2, tie_mode=1, move_log=False):
+                 max_sims_per_tick=8, noise_mode=2, tie_mode=1, move_log=False, net_dtype=torch.bfloat16):
         """network / evaluation_network: nn.Module (ResidualTower for the native tower; any board net for net='torch').
         env: a reference env class/instance (mapped by variant_string) or ``game`` id.  iterations == sims."""
-        self.game = game_id_of(env) if env is not None else int(game)
+        self.game = game_id_of(env if env is not None else game)
         self.network, self.evaluation_network = network, evaluation_network
         two = evaluation_network is not None
         if net == "tower":
@@ -64,7 +64,7 @@ class BatchedSelfPlay:
                 raise _lib.SpxError("two-network evaluation runs through net='torch' (native tower: one network per engine)")
             self.evaluator = nets.TowerEvaluator(network, self.game)
         elif net == "torch":
-            self.evaluator = nets.TorchNetEvaluator(network, self.game, module_opp=evaluation_network)
+            self.evaluator = nets.TorchNetEvaluator(network, self.game, module_opp=evaluation_network, dtype=net_dtype)
         elif net == "hash":
             self.evaluator = HashNetEvaluator(self.game, seed, None if not two else seed + 1)
         else:

@@ -58,3 +58,43 @@ def split_by_game(records, results):
     for r in results:
         res[int(r["game_index"])] = dict(reward=int(r["reward"]), swap=int(r["swap_sides"]), plies=int(r["plies"]))
     return recs, res
+
+
+def run_logged(engine):
+    """Drive an engine tick by tick, logging every network evaluation per (game slot, tree) in call order.
+    Returns logs[g][tree] = dict(own, opp, policy, value) usable by oracle.make_replay (one game per slot only)."""
+    import ctypes as C
+    import torch
+    from self_play_reinforcement_learning_b200 import _lib
+    G = engine.n_games
+    logs = [[dict(own=[], opp=[], policy=[], value=[]) for _ in (0, 1)] for _ in range(G)]
+    tree_t = torch.zeros(G, dtype=torch.int32, device=engine.device)
+    for _ in range(10_000_000):
+        engine.tick()
+        torch.cuda.synchronize()
+        need = engine.needs_eval.cpu().numpy().astype(bool)
+        if not need.any() and engine.all_idle():
+            break
+        own = engine.leaf_own.cpu().numpy().view(np.uint64)
+        opp = engine.leaf_opp.cpu().numpy().view(np.uint64)
+        pol, val = engine.policy.cpu().numpy(), engine.value.cpu().numpy()
+        _lib.check(_lib.lib().spx_pending_tree(engine._h, tree_t.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "spx_pending_tree")
+        tree = tree_t.cpu().numpy()
+        for g in np.flatnonzero(need):
+            L = logs[g][tree[g]]
+            L["own"].append(own[g]); L["opp"].append(opp[g]); L["policy"].append(pol[g].copy()); L["value"].append(val[g])
+    return logs
+
+
+def replay_in_oracle(game, sims, seed, game_index, noise_table, log, evaluate=False, strong_play=False, noise_mode=None):
+    """Oracle episode fed with the logged network outputs; asserts the oracle asked for exactly the same leaves."""
+    import ctypes as C
+    rs = ox.make_replay(game, log)
+    cfg = ox.make_cfg(game, sims, seed=seed, game_uid=game_index, noise_table=noise_table, evaluate=evaluate,
+                      strong_play=strong_play, noise_mode=noise_mode)
+    pair = (ox.fn_addr("ox_replaynet"), C.addressof(rs))
+    o = ox.play_episode(cfg, bool(game_index & 1), nets=(pair, pair))
+    assert rs.mismatches == 0 and rs.overruns == 0, (game_index, rs.mismatches, rs.overruns)
+    assert rs.cursor[0] == rs.n[0] and rs.cursor[1] == rs.n[1], game_index
+    return o

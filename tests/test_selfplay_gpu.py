@@ -1,0 +1,113 @@
+"""The public host API (selfplay.BatchedSelfPlay / run_tasks, nets.TorchNetEvaluator) on the GPU: reference-format
+outputs, the scheduler task protocol, config-1 (TicTacToe, repo's tictactoe net, 1 game, 100 sims) and config-4
+(head-to-head evaluation with two nets) shapes, each replayed bit-exactly through the oracle."""
+import queue
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import spec
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def test_run_tasks_protocol_and_move_format():
+    from self_play_reinforcement_learning_b200.selfplay import Move, run_tasks
+
+    class TaskQ:
+        done = 0
+
+        def task_done(self):
+            self.done += 1
+    tasks = [{"play": {"swap_sides": bool(i % 2), "update": True}} for i in range(7)]  # scheduler: swap_sides = i odd
+    rq, mq, tq = queue.Queue(), queue.Queue(), TaskQ()
+    moves, results = run_tasks(None, 0, tasks, result_queue=rq, memory_queue=mq, task_queue=tq, iterations=60, net="hash",
+                               seed=5, noise_mode=0)
+    assert tq.done == 7 and rq.qsize() == 7 and len(results) == 7
+    assert sum(r["swap_sides"] for r in results) == 3 and all(r["reward"] in (-1, 0, 1) for r in results)
+    assert mq.qsize() == len(moves) > 7 * 7
+    m = moves[0]
+    assert isinstance(m, Move) and m._fields == ("state", "actual_val", "tree_probs", "q")          # mcts.py:17
+    assert m.state.dtype == torch.int64 and tuple(m.state.shape) == (7, 6)                          # mcts.py:284
+    assert m.tree_probs.dtype == torch.float32 and tuple(m.tree_probs.shape) == (7,)                # mcts.py:286
+    assert m.q.dtype == torch.float32 and m.q.dim() == 0 and m.actual_val.dtype == torch.float32    # mcts.py:287,230
+    # game 0 (index 0, no swap) must be the oracle's game 0
+    o = H.oracle_episode(0, 60, 5, 0, None, net_seed=5)
+    first = [mv for mv in moves[:len(o["records"])]]
+    for a, b in zip(first, o["records"]):
+        assert np.array_equal(a.state.numpy(), b["state"]) and np.array_equal(a.tree_probs.numpy(), b["tree_probs"])
+        assert float(a.q) == float(b["q"]) and float(a.actual_val) == b["actual_val"]
+    # evaluation tasks: no records (update False), two nets
+    tasks = [{"play": {"swap_sides": bool(i % 2), "update": False}, "evaluate": True} for i in range(4)]
+    moves, results = run_tasks(None, 0, tasks, iterations=40, net="hash", seed=6, noise_mode=0, evaluation_network=object())
+    assert moves == [] and len(results) == 4
+
+
+def test_config1_tictactoe_repo_net_one_game_100_sims():
+    """BASELINE.json configs[0] shape on the GPU path: TicTacToe, ConvNetTicTacToe, 1 game, 100 sims/move (generic
+    nn.Module boundary through torch, fp32), replayed through the oracle."""
+    from self_play_reinforcement_learning_b200 import envs, nets
+    from self_play_reinforcement_learning_b200.selfplay import BatchedSelfPlay
+    torch.manual_seed(1)
+    net = nets.ConvNetTicTacToe(3, 3, 9).eval()
+    table = np.random.default_rng(1).dirichlet([1.0] * 9, size=(1, 2, 22))
+    sp = BatchedSelfPlay(net, env=envs.TicTacToeEnv, n_games=1, sims=100, net="torch", seed=2, games_target=1, noise_mode=1,
+                         move_log=True, net_dtype=torch.float32)
+    sp.engine.set_noise_table(table)
+    logs = H.run_logged(sp.engine)
+    recs, res = H.split_by_game(sp.engine.drain_records(), sp.engine.drain_results())
+    o = H.replay_in_oracle(1, 100, 2, 0, table[0], logs[0])
+    H.compare_game(1, sp.engine.move_log(0), recs[0], res[0], o)
+    assert 5 <= res[0]["plies"] <= 9
+    # the logged network outputs are the module's own fp32 outputs (value tolerance 1e-5, fp32 path)
+    own, opp = logs[0][0]["own"][0], logs[0][0]["opp"][0]
+    board = torch.from_numpy(spec.bits_to_board(int(own), int(opp), 1))[None]
+    with torch.no_grad():
+        p, v = net.cuda().float().forward(board.cuda())
+    assert np.allclose(p.cpu().numpy()[0], logs[0][0]["policy"][0], atol=1e-5) and abs(float(v) - logs[0][0]["value"][0]) < 1e-5
+    sp.close()
+
+
+def test_config4_shape_two_nets_evaluate_mode():
+    """elo.py head-to-head shape: two different random-init nets, evaluate mode (temp/20), no records; every game is
+    replayed through the oracle with the logged outputs of both nets."""
+    from self_play_reinforcement_learning_b200 import nets
+    from self_play_reinforcement_learning_b200.selfplay import BatchedSelfPlay
+    torch.manual_seed(0)
+    a = nets.ResidualTower(7, 6, 7, num_blocks=1).eval()
+    torch.manual_seed(1)
+    b = nets.ResidualTower(7, 6, 7, num_blocks=1).eval()
+    n_games, sims = 6, 40
+    sp = BatchedSelfPlay(a, game=0, n_games=n_games, sims=sims, net="torch", evaluation_network=b, evaluate=True, update=False,
+                         seed=3, games_target=n_games, noise_mode=0, move_log=True, net_dtype=torch.float32)
+    logs = H.run_logged(sp.engine)
+    recs, res = H.split_by_game(sp.engine.drain_records(), sp.engine.drain_results())
+    assert recs == {} and len(res) == n_games
+    for g in range(n_games):
+        o = H.replay_in_oracle(0, sims, 3, g, None, logs[g], evaluate=True)
+        assert res[g]["reward"] == o["reward"] and res[g]["plies"] == len(o["moves"])
+        ml = sp.engine.move_log(g)
+        assert [m["action"] for m in ml] == [m["action"] for m in o["moves"]] and [m["n"] for m in ml] == [list(m["n"]) for m in o["moves"]]
+    sp.close()
+
+
+def test_weight_refresh_changes_outputs():
+    from self_play_reinforcement_learning_b200 import nets
+    from self_play_reinforcement_learning_b200.selfplay import BatchedSelfPlay
+    torch.manual_seed(0)
+    a = nets.ResidualTower(7, 6, 7, num_blocks=2).eval()
+    torch.manual_seed(9)
+    b = nets.ResidualTower(7, 6, 7, num_blocks=2).eval()
+    sp = BatchedSelfPlay(a, game=0, n_games=8, sims=20, net="tower", seed=1)
+    sp.engine.run_ticks(3)
+    torch.cuda.synchronize()
+    p_a = sp.engine.policy.clone()
+    blob_b = sp.packed_weights_pinned(b)
+    out = sp.play_step(0, weights_host=blob_b)
+    assert out["h2d_bytes"] == blob_b.numel()
+    sp.evaluator(sp.engine)
+    torch.cuda.synchronize()
+    assert not torch.equal(p_a, sp.engine.policy)
+    sp.close()

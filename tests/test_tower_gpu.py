@@ -67,17 +67,9 @@ def test_tower_matches_fp32_reference(blocks, n):
     tw.close()
 
 
-def _pending_tree(e):
-    from self_play_reinforcement_learning_b200 import _lib
-    t = torch.zeros(e.n_games, dtype=torch.int32, device=e.device)
-    _lib.check(_lib.lib().spx_pending_tree(e._h, t.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "spx_pending_tree")
-    return t.cpu().numpy()
-
-
 def test_selfplay_with_tower_replays_bit_exact_in_oracle():
     """Self-play driven by the native tower: log every evaluation, replay it through the C oracle and require
     identical games ("visit counts bit-exact given identical network outputs")."""
-    from oracle import oracle as ox
     from self_play_reinforcement_learning_b200 import nets
     from self_play_reinforcement_learning_b200.engine import SelfPlayEngine
     from tests import helpers as H
@@ -85,32 +77,14 @@ def test_selfplay_with_tower_replays_bit_exact_in_oracle():
     net = nets.ResidualTower(7, 6, 7, num_blocks=2).eval()
     n_games, sims = 14, 40
     ev = nets.TowerEvaluator(net)
-    rng = np.random.default_rng(3)
-    table = rng.dirichlet([1.0] * 7, size=(n_games, 2, 22))
+    table = np.random.default_rng(3).dirichlet([1.0] * 7, size=(n_games, 2, 22))
     e = SelfPlayEngine(game=0, n_games=n_games, sims=sims, evaluator=ev, seed=11, noise_mode=1, games_target=n_games, move_log=True,
                        max_sims_per_tick=4)
     e.set_noise_table(table)
-    logs = [[dict(own=[], opp=[], policy=[], value=[]) for _ in (0, 1)] for _ in range(n_games)]
-    for _ in range(200000):
-        e.tick()
-        torch.cuda.synchronize()
-        need = e.needs_eval.cpu().numpy().astype(bool)
-        if not need.any() and e.all_idle():
-            break
-        own, opp = e.leaf_own.cpu().numpy().view(np.uint64), e.leaf_opp.cpu().numpy().view(np.uint64)
-        pol, val = e.policy.cpu().numpy(), e.value.cpu().numpy()
-        tree = _pending_tree(e)
-        for g in np.flatnonzero(need):
-            L = logs[g][tree[g]]
-            L["own"].append(own[g]); L["opp"].append(opp[g]); L["policy"].append(pol[g].copy()); L["value"].append(val[g])
+    logs = H.run_logged(e)
     recs, res = H.split_by_game(e.drain_records(), e.drain_results())
     assert len(res) == n_games
     for g in range(n_games):
-        rs = ox.make_replay(0, logs[g])
-        cfg = ox.make_cfg(0, sims, seed=11, game_uid=g, noise_table=table[g])
-        pair = (ox.fn_addr("ox_replaynet"), C.addressof(rs))
-        o = ox.play_episode(cfg, bool(g & 1), nets=(pair, pair))
-        assert rs.mismatches == 0 and rs.overruns == 0, (g, rs.mismatches, rs.overruns)
-        assert rs.cursor[0] == rs.n[0] and rs.cursor[1] == rs.n[1]
+        o = H.replay_in_oracle(0, sims, 11, g, table[g], logs[g])
         H.compare_game(0, e.move_log(g), recs[g], res[g], o)
     e.close()
