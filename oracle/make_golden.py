@@ -168,6 +168,25 @@ def main():
         nets[name + "_value"] = v.numpy()
         nets[name + "_wsum"] = np.array([sum(float(t.double().abs().sum()) for t in net.state_dict().values())])
         nets[name + "_seed"] = np.array([seed])
+    # ---- loss fixture: MCTreeSearch.loss (mcts.py:234-252) on a fixed batch with the reference's own code
+    import games.algos.mcts as ref_mcts
+    torch.manual_seed(3)
+    net = ResidualTower(7, 6, 7, num_blocks=2).eval()
+    lrng = np.random.default_rng(77)
+    batch = []
+    for _ in range(16):
+        st = torch.from_numpy(lrng.integers(-1, 2, size=(7, 6)).astype(np.int64))
+        pr = torch.from_numpy(lrng.dirichlet([1.0] * 7).astype(np.float32))
+        batch.append(ref_mcts.Move(st, torch.tensor(float(lrng.integers(-1, 2))), pr, torch.tensor(float(lrng.uniform(-1, 1)))))
+    holder = type("H", (), {})()
+    holder.network, holder.q_average = net, True
+    with torch.no_grad():
+        lval = float(ref_mcts.MCTreeSearch.loss(holder, batch))
+    nets["loss_states"] = np.stack([b.state.numpy() for b in batch]).astype(np.int8)
+    nets["loss_probs"] = np.stack([b.tree_probs.numpy() for b in batch])
+    nets["loss_val"] = np.array([float(b.actual_val) for b in batch], np.float32)
+    nets["loss_q"] = np.array([float(b.q) for b in batch], np.float32)
+    nets["loss_value"] = np.array([lval])
     np.savez_compressed(os.path.join(OUT, "nets.npz"), **nets)
     print("golden fixtures written to", OUT)
 

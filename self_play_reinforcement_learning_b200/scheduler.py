@@ -1,0 +1,161 @@
+"""SelfPlayScheduler: the reference's orchestration layer (games/algos/self_play_parallel.py:44-379) over the batched
+GPU engine -- same epoch structure, same result bookkeeping, same loss, with the worker processes, queues and
+checkpoint-file weight hand-off replaced by one BatchedSelfPlay per GPU and an NCCL weight broadcast.
+
+Row (f1)/(f2) of SURVEY.md 8: the training step itself is ordinary PyTorch autograd on rank 0 (the reference trains
+in one UpdateWorker, updateworker.py:141-149); it is host-side glue, not part of the measured hot path.
+"""
+from collections import deque
+
+import numpy as np
+import torch
+
+from . import nets, parallel
+from .selfplay import BatchedSelfPlay, Move, records_to_moves, results_to_dicts
+
+
+class Memory:
+    """rl_utils/memory.py:8-30: bounded FIFO of Move tuples with uniform sampling without replacement."""
+
+    def __init__(self, max_size=None):
+        self.max_size = max_size
+        self._buffer = deque(maxlen=max_size)
+
+    def __len__(self):
+        return len(self._buffer)
+
+    def add(self, experience):
+        self._buffer.append(experience)
+
+    def change_size(self, max_size):
+        self.max_size = max_size
+        self._buffer = deque(self._buffer, maxlen=max_size)
+
+    def sample(self, batch_size):
+        index = np.random.choice(np.arange(len(self._buffer)), size=batch_size, replace=False)
+        return [self._buffer[i] for i in index]
+
+    def reset(self):
+        self._buffer = deque(maxlen=self.max_size)
+
+
+def mcts_loss(network, batch, q_average=True):
+    """MCTreeSearch.loss (mcts.py:234-252): MSE(mean) of the value against actual_val (+ q when q_average) plus the
+    policy cross-entropy -sum(log p * tree_probs) / B."""
+    s, actual_val, tree_probs, q = Move(*zip(*batch))
+    dev = next(network.parameters()).device
+    net_probs, predict_val = network.forward(torch.stack(s).to(dev))
+    predict_val = predict_val.view(-1)
+    target = torch.stack(actual_val).to(dev)
+    if q_average:
+        target = target + torch.stack(q).to(dev)
+    value_loss = torch.nn.functional.mse_loss(predict_val, target.float())
+    prob_loss = -(net_probs.log() * torch.stack(tree_probs).to(dev)).sum() / net_probs.size(0)
+    return value_loss + prob_loss
+
+
+def parse_results(reward_list):
+    """self_play_parallel.py:302-327: (total_rewards, {"first": {...}, "second": {...}}); 'first' = swap_sides False."""
+    breakdown = {}
+    for j, start in enumerate(("first", "second")):
+        sel = [r for r in reward_list if r["swap_sides"] == bool(j)]
+        breakdown[start] = dict(wins=sum(r["reward"] == 1 for r in sel), draws=sum(r["reward"] == 0 for r in sel),
+                                losses=sum(r["reward"] == -1 for r in sel))
+    total_rewards = int(np.sum([r["reward"] for r in reward_list])) if reward_list else 0
+    return total_rewards, breakdown
+
+
+class SelfPlayScheduler:
+    def __init__(self, network, env, evaluation_network=None, iterations=800, epoch_length=1500, initial_games=64,
+                 evaluation_games=150, games_per_gpu=1024, memory_size=200000, batch_size=128, lr=0.01, momentum=0.9,
+                 weight_decay=1e-4, updates_per_epoch=100, alpha=1.0, seed=0, net="tower"):
+        self.network, self.env, self.evaluation_network = network, env, evaluation_network
+        self.iterations, self.epoch_length, self.initial_games, self.evaluation_games = iterations, epoch_length, initial_games, evaluation_games
+        self.games_per_gpu, self.batch_size, self.updates_per_epoch = games_per_gpu, batch_size, updates_per_epoch
+        self.alpha, self.seed, self.net = alpha, seed, net
+        self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        self.memory = Memory(memory_size)
+        # SGD(momentum 0.9, weight decay 1e-4): self_play_parallel.py:193
+        self.optim = torch.optim.SGD(network.parameters(), lr=lr, momentum=momentum, weight_decay=weight_decay)
+        self.games_played = 0
+        self.history = []
+
+    # ------------------------------------------------------------------ self-play on all ranks
+    def _play(self, n_games_total, evaluate, update, generation):
+        """n_games_total games (indices 0..n-1, swap_sides = index odd as in :250-253) sharded over the ranks."""
+        G = min(self.games_per_gpu, max(2, -(-n_games_total // self.world)))
+        G += G & 1
+        sp = BatchedSelfPlay(self.network, env=self.env, n_games=G, sims=self.iterations, net=self.net if not evaluate or self.evaluation_network is None else "torch",
+                             evaluation_network=self.evaluation_network if evaluate else None, evaluate=evaluate, update=update,
+                             alpha=self.alpha, seed=self.seed + 7919 * generation, rank=self.rank, world=self.world,
+                             games_target=n_games_total)
+        recs, res = [], []
+        while True:
+            sp.engine.run_ticks(512)
+            recs.append(sp.engine.drain_records())
+            res.append(sp.engine.drain_results())
+            if sp.engine.all_idle():
+                break
+        game = sp.game
+        sp.close()
+        recs, res = np.concatenate(recs), np.concatenate(res)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        all_recs = parallel.gather_structured(recs, dst=0, device=dev)       # replaces memory_queue
+        all_res = parallel.gather_structured(res, dst=0, device=dev)         # replaces result_queue
+        if self.rank != 0:
+            return [], []
+        return records_to_moves(all_recs, game), results_to_dicts(parallel.merge_results_in_game_order(all_res))
+
+    def _sync_weights(self):
+        """Replaces the checkpoint-file hand-off (updateworker.py:111-117 -> inference_worker.py:68-73)."""
+        if self.world == 1:
+            return
+        for p in list(self.network.parameters()) + list(self.network.buffers()):
+            torch.distributed.broadcast(p.data, src=0)
+
+    # ------------------------------------------------------------------ reference API
+    def compare_models(self):
+        """:355-379: epoch_length evaluation games policy vs evaluation policy, alternating sides."""
+        _, results = self._play(self.epoch_length, evaluate=True, update=False, generation=10_000)
+        return parse_results(results) if self.rank == 0 else (0, {})
+
+    def evaluate_policy(self, epoch):
+        """:329-353 (the evaluation-games half)."""
+        _, results = self._play(self.evaluation_games, evaluate=True, update=False, generation=20_000 + epoch)
+        return parse_results(results)[0] if self.rank == 0 else 0
+
+    def update(self):
+        """UpdateWorker.update (updateworker.py:141-149): `updates_per_epoch` SGD steps on uniform samples."""
+        if self.rank != 0 or len(self.memory) < self.batch_size:
+            return None
+        self.network.train()
+        last = None
+        for _ in range(self.updates_per_epoch):
+            loss = mcts_loss(self.network, self.memory.sample(self.batch_size))
+            self.optim.zero_grad()
+            loss.backward()
+            self.optim.step()
+            last = float(loss.detach())
+        self.network.eval()
+        return last
+
+    def train_model(self, num_epochs=10):
+        """:213-291: initial games, then per epoch: epoch_length self-play games -> update -> weight sync -> evaluation."""
+        self.network.eval()
+        gen = 0
+        moves, _ = self._play(self.initial_games, evaluate=False, update=True, generation=gen)
+        for m in moves:
+            self.memory.add(m)
+        for epoch in range(num_epochs):
+            gen += 1
+            moves, results = self._play(self.epoch_length, evaluate=False, update=True, generation=gen)
+            for m in moves:
+                self.memory.add(m)
+            self.games_played += self.epoch_length
+            loss = self.update()
+            self._sync_weights()
+            reward = self.evaluate_policy(epoch) if self.evaluation_games else 0
+            self.history.append(dict(epoch=epoch, loss=loss, self_play=parse_results(results)[0] if self.rank == 0 else None,
+                                     evaluation_reward=reward, memory=len(self.memory)))
+        return self.history

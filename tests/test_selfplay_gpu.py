@@ -111,3 +111,19 @@ def test_weight_refresh_changes_outputs():
     torch.cuda.synchronize()
     assert not torch.equal(p_a, sp.engine.policy)
     sp.close()
+
+
+def test_scheduler_train_loop_small():
+    """configs[4] shape at toy size: initial games -> epoch of self-play -> SGD updates -> evaluation, one GPU."""
+    from self_play_reinforcement_learning_b200 import nets
+    from self_play_reinforcement_learning_b200.scheduler import SelfPlayScheduler
+    torch.manual_seed(0)
+    net = nets.ResidualTower(7, 6, 7, num_blocks=1).cuda().eval()
+    before = net.linear_output.weight.detach().clone()
+    s = SelfPlayScheduler(net, 0, iterations=30, epoch_length=16, initial_games=8, evaluation_games=6, games_per_gpu=16, batch_size=32,
+                          updates_per_epoch=5, lr=0.01)
+    hist = s.train_model(num_epochs=1)
+    assert len(hist) == 1 and hist[0]["memory"] > 16 * 7 and np.isfinite(hist[0]["loss"])
+    assert not torch.equal(before, net.linear_output.weight.detach())
+    total, bd = s.compare_models()
+    assert set(bd) == {"first", "second"} and sum(sum(v.values()) for v in bd.values()) == 16
