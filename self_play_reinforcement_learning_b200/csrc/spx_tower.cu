@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -231,6 +232,9 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 const unsigned bytes = 2u * (unsigned)li.n * 16u * (unsigned)ksteps;
                 const int iters = li.taps * (li.kslices / ksteps);
                 for (int it = 0; it < iters; ++it) {
+#ifdef SPX_DBG_NO_TMA
+                    continue;
+#endif
                     mbar_wait(&S.empty[stage], sphase ^ 1u);
                     if (leader) {
                         mbar_expect_tx(&S.full[stage], bytes);
@@ -257,8 +261,10 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 for (int tap = 0; tap < li.taps; ++tap) {
                     const int shift = li.taps == 9 ? tap_shift(tap) : 0;
                     for (int kp = 0; kp < kpairs; ++kp) {
+#ifndef SPX_DBG_NO_TMA
                         mbar_wait(&S.full[stage], sphase);
                         tc_fence_after();
+#endif
                         const unsigned b_addr = smem_u32(S.wstage[stage]);
                         const unsigned a_addr0 = a_base + (unsigned)(2 * ksteps * kp) * CHUNK_BYTES + (unsigned)(shift * 16);
                         if (leader) {
@@ -271,7 +277,9 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                                 }
                                 acc = 1u;
                             }
+#ifndef SPX_DBG_NO_TMA
                             tc_commit(&S.empty[stage]);   // frees the weight slot once these MMAs retire
+#endif
                         }
                         acc = 1u;
                         __syncwarp();
@@ -397,6 +405,301 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
     tc_fence_before();
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ the 2-CTA tower kernel
+// Same dataflow, but two CTAs (one SM pair, cluster of 2) share every weight slice: tcgen05.mma.cta_group::2 with M=256
+// (128 rows of each CTA) x N=128; each CTA stages only HALF of the slice (64 output channels) and the pair exchanges B
+// through the tensor-core datapath.  Per CTA that halves the weight bytes written into and read from shared memory (the
+// shared-memory port is the limiter of M=128 x N=128 SS-MMAs) and doubles the ring depth (6 x 4 KB).  The leader CTA
+// (cluster rank 0) issues all MMAs; completion is multicast to both CTAs' barriers; the peer relays "my half has landed"
+// and "my epilogue is done" with remote mbarrier arrives.
+struct Smem2 {
+    unsigned char act[2][ACT_BYTES];
+    unsigned char wstage[2 * NSTAGE][STAGE_BYTES / 2];
+    unsigned long long full[2 * NSTAGE], empty[2 * NSTAGE], peer_full[2 * NSTAGE], acc_full, epi_done;
+    unsigned long long own[NB], opp[NB];
+    float bias[2][CH];
+    unsigned tmem_base;
+};
+constexpr int NSTAGE2 = 2 * NSTAGE;
+
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(void* bar, unsigned cta) {   // arrive on the same barrier in CTA `cta` of the cluster
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(void* bar, unsigned parity) {  // acquire at cluster scope (peer data)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_commit2(void* bar) {   // completion of this thread's cta_group::2 MMAs -> same barrier in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma2(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tower_kernel2(const unsigned long long* __restrict__ own_g, const unsigned long long* __restrict__ opp_g,
+             const unsigned char* __restrict__ needs, long long n_boards, int n_layers,
+             const unsigned char* __restrict__ wconv, const float* __restrict__ bias_all, float* __restrict__ head_out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem2& S = *reinterpret_cast<Smem2*>(smem_raw);
+    const unsigned crank = cluster_ctarank();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long n_groups = (n_boards + NB - 1) / NB;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE2; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); mbar_init(&S.peer_full[s], 1); }
+        mbar_init(&S.acc_full, 1);
+        mbar_init(&S.epi_done, EPI_THREADS + 1);   // local epilogue threads + one remote arrive from the peer CTA
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    // zero both activation buffers once: guard rows and padding cells must read as zero forever
+    for (int i = tid; i < 2 * ACT_BYTES / 16; i += NUM_THREADS) reinterpret_cast<uint4*>(S.act[0])[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // both CTAs' barriers initialised and buffers zeroed before any remote arrive / MMA
+    tc_fence_after();
+    const unsigned tmem_base = S.tmem_base;
+
+    unsigned stage = 0, sphase = 0;   // weight ring position (producer and MMA walk the same sequence)
+    unsigned lphase = 0;              // per-layer barrier parity (acc_full / epi_done)
+
+    const long long n_pairs = (n_groups + 1) / 2;
+    for (long long pair = blockIdx.x >> 1; pair < n_pairs; pair += gridDim.x >> 1) {
+        const long long grp = 2 * pair + crank;
+        // pair-uniform skip when none of the 14 boards of this CTA pair asked for an evaluation
+        bool any = needs == nullptr;
+        if (!any) for (int b = 0; b < 2 * NB; ++b) { long long gb = 2 * pair * NB + b; if (gb < n_boards && needs[gb]) any = true; }
+        if (!any) continue;
+
+        if (warp == 0) {
+            // ===================== TMA producer: stream the pre-packed weight slices in consumption order.
+            // The whole warp walks the loop (warp-uniform control flow keeps addresses in uniform registers);
+            // one elected lane issues the copies.
+            const bool leader = elect_one();
+            const unsigned char* wp = wconv;
+            for (int l = 0; l < n_layers; ++l) {
+                const LayerInfo li = layer_info(l, n_layers);
+                const int ksteps = li.kslices >= 2 ? 2 : 1;                  // K steps (of 16 channels) per ring stage
+                const unsigned bytes = (unsigned)li.n * 16u * (unsigned)ksteps;   // this CTA's half of the stage (n/2 output channels)
+                const int iters = li.taps * (li.kslices / ksteps);
+                for (int it = 0; it < iters; ++it) {
+#ifdef SPX_DBG_NO_TMA
+                    continue;
+#endif
+                    mbar_wait(&S.empty[stage], sphase ^ 1u);
+                    if (leader) {
+                        mbar_expect_tx(&S.full[stage], bytes);
+                        tma_bulk_g2s(S.wstage[stage], wp + (size_t)crank * bytes, bytes, &S.full[stage]);
+                    }
+                    __syncwarp();
+                    wp += 2u * bytes;
+                    if (++stage == NSTAGE2) { stage = 0; sphase ^= 1u; }
+                }
+            }
+        } else if (warp == 2 && crank == 1) {
+            // ===================== peer relay: tell the leader when this CTA's half of each weight stage has landed
+            const bool leader = elect_one();
+            for (int l = 0; l < n_layers; ++l) {
+                const LayerInfo li = layer_info(l, n_layers);
+                const int ksteps = li.kslices >= 2 ? 2 : 1;
+                const int iters = li.taps * (li.kslices / ksteps);
+                for (int it = 0; it < iters; ++it) {
+#ifdef SPX_DBG_NO_TMA
+                    continue;
+#endif
+                    mbar_wait(&S.full[stage], sphase);
+                    if (leader) mbar_arrive_remote(&S.peer_full[stage], 0);
+                    __syncwarp();
+                    if (++stage == NSTAGE2) { stage = 0; sphase ^= 1u; }
+                }
+            }
+        } else if (warp == 1 && crank == 0) {
+            // ===================== MMA issuer (leader CTA): warp-uniform loop, one elected lane issues cta_group::2 MMAs
+            const bool leader = elect_one();
+            for (int l = 0; l < n_layers; ++l) {
+                const LayerInfo li = layer_info(l, n_layers);
+                const unsigned idesc = make_idesc(256, li.n);
+                const int ksteps = li.kslices >= 2 ? 2 : 1;
+                const int kpairs = li.kslices / ksteps;
+                const unsigned kstep_bytes = (unsigned)li.n * 16u;            // per CTA: [2 k-chunks][n/2][8] bf16
+                const unsigned a_base = smem_u32(S.act[li.in_buf]) + GUARD * 16;
+                mbar_wait_cluster(&S.epi_done, lphase);   // both CTAs: inputs of this layer written, accumulators drained
+                tc_fence_after();
+                unsigned acc = 0;
+                for (int tap = 0; tap < li.taps; ++tap) {
+                    const int shift = li.taps == 9 ? tap_shift(tap) : 0;
+                    for (int kp = 0; kp < kpairs; ++kp) {
+#ifndef SPX_DBG_NO_TMA
+                        mbar_wait(&S.full[stage], sphase);
+                        mbar_wait_cluster(&S.peer_full[stage], sphase);
+                        tc_fence_after();
+#endif
+                        const unsigned b_addr = smem_u32(S.wstage[stage]);
+                        const unsigned a_addr0 = a_base + (unsigned)(2 * ksteps * kp) * CHUNK_BYTES + (unsigned)(shift * 16);
+                        if (leader) {
+                            for (int j = 0; j < ksteps; ++j) {
+                                const unsigned long long bdesc = make_desc(b_addr + (unsigned)j * kstep_bytes, (unsigned)li.n * 8u, 128u);
+#pragma unroll
+                                for (int t = 0; t < MT; ++t) {
+                                    const unsigned a_addr = a_addr0 + (unsigned)(2 * j) * CHUNK_BYTES + (unsigned)(t * 128 * 16);
+                                    tc_mma2(tmem_base + (unsigned)(t * 128), make_desc(a_addr, CHUNK_BYTES, 128u), bdesc, idesc, acc);
+                                }
+                                acc = 1u;
+                            }
+#ifndef SPX_DBG_NO_TMA
+                            tc_commit2(&S.empty[stage]);   // frees the weight slot in BOTH CTAs once these MMAs retire
+#endif
+                        }
+                        acc = 1u;
+                        __syncwarp();
+                        if (++stage == NSTAGE2) { stage = 0; sphase ^= 1u; }
+                    }
+                }
+                if (leader) tc_commit2(&S.acc_full);
+                __syncwarp();
+                lphase ^= 1u;
+            }
+        } else if (warp >= EPI_WARP0) {
+            // ===================== epilogue warps (also write the stem input)
+            const int et = tid - EPI_WARP0 * 32;          // 0..EPI_THREADS-1
+            const int quarter = warp & 3, part = (warp - EPI_WARP0) >> 2;   // TMEM lane quarter, column part
+            if (et < NB) {
+                const long long gb = grp * NB + et;
+                S.own[et] = gb < n_boards ? own_g[gb] : 0ULL;
+                S.opp[et] = gb < n_boards ? opp_g[gb] : 0ULL;
+            }
+            if (et < CH) S.bias[0][et] = __ldg(bias_all + et);
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+            // preprocess (modules.py:115-125): planes (empty, own, enemy) -> channels 0..2 of buffer 0, channels 3..15 zero
+            for (int row = et; row < ROWS; row += EPI_THREADS) {
+                int board, cell;
+                const bool real = row_is_cell(row, board, cell);
+                const int p = row - board * BOARD_ROWS;
+                unsigned o = 0, e = 0;
+                if (real) { o = (unsigned)((S.own[board] >> p) & 1ULL); e = (unsigned)((S.opp[board] >> p) & 1ULL); }
+                const unsigned emp = real ? (1u - o - e) : 0u;
+                const unsigned one = 0x3F80u;  // bf16(1.0)
+                uint4 v0 = make_uint4((emp ? one : 0u) | ((o ? one : 0u) << 16), e ? one : 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(S.act[0] + (GUARD + row) * 16) = v0;
+                *reinterpret_cast<uint4*>(S.act[0] + CHUNK_BYTES + (GUARD + row) * 16) = make_uint4(0, 0, 0, 0);
+            }
+            fence_proxy_async();
+            if (crank == 0) mbar_arrive(&S.epi_done);
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+            if (crank == 1 && et == 0) mbar_arrive_remote(&S.epi_done, 0);   // the peer's single arrive on the leader's barrier
+            // per-tile row bookkeeping is layer independent
+            bool real_t[MT]; int board_t[MT], cell_t[MT];
+#pragma unroll
+            for (int t = 0; t < MT; ++t) real_t[t] = row_is_cell(t * 128 + quarter * 32 + lane, board_t[t], cell_t[t]);
+            for (int l = 0; l < n_layers; ++l) {
+                const LayerInfo li = layer_info(l, n_layers);
+                const float* bias_s = S.bias[l & 1];
+                // stage the NEXT layer's folded-BN bias while this layer's MMAs are still running
+                if (l + 1 < n_layers && et < CH) S.bias[(l + 1) & 1][et] = __ldg(bias_all + (size_t)(l + 1) * CH + et);
+                mbar_wait(&S.acc_full, lphase);
+                tc_fence_after();
+                if (li.out_buf >= 0) {
+                    // trunk layer: this warp owns 128/EPI_SPLIT = 32 columns of its 32 rows, for each of the 3 row tiles
+                    const int ch0 = part * (CH / EPI_SPLIT);
+                    const unsigned tcol = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)ch0;
+                    unsigned v[2][32];
+                    tc_ld32_nowait(tcol, v[0]);
+#pragma unroll
+                    for (int t = 0; t < MT; ++t) {
+                        tc_wait_ld();
+                        if (t + 1 < MT) tc_ld32_nowait(tcol + (unsigned)((t + 1) * 128), v[(t + 1) & 1]);
+#ifdef SPX_DBG_SKIP_EPI
+                        continue;
+#endif
+                        const int row = t * 128 + quarter * 32 + lane;
+                        unsigned char* obase = S.act[li.out_buf] + (GUARD + row) * 16 + (ch0 >> 3) * CHUNK_BYTES;
+                        if (!real_t[t]) {   // padding / guard cell: must read as zero in the next layer
+#pragma unroll
+                            for (int g8 = 0; g8 < 4; ++g8) *reinterpret_cast<uint4*>(obase + g8 * CHUNK_BYTES) = make_uint4(0, 0, 0, 0);
+                            continue;
+                        }
+                        const unsigned* vv = v[t & 1];
+#pragma unroll
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch0 + g8 * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch0 + g8 * 8 + 4);
+                            float y[8] = {__uint_as_float(vv[g8 * 8 + 0]) + b0.x, __uint_as_float(vv[g8 * 8 + 1]) + b0.y,
+                                          __uint_as_float(vv[g8 * 8 + 2]) + b0.z, __uint_as_float(vv[g8 * 8 + 3]) + b0.w,
+                                          __uint_as_float(vv[g8 * 8 + 4]) + b1.x, __uint_as_float(vv[g8 * 8 + 5]) + b1.y,
+                                          __uint_as_float(vv[g8 * 8 + 6]) + b1.z, __uint_as_float(vv[g8 * 8 + 7]) + b1.w};
+                            uint4* dst = reinterpret_cast<uint4*>(obase + g8 * CHUNK_BYTES);
+                            if (li.residual) {  // out += identity (modules.py:37), identity lives in the output buffer
+                                const uint4 idv = *dst;
+                                const unsigned iw[4] = {idv.x, idv.y, idv.z, idv.w};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    y[2 * k] += __uint_as_float(iw[k] << 16);
+                                    y[2 * k + 1] += __uint_as_float(iw[k] & 0xFFFF0000u);
+                                }
+                            }
+                            unsigned pk[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(y[2 * k], 0.f), fmaxf(y[2 * k + 1], 0.f));
+                                pk[k] = *reinterpret_cast<unsigned*>(&h2);
+                            }
+                            *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                } else {
+                    // fused policy/value 1x1 head conv + BN + ReLU (modules.py:97,102) -> fp32 [board][ch*42 + cell];
+                    // 64 columns: each warp owns 64/EPI_SPLIT = 16 of them
+                    const int ch0 = part * (HEAD_CH / EPI_SPLIT);
+#pragma unroll
+                    for (int t = 0; t < MT; ++t) {
+                        unsigned v[16];
+                        tc_ld16(tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(t * 128 + ch0), v);
+                        const long long gb = grp * NB + board_t[t];
+                        if (real_t[t] && gb < n_boards) {
+                            float* ob = head_out + (size_t)gb * (HEAD_CH * CELLS) + cell_t[t];
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) ob[(size_t)(ch0 + k) * CELLS] = fmaxf(__uint_as_float(v[k]) + bias_s[ch0 + k], 0.f);
+                        }
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                lphase ^= 1u;
+                if (l + 1 < n_layers && crank == 0) mbar_arrive(&S.epi_done);
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));   // next layer's bias visible; this CTA's epilogue complete
+                if (l + 1 < n_layers && crank == 1 && et == 0) mbar_arrive_remote(&S.epi_done, 0);
+            }
+        }
+        // non-elected lanes of warps 0-1 and warps 2-3 fall through; ring/phase state persists in the elected lanes
+        __syncthreads();   // group boundary: accumulators drained, buffers reusable
+        cluster_sync_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ fully connected heads
@@ -534,7 +837,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ he
 
 // ================================================================================================== C ABI
 struct spx_tower {
-    int game, num_blocks, n_layers, A;
+    int game, num_blocks, n_layers, A, ncta;
     size_t off_bias, off_polw, off_polb, off_w1t, off_b1, off_w2, off_b2, blob_bytes;
     unsigned char* blob;    // device copy of the packed weights
     float* head_buf;        // [capacity][64*42] fp32 head-conv activations
@@ -573,6 +876,10 @@ int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
     if (!t) return spx::set_err(SPX_E_ARG, "spx_tower_create: out of host memory%s", "");
     memset(t, 0, sizeof(*t));
     t->game = game; t->num_blocks = num_blocks; t->n_layers = 2 * num_blocks + 2; t->A = 7;
+    {
+        const char* e = getenv("SPX_TOWER_NCTA");   // 2 (default): SM-pair kernel (cta_group::2); 1: single-CTA kernel
+        t->ncta = (e && e[0] == '1') ? 1 : 2;
+    }
     size_t conv = (size_t)9 * KSTEP_BYTES + (size_t)num_blocks * 2 * 72 * KSTEP_BYTES + (size_t)8 * (2 * HEAD_CH * 16);
     size_t off = align_up(conv, 256);
     t->off_bias = off; off = align_up(off + (size_t)t->n_layers * CH * 4, 256);
@@ -588,10 +895,14 @@ int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
     SPX_CUDA_T(cudaGetDevice(&dev));
     SPX_CUDA_T(cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev));
     SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem2)));
     SPX_CUDA_T(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM));
     *out = t;
     return 0;
 }
+
+/* 1 or 2: which weight-slice layout spx_tower_load expects (2 = output channels split across the SM pair) */
+int spx_tower_ncta(spx_tower* t) { return t ? t->ncta : 0; }
 
 int spx_tower_destroy(spx_tower* t) {
     if (!t) return 0;
@@ -619,10 +930,26 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
         t->capacity = n;
     }
     const long long groups = (n + NB - 1) / NB;
-    const int grid = (int)(groups < t->sm_count ? groups : t->sm_count);
     if (e0) SPX_CUDA_T(cudaEventRecord(e0, st));
-    tower_kernel<<<grid, NUM_THREADS, sizeof(Smem), st>>>((const unsigned long long*)own, (const unsigned long long*)opp, needs_eval, n,
-                                                              t->n_layers, t->blob, (const float*)(t->blob + t->off_bias), t->head_buf);
+    if (t->ncta == 2) {
+        const long long pairs = (groups + 1) / 2, max_pairs = t->sm_count / 2;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = sizeof(Smem2);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        SPX_CUDA_T(cudaLaunchKernelEx(&cfg, tower_kernel2, (const unsigned long long*)own, (const unsigned long long*)opp, needs_eval,
+                                      (long long)n, t->n_layers, (const unsigned char*)t->blob, (const float*)(t->blob + t->off_bias), t->head_buf));
+    } else {
+        const int grid = (int)(groups < t->sm_count ? groups : t->sm_count);
+        tower_kernel<<<grid, NUM_THREADS, sizeof(Smem), st>>>((const unsigned long long*)own, (const unsigned long long*)opp, needs_eval, n,
+                                                            t->n_layers, t->blob, (const float*)(t->blob + t->off_bias), t->head_buf);
+    }
     spx::count_launch();
     SPX_CUDA_T(cudaGetLastError());
     if (e1) SPX_CUDA_T(cudaEventRecord(e1, st));

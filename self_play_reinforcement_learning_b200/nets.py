@@ -214,15 +214,23 @@ def _fold(conv, bn):
     return w.cpu(), b.cpu()
 
 
-def _stage_blocks(w):
+def _stage_blocks(w, ncta=1):
     """[N, Cin(multiple of 16), kh, kw] -> bf16 elements in MMA consumption order: tap-major, then 16-channel K
-    slices, each slice stored as [2 k-chunks][N][8] (the no-swizzle K-major core-matrix layout)."""
+    slices, each slice stored as [2 k-chunks][N][8] (the no-swizzle K-major core-matrix layout).
+    ncta=2 (SM-pair kernel): ring stages carry two K slices (one for the 3-channel stem) and every stage is stored as
+    [half of the output channels][K slice][2 k-chunks][N/2][8], so each CTA of the pair copies one contiguous half."""
     N, Cin, KH, KW = w.shape
-    x = w.reshape(N, Cin // 16, 2, 8, KH, KW).permute(4, 5, 1, 2, 0, 3).contiguous()
+    ks = Cin // 16
+    if ncta == 1:
+        x = w.reshape(N, ks, 2, 8, KH, KW).permute(4, 5, 1, 2, 0, 3).contiguous()
+        return x.to(torch.bfloat16).reshape(-1)
+    per = 2 if ks >= 2 else 1                       # K slices per ring stage
+    x = w.reshape(2, N // 2, ks // per, per, 2, 8, KH, KW)   # [h, n, kpair, j, kc, e, kh, kw]
+    x = x.permute(6, 7, 2, 0, 3, 4, 1, 5).contiguous()       # [kh, kw, kpair, h, j, kc, n, e]
     return x.to(torch.bfloat16).reshape(-1)
 
 
-def pack_tower_blob(module):
+def pack_tower_blob(module, ncta=2):
     """ResidualTower (7x6, 128 trunk channels) -> one flat uint8 tensor in the layout spx_tower_load expects."""
     m = module
     assert hasattr(m, "residual_blocks"), "the native tower needs a ResidualTower"
@@ -235,18 +243,18 @@ def pack_tower_blob(module):
     w, b = _fold(m.conv1, m.bn1)
     wp = torch.zeros(128, 16, 3, 3)
     wp[:, :3] = w
-    conv_parts.append(_stage_blocks(wp))
+    conv_parts.append(_stage_blocks(wp, ncta))
     biases[0] = b
     li = 1
     for blk in blocks:
         for conv, bn in ((blk.conv1, blk.bn1), (blk.conv2, blk.bn2)):
             w, b = _fold(conv, bn)
-            conv_parts.append(_stage_blocks(w))
+            conv_parts.append(_stage_blocks(w, ncta))
             biases[li] = b
             li += 1
     wpol, bpol = _fold(m.conv_policy, m.policy_bn)
     wval, bval = _fold(m.conv_value, m.value_bn)
-    conv_parts.append(_stage_blocks(torch.cat([wpol, wval], 0)))
+    conv_parts.append(_stage_blocks(torch.cat([wpol, wval], 0), ncta))
     biases[li, :64] = torch.cat([bpol, bval])
     f32 = lambda t: t.detach().float().cpu().contiguous()  # noqa: E731
     pieces = [torch.cat(conv_parts).view(torch.uint8),
@@ -276,11 +284,12 @@ class NativeTower:
         self.A = module.linear_policy.out_features
         self._h = C.c_void_p()
         check(lib().spx_tower_create(game, self.num_blocks, C.byref(self._h)), "spx_tower_create")
+        self.ncta = lib().spx_tower_ncta(self._h)
         self.load(module)
 
     def load(self, module_or_blob):
         """module (packed on the host, then H2D) or an already packed uint8 blob (pinned host or device tensor)."""
-        blob = module_or_blob if torch.is_tensor(module_or_blob) else pack_tower_blob(module_or_blob)
+        blob = module_or_blob if torch.is_tensor(module_or_blob) else pack_tower_blob(module_or_blob, self.ncta)
         want = lib().spx_tower_blob_bytes(self.game, self.num_blocks)
         assert blob.numel() == want, (blob.numel(), want)
         self.blob_dev = blob.to("cuda", non_blocking=True)

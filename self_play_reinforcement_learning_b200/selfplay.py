@@ -79,7 +79,8 @@ class BatchedSelfPlay:
     # ------------------------------------------------------------------ weights
     def packed_weights_pinned(self, module=None):
         """Packed weight blob of ``module`` (default: the construction network) in pinned host memory."""
-        blob = nets.pack_tower_blob(module if module is not None else self.network)
+        ncta = self.evaluator.tower.ncta if self.net_kind == "tower" else 2
+        blob = nets.pack_tower_blob(module if module is not None else self.network, ncta)
         self._pinned = blob.pin_memory()
         return self._pinned
 
