@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bounded CPU-baseline sample per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--max-sims-per-tick", type=int, default=8)
     return ap.parse_args()
 
 
@@ -215,7 +216,8 @@ def main():
     G, T = args.games, args.ticks_per_step
 
     # ---- public-API object (also used for the resident-data measurement through its engine)
-    sp = BatchedSelfPlay(module, game=0, n_games=G, sims=args.sims, net=args.net, seed=0, rank=rank, world=world)
+    sp = BatchedSelfPlay(module, game=0, n_games=G, sims=args.sims, net=args.net, seed=0, rank=rank, world=world,
+                         max_sims_per_tick=args.max_sims_per_tick)
     eng, ev = sp.engine, sp.evaluator
     blob_host = sp.packed_weights_pinned() if args.net == "tower" else None
 

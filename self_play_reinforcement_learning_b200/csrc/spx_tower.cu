@@ -77,7 +77,7 @@ struct Smem {
     unsigned char wstage[NSTAGE][STAGE_BYTES];
     unsigned long long full[NSTAGE], empty[NSTAGE], acc_full, epi_done;
     unsigned long long own[NB], opp[NB];
-    float bias[2][CH];
+    float bias[3][CH];
     unsigned tmem_base;
 };
 
@@ -144,6 +144,34 @@ __device__ __forceinline__ void tc_ld32_nowait(unsigned taddr, unsigned (&v)[32]
           "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
+}
+__device__ __forceinline__ void tc_st32(unsigned taddr, const unsigned (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+          "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+          "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// the folded-BN bias of a layer is pre-stored into the accumulator columns by the epilogue warps, so every MMA accumulates
+__device__ __forceinline__ void store_bias_to_tmem(unsigned tcol, const float* bias_s) {
+    unsigned b[32];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 f = *reinterpret_cast<const float4*>(bias_s + 4 * k);
+        b[4 * k] = __float_as_uint(f.x); b[4 * k + 1] = __float_as_uint(f.y); b[4 * k + 2] = __float_as_uint(f.z); b[4 * k + 3] = __float_as_uint(f.w);
+    }
+#pragma unroll
+    for (int t = 0; t < MT; ++t) tc_st32(tcol + (unsigned)(t * 128), b);
+    tc_wait_st();
+}
+__device__ __forceinline__ unsigned relu_pack_bf16x2(float lo, float hi) {   // max(x,0) and round-to-nearest bf16 in one instruction
+    unsigned r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 __device__ __forceinline__ void tc_ld16(unsigned taddr, unsigned (&v)[16]) {
     asm volatile(
@@ -257,7 +285,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 const unsigned a_base = smem_u32(S.act[li.in_buf]) + GUARD * 16;
                 mbar_wait(&S.epi_done, lphase);   // inputs of this layer written, accumulators drained
                 tc_fence_after();
-                unsigned acc = 0;
+                const unsigned acc = 1u;   // the accumulators start from the pre-stored bias
                 for (int tap = 0; tap < li.taps; ++tap) {
                     const int shift = li.taps == 9 ? tap_shift(tap) : 0;
                     for (int kp = 0; kp < kpairs; ++kp) {
@@ -275,13 +303,11 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                                     const unsigned a_addr = a_addr0 + (unsigned)(2 * j) * CHUNK_BYTES + (unsigned)(t * 128 * 16);
                                     tc_mma(tmem_base + (unsigned)(t * 128), make_desc(a_addr, CHUNK_BYTES, 128u), bdesc, idesc, acc);
                                 }
-                                acc = 1u;
                             }
 #ifndef SPX_DBG_NO_TMA
                             tc_commit(&S.empty[stage]);   // frees the weight slot once these MMAs retire
 #endif
                         }
-                        acc = 1u;
                         __syncwarp();
                         if (++stage == NSTAGE) { stage = 0; sphase ^= 1u; }
                     }
@@ -299,8 +325,10 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 S.own[et] = gb < n_boards ? own_g[gb] : 0ULL;
                 S.opp[et] = gb < n_boards ? opp_g[gb] : 0ULL;
             }
-            if (et < CH) S.bias[0][et] = __ldg(bias_all + et);
+            if (et < CH) { S.bias[0][et] = __ldg(bias_all + et); S.bias[1][et] = __ldg(bias_all + CH + et); }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+            store_bias_to_tmem(tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(part * (CH / EPI_SPLIT)), S.bias[0] + part * (CH / EPI_SPLIT));
+            tc_fence_before();
             // preprocess (modules.py:115-125): planes (empty, own, enemy) -> channels 0..2 of buffer 0, channels 3..15 zero
             for (int row = et; row < ROWS; row += EPI_THREADS) {
                 int board, cell;
@@ -322,9 +350,8 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
             for (int t = 0; t < MT; ++t) real_t[t] = row_is_cell(t * 128 + quarter * 32 + lane, board_t[t], cell_t[t]);
             for (int l = 0; l < n_layers; ++l) {
                 const LayerInfo li = layer_info(l, n_layers);
-                const float* bias_s = S.bias[l & 1];
-                // stage the NEXT layer's folded-BN bias while this layer's MMAs are still running
-                if (l + 1 < n_layers && et < CH) S.bias[(l + 1) & 1][et] = __ldg(bias_all + (size_t)(l + 1) * CH + et);
+                // stage the bias of layer l+2 while this layer's MMAs are still running (layer l+1's is already visible)
+                if (l + 2 < n_layers && et < CH) S.bias[(l + 2) % 3][et] = __ldg(bias_all + (size_t)(l + 2) * CH + et);
                 mbar_wait(&S.acc_full, lphase);
                 tc_fence_after();
                 if (li.out_buf >= 0) {
@@ -350,12 +377,9 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                         const unsigned* vv = v[t & 1];
 #pragma unroll
                         for (int g8 = 0; g8 < 4; ++g8) {
-                            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch0 + g8 * 8);
-                            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch0 + g8 * 8 + 4);
-                            float y[8] = {__uint_as_float(vv[g8 * 8 + 0]) + b0.x, __uint_as_float(vv[g8 * 8 + 1]) + b0.y,
-                                          __uint_as_float(vv[g8 * 8 + 2]) + b0.z, __uint_as_float(vv[g8 * 8 + 3]) + b0.w,
-                                          __uint_as_float(vv[g8 * 8 + 4]) + b1.x, __uint_as_float(vv[g8 * 8 + 5]) + b1.y,
-                                          __uint_as_float(vv[g8 * 8 + 6]) + b1.z, __uint_as_float(vv[g8 * 8 + 7]) + b1.w};
+                            float y[8];   // accumulator already contains the folded-BN bias
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) y[k] = __uint_as_float(vv[g8 * 8 + k]);
                             uint4* dst = reinterpret_cast<uint4*>(obase + g8 * CHUNK_BYTES);
                             if (li.residual) {  // out += identity (modules.py:37), identity lives in the output buffer
                                 const uint4 idv = *dst;
@@ -368,13 +392,11 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                             }
                             unsigned pk[4];
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(y[2 * k], 0.f), fmaxf(y[2 * k + 1], 0.f));
-                                pk[k] = *reinterpret_cast<unsigned*>(&h2);
-                            }
+                            for (int k = 0; k < 4; ++k) pk[k] = relu_pack_bf16x2(y[2 * k], y[2 * k + 1]);
                             *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
                     }
+                    if (l + 1 < n_layers) store_bias_to_tmem(tcol, S.bias[(l + 1) % 3] + ch0);
                 } else {
                     // fused policy/value 1x1 head conv + BN + ReLU (modules.py:97,102) -> fp32 [board][ch*42 + cell];
                     // 64 columns: each warp owns 64/EPI_SPLIT = 16 of them
@@ -387,7 +409,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                         if (real_t[t] && gb < n_boards) {
                             float* ob = head_out + (size_t)gb * (HEAD_CH * CELLS) + cell_t[t];
 #pragma unroll
-                            for (int k = 0; k < 16; ++k) ob[(size_t)(ch0 + k) * CELLS] = fmaxf(__uint_as_float(v[k]) + bias_s[ch0 + k], 0.f);
+                            for (int k = 0; k < 16; ++k) ob[(size_t)(ch0 + k) * CELLS] = fmaxf(__uint_as_float(v[k]), 0.f);
                         }
                     }
                 }
@@ -419,7 +441,7 @@ struct Smem2 {
     unsigned char wstage[2 * NSTAGE][STAGE_BYTES / 2];
     unsigned long long full[2 * NSTAGE], empty[2 * NSTAGE], peer_full[2 * NSTAGE], acc_full, epi_done;
     unsigned long long own[NB], opp[NB];
-    float bias[2][CH];
+    float bias[3][CH];
     unsigned tmem_base;
 };
 constexpr int NSTAGE2 = 2 * NSTAGE;
@@ -546,7 +568,7 @@ tower_kernel2(const unsigned long long* __restrict__ own_g, const unsigned long 
                 const unsigned a_base = smem_u32(S.act[li.in_buf]) + GUARD * 16;
                 mbar_wait_cluster(&S.epi_done, lphase);   // both CTAs: inputs of this layer written, accumulators drained
                 tc_fence_after();
-                unsigned acc = 0;
+                const unsigned acc = 1u;   // the accumulators start from the pre-stored bias
                 for (int tap = 0; tap < li.taps; ++tap) {
                     const int shift = li.taps == 9 ? tap_shift(tap) : 0;
                     for (int kp = 0; kp < kpairs; ++kp) {
@@ -565,13 +587,11 @@ tower_kernel2(const unsigned long long* __restrict__ own_g, const unsigned long 
                                     const unsigned a_addr = a_addr0 + (unsigned)(2 * j) * CHUNK_BYTES + (unsigned)(t * 128 * 16);
                                     tc_mma2(tmem_base + (unsigned)(t * 128), make_desc(a_addr, CHUNK_BYTES, 128u), bdesc, idesc, acc);
                                 }
-                                acc = 1u;
                             }
 #ifndef SPX_DBG_NO_TMA
                             tc_commit2(&S.empty[stage]);   // frees the weight slot in BOTH CTAs once these MMAs retire
 #endif
                         }
-                        acc = 1u;
                         __syncwarp();
                         if (++stage == NSTAGE2) { stage = 0; sphase ^= 1u; }
                     }
@@ -589,8 +609,10 @@ tower_kernel2(const unsigned long long* __restrict__ own_g, const unsigned long 
                 S.own[et] = gb < n_boards ? own_g[gb] : 0ULL;
                 S.opp[et] = gb < n_boards ? opp_g[gb] : 0ULL;
             }
-            if (et < CH) S.bias[0][et] = __ldg(bias_all + et);
+            if (et < CH) { S.bias[0][et] = __ldg(bias_all + et); S.bias[1][et] = __ldg(bias_all + CH + et); }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+            store_bias_to_tmem(tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(part * (CH / EPI_SPLIT)), S.bias[0] + part * (CH / EPI_SPLIT));
+            tc_fence_before();
             // preprocess (modules.py:115-125): planes (empty, own, enemy) -> channels 0..2 of buffer 0, channels 3..15 zero
             for (int row = et; row < ROWS; row += EPI_THREADS) {
                 int board, cell;
@@ -614,9 +636,8 @@ tower_kernel2(const unsigned long long* __restrict__ own_g, const unsigned long 
             for (int t = 0; t < MT; ++t) real_t[t] = row_is_cell(t * 128 + quarter * 32 + lane, board_t[t], cell_t[t]);
             for (int l = 0; l < n_layers; ++l) {
                 const LayerInfo li = layer_info(l, n_layers);
-                const float* bias_s = S.bias[l & 1];
-                // stage the NEXT layer's folded-BN bias while this layer's MMAs are still running
-                if (l + 1 < n_layers && et < CH) S.bias[(l + 1) & 1][et] = __ldg(bias_all + (size_t)(l + 1) * CH + et);
+                // stage the bias of layer l+2 while this layer's MMAs are still running (layer l+1's is already visible)
+                if (l + 2 < n_layers && et < CH) S.bias[(l + 2) % 3][et] = __ldg(bias_all + (size_t)(l + 2) * CH + et);
                 mbar_wait(&S.acc_full, lphase);
                 tc_fence_after();
                 if (li.out_buf >= 0) {
@@ -642,12 +663,9 @@ tower_kernel2(const unsigned long long* __restrict__ own_g, const unsigned long 
                         const unsigned* vv = v[t & 1];
 #pragma unroll
                         for (int g8 = 0; g8 < 4; ++g8) {
-                            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch0 + g8 * 8);
-                            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch0 + g8 * 8 + 4);
-                            float y[8] = {__uint_as_float(vv[g8 * 8 + 0]) + b0.x, __uint_as_float(vv[g8 * 8 + 1]) + b0.y,
-                                          __uint_as_float(vv[g8 * 8 + 2]) + b0.z, __uint_as_float(vv[g8 * 8 + 3]) + b0.w,
-                                          __uint_as_float(vv[g8 * 8 + 4]) + b1.x, __uint_as_float(vv[g8 * 8 + 5]) + b1.y,
-                                          __uint_as_float(vv[g8 * 8 + 6]) + b1.z, __uint_as_float(vv[g8 * 8 + 7]) + b1.w};
+                            float y[8];   // accumulator already contains the folded-BN bias
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) y[k] = __uint_as_float(vv[g8 * 8 + k]);
                             uint4* dst = reinterpret_cast<uint4*>(obase + g8 * CHUNK_BYTES);
                             if (li.residual) {  // out += identity (modules.py:37), identity lives in the output buffer
                                 const uint4 idv = *dst;
@@ -660,13 +678,11 @@ tower_kernel2(const unsigned long long* __restrict__ own_g, const unsigned long 
                             }
                             unsigned pk[4];
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(y[2 * k], 0.f), fmaxf(y[2 * k + 1], 0.f));
-                                pk[k] = *reinterpret_cast<unsigned*>(&h2);
-                            }
+                            for (int k = 0; k < 4; ++k) pk[k] = relu_pack_bf16x2(y[2 * k], y[2 * k + 1]);
                             *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
                     }
+                    if (l + 1 < n_layers) store_bias_to_tmem(tcol, S.bias[(l + 1) % 3] + ch0);
                 } else {
                     // fused policy/value 1x1 head conv + BN + ReLU (modules.py:97,102) -> fp32 [board][ch*42 + cell];
                     // 64 columns: each warp owns 64/EPI_SPLIT = 16 of them
@@ -679,7 +695,7 @@ tower_kernel2(const unsigned long long* __restrict__ own_g, const unsigned long 
                         if (real_t[t] && gb < n_boards) {
                             float* ob = head_out + (size_t)gb * (HEAD_CH * CELLS) + cell_t[t];
 #pragma unroll
-                            for (int k = 0; k < 16; ++k) ob[(size_t)(ch0 + k) * CELLS] = fmaxf(__uint_as_float(v[k]) + bias_s[ch0 + k], 0.f);
+                            for (int k = 0; k < 16; ++k) ob[(size_t)(ch0 + k) * CELLS] = fmaxf(__uint_as_float(v[k]), 0.f);
                         }
                     }
                 }
