@@ -95,6 +95,27 @@ __host__ __device__ __forceinline__ int reward_at(u64 mover_bits, int x, int y) 
                ? 1 : 0;
 }
 
+// Connect4 fast path: the same four full-line folds, as shift-AND run detection on masked bitboards.
+// (bit = col*7+row; the sentinel bit 6 of every column keeps shifted runs from leaking across columns.)
+template <>
+__host__ __device__ __forceinline__ int reward_at<SPX_GAME_CONNECT4>(u64 m, int x, int y) {
+    const u64 v = m & (0x3FULL << (7 * x));                                  // board[x, :]
+    u64 hit = v & (v >> 1) & (v >> 2) & (v >> 3);
+    const u64 h = m & (0x0000040810204081ULL << y);                          // board[:, y]
+    hit |= h & (h >> 7) & (h >> 14) & (h >> 21);
+    u64 d1 = 0, d2 = 0;                                                      // the two diagonals through (x, y)
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        const int r1 = c - (x - y), r2 = (x + y) - c;
+        if (r1 >= 0 && r1 < 6) d1 |= 1ULL << (7 * c + r1);
+        if (r2 >= 0 && r2 < 6) d2 |= 1ULL << (7 * c + r2);
+    }
+    d1 &= m; d2 &= m;
+    hit |= d1 & (d1 >> 8) & (d1 >> 16) & (d1 >> 24);
+    hit |= d2 & (d2 >> 6) & (d2 >> 12) & (d2 >> 18);
+    return hit != 0 ? 1 : 0;
+}
+
 template <int GAME>
 __host__ __device__ __forceinline__ unsigned valid_mask(u64 own, u64 opp) {
     typedef Rules<GAME> R;

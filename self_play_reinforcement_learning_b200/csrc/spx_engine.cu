@@ -625,26 +625,39 @@ __global__ void idle_kernel(EngineDev E, int* out) {
 
 // ------------------------------------------------------------------------------------------------ env / hashnet kernels
 template <int GAME>
-__global__ void env_step_kernel(long long n, ulonglong2* __restrict__ state, unsigned char* __restrict__ done,
+__global__ void __launch_bounds__(256) env_step_kernel(long long n, ulonglong2* __restrict__ state, unsigned char* __restrict__ done,
                                 const int* __restrict__ action, const signed char* __restrict__ player,
                                 signed char* __restrict__ reward, unsigned short* __restrict__ valid,
                                 signed char* __restrict__ status) {
+    // grid-stride loop, 4 boards per thread per trip with all loads issued before any use (memory-level parallelism);
+    // every load/store of a warp is one contiguous run: 512 B of state, 128 B of actions, 32 B of byte flags.
+    constexpr int U = 4;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        ulonglong2 st = state[i];  // one 16-byte coalesced load per game
-        const int a = action[i];
-        int r = 0, d = done[i], code = SPX_ENV_OK;
-        if (a < 0) code = SPX_ENV_SKIPPED;
-        else if (d) code = SPX_ENV_GAME_OVER;
-        else {
-            u64 own = st.x, opp = st.y;
-            int dn = 0;
-            code = env_step<GAME>(own, opp, a, player[i], r, dn);
-            if (code == SPX_ENV_OK) { st.x = own; st.y = opp; d = dn; state[i] = st; done[i] = (unsigned char)d; }
+    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * U) {
+        ulonglong2 st[U];
+        int a[U], d[U], pl[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = base + u * stride;
+            if (i < n) { st[u] = state[i]; a[u] = action[i]; d[u] = done[i]; pl[u] = player[i]; }
         }
-        reward[i] = (signed char)r;
-        valid[i] = (unsigned short)valid_mask<GAME>(st.x, st.y);
-        status[i] = (signed char)code;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = base + u * stride;
+            if (i >= n) continue;
+            int r = 0, code = SPX_ENV_OK;
+            if (a[u] < 0) code = SPX_ENV_SKIPPED;
+            else if (d[u]) code = SPX_ENV_GAME_OVER;
+            else {
+                u64 own = st[u].x, opp = st[u].y;
+                int dn = 0;
+                code = env_step<GAME>(own, opp, a[u], pl[u], r, dn);
+                if (code == SPX_ENV_OK) { st[u].x = own; st[u].y = opp; state[i] = st[u]; done[i] = (unsigned char)dn; }
+            }
+            reward[i] = (signed char)r;
+            valid[i] = (unsigned short)valid_mask<GAME>(st[u].x, st[u].y);
+            status[i] = (signed char)code;
+        }
     }
 }
 
@@ -700,7 +713,7 @@ uint64_t spx_launch_count(void) { return g_launches.load(); }
 
 static int grid_for(long long n, int block) {
     long long b = (n + block - 1) / block;
-    const long long cap = 148LL * 16;  // persistent-style cap: a multiple of the 148 SMs
+    const long long cap = 148LL * 8;  // persistent-style cap: 8 resident 256-thread CTAs on each of the 148 SMs
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
