@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Turns the raw ncu outputs in gpurun_out/ into the tracked summaries under profiles/ (run here, no GPU needed)."""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1b"
+launches = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
+rep = os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
+out_dir = os.path.join(ROOT, "profiles")
+os.makedirs(out_dir, exist_ok=True)
+
+rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
+hdr = rows[0]
+ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+agg = collections.defaultdict(list)
+for r in rows[1:]:
+    try:
+        v = float(r[iv].replace(",", ""))
+    except ValueError:
+        continue
+    agg[r[ik].split("(")[0]].append(v / 1000 if r[iu] == "ns" else v)
+tot = sum(sum(v) for v in agg.values())
+lines = [f"# {tag} ncu launch list summary (gpu__time_duration.sum, --clock-control none; cold-cache serialised launches: compare SHARES)",
+         "# command: python bench.py --steps 1 --warmup 3 --ticks-per-step 40 --no-cpu-baseline --no-e2e",
+         "kernel,launches,mean_us,share"]
+for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+    lines.append(f"{k},{len(v)},{sum(v) / len(v):.2f},{sum(v) / tot:.4f}")
+open(os.path.join(out_dir, f"{tag}_launches_summary.csv"), "w").write("\n".join(lines) + "\n")
+print("\n".join(lines))
+
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+open(os.path.join(out_dir, f"{tag}_ncu_full_raw.csv"), "w").write(raw)
+rr = list(csv.reader(raw.splitlines()))
+h = rr[0]
+want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
+        "gpc__cycles_elapsed.avg.per_second", "launch__cluster_dim_x", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum"]
+idx = [(w, h.index(w)) for w in want if w in h]
+units = rr[1]
+summ = []
+for r in rr[2:]:
+    summ.append({w: (r[i] + (" " + units[i] if units[i] else "")) for w, i in idx})
+json.dump(summ, open(os.path.join(out_dir, f"{tag}_ncu_kernels.json"), "w"), indent=1)
+tw = [x for x in summ if "tower_kernel" in x["Kernel Name"]]
+if tw:
+    def to_bytes(s):
+        v, u = s.split()[0], (s.split() + [""])[1]
+        return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+    tr = [to_bytes(x["dram__bytes_read.sum"]) + to_bytes(x["dram__bytes_write.sum"]) for x in tw]
+    json.dump({"dram_bytes_per_launch": sum(tr) / len(tr), "source": f"profiles/{tag}_ncu_full_raw.csv (ncu --set full, tower_kernel2, {len(tr)} launches)"},
+              open(os.path.join(out_dir, "tower_traffic.json"), "w"))
+for x in summ:
+    print({k: v for k, v in x.items()})
