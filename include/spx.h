@@ -33,6 +33,10 @@ extern "C" {
 
 #define SPX_MAX_ACTIONS 9
 
+#define SPX_OPP_MCTS 0
+#define SPX_OPP_LOOKAHEAD 1 /* general/hardcoded_players.py:8-37  */
+#define SPX_OPP_RANDOM 2    /* general/hardcoded_players.py:40-56 */
+
 #define SPX_E_ARG (-1)      /* bad argument                       */
 #define SPX_E_CUDA (-2)     /* CUDA runtime error / no device      */
 #define SPX_E_STATE (-3)    /* call made in the wrong engine state */
@@ -61,6 +65,8 @@ typedef struct spx_config {
     int32_t nodes_per_tree;    /* 0: worst-case bound (sims+1)*ceil(max_moves/2)+max_moves+2        */
     int32_t move_log;          /* 1: keep per-move root statistics for spx_read_move_log (debug)    */
     int32_t two_nets;          /* 1: tree 1 is evaluated by net 1 (compare_models / elo.py:73-91)   */
+    int32_t opponent_kind;     /* 0: MCTS; 1: OneStepLookahead, 2: Random (hardcoded_players.py:8-56) */
+    int32_t reserved0;
     double alpha;              /* Dirichlet alpha                                   mcts.py:135      */
     uint64_t seed;             /* counter-stream seed (oracle/spec.py)                              */
     int64_t slot_offset;       /* global index of this device's slot 0 (multi-GPU sharding)         */

@@ -146,6 +146,21 @@ def main():
         print("episode", i, game, sims, swap, ev, "reward", r["reward"], "plies", len(r["moves"]))
     with open(os.path.join(OUT, "episodes.json"), "w") as f:
         json.dump(eps, f)
+
+    # ---- evaluation games against the reference's hard-coded players (general/hardcoded_players.py)
+    vs = []
+    k = 0
+    for game in (0, 1):
+        for kind in (spec.OPP_LOOKAHEAD, spec.OPP_RANDOM):
+            for swap in (False, True):
+                for rep in range(2):
+                    uid = 5000 + 2 * k + int(swap)
+                    k += 1
+                    r = rh.run_episode_vs_hardcoded(game, 40, kind, seed=900 + k, game_uid=uid, swap_sides=swap, net_seed=k)
+                    vs.append(dict(game=game, kind=kind, swap=swap, sims=40, seed=900 + k, game_uid=uid, net_seed=k, reward=r["reward"],
+                                   moves=[[m["tree"], m["ply"], m["action"]] for m in r["moves"]], final_state=r["final_state"].tolist()))
+    with open(os.path.join(OUT, "episodes_vs_hardcoded.json"), "w") as f:
+        json.dump(vs, f)
     # ---- network fixtures: the reference's own classes, random init under a fixed seed, fp32 CPU
     import torch
     rh._import_reference()

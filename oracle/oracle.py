@@ -78,6 +78,7 @@ def lib():
         L.ox_tree_counter.argtypes = [C.c_void_p, C.c_int]
         L.ox_tree_counter.restype = C.c_long
         L.ox_play_episode.argtypes = [C.POINTER(Cfg), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Episode)]
+        L.ox_play_episode_vs.argtypes = [C.POINTER(Cfg), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Episode)]
         L.ox_hashnet_bits.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
         L.ox_set_live_counters.argtypes = [C.c_void_p]
         L.ox_env_playout.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
@@ -246,3 +247,13 @@ def make_replay(game, logs):
         rs.value[t] = val.ctypes.data_as(C.POINTER(C.c_float))
     rs._keep = keep
     return rs
+
+
+def play_episode_vs(cfg, swap_sides, kind, net_seed=0, net=None):
+    """Policy (MCTS, hash net unless ``net`` = (addr, user)) against a hard-coded opponent (spec.OPP_LOOKAHEAD / OPP_RANDOM)."""
+    ep = Episode()
+    if net is None:
+        hs = HashNetState(cfg.game, net_seed, 0)
+        net = (fn_addr("ox_hashnet"), C.addressof(hs))
+    lib().ox_play_episode_vs(C.byref(cfg), int(swap_sides), kind, net[0], net[1], C.byref(ep))
+    return episode_to_dict(ep, cfg.game)

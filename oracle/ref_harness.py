@@ -252,3 +252,40 @@ def ref_env_playout(game, actions, first_player=None):
             if st == 0:
                 player = -player
     return out
+
+
+def run_episode_vs_hardcoded(game, sims, kind, seed=0, game_uid=0, swap_sides=False, noise_table=None, net_seed=0):
+    """SelfPlayer.play_episode(update=False) of a traced MCTreeSearch (evaluate mode, as SelfPlayWorker.set_up_policies
+    does for evaluation games, selfplayworker.py:70-81) against the reference's OneStepLookahead / Random player whose
+    ``random.choice`` is replaced by the spec stream (PURPOSE_OPPONENT)."""
+    mcts, SelfPlayer, _, _ = _import_reference()
+    import games.general.hardcoded_players as hp
+    Tree = _make_tree_class(mcts)
+    env_cls = _env_cls(game)
+    CTX.seed, CTX.game_uid, CTX.tie_mode = seed, game_uid, 1
+    CTX.noise_table = noise_table
+    memq, resq = queue.Queue(), queue.Queue()
+    move_log = []
+    opp_cls = hp.OneStepLookahead if kind == spec.OPP_LOOKAHEAD else hp.Random
+
+    class TracedOpp(opp_cls):
+        def __call__(self, s):
+            ply = int(np.sum(np.abs(self.env.board)))
+            saved = hp.random.choice
+            hp.random.choice = lambda seq: seq[min(int(spec.rng_uniform(seed, game_uid, 1, spec.PURPOSE_OPPONENT, ply, 0, 0, 0) * len(seq)), len(seq) - 1)]
+            try:
+                a = super().__call__(s)
+            finally:
+                hp.random.choice = saved
+            move_log.append(dict(tree=1, ply=ply, action=int(a)))
+            return a
+    with hooked():
+        t = Tree(HashNet(game, net_seed), env_cls, memory_queue=memq, iterations=sims, thread_count=1)
+        t.tree_id, t.move_log = 0, move_log
+        t.evaluate(True)
+        opp = TracedOpp(env_cls)
+        opp.env = env_cls()
+        sp = SelfPlayer(t, opp, env_cls(), resq)
+        out = sp.play_episode(swap_sides=swap_sides, update=False)
+    assert out is not None, "reference play_episode swallowed an exception"
+    return dict(reward=int(out[1]), moves=move_log, final_state=np.asarray(out[0][-1]).astype(np.int8))

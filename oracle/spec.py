@@ -23,6 +23,9 @@ M64 = (1 << 64) - 1
 PURPOSE_TIE = 0      # tie-break noise, one value per (sim, depth, action)
 PURPOSE_GAMMA = 1    # Dirichlet/Gamma variate stream (device-generated noise mode)
 PURPOSE_ACTION = 2   # the single uniform that np.random.choice consumes per move
+PURPOSE_OPPONENT = 3 # random.choice of the hard-coded opponents (hardcoded_players.py:29,49): index = int(u * n)
+
+OPP_MCTS, OPP_LOOKAHEAD, OPP_RANDOM = 0, 1, 2
 
 GAME_CONNECT4 = 0
 GAME_TICTACTOE = 1

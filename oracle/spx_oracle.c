@@ -32,7 +32,8 @@
 #define OX_MAX_MOVES 42
 
 enum { OX_CONNECT4 = 0, OX_TICTACTOE = 1 };
-enum { OX_PURPOSE_TIE = 0, OX_PURPOSE_GAMMA = 1, OX_PURPOSE_ACTION = 2 };
+enum { OX_PURPOSE_TIE = 0, OX_PURPOSE_GAMMA = 1, OX_PURPOSE_ACTION = 2, OX_PURPOSE_OPPONENT = 3 };
+enum { OX_OPP_MCTS = 0, OX_OPP_LOOKAHEAD = 1, OX_OPP_RANDOM = 2 };
 
 /* ------------------------------------------------------------------ spec stream (oracle/spec.py) */
 static uint64_t sm64(uint64_t x) {
@@ -559,6 +560,68 @@ int ox_play_episode(const ox_cfg* cfg, int swap_sides, ox_net_fn net0, void* use
         out->sims += t->sims_done; out->net_calls += t->net_calls; out->path_len_sum += t->path_len_sum;
     }
     ox_tree_free(sp.t[0]); ox_tree_free(sp.t[1]);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ hard-coded opponents (general/hardcoded_players.py)
+ * The opponent keeps its OWN env in its OWN frame: play_action(a, player) steps it with the player the SelfPlayer
+ * passes (selfplayworker.py:221-224: the opponent's moves arrive as +1, the policy's as -1). */
+typedef struct { int kind, player; ox_env env; } ox_hardcoded;
+
+static int hardcoded_move(ox_hardcoded* h, const ox_cfg* cfg) {
+    uint8_t valid[OX_MAX_A]; int moves[OX_MAX_A], n = 0;
+    ox_env_valid_moves(&h->env, valid);
+    for (int a = 0; a < h->env.A; ++a) if (valid[a]) moves[n++] = a;      /* possible_moves, :18,47 */
+    if (h->kind == OX_OPP_LOOKAHEAD) {                                      /* OneStepLookahead.__call__ :15-30 */
+        for (int pass = 0; pass < 2; ++pass) {
+            int who = pass == 0 ? h->player : -h->player;                   /* "can win" uses self.player, then the block */
+            for (int i = 0; i < n; ++i) {
+                ox_env t = h->env; t.episode_over = 0;                      /* test_env.set_state(copy(state)) on a fresh env */
+                int r = 0, done = 0;
+                ox_env_step(&t, moves[i], who, &r, &done);
+                if (done) return moves[i];
+            }
+        }
+    }
+    int ply = 0; for (int i = 0; i < h->env.W * h->env.H; ++i) ply += abs(h->env.board[i]);
+    double u = ox_rng_uniform(cfg->seed, cfg->game_uid, 1, OX_PURPOSE_OPPONENT, ply, 0, 0, 0);
+    int idx = (int)(u * (double)n);                                         /* random.choice, injected */
+    if (idx >= n) idx = n - 1;
+    return moves[idx];
+}
+
+/* SelfPlayer.play_episode with update=False, policy = MCTreeSearch (tree 0), opposing = hard-coded player */
+int ox_play_episode_vs(const ox_cfg* cfg, int swap_sides, int kind, ox_net_fn net0, void* user0, ox_episode* out) {
+    memset(out, 0, sizeof(*out));
+    ox_tree* t0 = ox_tree_new(cfg, 0, net0, user0);
+    ox_hardcoded h; h.kind = kind;
+    ox_env env; ox_env_reset(&env, cfg->game);
+    ox_tree_reset(t0, swap_sides ? -1 : 1);
+    h.player = swap_sides ? 1 : -1;                                         /* reset(player=...) :32-34 (Random ignores it) */
+    ox_env_reset(&h.env, cfg->game);
+    int r = 0, done = 0, max_moves = env.W * env.H;
+    for (int turn = swap_sides ? -1 : 0; turn < 2 * max_moves && !done; ++turn) {
+        int player = (turn < 0 || (turn & 1)) ? -1 : 1;                     /* swap: opponent first, then policy/opponent rounds */
+        int a;
+        if (player == 1) {
+            ox_tree_search(t0);
+            a = ox_tree_play(t0, &out->moves[out->n_moves]);
+        } else {
+            a = hardcoded_move(&h, cfg);
+            ox_move* m = &out->moves[out->n_moves];
+            memset(m, 0, sizeof(*m)); m->tree = 1; m->action = a;
+            for (int i = 0; i < env.W * env.H; ++i) m->ply += abs(env.board[i]);
+        }
+        out->n_moves++;
+        ox_tree_play_action(t0, a);                                         /* play_move :221-224 */
+        { int rr, dd; ox_env_step(&h.env, a, player * -1, &rr, &dd); }
+        ox_env_step(&env, a, player, &r, &done);
+        if (player != 1) r = r * player;
+    }
+    out->reward = r;
+    memcpy(out->final_state, env.board, sizeof(out->final_state));
+    out->sims = t0->sims_done; out->net_calls = t0->net_calls; out->path_len_sum = t0->path_len_sum;
+    ox_tree_free(t0);
     return 0;
 }
 

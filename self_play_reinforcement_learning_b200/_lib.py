@@ -19,7 +19,8 @@ class Config(C.Structure):
     _fields_ = [("game", C.c_int32), ("n_games", C.c_int32), ("sims", C.c_int32), ("evaluate", C.c_int32),
                 ("strong_play", C.c_int32), ("tie_mode", C.c_int32), ("noise_mode", C.c_int32),
                 ("emit_records", C.c_int32), ("max_sims_per_tick", C.c_int32), ("nodes_per_tree", C.c_int32),
-                ("move_log", C.c_int32), ("two_nets", C.c_int32), ("alpha", C.c_double), ("seed", C.c_uint64),
+                ("move_log", C.c_int32), ("two_nets", C.c_int32), ("opponent_kind", C.c_int32), ("reserved0", C.c_int32),
+                ("alpha", C.c_double), ("seed", C.c_uint64),
                 ("slot_offset", C.c_int64), ("slot_stride", C.c_int64), ("games_target", C.c_int64),
                 ("record_capacity", C.c_int64), ("result_capacity", C.c_int64)]
 

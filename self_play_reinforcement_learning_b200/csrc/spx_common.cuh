@@ -12,7 +12,7 @@ typedef unsigned long long u64;
 
 namespace spx {
 
-enum { PURPOSE_TIE = 0, PURPOSE_GAMMA = 1, PURPOSE_ACTION = 2 };
+enum { PURPOSE_TIE = 0, PURPOSE_GAMMA = 1, PURPOSE_ACTION = 2, PURPOSE_OPPONENT = 3 };
 
 __host__ __device__ __forceinline__ u64 sm64(u64 x) {
     x += 0x9E3779B97F4A7C15ULL;

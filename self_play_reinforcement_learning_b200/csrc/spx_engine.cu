@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(128) advance_kernel(EngineDev E, const float* 
             ts.root = idx; ts.root_n = 0; ts.root_w = 0.0; ts.root_player = player; ts.moves_played = 0; ts.n_rec = 0;
             s.cnt_nodes += 1;
             s.tree[T] = ts;
-            if (T == 0) { s.phase = PH_RESET; s.sub_tree = 1; s.n_moves_logged = 0; }
+            if (T == 0) s.n_moves_logged = 0;
+            if (T == 0 && !cfg.opponent_kind) { s.phase = PH_RESET; s.sub_tree = 1; }
             else { s.mover_tree = s.swap ? 1 : 0; s.phase = PH_SEARCH; s.sims_done = -1; /* -1: search not begun */ }
         } else {
             // _expand_node's network branch (mcts.py:316-320) + backup (:361 / :207)
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(128) advance_kernel(EngineDev E, const float* 
                 if (s.pend_kind == PK_EXPAND) s.sims_done += 1;
                 else {  // _set_root(node) (mcts.py:209)
                     ts.root = idx; ts.root_n = 1; ts.root_w = v; ts.root_player = -pplayer;
-                    if (s.sub_tree == 0) s.sub_tree = 1; else s.phase = PH_ENVSTEP;
+                    if (s.sub_tree == 0 && !cfg.opponent_kind) s.sub_tree = 1; else s.phase = PH_ENVSTEP;
                 }
             }
             s.tree[T] = ts;
@@ -301,6 +302,44 @@ __global__ void __launch_bounds__(128) advance_kernel(EngineDev E, const float* 
             s.pend_kind = PK_ROOT; s.pend_tree = s.sub_tree;
             emitted = true;
             break;
+        }
+        if (s.phase == PH_SEARCH && s.mover_tree == 1 && cfg.opponent_kind) {
+            // OneStepLookahead / Random (hardcoded_players.py:15-30,45-50).  The opponent's own env holds its pieces as +1:
+            // own-frame "own" = env_opp, "enemy" = env_own; self.player = +1 if swap_sides else -1 (selfplayworker.py:176),
+            // so without swap_sides the reference's "can I win" pass actually tests the ENEMY's move first -- kept as is.
+            const int self_player = s.swap ? 1 : -1;
+            const unsigned vmask = valid_mask<GAME>(s.env_own, s.env_opp);
+            unsigned done_first = 0, done_second = 0;
+            if (cfg.opponent_kind == SPX_OPP_LOOKAHEAD && lane < A && ((vmask >> lane) & 1u)) {
+                for (int pass = 0; pass < 2; ++pass) {
+                    u64 o = s.env_opp, e = s.env_own;   // opponent frame: own, enemy
+                    int r = 0, dn = 0;
+                    env_step<GAME>(o, e, lane, pass == 0 ? self_player : -self_player, r, dn);
+                    if (dn) { if (pass == 0) done_first = 1; else done_second = 1; }
+                }
+            }
+            const unsigned b0 = __ballot_sync(0xffffffffu, done_first != 0), b1 = __ballot_sync(0xffffffffu, done_second != 0);
+            int action;
+            if (b0) action = __ffs(b0) - 1;
+            else if (b1) action = __ffs(b1) - 1;
+            else {
+                const int n = __popc(vmask);
+                const double u = rng_uniform_from(rng_prefix(cfg.seed, s.game_index, 1, PURPOSE_OPPONENT, s.ply), 0, 0, 0);
+                int idx = (int)(u * (double)n);
+                if (idx >= n) idx = n - 1;
+                unsigned m = vmask;
+                for (int i = 0; i < idx; ++i) m &= m - 1;   // drop the idx lowest legal moves
+                action = __ffs(m) - 1;
+            }
+            if (E.mlog && s.n_moves_logged < SPX_MAX_PLIES) {
+                spx_move_log* ml = E.mlog + (size_t)g * SPX_MAX_PLIES + s.n_moves_logged;
+                if (lane < A) { ml->n[lane] = 0; ml->w[lane] = 0.0; ml->noise[lane] = 0.0; }
+                if (lane == 0) { ml->tree = 1; ml->ply = s.ply; ml->action = action; ml->root_n = 0; ml->root_w = 0.0; }
+                s.n_moves_logged += 1;
+            }
+            s.last_action = action;
+            s.phase = PH_REROOT; s.sub_tree = 0;
+            continue;
         }
         if (s.phase == PH_SEARCH) {
             const int T = s.mover_tree;
@@ -498,7 +537,7 @@ __global__ void __launch_bounds__(128) advance_kernel(EngineDev E, const float* 
             }
             s.tree[T] = ts;
             if (parked) { emitted = true; break; }
-            if (T == 0) s.sub_tree = 1; else s.phase = PH_ENVSTEP;
+            if (T == 0 && !cfg.opponent_kind) s.sub_tree = 1; else s.phase = PH_ENVSTEP;
             continue;
         }
         if (s.phase == PH_ENVSTEP) {

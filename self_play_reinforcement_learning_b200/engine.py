@@ -61,7 +61,7 @@ class SelfPlayEngine:
 
     def __init__(self, game, n_games, sims, evaluator, *, evaluate=False, strong_play=False, alpha=1.0, seed=0,
                  tie_mode=1, noise_mode=2, emit_records=True, max_sims_per_tick=8, nodes_per_tree=0, move_log=False,
-                 two_nets=False, slot_offset=0, slot_stride=None, games_target=None, record_capacity=None,
+                 two_nets=False, opponent_kind=0, slot_offset=0, slot_stride=None, games_target=None, record_capacity=None,
                  result_capacity=None):
         if not torch.cuda.is_available():
             raise _lib.SpxError("SelfPlayEngine needs a CUDA device (B200); there is no CPU fallback")
@@ -73,6 +73,7 @@ class SelfPlayEngine:
         cfg.evaluate, cfg.strong_play, cfg.tie_mode, cfg.noise_mode = int(evaluate), int(strong_play), tie_mode, noise_mode
         cfg.emit_records, cfg.max_sims_per_tick, cfg.nodes_per_tree = int(emit_records), max_sims_per_tick, nodes_per_tree
         cfg.move_log, cfg.two_nets, cfg.alpha, cfg.seed = int(move_log), int(two_nets), float(alpha), int(seed)
+        cfg.opponent_kind = int(opponent_kind)
         cfg.slot_offset = slot_offset
         cfg.slot_stride = n_games if slot_stride is None else slot_stride
         cfg.games_target = (1 << 62) if games_target is None else games_target

@@ -68,11 +68,13 @@ def parse_results(reward_list):
 class SelfPlayScheduler:
     def __init__(self, network, env, evaluation_network=None, iterations=800, epoch_length=1500, initial_games=64,
                  evaluation_games=150, games_per_gpu=1024, memory_size=200000, batch_size=128, lr=0.01, momentum=0.9,
-                 weight_decay=1e-4, updates_per_epoch=100, alpha=1.0, seed=0, net="tower"):
+                 weight_decay=1e-4, updates_per_epoch=100, alpha=1.0, seed=0, net="tower", evaluation_opponent=None):
+        """evaluation_opponent: None (evaluation_network, or the policy itself), "lookahead" or "random": the hard-coded
+        evaluation_policy_container of the reference's train command (main.py:66, hardcoded_players.py)."""
         self.network, self.env, self.evaluation_network = network, env, evaluation_network
         self.iterations, self.epoch_length, self.initial_games, self.evaluation_games = iterations, epoch_length, initial_games, evaluation_games
         self.games_per_gpu, self.batch_size, self.updates_per_epoch = games_per_gpu, batch_size, updates_per_epoch
-        self.alpha, self.seed, self.net = alpha, seed, net
+        self.alpha, self.seed, self.net, self.evaluation_opponent = alpha, seed, net, evaluation_opponent
         self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
         self.memory = Memory(memory_size)
@@ -89,7 +91,7 @@ class SelfPlayScheduler:
         sp = BatchedSelfPlay(self.network, env=self.env, n_games=G, sims=self.iterations, net=self.net if not evaluate or self.evaluation_network is None else "torch",
                              evaluation_network=self.evaluation_network if evaluate else None, evaluate=evaluate, update=update,
                              alpha=self.alpha, seed=self.seed + 7919 * generation, rank=self.rank, world=self.world,
-                             games_target=n_games_total)
+                             games_target=n_games_total, opponent=self.evaluation_opponent if evaluate else None)
         recs, res = [], []
         while True:
             sp.engine.run_ticks(512)

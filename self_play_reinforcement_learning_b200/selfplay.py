@@ -53,9 +53,12 @@ def results_to_dicts(results):
 class BatchedSelfPlay:
     def __init__(self, network, game=None, env=None, n_games=1024, sims=800, net="tower", evaluation_network=None,
                  evaluate=False, update=True, alpha=1.0, strong_play=False, seed=0, rank=0, world=1, games_target=None,
-                 max_sims_per_tick=8, noise_mode=2, tie_mode=1, move_log=False, net_dtype=torch.bfloat16):
+                 max_sims_per_tick=8, noise_mode=2, tie_mode=1, move_log=False, net_dtype=torch.bfloat16, opponent=None):
         """network / evaluation_network: nn.Module (ResidualTower for the native tower; any board net for net='torch').
-        env: a reference env class/instance (mapped by variant_string) or ``game`` id.  iterations == sims."""
+        env: a reference env class/instance (mapped by variant_string) or ``game`` id.  iterations == sims.
+        opponent: None (MCTS self-play / evaluation network), "lookahead" or "random": the reference's hard-coded
+        evaluation opponents (general/hardcoded_players.py; the default evaluation_policy_container of main.py:66)."""
+        self.opponent_kind = {None: 0, "mcts": 0, "lookahead": 1, "random": 2}[opponent]
         self.game = game_id_of(env if env is not None else game)
         self.network, self.evaluation_network = network, evaluation_network
         two = evaluation_network is not None
@@ -72,7 +75,8 @@ class BatchedSelfPlay:
         self.net_kind = net
         self.engine = SelfPlayEngine(self.game, n_games, sims, self.evaluator, evaluate=evaluate, strong_play=strong_play, alpha=alpha,
                                      seed=seed, tie_mode=tie_mode, noise_mode=noise_mode, emit_records=update, two_nets=two,
-                                     max_sims_per_tick=max_sims_per_tick, move_log=move_log, slot_offset=rank * n_games,
+                                     max_sims_per_tick=max_sims_per_tick, move_log=move_log, opponent_kind=self.opponent_kind,
+                                     slot_offset=rank * n_games,
                                      slot_stride=world * n_games, games_target=games_target)
         self._pinned = None
 

@@ -116,3 +116,16 @@ def test_exact_integer_power_is_correctly_rounded():
     for n in list(range(0, 400)) + [799, 800, 801, 1599, 1600, 1601, 65535]:
         assert ox.lib().ox_pow_int_exact(n, 20) == float(n ** 20)
         assert ox.lib().ox_pow_int_exact(n, 3) == float(n ** 3)
+
+
+def test_hardcoded_opponent_episodes_match_reference(golden_dir):
+    """OneStepLookahead / Random evaluation games (general/hardcoded_players.py) incl. the reference's frame quirk."""
+    with open(os.path.join(golden_dir, "episodes_vs_hardcoded.json")) as f:
+        eps = json.load(f)
+    assert len(eps) >= 16
+    for e in eps:
+        cfg = ox.make_cfg(e["game"], e["sims"], seed=e["seed"], game_uid=e["game_uid"], evaluate=True)
+        o = ox.play_episode_vs(cfg, e["swap"], e["kind"], net_seed=e["net_seed"])
+        assert o["reward"] == e["reward"]
+        assert [[m["tree"], m["ply"], m["action"]] for m in o["moves"]] == e["moves"]
+        assert o["final_state"].tolist() == e["final_state"]

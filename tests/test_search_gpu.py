@@ -167,3 +167,29 @@ def test_full_size_invariants():
     assert np.allclose(recs["tree_probs"][:, :A].sum(axis=1), 1.0, atol=1e-5)
     assert set(np.unique(recs["actual_val"])).issubset({-1.0, 0.0, 1.0})
     e.close()
+
+
+@pytest.mark.parametrize("game,kind", [(0, 1), (0, 2), (1, 1), (1, 2)])
+def test_hardcoded_opponents_vs_oracle(game, kind):
+    """Evaluation games against OneStepLookahead / Random (hardcoded_players.py): every game equals the oracle
+    (which is pinned against the live reference in tests/test_oracle_vs_reference_live.py and the goldens)."""
+    from self_play_reinforcement_learning_b200.engine import HashNetEvaluator
+    n_games, sims = 48, 40
+    e = _engine(game=game, n_games=n_games, sims=sims, evaluator=HashNetEvaluator(game, 4), seed=21, noise_mode=0, evaluate=True,
+                emit_records=False, opponent_kind=kind, games_target=n_games, move_log=True)
+    e.run_until_idle(max_ticks=200000, poll_every=256)
+    _, res = H.split_by_game(e.drain_records(), e.drain_results())
+    assert len(res) == n_games and e.counters()["errors"] == 0
+    outcomes = set()
+    for g in range(n_games):
+        cfg = ox.make_cfg(game, sims, seed=21, game_uid=g, evaluate=True)
+        o = ox.play_episode_vs(cfg, bool(g & 1), kind, net_seed=4)
+        ml = e.move_log(g)
+        assert res[g]["reward"] == o["reward"] and res[g]["plies"] == len(o["moves"]), g
+        assert [(m["tree"], m["ply"], m["action"]) for m in ml] == [(m["tree"], m["ply"], m["action"]) for m in o["moves"]], g
+        for a, b in zip(ml, o["moves"]):
+            if a["tree"] == 0:
+                assert a["n"] == list(b["n"]) and a["w"] == list(b["w"]) and a["root_n"] == b["root_n"]
+        outcomes.add(o["reward"])
+    assert len(outcomes) >= 2
+    e.close()
