@@ -431,6 +431,11 @@ __global__ void __launch_bounds__(128) advance_kernel(EngineDev E, const float* 
                     const float p = ((const float*)(nd + L::OFF_P))[lane];
                     ch = ((const int*)(nd + L::OFF_CHILD))[lane];
                     const unsigned meta = *(const unsigned*)(nd + L::OFF_META);
+                    if (ch >= 0) {   // pull every expanded child towards L2 while the scores are computed (the next level is one of them)
+                        const char* cn = c.node(ch);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(cn));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(cn + 128));
+                    }
                     if ((meta >> lane) & 1u) {
                         const double q = n ? __ddiv_rn(w, (double)n) : 0.0;                               // :59-62 (vl = 0)
                         double p_eff = (double)p;
