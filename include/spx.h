@@ -36,6 +36,7 @@ extern "C" {
 #define SPX_OPP_MCTS 0
 #define SPX_OPP_LOOKAHEAD 1 /* general/hardcoded_players.py:8-37  */
 #define SPX_OPP_RANDOM 2    /* general/hardcoded_players.py:40-56 */
+#define SPX_OPP_EXTERNAL 3  /* any host-side BasePlayer: moves delivered with spx_set_external_actions */
 
 #define SPX_E_ARG (-1)      /* bad argument                       */
 #define SPX_E_CUDA (-2)     /* CUDA runtime error / no device      */
@@ -65,7 +66,7 @@ typedef struct spx_config {
     int32_t nodes_per_tree;    /* 0: worst-case bound (sims+1)*ceil(max_moves/2)+max_moves+2        */
     int32_t move_log;          /* 1: keep per-move root statistics for spx_read_move_log (debug)    */
     int32_t two_nets;          /* 1: tree 1 is evaluated by net 1 (compare_models / elo.py:73-91)   */
-    int32_t opponent_kind;     /* 0: MCTS; 1: OneStepLookahead, 2: Random (hardcoded_players.py:8-56) */
+    int32_t opponent_kind;     /* SPX_OPP_*: 0 MCTS, 1 OneStepLookahead, 2 Random, 3 external (host)  */
     int32_t reserved0;
     double alpha;              /* Dirichlet alpha                                   mcts.py:135      */
     uint64_t seed;             /* counter-stream seed (oracle/spec.py)                              */
@@ -176,6 +177,15 @@ int spx_counters_read(spx_engine* e, spx_counters* host_out, void* stream);
 /* 1 when every slot is idle (games_target reached) */
 int spx_all_idle(spx_engine* e, int32_t* idle_out, void* stream);
 int64_t spx_device_bytes(spx_engine* e);
+/* (re)start with a new global index for slot 0 and a new games_target (the per-game Policy facade starts every
+ * episode this way: one game, then the slot idles) */
+int spx_restart(spx_engine* e, int64_t slot_offset, int64_t games_target, void* stream);
+/* SPX_OPP_EXTERNAL: deliver the opposing player's moves, dev i32[n_games] (-1 = none for that slot).  Replaces
+ * opposing_policy(s) + policy.play_action(a, -player) in SelfPlayer.get_and_play_moves (selfplayworker.py:206-224). */
+int spx_set_external_actions(spx_engine* e, const int32_t* actions, void* stream);
+/* dev i32[n_games][6]: {state: 0 running / 1 waiting for an external move / 2 idle, ply, moves played by the policy in
+ * this game, the policy's latest action, games finished on this slot, swap_sides} */
+int spx_slot_status(spx_engine* e, int32_t* status_out, void* stream);
 /* dev i32[n_games]: the tree (0/1) whose evaluation each slot is waiting for, -1 if none (replay logging) */
 int spx_pending_tree(spx_engine* e, int32_t* tree_out, void* stream);
 

@@ -53,7 +53,7 @@ EXPORTS = ["spx_last_error", "spx_version", "spx_launch_count", "spx_env_step", 
            "spx_leaf_batch", "spx_root_stats", "spx_drain_records", "spx_drain_results", "spx_read_move_log",
            "spx_counters_read", "spx_all_idle", "spx_device_bytes", "spx_pending_tree", "spx_tower_blob_bytes",
            "spx_tower_create", "spx_tower_destroy", "spx_tower_ncta", "spx_tower_load", "spx_tower_forward", "spx_tower_forward_timed",
-           "spx_advance_timed", "spx_event_create", "spx_event_destroy", "spx_event_elapsed_ms"]
+           "spx_advance_timed", "spx_restart", "spx_set_external_actions", "spx_slot_status", "spx_event_create", "spx_event_destroy", "spx_event_elapsed_ms"]
 
 _lib = None
 
@@ -87,6 +87,9 @@ def lib():
         L.spx_counters_read.argtypes = [vp, C.POINTER(Counters), vp]
         L.spx_all_idle.argtypes = [vp, C.POINTER(i32), vp]
         L.spx_pending_tree.argtypes = [vp, vp, vp]
+        L.spx_restart.argtypes = [vp, i64, i64, vp]
+        L.spx_set_external_actions.argtypes = [vp, vp, vp]
+        L.spx_slot_status.argtypes = [vp, vp, vp]
         L.spx_tower_blob_bytes.restype = C.c_int64
         L.spx_tower_blob_bytes.argtypes = [i32, i32]
         L.spx_tower_create.argtypes = [i32, i32, C.POINTER(vp)]

@@ -93,6 +93,8 @@ struct EngineDev {
     const double* noise_table; long long table_first, table_games; int table_moves;
     u64* leaf_own; u64* leaf_opp; unsigned char* needs_eval; unsigned char* net_id;
     unsigned long long* ticks;
+    int* ext_action;       // [G] external opponent's next move (>= 0) or -1 (opponent_kind == SPX_OPP_EXTERNAL)
+    int* own_action;       // [G][2]: {number of moves the policy (tree 0) has played this game, its latest action}
 };
 
 }  // namespace spx
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(128) advance_kernel(EngineDev E, const float* 
             ts.root = idx; ts.root_n = 0; ts.root_w = 0.0; ts.root_player = player; ts.moves_played = 0; ts.n_rec = 0;
             s.cnt_nodes += 1;
             s.tree[T] = ts;
-            if (T == 0) s.n_moves_logged = 0;
+            if (T == 0) { s.n_moves_logged = 0; if (lane == 0) { E.own_action[2 * g] = 0; E.own_action[2 * g + 1] = -1; } }
             if (T == 0 && !cfg.opponent_kind) { s.phase = PH_RESET; s.sub_tree = 1; }
             else { s.mover_tree = s.swap ? 1 : 0; s.phase = PH_SEARCH; s.sims_done = -1; /* -1: search not begun */ }
         } else {
@@ -302,6 +304,16 @@ __global__ void __launch_bounds__(128) advance_kernel(EngineDev E, const float* 
             s.pend_kind = PK_ROOT; s.pend_tree = s.sub_tree;
             emitted = true;
             break;
+        }
+        if (s.phase == PH_SEARCH && s.mover_tree == 1 && cfg.opponent_kind == SPX_OPP_EXTERNAL) {
+            // the opposing player lives on the host (any BasePlayer): park until spx_set_external_actions delivers its move
+            const int a = E.ext_action[g];
+            if (a < 0) break;
+            __syncwarp();
+            if (lane == 0) E.ext_action[g] = -1;
+            s.last_action = a;
+            s.phase = PH_REROOT; s.sub_tree = 0;
+            continue;
         }
         if (s.phase == PH_SEARCH && s.mover_tree == 1 && cfg.opponent_kind) {
             // OneStepLookahead / Random (hardcoded_players.py:15-30,45-50).  The opponent's own env holds its pieces as +1:
@@ -408,6 +420,7 @@ __global__ void __launch_bounds__(128) advance_kernel(EngineDev E, const float* 
                 }
                 ts.moves_played += 1;
                 s.cnt_moves += 1;
+                if (lane == 0 && T == 0) { E.own_action[2 * g] = ts.moves_played; E.own_action[2 * g + 1] = action; }
                 s.tree[T] = ts;
                 s.last_action = action;
                 s.phase = PH_REROOT; s.sub_tree = 0;
@@ -616,6 +629,7 @@ __global__ void reset_kernel(EngineDev E) {
     s.tree[0].root = s.tree[1].root = -1;
     E.games[g] = s;
     E.leaf_own[g] = 0; E.leaf_opp[g] = 0; E.needs_eval[g] = 0; E.net_id[g] = 0;
+    E.ext_action[g] = -1; E.own_action[2 * g] = 0; E.own_action[2 * g + 1] = -1;
     if (g == 0) { *E.rec_count = 0; *E.res_count = 0; *E.rec_dropped = 0; *E.ticks = 0; }
 }
 
@@ -852,6 +866,8 @@ int spx_create(const spx_config* cfg, spx_engine** out) {
     SPX_ALLOC(d.leaf_opp, u64, G);
     SPX_ALLOC(d.needs_eval, unsigned char, G);
     SPX_ALLOC(d.net_id, unsigned char, G);
+    SPX_ALLOC(d.ext_action, int, G);
+    SPX_ALLOC(d.own_action, int, 2 * G);
 #undef SPX_ALLOC
     e->bytes = bytes;
     *out = e;
@@ -862,7 +878,7 @@ int spx_destroy(spx_engine* e) {
     if (!e) return 0;
     EngineDev& d = e->d;
     void* ptrs[] = {d.games, d.pool, d.paths, d.noise, d.temp_rec, d.mlog, d.rec_ring, d.res_ring, d.rec_count, d.res_count,
-                    d.rec_dropped, d.ticks, d.leaf_own, d.leaf_opp, d.needs_eval, d.net_id};
+                    d.rec_dropped, d.ticks, d.leaf_own, d.leaf_opp, d.needs_eval, d.net_id, d.ext_action, d.own_action};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete e;
     return 0;
@@ -983,6 +999,47 @@ int spx_all_idle(spx_engine* e, int32_t* idle_out, void* stream) {
 }
 
 int64_t spx_device_bytes(spx_engine* e) { return e ? e->bytes : 0; }
+
+int spx_restart(spx_engine* e, int64_t slot_offset, int64_t games_target, void* stream) {
+    if (!e) return set_err(SPX_E_ARG, "spx_restart: null engine%s", "");
+    e->d.cfg.slot_offset = slot_offset;
+    e->d.cfg.games_target = games_target;
+    return spx_reset(e, stream);
+}
+
+__global__ void set_external_kernel(EngineDev E, const int* actions) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < E.cfg.n_games && actions[g] >= 0) E.ext_action[g] = actions[g];
+}
+__global__ void slot_status_kernel(EngineDev E, int* out) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= E.cfg.n_games) return;
+    const GameState& s = E.games[g];
+    const bool waiting = s.phase == PH_SEARCH && s.mover_tree == 1 && E.cfg.opponent_kind == SPX_OPP_EXTERNAL && E.ext_action[g] < 0;
+    out[6 * g + 0] = s.phase == PH_IDLE ? 2 : (waiting ? 1 : 0);
+    out[6 * g + 1] = s.ply;
+    out[6 * g + 2] = E.own_action[2 * g];
+    out[6 * g + 3] = E.own_action[2 * g + 1];
+    out[6 * g + 4] = (int)s.cnt_games;
+    out[6 * g + 5] = s.swap;
+}
+
+int spx_set_external_actions(spx_engine* e, const int32_t* actions, void* stream) {
+    if (!e || !actions) return set_err(SPX_E_ARG, "spx_set_external_actions: bad argument%s", "");
+    if (e->d.cfg.opponent_kind != SPX_OPP_EXTERNAL) return set_err(SPX_E_STATE, "spx_set_external_actions: engine not created with SPX_OPP_EXTERNAL%s", "");
+    set_external_kernel<<<(e->d.cfg.n_games + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e->d, actions);
+    count_launch();
+    SPX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int spx_slot_status(spx_engine* e, int32_t* status_out, void* stream) {
+    if (!e || !status_out) return set_err(SPX_E_ARG, "spx_slot_status: bad argument%s", "");
+    slot_status_kernel<<<(e->d.cfg.n_games + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e->d, status_out);
+    count_launch();
+    SPX_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int spx_pending_tree(spx_engine* e, int32_t* tree_out, void* stream) {
     if (!e || !tree_out) return set_err(SPX_E_ARG, "spx_pending_tree: bad argument%s", "");

@@ -127,3 +127,72 @@ def test_scheduler_train_loop_small():
     assert not torch.equal(before, net.linear_output.weight.detach())
     total, bd = s.compare_models()
     assert set(bd) == {"first", "second"} and sum(sum(v.values()) for v in bd.values()) == 16
+
+
+class _StreamRandomOpponent:
+    """A host-side BasePlayer (general/base_model.py:10-29) that plays the spec-stream random move -- the same rule the
+    oracle's OPP_RANDOM uses, so a facade-vs-host game can be compared with ox.play_episode_vs move for move."""
+
+    def __init__(self, game, seed):
+        self.game, self.seed = game, seed
+
+    def reset(self, player=None, game_index=0):
+        W, Hh, _ = spec.GAME_DIMS[self.game]
+        self.board = np.zeros((W, Hh), np.int64)
+        self.game_index = game_index
+
+    def valid(self):
+        return (np.abs(self.board).sum(1) < self.board.shape[1]) if self.game == 0 else (self.board.reshape(-1) == 0)
+
+    def __call__(self, s=None):
+        moves = np.flatnonzero(self.valid())
+        ply = int(np.abs(self.board).sum())
+        u = spec.rng_uniform(self.seed, self.game_index, 1, spec.PURPOSE_OPPONENT, ply, 0, 0, 0)
+        return int(moves[min(int(u * len(moves)), len(moves) - 1)])
+
+    def play_action(self, a, player):
+        if self.game == 0:
+            self.board[a, int(np.abs(self.board[a]).sum())] = player
+        else:
+            self.board[a // 3, a % 3] = player
+
+
+@pytest.mark.parametrize("swap", [False, True])
+def test_policy_facade_drives_reference_style_episode(swap):
+    """The per-game Policy facade (mcts.MCTreeSearch) inside a SelfPlayer-style loop (selfplayworker.py:172-224) against a
+    host-side opponent; the whole game must equal the oracle's play_episode_vs with the same random opponent."""
+    import queue as pyqueue
+    from oracle import oracle as ox
+    from self_play_reinforcement_learning_b200 import envs
+    from self_play_reinforcement_learning_b200.mcts import MCTreeSearch
+    sims, seed = 60, 17
+    memq = pyqueue.Queue()
+    policy = MCTreeSearch(None, envs.Connect4Env, memory_queue=memq, iterations=sims, net="hash", seed=seed, noise_mode=0)
+    policy.evaluate(True)
+    opp = _StreamRandomOpponent(0, seed)
+    policy.reset(player=-1 if swap else 1)
+    opp.reset(game_index=policy.game_index)
+    gi = policy.game_index
+    assert (gi & 1) == int(swap)
+    actions, r, done, player = [], 0, False, (-1 if swap else 1)
+    env_pieces = np.zeros((7, 6), np.int64)
+    while not done:
+        a = policy(None) if player == 1 else opp(None)
+        policy.play_action(a, player)            # selfplayworker.py:221-224
+        opp.play_action(a, player * -1)
+        env_pieces[a, int(np.abs(env_pieces[a]).sum())] = player
+        actions.append(a)
+        cfg = ox.make_cfg(0, sims, seed=seed, game_uid=gi, evaluate=True)
+        done = len(actions) == len(ox.play_episode_vs(cfg, swap, spec.OPP_RANDOM, net_seed=seed)["moves"])
+        player = -player
+    o = ox.play_episode_vs(ox.make_cfg(0, sims, seed=seed, game_uid=gi, evaluate=True), swap, spec.OPP_RANDOM, net_seed=seed)
+    assert actions == [m["action"] for m in o["moves"]]
+    policy.push_to_queue(done=True, r=o["reward"])
+    n_own = sum(1 for m in o["moves"] if m["tree"] == 0)
+    assert memq.qsize() == n_own
+    m = memq.get()
+    assert float(m.actual_val) == float(o["reward"]) and m.state.dtype == torch.int64 and tuple(m.tree_probs.shape) == (7,)
+    # a second episode on the same object works (new game index, engine restarted)
+    policy.reset(player=1)
+    assert policy.game_index == 4 and isinstance(policy(None), int)
+    policy.close()
