@@ -30,10 +30,10 @@ FLOP_PER_LEAF_20 = 497_138_048  # ResidualTower-20, SURVEY.md 6 / 8(d)
 TICKS_PER_STEP = 800
 
 
-def flop_per_leaf(blocks):
+def flop_per_leaf(blocks, conv_only=False):
     conv = 2 * 42 * (9 * 3 * 128 + blocks * 2 * 9 * 128 * 128 + 128 * 64)
     fc = 2 * (1344 * 7 + 1344 * 256 + 256)
-    return conv + fc
+    return conv if conv_only else conv + fc
 
 
 def parse():
@@ -299,37 +299,44 @@ def main():
         e2e = {"value": s2 / (ms2 / 1e3), "unit": "sims/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                "ms_per_step": ms2 / args.steps}
 
-    # ---- search-only leg (hash net): HBM roofline of the search/env kernel
+    # ---- search-only legs (hash net): HBM roofline of the search kernel at the workload's G and with 16x more trees
     search = None
     if rank == 0 and args.net == "tower":
         sp.close()
-        e2 = SelfPlayEngine(game=0, n_games=G, sims=args.sims, evaluator=HashNetEvaluator(0, 1), seed=1, noise_mode=2)
-        e2.run_ticks(3 * T)
-        torch.cuda.synchronize()
-        k0 = e2.counters()
-        evs = []
-        for t in range(2 * T):
-            a = (_lib.Event(), _lib.Event())
-            e2.tick(advance_events=a)
-            evs.append(a)
-        torch.cuda.synchronize()
-        k1 = e2.counters()
-        a_ms = sum(a[0].elapsed_time(a[1]) for a in evs)
-        s_ = k1["sims"] - k0["sims"]
-        L = (k1["path_len_sum"] - k0["path_len_sum"]) / max(s_, 1)
-        bytes_per_sim = 136.0 * L + 212.0
         peaks_s = _peaks()
-        search = {"sims_per_s_kernel_only": s_ / (a_ms / 1e3), "mean_path_len": L, "bytes_per_sim": bytes_per_sim,
-                  "achieved_GBps": s_ * bytes_per_sim / (a_ms / 1e3) / 1e9, "peak_GBps": peaks_s["hbm_gbs"],
-                  "frac": s_ * bytes_per_sim / (a_ms / 1e3) / 1e9 / peaks_s["hbm_gbs"], "advance_ms_per_launch": a_ms / len(evs)}
-        e2.close()
+
+        def search_leg(n_games, ticks):
+            e2 = SelfPlayEngine(game=0, n_games=n_games, sims=args.sims, evaluator=HashNetEvaluator(0, 1), seed=1, noise_mode=2)
+            e2.run_ticks(3 * ticks // 2)
+            torch.cuda.synchronize()
+            k0 = e2.counters()
+            evs = []
+            for t in range(ticks):
+                a = (_lib.Event(), _lib.Event())
+                e2.tick(advance_events=a)
+                evs.append(a)
+            torch.cuda.synchronize()
+            k1 = e2.counters()
+            a_ms = sum(a[0].elapsed_time(a[1]) for a in evs)
+            s_ = k1["sims"] - k0["sims"]
+            L = (k1["path_len_sum"] - k0["path_len_sum"]) / max(s_, 1)
+            bytes_per_sim = 136.0 * L + 212.0
+            gbs = s_ * bytes_per_sim / (a_ms / 1e3) / 1e9
+            e2.close()
+            return {"games": n_games, "sims_per_s_kernel_only": s_ / (a_ms / 1e3), "mean_path_len": L, "bytes_per_sim": bytes_per_sim,
+                    "achieved_GBps": gbs, "peak_GBps": peaks_s["hbm_gbs"], "frac": gbs / peaks_s["hbm_gbs"],
+                    "advance_ms_per_launch": a_ms / len(evs)}
+        search = search_leg(G, 2 * T)
+        free_b, _tot = torch.cuda.mem_get_info()
+        if free_b > 110e9:   # 16384 games x 2 trees x 2.7 MB node pool = 88 GB
+            search["with_16384_games"] = search_leg(16384, 600)
 
     env_roof = None
     if rank == 0 and args.net == "tower":
         env_roof = _env_roofline(_lib, torch)
     if rank == 0:
         peaks = _peaks()
-        fl = flop_per_leaf(args.blocks)
+        fl = flop_per_leaf(args.blocks, conv_only=True)   # the tower kernel computes the convolutions; the FC heads are heads_kernel
         roof = None
         if tower_ms:
             leaves_per_launch = evals / max(ticks, 1)
