@@ -54,7 +54,7 @@ if tw:
         v, u = s.split()[0], (s.split() + [""])[1]
         return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
     tr = [to_bytes(x["dram__bytes_read.sum"]) + to_bytes(x["dram__bytes_write.sum"]) for x in tw]
-    json.dump({"dram_bytes_per_launch": sum(tr) / len(tr), "source": f"profiles/{tag}_ncu_full_raw.csv (ncu --set full, tower_kernel2, {len(tr)} launches)"},
+    json.dump({"dram_bytes_per_launch": sum(tr) / len(tr), "source": f"profiles/{tag}_ncu_full_raw.csv (ncu --set full, tower_kernel<2>, {len(tr)} launches)"},
               open(os.path.join(out_dir, "tower_traffic.json"), "w"))
 for x in summ:
     print({k: v for k, v in x.items()})

@@ -72,14 +72,6 @@ static_assert(EPI_SPLIT == 4, "epilogue column split is written for 4 parts of 3
 constexpr int FLAT = 32 * CELLS;             // 1344 inputs of each head's first Linear
 constexpr int FC_HIDDEN = 256;
 
-struct Smem {
-    unsigned char act[2][ACT_BYTES];
-    unsigned char wstage[NSTAGE][STAGE_BYTES];
-    unsigned long long full[NSTAGE], empty[NSTAGE], acc_full, epi_done;
-    unsigned long long own[NB], opp[NB];
-    float bias[3][CH];
-    unsigned tmem_base;
-};
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -113,16 +105,6 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(void* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void tc_mma(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
 __device__ __forceinline__ void tc_ld32(unsigned taddr, unsigned (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -212,306 +194,97 @@ __device__ __forceinline__ LayerInfo layer_info(int l, int n_layers) {
 __device__ __forceinline__ int tap_shift(int tap) { return (tap / 3 - 1) * PAD_STRIDE + (tap % 3 - 1); }  // (kh-1)*7 + (kw-1)
 
 // ------------------------------------------------------------------------------------------------ the tower kernel
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long long* __restrict__ opp_g,
-             const unsigned char* __restrict__ needs, long long n_boards, int n_layers,
-             const unsigned char* __restrict__ wconv, const float* __restrict__ bias_all, float* __restrict__ head_out) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Smem& S = *reinterpret_cast<Smem*>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long n_groups = (n_boards + NB - 1) / NB;
-
-    if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-        mbar_init(&S.acc_full, 1);
-        mbar_init(&S.epi_done, EPI_THREADS);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // zero both activation buffers once: guard rows and padding cells must read as zero forever
-    for (int i = tid; i < 2 * ACT_BYTES / 16; i += NUM_THREADS) reinterpret_cast<uint4*>(S.act[0])[i] = make_uint4(0, 0, 0, 0);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const unsigned tmem_base = S.tmem_base;
-
-    unsigned stage = 0, sphase = 0;   // weight ring position (producer and MMA walk the same sequence)
-    unsigned lphase = 0;              // per-layer barrier parity (acc_full / epi_done)
-
-    for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        // CTA-uniform skip when none of the boards of this group asked for an evaluation
-        bool any = needs == nullptr;
-        if (!any) for (int b = 0; b < NB; ++b) { long long gb = grp * NB + b; if (gb < n_boards && needs[gb]) any = true; }
-        if (!any) continue;
-
-        if (warp == 0) {
-            // ===================== TMA producer: stream the pre-packed weight slices in consumption order.
-            // The whole warp walks the loop (warp-uniform control flow keeps addresses in uniform registers);
-            // one elected lane issues the copies.
-            const bool leader = elect_one();
-            const unsigned char* wp = wconv;
-            for (int l = 0; l < n_layers; ++l) {
-                const LayerInfo li = layer_info(l, n_layers);
-                const int ksteps = li.kslices >= 2 ? 2 : 1;                  // K steps (of 16 channels) per ring stage
-                const unsigned bytes = 2u * (unsigned)li.n * 16u * (unsigned)ksteps;
-                const int iters = li.taps * (li.kslices / ksteps);
-                for (int it = 0; it < iters; ++it) {
-#ifdef SPX_DBG_NO_TMA
-                    continue;
-#endif
-                    mbar_wait(&S.empty[stage], sphase ^ 1u);
-                    if (leader) {
-                        mbar_expect_tx(&S.full[stage], bytes);
-                        tma_bulk_g2s(S.wstage[stage], wp, bytes, &S.full[stage]);
-                    }
-                    __syncwarp();
-                    wp += bytes;
-                    if (++stage == NSTAGE) { stage = 0; sphase ^= 1u; }
-                }
-            }
-        } else if (warp == 1) {
-            // ===================== MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit
-            const bool leader = elect_one();
-            for (int l = 0; l < n_layers; ++l) {
-                const LayerInfo li = layer_info(l, n_layers);
-                const unsigned idesc = make_idesc(128, li.n);
-                const int ksteps = li.kslices >= 2 ? 2 : 1;
-                const int kpairs = li.kslices / ksteps;
-                const unsigned kstep_bytes = 2u * (unsigned)li.n * 16u;
-                const unsigned a_base = smem_u32(S.act[li.in_buf]) + GUARD * 16;
-                mbar_wait(&S.epi_done, lphase);   // inputs of this layer written, accumulators drained
-                tc_fence_after();
-                const unsigned acc = 1u;   // the accumulators start from the pre-stored bias
-                for (int tap = 0; tap < li.taps; ++tap) {
-                    const int shift = li.taps == 9 ? tap_shift(tap) : 0;
-                    for (int kp = 0; kp < kpairs; ++kp) {
-#ifndef SPX_DBG_NO_TMA
-                        mbar_wait(&S.full[stage], sphase);
-                        tc_fence_after();
-#endif
-                        const unsigned b_addr = smem_u32(S.wstage[stage]);
-                        const unsigned a_addr0 = a_base + (unsigned)(2 * ksteps * kp) * CHUNK_BYTES + (unsigned)(shift * 16);
-                        if (leader) {
-                            for (int j = 0; j < ksteps; ++j) {
-                                const unsigned long long bdesc = make_desc(b_addr + (unsigned)j * kstep_bytes, (unsigned)li.n * 16u, 128u);
-#pragma unroll
-                                for (int t = 0; t < MT; ++t) {
-                                    const unsigned a_addr = a_addr0 + (unsigned)(2 * j) * CHUNK_BYTES + (unsigned)(t * 128 * 16);
-                                    tc_mma(tmem_base + (unsigned)(t * 128), make_desc(a_addr, CHUNK_BYTES, 128u), bdesc, idesc, acc);
-                                }
-                            }
-#ifndef SPX_DBG_NO_TMA
-                            tc_commit(&S.empty[stage]);   // frees the weight slot once these MMAs retire
-#endif
-                        }
-                        __syncwarp();
-                        if (++stage == NSTAGE) { stage = 0; sphase ^= 1u; }
-                    }
-                }
-                if (leader) tc_commit(&S.acc_full);
-                __syncwarp();
-                lphase ^= 1u;
-            }
-        } else if (warp >= EPI_WARP0) {
-            // ===================== epilogue warps (also write the stem input)
-            const int et = tid - EPI_WARP0 * 32;          // 0..EPI_THREADS-1
-            const int quarter = warp & 3, part = (warp - EPI_WARP0) >> 2;   // TMEM lane quarter, column part
-            if (et < NB) {
-                const long long gb = grp * NB + et;
-                S.own[et] = gb < n_boards ? own_g[gb] : 0ULL;
-                S.opp[et] = gb < n_boards ? opp_g[gb] : 0ULL;
-            }
-            if (et < CH) { S.bias[0][et] = __ldg(bias_all + et); S.bias[1][et] = __ldg(bias_all + CH + et); }
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
-            store_bias_to_tmem(tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(part * (CH / EPI_SPLIT)), S.bias[0] + part * (CH / EPI_SPLIT));
-            tc_fence_before();
-            // preprocess (modules.py:115-125): planes (empty, own, enemy) -> channels 0..2 of buffer 0, channels 3..15 zero
-            for (int row = et; row < ROWS; row += EPI_THREADS) {
-                int board, cell;
-                const bool real = row_is_cell(row, board, cell);
-                const int p = row - board * BOARD_ROWS;
-                unsigned o = 0, e = 0;
-                if (real) { o = (unsigned)((S.own[board] >> p) & 1ULL); e = (unsigned)((S.opp[board] >> p) & 1ULL); }
-                const unsigned emp = real ? (1u - o - e) : 0u;
-                const unsigned one = 0x3F80u;  // bf16(1.0)
-                uint4 v0 = make_uint4((emp ? one : 0u) | ((o ? one : 0u) << 16), e ? one : 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(S.act[0] + (GUARD + row) * 16) = v0;
-                *reinterpret_cast<uint4*>(S.act[0] + CHUNK_BYTES + (GUARD + row) * 16) = make_uint4(0, 0, 0, 0);
-            }
-            fence_proxy_async();
-            mbar_arrive(&S.epi_done);
-            // per-tile row bookkeeping is layer independent
-            bool real_t[MT]; int board_t[MT], cell_t[MT];
-#pragma unroll
-            for (int t = 0; t < MT; ++t) real_t[t] = row_is_cell(t * 128 + quarter * 32 + lane, board_t[t], cell_t[t]);
-            for (int l = 0; l < n_layers; ++l) {
-                const LayerInfo li = layer_info(l, n_layers);
-                // stage the bias of layer l+2 while this layer's MMAs are still running (layer l+1's is already visible)
-                if (l + 2 < n_layers && et < CH) S.bias[(l + 2) % 3][et] = __ldg(bias_all + (size_t)(l + 2) * CH + et);
-                mbar_wait(&S.acc_full, lphase);
-                tc_fence_after();
-                if (li.out_buf >= 0) {
-                    // trunk layer: this warp owns 128/EPI_SPLIT = 32 columns of its 32 rows, for each of the 3 row tiles
-                    const int ch0 = part * (CH / EPI_SPLIT);
-                    const unsigned tcol = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)ch0;
-                    unsigned v[2][32];
-                    tc_ld32_nowait(tcol, v[0]);
-#pragma unroll
-                    for (int t = 0; t < MT; ++t) {
-                        tc_wait_ld();
-                        if (t + 1 < MT) tc_ld32_nowait(tcol + (unsigned)((t + 1) * 128), v[(t + 1) & 1]);
-#ifdef SPX_DBG_SKIP_EPI
-                        continue;
-#endif
-                        const int row = t * 128 + quarter * 32 + lane;
-                        unsigned char* obase = S.act[li.out_buf] + (GUARD + row) * 16 + (ch0 >> 3) * CHUNK_BYTES;
-                        if (!real_t[t]) {   // padding / guard cell: must read as zero in the next layer
-#pragma unroll
-                            for (int g8 = 0; g8 < 4; ++g8) *reinterpret_cast<uint4*>(obase + g8 * CHUNK_BYTES) = make_uint4(0, 0, 0, 0);
-                            continue;
-                        }
-                        const unsigned* vv = v[t & 1];
-#pragma unroll
-                        for (int g8 = 0; g8 < 4; ++g8) {
-                            float y[8];   // accumulator already contains the folded-BN bias
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) y[k] = __uint_as_float(vv[g8 * 8 + k]);
-                            uint4* dst = reinterpret_cast<uint4*>(obase + g8 * CHUNK_BYTES);
-                            if (li.residual) {  // out += identity (modules.py:37), identity lives in the output buffer
-                                const uint4 idv = *dst;
-                                const unsigned iw[4] = {idv.x, idv.y, idv.z, idv.w};
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    y[2 * k] += __uint_as_float(iw[k] << 16);
-                                    y[2 * k + 1] += __uint_as_float(iw[k] & 0xFFFF0000u);
-                                }
-                            }
-                            unsigned pk[4];
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) pk[k] = relu_pack_bf16x2(y[2 * k], y[2 * k + 1]);
-                            *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        }
-                    }
-                    if (l + 1 < n_layers) store_bias_to_tmem(tcol, S.bias[(l + 1) % 3] + ch0);
-                } else {
-                    // fused policy/value 1x1 head conv + BN + ReLU (modules.py:97,102) -> fp32 [board][ch*42 + cell];
-                    // 64 columns: each warp owns 64/EPI_SPLIT = 16 of them
-                    const int ch0 = part * (HEAD_CH / EPI_SPLIT);
-#pragma unroll
-                    for (int t = 0; t < MT; ++t) {
-                        unsigned v[16];
-                        tc_ld16(tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(t * 128 + ch0), v);
-                        const long long gb = grp * NB + board_t[t];
-                        if (real_t[t] && gb < n_boards) {
-                            float* ob = head_out + (size_t)gb * (HEAD_CH * CELLS) + cell_t[t];
-#pragma unroll
-                            for (int k = 0; k < 16; ++k) ob[(size_t)(ch0 + k) * CELLS] = fmaxf(__uint_as_float(v[k]), 0.f);
-                        }
-                    }
-                }
-                tc_fence_before();
-                fence_proxy_async();
-                lphase ^= 1u;
-                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));   // next layer's bias visible to every epilogue warp
-                if (l + 1 < n_layers) mbar_arrive(&S.epi_done);
-            }
-        }
-        // non-elected lanes of warps 0-1 and warps 2-3 fall through; ring/phase state persists in the elected lanes
-        __syncthreads();   // group boundary: accumulators drained, buffers reusable
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-}
-
-// ------------------------------------------------------------------------------------------------ the 2-CTA tower kernel
-// Same dataflow, but two CTAs (one SM pair, cluster of 2) share every weight slice: tcgen05.mma.cta_group::2 with M=256
-// (128 rows of each CTA) x N=128; each CTA stages only HALF of the slice (64 output channels) and the pair exchanges B
-// through the tensor-core datapath.  Per CTA that halves the weight bytes written into and read from shared memory (the
-// shared-memory port is the limiter of M=128 x N=128 SS-MMAs) and doubles the ring depth (6 x 4 KB).  The leader CTA
-// (cluster rank 0) issues all MMAs; completion is multicast to both CTAs' barriers; the peer relays "my half has landed"
-// and "my epilogue is done" with remote mbarrier arrives.
-struct Smem2 {
+// One template, two variants:
+//   NCTA == 2 (default): two CTAs (one SM pair, cluster of 2) share every weight slice: tcgen05.mma.cta_group::2 with
+//     M=256 (128 rows of each CTA) x N=128; each CTA stages only HALF of the slice (64 output channels) and the pair
+//     exchanges B through the tensor-core datapath, which halves the weight bytes written into / read from shared memory
+//     per CTA and doubles the ring depth (6 x 4 KB).  The leader CTA (cluster rank 0) issues all MMAs; completion is
+//     multicast to both CTAs' barriers; the peer relays "my half has landed" and "my epilogue is done" with remote
+//     mbarrier arrives.
+//   NCTA == 1 (SPX_TOWER_NCTA=1, fallback): every CTA is on its own (cta_group::1, M=128, 3 x 8 KB ring).
+template <int NCTA> struct SmemT {
+    static constexpr int STAGES = NCTA * NSTAGE;
     unsigned char act[2][ACT_BYTES];
-    unsigned char wstage[2 * NSTAGE][STAGE_BYTES / 2];
-    unsigned long long full[2 * NSTAGE], empty[2 * NSTAGE], peer_full[2 * NSTAGE], acc_full, epi_done;
+    unsigned char wstage[STAGES][STAGE_BYTES / NCTA];
+    unsigned long long full[STAGES], empty[STAGES], peer_full[STAGES], acc_full, epi_done;
     unsigned long long own[NB], opp[NB];
-    float bias[3][CH];
+    alignas(16) float bias[3][CH];   // read as float4
     unsigned tmem_base;
 };
-constexpr int NSTAGE2 = 2 * NSTAGE;
 
 __device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote(void* bar, unsigned cta) {   // arrive on the same barrier in CTA `cta` of the cluster
+// arrive on the same barrier in CTA `cta` of the cluster.  Waits stay plain CTA-scope try_wait: an acquire.cluster wait
+// on these barriers cost +55 % kernel time.
+__device__ __forceinline__ void mbar_arrive_remote(void* bar, unsigned cta) {
     asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
                  "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(void* bar, unsigned parity) {  // acquire at cluster scope (peer data)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+template <int NCTA> __device__ __forceinline__ void tc_commit_t(void* bar) {
+    if constexpr (NCTA == 2)   // completion of this thread's cta_group::2 MMAs -> the same barrier in both CTAs
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                     "h"((unsigned short)3) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_commit2(void* bar) {   // completion of this thread's cta_group::2 MMAs -> same barrier in both CTAs
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-                 "h"((unsigned short)3) : "memory");
-}
-__device__ __forceinline__ void tc_mma2(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
+// D[tmem] += A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate (the accumulators start from the pre-stored bias)
+template <int NCTA> __device__ __forceinline__ void tc_mma_t(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned idesc) {
+    if constexpr (NCTA == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                     "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                     "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
 }
 
+template <int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tower_kernel2(const unsigned long long* __restrict__ own_g, const unsigned long long* __restrict__ opp_g,
+tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long long* __restrict__ opp_g,
              const unsigned char* __restrict__ needs, long long n_boards, int n_layers,
              const unsigned char* __restrict__ wconv, const float* __restrict__ bias_all, float* __restrict__ head_out) {
+    typedef SmemT<NCTA> Smem;
+    constexpr int STAGES = Smem::STAGES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Smem2& S = *reinterpret_cast<Smem2*>(smem_raw);
-    const unsigned crank = cluster_ctarank();
+    Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+    const unsigned crank = NCTA == 2 ? cluster_ctarank() : 0u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long n_groups = (n_boards + NB - 1) / NB;
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE2; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); mbar_init(&S.peer_full[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); mbar_init(&S.peer_full[s], 1); }
         mbar_init(&S.acc_full, 1);
-        mbar_init(&S.epi_done, EPI_THREADS + 1);   // local epilogue threads + one remote arrive from the peer CTA
+        mbar_init(&S.epi_done, EPI_THREADS + (NCTA - 1));   // local epilogue threads (+ one remote arrive from the peer CTA)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        if constexpr (NCTA == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     // zero both activation buffers once: guard rows and padding cells must read as zero forever
     for (int i = tid; i < 2 * ACT_BYTES / 16; i += NUM_THREADS) reinterpret_cast<uint4*>(S.act[0])[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();   // both CTAs' barriers initialised and buffers zeroed before any remote arrive / MMA
+    if constexpr (NCTA == 2) cluster_sync_all();   // both CTAs' barriers initialised and buffers zeroed before any remote arrive / MMA
     tc_fence_after();
     const unsigned tmem_base = S.tmem_base;
 
-    unsigned stage = 0, sphase = 0;   // weight ring position (producer and MMA walk the same sequence)
+    unsigned stage = 0, sphase = 0;   // weight ring position (producer, relay and MMA issuer walk the same sequence)
     unsigned lphase = 0;              // per-layer barrier parity (acc_full / epi_done)
 
-    const long long n_pairs = (n_groups + 1) / 2;
-    for (long long pair = blockIdx.x >> 1; pair < n_pairs; pair += gridDim.x >> 1) {
-        const long long grp = 2 * pair + crank;
-        // pair-uniform skip when none of the 14 boards of this CTA pair asked for an evaluation
+    const long long n_units = (n_groups + NCTA - 1) / NCTA;      // a unit = the NCTA board groups one cluster works on together
+    for (long long unit = blockIdx.x / NCTA; unit < n_units; unit += gridDim.x / NCTA) {
+        const long long grp = NCTA * unit + crank;
+        // cluster-uniform skip when none of the boards of this unit asked for an evaluation
         bool any = needs == nullptr;
-        if (!any) for (int b = 0; b < 2 * NB; ++b) { long long gb = 2 * pair * NB + b; if (gb < n_boards && needs[gb]) any = true; }
+        if (!any) for (int b = 0; b < NCTA * NB; ++b) { long long gb = unit * NCTA * NB + b; if (gb < n_boards && needs[gb]) any = true; }
         if (!any) continue;
 
         if (warp == 0) {
@@ -522,8 +295,8 @@ tower_kernel2(const unsigned long long* __restrict__ own_g, const unsigned long 
             const unsigned char* wp = wconv;
             for (int l = 0; l < n_layers; ++l) {
                 const LayerInfo li = layer_info(l, n_layers);
-                const int ksteps = li.kslices >= 2 ? 2 : 1;                  // K steps (of 16 channels) per ring stage
-                const unsigned bytes = (unsigned)li.n * 16u * (unsigned)ksteps;   // this CTA's half of the stage (n/2 output channels)
+                const int ksteps = li.kslices >= 2 ? 2 : 1;                                   // K steps (of 16 channels) per ring stage
+                const unsigned bytes = 2u * (unsigned)li.n * 16u * (unsigned)ksteps / NCTA;   // this CTA's share of the stage
                 const int iters = li.taps * (li.kslices / ksteps);
                 for (int it = 0; it < iters; ++it) {
 #ifdef SPX_DBG_NO_TMA
@@ -535,11 +308,11 @@ tower_kernel2(const unsigned long long* __restrict__ own_g, const unsigned long 
                         tma_bulk_g2s(S.wstage[stage], wp + (size_t)crank * bytes, bytes, &S.full[stage]);
                     }
                     __syncwarp();
-                    wp += 2u * bytes;
-                    if (++stage == NSTAGE2) { stage = 0; sphase ^= 1u; }
+                    wp += (unsigned)NCTA * bytes;
+                    if (++stage == STAGES) { stage = 0; sphase ^= 1u; }
                 }
             }
-        } else if (warp == 2 && crank == 1) {
+        } else if (NCTA == 2 && warp == 2 && crank == 1) {
             // ===================== peer relay: tell the leader when this CTA's half of each weight stage has landed
             const bool leader = elect_one();
             for (int l = 0; l < n_layers; ++l) {
@@ -553,50 +326,50 @@ tower_kernel2(const unsigned long long* __restrict__ own_g, const unsigned long 
                     mbar_wait(&S.full[stage], sphase);
                     if (leader) mbar_arrive_remote(&S.peer_full[stage], 0);
                     __syncwarp();
-                    if (++stage == NSTAGE2) { stage = 0; sphase ^= 1u; }
+                    if (++stage == STAGES) { stage = 0; sphase ^= 1u; }
                 }
             }
         } else if (warp == 1 && crank == 0) {
-            // ===================== MMA issuer (leader CTA): warp-uniform loop, one elected lane issues cta_group::2 MMAs
+            // ===================== MMA issuer (leader CTA): warp-uniform loop, one elected lane issues tcgen05.mma / commit
             const bool leader = elect_one();
             for (int l = 0; l < n_layers; ++l) {
                 const LayerInfo li = layer_info(l, n_layers);
-                const unsigned idesc = make_idesc(256, li.n);
+                const unsigned idesc = make_idesc(128 * NCTA, li.n);
                 const int ksteps = li.kslices >= 2 ? 2 : 1;
                 const int kpairs = li.kslices / ksteps;
-                const unsigned kstep_bytes = (unsigned)li.n * 16u;            // per CTA: [2 k-chunks][n/2][8] bf16
+                const unsigned kstep_bytes = 2u * (unsigned)li.n * 16u / NCTA;        // per CTA: [2 k-chunks][n/NCTA][8] bf16
+                const unsigned b_lbo = (unsigned)li.n * 16u / NCTA;                   // stride between the two k-chunks
                 const unsigned a_base = smem_u32(S.act[li.in_buf]) + GUARD * 16;
-                mbar_wait_cluster(&S.epi_done, lphase);   // both CTAs: inputs of this layer written, accumulators drained
+                mbar_wait(&S.epi_done, lphase);   // (both CTAs:) inputs of this layer written, accumulators drained
                 tc_fence_after();
-                const unsigned acc = 1u;   // the accumulators start from the pre-stored bias
                 for (int tap = 0; tap < li.taps; ++tap) {
                     const int shift = li.taps == 9 ? tap_shift(tap) : 0;
                     for (int kp = 0; kp < kpairs; ++kp) {
 #ifndef SPX_DBG_NO_TMA
                         mbar_wait(&S.full[stage], sphase);
-                        mbar_wait_cluster(&S.peer_full[stage], sphase);
+                        if constexpr (NCTA == 2) mbar_wait(&S.peer_full[stage], sphase);
                         tc_fence_after();
 #endif
                         const unsigned b_addr = smem_u32(S.wstage[stage]);
                         const unsigned a_addr0 = a_base + (unsigned)(2 * ksteps * kp) * CHUNK_BYTES + (unsigned)(shift * 16);
                         if (leader) {
                             for (int j = 0; j < ksteps; ++j) {
-                                const unsigned long long bdesc = make_desc(b_addr + (unsigned)j * kstep_bytes, (unsigned)li.n * 8u, 128u);
+                                const unsigned long long bdesc = make_desc(b_addr + (unsigned)j * kstep_bytes, b_lbo, 128u);
 #pragma unroll
                                 for (int t = 0; t < MT; ++t) {
                                     const unsigned a_addr = a_addr0 + (unsigned)(2 * j) * CHUNK_BYTES + (unsigned)(t * 128 * 16);
-                                    tc_mma2(tmem_base + (unsigned)(t * 128), make_desc(a_addr, CHUNK_BYTES, 128u), bdesc, idesc, acc);
+                                    tc_mma_t<NCTA>(tmem_base + (unsigned)(t * 128), make_desc(a_addr, CHUNK_BYTES, 128u), bdesc, idesc);
                                 }
                             }
 #ifndef SPX_DBG_NO_TMA
-                            tc_commit2(&S.empty[stage]);   // frees the weight slot in BOTH CTAs once these MMAs retire
+                            tc_commit_t<NCTA>(&S.empty[stage]);   // frees the weight slot (in both CTAs) once these MMAs retire
 #endif
                         }
                         __syncwarp();
-                        if (++stage == NSTAGE2) { stage = 0; sphase ^= 1u; }
+                        if (++stage == STAGES) { stage = 0; sphase ^= 1u; }
                     }
                 }
-                if (leader) tc_commit2(&S.acc_full);
+                if (leader) tc_commit_t<NCTA>(&S.acc_full);
                 __syncwarp();
                 lphase ^= 1u;
             }
@@ -604,6 +377,13 @@ tower_kernel2(const unsigned long long* __restrict__ own_g, const unsigned long 
             // ===================== epilogue warps (also write the stem input)
             const int et = tid - EPI_WARP0 * 32;          // 0..EPI_THREADS-1
             const int quarter = warp & 3, part = (warp - EPI_WARP0) >> 2;   // TMEM lane quarter, column part
+            // "this CTA's activations for the next layer are in place": the leader's threads arrive locally, the peer CTA
+            // meets on a named barrier and sends ONE remote arrive to the leader's barrier
+            auto signal_epi_done = [&]() {
+                if (crank == 0) mbar_arrive(&S.epi_done);
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));   // also publishes the next layer's staged bias
+                if (NCTA == 2 && crank == 1 && et == 0) mbar_arrive_remote(&S.epi_done, 0);
+            };
             if (et < NB) {
                 const long long gb = grp * NB + et;
                 S.own[et] = gb < n_boards ? own_g[gb] : 0ULL;
@@ -627,9 +407,7 @@ tower_kernel2(const unsigned long long* __restrict__ own_g, const unsigned long 
                 *reinterpret_cast<uint4*>(S.act[0] + CHUNK_BYTES + (GUARD + row) * 16) = make_uint4(0, 0, 0, 0);
             }
             fence_proxy_async();
-            if (crank == 0) mbar_arrive(&S.epi_done);
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
-            if (crank == 1 && et == 0) mbar_arrive_remote(&S.epi_done, 0);   // the peer's single arrive on the leader's barrier
+            signal_epi_done();
             // per-tile row bookkeeping is layer independent
             bool real_t[MT]; int board_t[MT], cell_t[MT];
 #pragma unroll
@@ -702,20 +480,23 @@ tower_kernel2(const unsigned long long* __restrict__ own_g, const unsigned long 
                 tc_fence_before();
                 fence_proxy_async();
                 lphase ^= 1u;
-                if (l + 1 < n_layers && crank == 0) mbar_arrive(&S.epi_done);
-                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));   // next layer's bias visible; this CTA's epilogue complete
-                if (l + 1 < n_layers && crank == 1 && et == 0) mbar_arrive_remote(&S.epi_done, 0);
+                if (l + 1 < n_layers) signal_epi_done();
+                else asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
             }
         }
-        // non-elected lanes of warps 0-1 and warps 2-3 fall through; ring/phase state persists in the elected lanes
-        __syncthreads();   // group boundary: accumulators drained, buffers reusable
-        cluster_sync_all();
+        // non-elected lanes of warps 0-2 and warp 3 fall through; ring/phase state persists in the role warps
+        __syncthreads();   // unit boundary: accumulators drained, buffers reusable
+        if constexpr (NCTA == 2) cluster_sync_all();
     }
 
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if constexpr (NCTA == 2) {
+        cluster_sync_all();
+        if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    } else {
+        if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ fully connected heads
@@ -910,8 +691,8 @@ int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
     int dev = 0;
     SPX_CUDA_T(cudaGetDevice(&dev));
     SPX_CUDA_T(cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev));
-    SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-    SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem2)));
+    SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<1>)));
+    SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<2>)));
     SPX_CUDA_T(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM));
     *out = t;
     return 0;
@@ -953,17 +734,17 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));
         cfg.blockDim = dim3(NUM_THREADS);
-        cfg.dynamicSmemBytes = sizeof(Smem2);
+        cfg.dynamicSmemBytes = sizeof(SmemT<2>);
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        SPX_CUDA_T(cudaLaunchKernelEx(&cfg, tower_kernel2, (const unsigned long long*)own, (const unsigned long long*)opp, needs_eval,
+        SPX_CUDA_T(cudaLaunchKernelEx(&cfg, tower_kernel<2>, (const unsigned long long*)own, (const unsigned long long*)opp, needs_eval,
                                       (long long)n, t->n_layers, (const unsigned char*)t->blob, (const float*)(t->blob + t->off_bias), t->head_buf));
     } else {
         const int grid = (int)(groups < t->sm_count ? groups : t->sm_count);
-        tower_kernel<<<grid, NUM_THREADS, sizeof(Smem), st>>>((const unsigned long long*)own, (const unsigned long long*)opp, needs_eval, n,
+        tower_kernel<1><<<grid, NUM_THREADS, sizeof(SmemT<1>), st>>>((const unsigned long long*)own, (const unsigned long long*)opp, needs_eval, n,
                                                             t->n_layers, t->blob, (const float*)(t->blob + t->off_bias), t->head_buf);
     }
     spx::count_launch();
