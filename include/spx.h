@@ -210,6 +210,17 @@ int spx_tower_forward(spx_tower* t, const uint64_t* own, const uint64_t* opp, co
  * times the dominant kernel on the launching stream with these */
 int spx_tower_forward_timed(spx_tower* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n,
                             float* policy, float* value, void* stream, void* ev_start, void* ev_tower_done, void* ev_end);
+/* ---------------------------------------------------------------- TicTacToe network (fp32 CUDA cores)
+ * Replaces ConvNetTicTacToe.forward (games/tictactoe/modules.py:55-81, BN in eval mode folded): the "repo's tictactoe net" of
+ * BASELINE.json configs[0].  Weights: one fp32 device blob (layout: nets.pack_tttnet_blob, spx_tttnet_blob_floats()). */
+typedef struct spx_tttnet spx_tttnet;
+int64_t spx_tttnet_blob_floats(void);
+int spx_tttnet_create(spx_tttnet** out);
+int spx_tttnet_destroy(spx_tttnet* t);
+int spx_tttnet_load(spx_tttnet* t, const float* dev_blob, int64_t n_floats, void* stream);
+int spx_tttnet_forward(spx_tttnet* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n, float* policy,
+                       float* value, void* stream);
+
 /* timing-event helpers (cudaEvent_t behind void*), so hosts without a CUDA binding can time on the launching stream */
 int spx_event_create(void** ev_out);
 int spx_event_destroy(void* ev);

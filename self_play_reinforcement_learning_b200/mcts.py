@@ -54,10 +54,14 @@ class MCTreeSearch:
             ok = isinstance(self.network, nets.ResidualTower) or hasattr(self.network, "residual_blocks")
             ok = ok and self.game == _lib.GAME_CONNECT4 and getattr(self.network.conv1, "out_channels", 0) == 128
             kind = "tower" if ok else ("hash" if self.network is None else "torch")
+            if isinstance(self.network, nets.ConvNetTicTacToe) and self.game == _lib.GAME_TICTACTOE and self.network.action_size == 9:
+                kind = "tttnet"
         if kind == "tower":
             return nets.TowerEvaluator(self.network, self.game)
         if kind == "hash":
             return HashNetEvaluator(self.game, self.seed)
+        if kind == "tttnet":
+            return nets.TTTNetEvaluator(self.network)
         return nets.TorchNetEvaluator(self.network, self.game, dtype=self._net_dtype)
 
     def _ensure_engine(self):

@@ -341,6 +341,72 @@ class TowerEvaluator:
         self.tower.forward_bits(engine.leaf_own, engine.leaf_opp, engine.needs_eval, engine.policy, engine.value, events)
 
 
+# --------------------------------------------------------------------------------------------- native TicTacToe net
+def pack_tttnet_blob(module):
+    """ConvNetTicTacToe (3x3, action_size 9) -> fp32 blob in the layout of csrc/spx_tttnet.cu: conv weights as
+    [ic][tap][oc] with eval-mode BN folded, then the head convs, linear_policy, fc_value, linear_output."""
+    m = module
+    assert m.width == 3 and m.height == 3 and m.linear_policy.out_features == 9 and m.conv3.out_channels == 64
+    parts = []
+    for conv, bn in ((m.conv1, m.bn1), (m.conv2, m.bn2), (m.conv3, m.bn3)):
+        w, b = _fold(conv, bn)                                   # [oc, ic, 3, 3]
+        parts += [w.permute(1, 2, 3, 0).reshape(-1), b]          # [ic][tap = kh*3+kw][oc]
+    wp, bp = _fold(m.conv_policy, m.policy_bn)                   # [2, 64, 1, 1]
+    wv, bv = _fold(m.conv_value, m.value_bn)                     # [1, 64, 1, 1]
+    f32 = lambda t: t.detach().float().cpu().contiguous()        # noqa: E731
+    parts += [wp.reshape(2, 64).t().reshape(-1), bp, wv.reshape(-1), bv,
+              f32(m.linear_policy.weight).reshape(-1), f32(m.linear_policy.bias),
+              f32(m.fc_value.weight).reshape(-1), f32(m.fc_value.bias),
+              f32(m.linear_output.weight).reshape(-1), f32(m.linear_output.bias)]
+    blob = torch.cat([p.contiguous().reshape(-1) for p in parts]).contiguous()
+    assert blob.numel() == lib().spx_tttnet_blob_floats(), (blob.numel(), lib().spx_tttnet_blob_floats())
+    return blob
+
+
+class TTTNetEvaluator:
+    """Evaluates TicTacToe leaves with the hand-written fp32 kernel of ConvNetTicTacToe (the repo's tictactoe net)."""
+
+    def __init__(self, module):
+        if not torch.cuda.is_available():
+            raise _lib.SpxError("the native TicTacToe net runs on the GPU only (no CPU fallback)")
+        self._h = C.c_void_p()
+        check(lib().spx_tttnet_create(C.byref(self._h)), "spx_tttnet_create")
+        self.load(module)
+
+    def bind(self, engine):
+        pass
+
+    def load(self, module_or_blob):
+        blob = module_or_blob if torch.is_tensor(module_or_blob) else pack_tttnet_blob(module_or_blob)
+        self.blob_dev = blob.to("cuda", torch.float32)
+        check(lib().spx_tttnet_load(self._h, self.blob_dev.data_ptr(), self.blob_dev.numel(),
+                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), "spx_tttnet_load")
+
+    def forward_bits(self, own, opp, needs_eval=None, policy=None, value=None):
+        n = own.numel()
+        policy = torch.empty(n, 9, dtype=torch.float32, device=own.device) if policy is None else policy
+        value = torch.empty(n, dtype=torch.float32, device=own.device) if value is None else value
+        check(lib().spx_tttnet_forward(self._h, own.data_ptr(), opp.data_ptr(), None if needs_eval is None else needs_eval.data_ptr(), n,
+                                       policy.data_ptr(), value.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+              "spx_tttnet_forward")
+        return policy, value
+
+    def __call__(self, engine, events=None):
+        self.forward_bits(engine.leaf_own, engine.leaf_opp, engine.needs_eval, engine.policy, engine.value)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            torch.cuda.synchronize()
+            lib().spx_tttnet_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def smoke_check():
     """Tiny tower forward on cuda:0 against the fp32 torch forward of the same module."""
     torch.manual_seed(0)

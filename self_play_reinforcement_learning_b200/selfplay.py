@@ -66,6 +66,8 @@ class BatchedSelfPlay:
             if two:
                 raise _lib.SpxError("two-network evaluation runs through net='torch' (native tower: one network per engine)")
             self.evaluator = nets.TowerEvaluator(network, self.game)
+        elif net == "tttnet":
+            self.evaluator = nets.TTTNetEvaluator(network)
         elif net == "torch":
             self.evaluator = nets.TorchNetEvaluator(network, self.game, module_opp=evaluation_network, dtype=net_dtype)
         elif net == "hash":

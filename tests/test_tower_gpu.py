@@ -53,6 +53,8 @@ def test_tower_matches_fp32_reference(blocks, n):
     tw = nets.NativeTower(net)
     p, v = tw.forward_bits(bits[:, 0].contiguous(), bits[:, 1].contiguous())
     torch.cuda.synchronize()
+    torch.backends.cudnn.allow_tf32 = False          # the reference must be true fp32 (cuDNN convolutions default to TF32)
+    torch.backends.cuda.matmul.allow_tf32 = False
     with torch.no_grad():
         pr, vr = net.cuda().float().forward(boards.cuda())
     dp = (p - pr).abs().max().item()
