@@ -221,6 +221,15 @@ int spx_tttnet_load(spx_tttnet* t, const float* dev_blob, int64_t n_floats, void
 int spx_tttnet_forward(spx_tttnet* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n, float* policy,
                        float* value, void* stream);
 
+/* ---------------------------------------------------------------- two-network evaluation (compare_models / elo.py:73-91)
+ * Route the leaf batch to two networks: rows with net_id == k and needs_eval are packed (stable, by slot) to the front of
+ * dense batch k: own2/opp2 dev u64[2][n], needs2 dev u8[2][n], map2 dev i32[2][n] (dense row -> slot).  Each tower then only
+ * pays for its own rows (its CTAs skip rows whose needs2 is 0); spx_scatter_outputs copies the results back to the slots. */
+int spx_partition_leaves(int64_t n, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, const uint8_t* net_id,
+                         uint64_t* own2, uint64_t* opp2, uint8_t* needs2, int32_t* map2, void* stream);
+int spx_scatter_outputs(int64_t n, int32_t n_actions, const uint8_t* needs2, const int32_t* map2, const float* policy2, const float* value2,
+                        float* policy, float* value, void* stream);
+
 /* timing-event helpers (cudaEvent_t behind void*), so hosts without a CUDA binding can time on the launching stream */
 int spx_event_create(void** ev_out);
 int spx_event_destroy(void* ev);

@@ -744,6 +744,51 @@ __global__ void hashnet_kernel(int A, long long n, const u64* __restrict__ own, 
     value[i] = __fdiv_rn(vv, 81920.0f);
 }
 
+// ------------------------------------------------------------------------------------------------ two-network leaf routing
+// Head-to-head evaluation (compare_models / elo.py): tree 0 is evaluated by network 0, tree 1 by network 1.  The leaves of
+// each network are packed to the front of their own dense batch (stable, by slot index) so that each tower only pays for
+// its own rows; one CTA scans the whole batch (G <= 65536).
+__global__ void __launch_bounds__(1024) partition_kernel(int n, const u64* __restrict__ own, const u64* __restrict__ opp,
+                                                         const unsigned char* __restrict__ needs, const unsigned char* __restrict__ net_id,
+                                                         u64* __restrict__ own2, u64* __restrict__ opp2, unsigned char* __restrict__ needs2,
+                                                         int* __restrict__ map2) {
+    __shared__ int warp_cnt[2][32];
+    __shared__ int start[2];   // rows already written to each list before the current pass
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 2) start[tid] = 0;
+    for (int i = tid; i < 2 * n; i += 1024) needs2[i] = 0;
+    __syncthreads();
+    for (int s = 0; s < n; s += 1024) {
+        const int i = s + tid;
+        const int which = (i < n && needs[i]) ? (net_id[i] ? 1 : 0) : -1;
+        const unsigned m0 = __ballot_sync(0xffffffffu, which == 0), m1 = __ballot_sync(0xffffffffu, which == 1);
+        const unsigned lt = (1u << lane) - 1u;
+        if (lane == 0) { warp_cnt[0][warp] = __popc(m0); warp_cnt[1][warp] = __popc(m1); }
+        __syncthreads();
+        if (which >= 0) {
+            int dst = start[which] + __popc((which ? m1 : m0) & lt);
+            for (int w = 0; w < warp; ++w) dst += warp_cnt[which][w];
+            own2[(size_t)which * n + dst] = own[i];
+            opp2[(size_t)which * n + dst] = opp[i];
+            needs2[(size_t)which * n + dst] = 1;
+            map2[(size_t)which * n + dst] = i;
+        }
+        __syncthreads();
+        if (tid < 2) { int tot = 0; for (int w = 0; w < 32; ++w) tot += warp_cnt[tid][w]; start[tid] += tot; }
+        __syncthreads();
+    }
+}
+
+__global__ void scatter_kernel(int n, int A, const unsigned char* __restrict__ needs2, const int* __restrict__ map2,
+                               const float* __restrict__ pol2, const float* __restrict__ val2, float* __restrict__ policy,
+                               float* __restrict__ value) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;   // row of the concatenated [2][n] dense batches
+    if (j >= 2 * n || !needs2[j]) return;
+    const int i = map2[j];
+    for (int a = 0; a < A; ++a) policy[(size_t)i * A + a] = pol2[(size_t)j * A + a];
+    value[i] = val2[j];
+}
+
 }  // namespace spx
 
 // ================================================================================================== C ABI
@@ -999,6 +1044,26 @@ int spx_all_idle(spx_engine* e, int32_t* idle_out, void* stream) {
 }
 
 int64_t spx_device_bytes(spx_engine* e) { return e ? e->bytes : 0; }
+
+int spx_partition_leaves(int64_t n, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, const uint8_t* net_id,
+                         uint64_t* own2, uint64_t* opp2, uint8_t* needs2, int32_t* map2, void* stream) {
+    if (n <= 0) return 0;
+    if (n > 65536 || !own || !opp || !needs_eval || !net_id || !own2 || !opp2 || !needs2 || !map2) return set_err(SPX_E_ARG, "spx_partition_leaves: bad argument%s", "");
+    partition_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((int)n, (const u64*)own, (const u64*)opp, needs_eval, net_id, (u64*)own2, (u64*)opp2, needs2, map2);
+    count_launch();
+    SPX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int spx_scatter_outputs(int64_t n, int32_t n_actions, const uint8_t* needs2, const int32_t* map2, const float* policy2, const float* value2,
+                        float* policy, float* value, void* stream) {
+    if (n <= 0) return 0;
+    if (!needs2 || !map2 || !policy2 || !value2 || !policy || !value) return set_err(SPX_E_ARG, "spx_scatter_outputs: null pointer%s", "");
+    scatter_kernel<<<(int)((2 * n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((int)n, n_actions, needs2, map2, policy2, value2, policy, value);
+    count_launch();
+    SPX_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int spx_restart(spx_engine* e, int64_t slot_offset, int64_t games_target, void* stream) {
     if (!e) return set_err(SPX_E_ARG, "spx_restart: null engine%s", "");

@@ -341,6 +341,42 @@ class TowerEvaluator:
         self.tower.forward_bits(engine.leaf_own, engine.leaf_opp, engine.needs_eval, engine.policy, engine.value, events)
 
 
+class TwoTowerEvaluator:
+    """Head-to-head evaluation with two native towers (tree 0 -> network 0, tree 1 -> network 1): the leaf batch is
+    partitioned by network on the device, each tower evaluates only its own rows, the outputs are scattered back."""
+
+    def __init__(self, module, module_opp, game=GAME_CONNECT4):
+        self.towers = [NativeTower(module, game), NativeTower(module_opp, game)]
+        self.tower = self.towers[0]
+
+    def bind(self, engine):
+        n, dev, A = engine.n_games, engine.device, engine.A
+        self.own2 = torch.zeros(2, n, dtype=torch.int64, device=dev)
+        self.opp2 = torch.zeros(2, n, dtype=torch.int64, device=dev)
+        self.needs2 = torch.zeros(2, n, dtype=torch.uint8, device=dev)
+        self.map2 = torch.zeros(2, n, dtype=torch.int32, device=dev)
+        self.pol2 = torch.zeros(2, n, A, dtype=torch.float32, device=dev)
+        self.val2 = torch.zeros(2, n, dtype=torch.float32, device=dev)
+
+    def load(self, module_or_blob, which=0):
+        self.towers[which].load(module_or_blob)
+
+    def __call__(self, engine, events=None):
+        n = engine.n_games
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(lib().spx_partition_leaves(n, engine.leaf_own.data_ptr(), engine.leaf_opp.data_ptr(), engine.needs_eval.data_ptr(),
+                                         engine.net_id.data_ptr(), self.own2.data_ptr(), self.opp2.data_ptr(), self.needs2.data_ptr(),
+                                         self.map2.data_ptr(), st), "spx_partition_leaves")
+        for k in (0, 1):
+            self.towers[k].forward_bits(self.own2[k], self.opp2[k], self.needs2[k], self.pol2[k], self.val2[k])
+        check(lib().spx_scatter_outputs(n, engine.A, self.needs2.data_ptr(), self.map2.data_ptr(), self.pol2.data_ptr(),
+                                        self.val2.data_ptr(), engine.policy.data_ptr(), engine.value.data_ptr(), st), "spx_scatter_outputs")
+
+    def close(self):
+        for t in self.towers:
+            t.close()
+
+
 # --------------------------------------------------------------------------------------------- native TicTacToe net
 def pack_tttnet_blob(module):
     """ConvNetTicTacToe (3x3, action_size 9) -> fp32 blob in the layout of csrc/spx_tttnet.cu: conv weights as

@@ -88,7 +88,7 @@ class SelfPlayScheduler:
         """n_games_total games (indices 0..n-1, swap_sides = index odd as in :250-253) sharded over the ranks."""
         G = min(self.games_per_gpu, max(2, -(-n_games_total // self.world)))
         G += G & 1
-        sp = BatchedSelfPlay(self.network, env=self.env, n_games=G, sims=self.iterations, net=self.net if not evaluate or self.evaluation_network is None else "torch",
+        sp = BatchedSelfPlay(self.network, env=self.env, n_games=G, sims=self.iterations, net=self.net,
                              evaluation_network=self.evaluation_network if evaluate else None, evaluate=evaluate, update=update,
                              alpha=self.alpha, seed=self.seed + 7919 * generation, rank=self.rank, world=self.world,
                              games_target=n_games_total, opponent=self.evaluation_opponent if evaluate else None)

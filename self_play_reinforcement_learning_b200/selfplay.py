@@ -63,9 +63,7 @@ class BatchedSelfPlay:
         self.network, self.evaluation_network = network, evaluation_network
         two = evaluation_network is not None
         if net == "tower":
-            if two:
-                raise _lib.SpxError("two-network evaluation runs through net='torch' (native tower: one network per engine)")
-            self.evaluator = nets.TowerEvaluator(network, self.game)
+            self.evaluator = nets.TwoTowerEvaluator(network, evaluation_network, self.game) if two else nets.TowerEvaluator(network, self.game)
         elif net == "tttnet":
             self.evaluator = nets.TTTNetEvaluator(network)
         elif net == "torch":
@@ -131,9 +129,12 @@ class BatchedSelfPlay:
 
     def close(self):
         self.engine.close()
-        tw = getattr(self.evaluator, "tower", None)
-        if tw is not None:
-            tw.close()
+        if hasattr(self.evaluator, "close"):
+            self.evaluator.close()
+        else:
+            tw = getattr(self.evaluator, "tower", None)
+            if tw is not None:
+                tw.close()
 
 
 def run_tasks(network, env, tasks, result_queue=None, memory_queue=None, task_queue=None, iterations=800, n_games=None,

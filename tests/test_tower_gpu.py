@@ -90,3 +90,35 @@ def test_selfplay_with_tower_replays_bit_exact_in_oracle():
         o = H.replay_in_oracle(0, sims, 11, g, table[g], logs[g])
         H.compare_game(0, e.move_log(g), recs[g], res[g], o)
     e.close()
+
+
+def test_two_native_towers_head_to_head_replays_in_oracle():
+    """BASELINE.json configs[3] shape (elo.py head-to-head, two random-init nets, evaluate mode) on the native path:
+    leaves are partitioned by network on the device; every game is replayed through the oracle with the logged outputs, and
+    each tower's outputs equal what it returns for the same boards on its own."""
+    from self_play_reinforcement_learning_b200 import nets
+    from self_play_reinforcement_learning_b200.selfplay import BatchedSelfPlay
+    from tests import helpers as H
+    torch.manual_seed(0)
+    a = nets.ResidualTower(7, 6, 7, num_blocks=2).eval()
+    torch.manual_seed(1)
+    b = nets.ResidualTower(7, 6, 7, num_blocks=2).eval()
+    n_games, sims = 30, 40
+    sp = BatchedSelfPlay(a, game=0, n_games=n_games, sims=sims, net="tower", evaluation_network=b, evaluate=True, update=False, seed=5,
+                         games_target=n_games, noise_mode=0, move_log=True)
+    assert isinstance(sp.evaluator, nets.TwoTowerEvaluator)
+    logs = H.run_logged(sp.engine)
+    _, res = H.split_by_game(sp.engine.drain_records(), sp.engine.drain_results())
+    assert len(res) == n_games
+    for g in range(n_games):
+        o = H.replay_in_oracle(0, sims, 5, g, None, logs[g], evaluate=True)
+        assert res[g]["reward"] == o["reward"] and res[g]["plies"] == len(o["moves"])
+        ml = sp.engine.move_log(g)
+        assert [m["action"] for m in ml] == [m["action"] for m in o["moves"]] and [m["n"] for m in ml] == [list(m["n"]) for m in o["moves"]]
+    # routing check: tree-k evaluations equal tower k evaluated directly on the logged boards
+    for k, tw in enumerate(sp.evaluator.towers):
+        own = torch.tensor(np.array(logs[3][k]["own"], dtype=np.uint64).view(np.int64), device="cuda")
+        opp = torch.tensor(np.array(logs[3][k]["opp"], dtype=np.uint64).view(np.int64), device="cuda")
+        p, v = tw.forward_bits(own, opp)
+        assert np.array_equal(p.cpu().numpy(), np.array(logs[3][k]["policy"])) and np.array_equal(v.cpu().numpy(), np.array(logs[3][k]["value"], np.float32))
+    sp.close()
