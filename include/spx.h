@@ -230,6 +230,37 @@ int spx_partition_leaves(int64_t n, const uint64_t* own, const uint64_t* opp, co
 int spx_scatter_outputs(int64_t n, int32_t n_actions, const uint8_t* needs2, const int32_t* map2, const float* policy2, const float* value2,
                         float* policy, float* value, void* stream);
 
+/* ---------------------------------------------------------------- device-resident replay memory
+ * Replaces memory_queue -> MCTreeSearch.pull_from_queue (mcts.py:217-222) -> Memory (rl_utils/memory.py:8-30): the Move
+ * records never leave HBM.  A bounded FIFO (deque(maxlen=max_size) semantics: appending beyond max_size evicts the oldest),
+ * uniform sampling WITHOUT replacement (memory.py:26-30), and the batch assembly of MCTreeSearch.loss (mcts.py:234-243:
+ * stacked states -> preprocess planes general/modules.py:115-125, tree_probs, actual_val, q).
+ * Logical index 0 is the oldest record.  Host-side bookkeeping (size, head) is exact; none of these calls launches work on
+ * an empty memory. */
+typedef struct spx_replay spx_replay;
+/* max_size: the deque's maxlen; physical_capacity >= max_size: the largest size change_size may ever ask for
+ * (UpdateWorker.stagger_memory grows the buffer towards max_mem, updateworker.py:107-109). */
+int spx_replay_create(int64_t max_size, int64_t physical_capacity, spx_replay** out);
+int spx_replay_destroy(spx_replay* r);
+int64_t spx_replay_size(spx_replay* r);     /* len(memory) */
+int64_t spx_replay_max_size(spx_replay* r); /* memory.max_size */
+int spx_replay_change_size(spx_replay* r, int64_t max_size); /* Memory.change_size (memory.py:22-24): keeps the newest */
+int spx_replay_reset(spx_replay* r);                         /* Memory.reset (memory.py:32-33) */
+/* Drain the engine's record ring into dev_out (device memory, `capacity` records), sorted by (game_index, tree, ply) so the
+ * order does not depend on which warp finished first; *n_out = records written.  Synchronises `stream` (it needs the count). */
+int spx_drain_records_device(spx_engine* e, spx_record* dev_out, int64_t capacity, int64_t* n_out, void* stream);
+/* Memory.add for n records in device memory, in order (only the last max_size survive) */
+int spx_replay_append(spx_replay* r, const spx_record* dev_records, int64_t n, void* stream);
+/* copy logical records [first, first+n) to HOST memory (save_memory updateworker.py:123-139, tests) */
+int spx_replay_read(spx_replay* r, int64_t first, int64_t n, spx_record* host_out, void* stream);
+/* Memory.sample(batch) + the tensor stacking of MCTreeSearch.loss.  Indices: partial Fisher-Yates over the logical index
+ * space, draw i from the counter stream (seed, game_uid = step, tree 0, purpose 4, ply 0, sim i, depth 0, idx 0) as
+ * j = i + rng_u64 % (size - i)  (integer only: identical on CPU and GPU; oracle/replay.py).  Outputs (device, any may be NULL):
+ * idx i64[batch]; boards i64[batch][W][H] (Move.state, +1 own / -1 enemy); planes f32[batch][3][W][H] ([==0, ==+1, ==-1]);
+ * tree_probs f32[batch][A]; actual_val f32[batch]; q f32[batch].  batch <= min(size, 4096). */
+int spx_replay_sample(spx_replay* r, int32_t game, int64_t batch, uint64_t seed, uint64_t step, int64_t* idx, int64_t* boards,
+                      float* planes, float* tree_probs, float* actual_val, float* q, void* stream);
+
 /* timing-event helpers (cudaEvent_t behind void*), so hosts without a CUDA binding can time on the launching stream */
 int spx_event_create(void** ev_out);
 int spx_event_destroy(void* ev);

@@ -1,0 +1,65 @@
+"""CPU restatement of the reference's replay memory and loss-batch assembly.  TEST INFRASTRUCTURE ONLY (see oracle/README
+note in DESIGN.md section 4): the product path is csrc/spx_replay.cu.
+
+Follows rl_utils/memory.py:8-30 (Memory: deque(maxlen), add, change_size, reset, sample = uniform without replacement) and
+games/algos/mcts.py:234-243 (stacking of a sampled batch) + games/general/modules.py:115-125 (preprocess planes).
+
+The one thing that cannot be shared with the reference is numpy's global MT19937 (memory.py:28 np.random.choice): as for the
+search (oracle/spec.py) the randomness is injected -- `sample_indices` defines the index stream, the live test
+(tests/test_oracle_vs_reference_live.py) hooks np.random.choice in the reference's Memory with it and compares batches.
+"""
+from collections import deque
+
+import numpy as np
+
+from . import spec
+
+PURPOSE_SAMPLE = 4
+
+
+def sample_indices(seed, step, size, batch):
+    """`batch` distinct indices in [0, size): partial Fisher-Yates over the virtual array a[k] = k, draw i taken from the
+    counter stream as j = i + rng_u64(seed, step, 0, PURPOSE_SAMPLE, 0, i, 0, 0) % (size - i); result[i] = a[j], a[j] = a[i]."""
+    assert 1 <= batch <= size
+    moved = {}
+    out = np.empty(batch, dtype=np.int64)
+    for i in range(batch):
+        j = i + spec.rng_u64(seed, step, 0, PURPOSE_SAMPLE, 0, i, 0, 0) % (size - i)
+        vi, vj = moved.get(i, i), moved.get(j, j)
+        out[i] = vj
+        moved[j] = vi
+    return out
+
+
+class Memory:
+    """memory.py:8-33 over plain record dicts / structured rows."""
+
+    def __init__(self, max_size=None):
+        self.max_size = max_size
+        self._buffer = deque(maxlen=max_size)
+
+    def __len__(self):
+        return len(self._buffer)
+
+    def add(self, experience):
+        self._buffer.append(experience)
+
+    def change_size(self, max_size):
+        self.max_size = max_size
+        self._buffer = deque(self._buffer, maxlen=max_size)
+
+    def reset(self):
+        self._buffer = deque(maxlen=self.max_size)
+
+    def sample(self, batch_size, seed, step):
+        return [self._buffer[int(i)] for i in sample_indices(seed, step, len(self._buffer), batch_size)]
+
+
+def assemble(records, game):
+    """records: rows with own/opp/tree_probs/q/actual_val -> the tensors MCTreeSearch.loss stacks (mcts.py:236-243)."""
+    W, H, A = spec.GAME_DIMS[game]
+    boards = np.stack([spec.bits_to_board(int(r["own"]), int(r["opp"]), game) for r in records]).astype(np.int64)
+    planes = np.stack([(boards == 0), (boards == 1), (boards == -1)], axis=1).astype(np.float32)   # modules.py:115-125
+    probs = np.stack([np.asarray(r["tree_probs"], dtype=np.float32)[:A] for r in records])
+    return dict(boards=boards, planes=planes, tree_probs=probs, actual_val=np.array([r["actual_val"] for r in records], np.float32),
+                q=np.array([r["q"] for r in records], np.float32))

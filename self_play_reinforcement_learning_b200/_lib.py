@@ -54,7 +54,9 @@ EXPORTS = ["spx_last_error", "spx_version", "spx_launch_count", "spx_env_step", 
            "spx_counters_read", "spx_all_idle", "spx_device_bytes", "spx_pending_tree", "spx_tower_blob_bytes",
            "spx_tower_create", "spx_tower_destroy", "spx_tower_ncta", "spx_tower_load", "spx_tower_forward", "spx_tower_forward_timed", "spx_partition_leaves", "spx_scatter_outputs", "spx_tttnet_blob_floats", "spx_tttnet_create", "spx_tttnet_destroy",
            "spx_tttnet_load", "spx_tttnet_forward",
-           "spx_advance_timed", "spx_restart", "spx_set_external_actions", "spx_slot_status", "spx_event_create", "spx_event_destroy", "spx_event_elapsed_ms"]
+           "spx_advance_timed", "spx_restart", "spx_set_external_actions", "spx_slot_status", "spx_event_create", "spx_event_destroy", "spx_event_elapsed_ms",
+           "spx_replay_create", "spx_replay_destroy", "spx_replay_size", "spx_replay_max_size", "spx_replay_change_size", "spx_replay_reset",
+           "spx_drain_records_device", "spx_replay_append", "spx_replay_read", "spx_replay_sample"]
 
 _lib = None
 
@@ -107,6 +109,18 @@ def lib():
         L.spx_tttnet_destroy.argtypes = [vp]
         L.spx_tttnet_load.argtypes = [vp, vp, i64, vp]
         L.spx_tttnet_forward.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
+        L.spx_replay_create.argtypes = [i64, i64, C.POINTER(vp)]
+        L.spx_replay_destroy.argtypes = [vp]
+        L.spx_replay_size.restype = C.c_int64
+        L.spx_replay_size.argtypes = [vp]
+        L.spx_replay_max_size.restype = C.c_int64
+        L.spx_replay_max_size.argtypes = [vp]
+        L.spx_replay_change_size.argtypes = [vp, i64]
+        L.spx_replay_reset.argtypes = [vp]
+        L.spx_drain_records_device.argtypes = [vp, vp, i64, C.POINTER(i64), vp]
+        L.spx_replay_append.argtypes = [vp, vp, i64, vp]
+        L.spx_replay_read.argtypes = [vp, i64, i64, vp, vp]
+        L.spx_replay_sample.argtypes = [vp, i32, i64, u64, u64, vp, vp, vp, vp, vp, vp, vp]
         L.spx_event_create.argtypes = [C.POINTER(vp)]
         L.spx_event_destroy.argtypes = [vp]
         L.spx_event_elapsed_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]

@@ -23,6 +23,8 @@
 #include <atomic>
 #include <new>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "spx_common.cuh"
 
 namespace spx {
@@ -794,6 +796,22 @@ __global__ void scatter_kernel(int n, int A, const unsigned char* __restrict__ n
 // ================================================================================================== C ABI
 using namespace spx;
 
+// ---- device-to-device drain of the record ring, sorted by (game_index, tree, ply) (spx_drain_records_device)
+__global__ void record_keys_kernel(const spx_record* __restrict__ ring, long long n, unsigned long long* __restrict__ keys, unsigned* __restrict__ vals) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        keys[i] = (ring[i].game_index << 8) | ((unsigned long long)(ring[i].tree & 1) << 7) | (unsigned long long)(ring[i].ply & 0x7F);
+        vals[i] = (unsigned)i;
+    }
+}
+__global__ void record_permute_kernel(const spx_record* __restrict__ ring, const unsigned* __restrict__ order, long long n, spx_record* __restrict__ out) {
+    const uint4* s = reinterpret_cast<const uint4*>(ring);
+    uint4* d = reinterpret_cast<uint4*>(out);
+    for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < n * 5; w += (long long)gridDim.x * blockDim.x) {
+        const long long rec = w / 5, part = w - rec * 5;
+        d[w] = s[(long long)order[rec] * 5 + part];
+    }
+}
+
 template <typename T>
 static int drain(T* ring, unsigned long long* count, int64_t ring_cap, T* host_out, int64_t capacity, int64_t* n_out, cudaStream_t st) {
     unsigned long long n = 0;
@@ -998,6 +1016,39 @@ int spx_root_stats(spx_engine* e, int32_t tree, int32_t* n, double* w, int32_t* 
 int spx_drain_records(spx_engine* e, spx_record* host_out, int64_t capacity, int64_t* n_out, void* stream) {
     if (!e || !host_out || !n_out) return set_err(SPX_E_ARG, "spx_drain_records: bad argument%s", "");
     return drain<spx_record>(e->d.rec_ring, e->d.rec_count, e->d.cfg.record_capacity, host_out, capacity, n_out, (cudaStream_t)stream);
+}
+int spx_drain_records_device(spx_engine* e, spx_record* dev_out, int64_t capacity, int64_t* n_out, void* stream) {
+    if (!e || !dev_out || !n_out) return set_err(SPX_E_ARG, "spx_drain_records_device: bad argument%s", "");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long n = 0;
+    SPX_CUDA(cudaMemcpyAsync(&n, e->d.rec_count, sizeof(n), cudaMemcpyDeviceToHost, st));
+    SPX_CUDA(cudaStreamSynchronize(st));
+    if ((int64_t)n > e->d.cfg.record_capacity) n = (unsigned long long)e->d.cfg.record_capacity;
+    if ((int64_t)n > capacity) return set_err(SPX_E_OVERFLOW, "spx_drain_records_device: output buffer smaller than the buffered records%s", "");
+    *n_out = (int64_t)n;
+    if (n == 0) return 0;
+    // scratch: keys in/out, order in/out, CUB temp storage -- one allocation per drain (a per-epoch operation)
+    size_t temp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const unsigned*)nullptr, (unsigned*)nullptr, (int)n);
+    const size_t kb = (sizeof(unsigned long long) * n + 255) & ~(size_t)255, vb = (sizeof(unsigned) * n + 255) & ~(size_t)255;
+    unsigned char* scratch = nullptr;
+    SPX_CUDA(cudaMalloc((void**)&scratch, 2 * kb + 2 * vb + temp_bytes));
+    unsigned long long *k0 = (unsigned long long*)scratch, *k1 = (unsigned long long*)(scratch + kb);
+    unsigned *v0 = (unsigned*)(scratch + 2 * kb), *v1 = (unsigned*)(scratch + 2 * kb + vb);
+    const int grid = grid_for((long long)n, 256);
+    record_keys_kernel<<<grid, 256, 0, st>>>(e->d.rec_ring, (long long)n, k0, v0);
+    count_launch();
+    cudaError_t ce = cub::DeviceRadixSort::SortPairs(scratch + 2 * kb + 2 * vb, temp_bytes, k0, k1, v0, v1, (int)n, 0, 64, st);
+    if (ce == cudaSuccess) {
+        record_permute_kernel<<<grid_for((long long)n * 5, 256), 256, 0, st>>>(e->d.rec_ring, v1, (long long)n, dev_out);
+        count_launch();
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(e->d.rec_count, 0, sizeof(unsigned long long), st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(scratch);
+    if (ce != cudaSuccess) return set_err(SPX_E_CUDA, "spx_drain_records_device: %s", cudaGetErrorString(ce));
+    return 0;
 }
 int spx_drain_results(spx_engine* e, spx_result* host_out, int64_t capacity, int64_t* n_out, void* stream) {
     if (!e || !host_out || !n_out) return set_err(SPX_E_ARG, "spx_drain_results: bad argument%s", "");

@@ -57,6 +57,26 @@ def gather_structured(arr, dst=0, group=None, device="cpu"):
     return np.concatenate([np.frombuffer(p, dtype=arr.dtype) for p in parts]) if parts else arr[:0]
 
 
+def gather_device_rows(rows, dst=0, group=None):
+    """Gather a [n_r, k] tensor with a different n_r on every rank (device-resident Move records, n_r x 80 bytes) to rank
+    ``dst`` without a host copy: all_gather of the row counts, then one padded all_gather.  Returns the list of per-rank
+    tensors on ``dst`` and None elsewhere; the memory_queue of the reference (mcts.py:225-232) for ranks > 0."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return [rows]
+    world = dist.get_world_size(group)
+    n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    padded = torch.zeros((max(max(sizes), 1),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    padded[:rows.shape[0]] = rows
+    out = [torch.zeros_like(padded) for _ in range(world)]
+    dist.all_gather(out, padded, group=group)
+    if dist.get_rank(group) != dst:
+        return None
+    return [o[:k] for o, k in zip(out, sizes)]
+
+
 def reduce_counters(counters, group=None, device="cpu"):
     """Sum the per-rank counter dicts (every rank gets the total)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:

@@ -2,8 +2,9 @@
 GPU engine -- same epoch structure, same result bookkeeping, same loss, with the worker processes, queues and
 checkpoint-file weight hand-off replaced by one BatchedSelfPlay per GPU and an NCCL weight broadcast.
 
-Row (f1)/(f2) of SURVEY.md 8: the training step itself is ordinary PyTorch autograd on rank 0 (the reference trains
-in one UpdateWorker, updateworker.py:141-149); it is host-side glue, not part of the measured hot path.
+Row (f1)/(f2) of SURVEY.md 8: records flow engine -> device replay memory (replay.DeviceReplay, csrc/spx_replay.cu) ->
+sampled training batch without touching the host; the forward/backward itself is PyTorch autograd on rank 0 (the
+reference trains in one UpdateWorker, updateworker.py:141-149) and is not part of the measured hot path.
 """
 from collections import deque
 
@@ -11,6 +12,7 @@ import numpy as np
 import torch
 
 from . import nets, parallel
+from .replay import DeviceReplay, loss_from_batch
 from .selfplay import BatchedSelfPlay, Move, records_to_moves, results_to_dicts
 
 
@@ -68,8 +70,11 @@ def parse_results(reward_list):
 class SelfPlayScheduler:
     def __init__(self, network, env, evaluation_network=None, iterations=800, epoch_length=1500, initial_games=64,
                  evaluation_games=150, games_per_gpu=1024, memory_size=200000, batch_size=128, lr=0.01, momentum=0.9,
-                 weight_decay=1e-4, updates_per_epoch=100, alpha=1.0, seed=0, net="tower", evaluation_opponent=None):
-        """evaluation_opponent: None (evaluation_network, or the policy itself), "lookahead" or "random": the hard-coded
+                 weight_decay=1e-4, updates_per_epoch=100, alpha=1.0, seed=0, net="tower", evaluation_opponent=None,
+                 replay="device", max_memory_size=None, memory_step=0):
+        """replay: "device" (records stay in HBM: DeviceReplay) or "host" (reference-style Memory of Move tuples).
+        max_memory_size / memory_step: UpdateWorker's staggered buffer growth (updateworker.py:107-109).
+        evaluation_opponent: None (evaluation_network, or the policy itself), "lookahead" or "random": the hard-coded
         evaluation_policy_container of the reference's train command (main.py:66, hardcoded_players.py)."""
         self.network, self.env, self.evaluation_network = network, env, evaluation_network
         self.iterations, self.epoch_length, self.initial_games, self.evaluation_games = iterations, epoch_length, initial_games, evaluation_games
@@ -77,7 +82,9 @@ class SelfPlayScheduler:
         self.alpha, self.seed, self.net, self.evaluation_opponent = alpha, seed, net, evaluation_opponent
         self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
-        self.memory = Memory(memory_size)
+        self.replay_kind, self.memory_step, self.max_memory_size = replay, memory_step, max_memory_size or memory_size
+        self.memory = None if replay == "device" else Memory(memory_size)   # the device memory is created with the first games
+        self._memory_size = memory_size
         # SGD(momentum 0.9, weight decay 1e-4): self_play_parallel.py:193
         self.optim = torch.optim.SGD(network.parameters(), lr=lr, momentum=momentum, weight_decay=weight_decay)
         self.games_played = 0
@@ -92,22 +99,37 @@ class SelfPlayScheduler:
                              evaluation_network=self.evaluation_network if evaluate else None, evaluate=evaluate, update=update,
                              alpha=self.alpha, seed=self.seed + 7919 * generation, rank=self.rank, world=self.world,
                              games_target=n_games_total, opponent=self.evaluation_opponent if evaluate else None)
+        device_replay = update and self.replay_kind == "device"
+        if device_replay and self.memory is None:
+            self.memory = DeviceReplay(sp.game, self._memory_size, self.max_memory_size, seed=self.seed)
         recs, res = [], []
         while True:
             sp.engine.run_ticks(512)
-            recs.append(sp.engine.drain_records())
+            if device_replay:       # pull_from_queue without the queue: device ring -> device memory
+                r = self.memory.drain_engine(sp.engine, append=self.world == 1)
+                recs.append(r.clone() if self.world > 1 else r.shape[0])
+            else:
+                recs.append(sp.engine.drain_records())
             res.append(sp.engine.drain_results())
             if sp.engine.all_idle():
                 break
         game = sp.game
         sp.close()
-        recs, res = np.concatenate(recs), np.concatenate(res)
         dev = torch.device("cuda", torch.cuda.current_device())
-        all_recs = parallel.gather_structured(recs, dst=0, device=dev)       # replaces memory_queue
-        all_res = parallel.gather_structured(res, dst=0, device=dev)         # replaces result_queue
+        all_res = parallel.gather_structured(np.concatenate(res), dst=0, device=dev)         # replaces result_queue
+        results = results_to_dicts(parallel.merge_results_in_game_order(all_res)) if self.rank == 0 else []
+        if device_replay:
+            if self.world == 1:
+                return int(sum(recs)), results
+            mine = torch.cat(recs) if recs else torch.empty(0, 80, dtype=torch.uint8, device=dev)
+            everyone = parallel.gather_device_rows(mine, dst=0)                                # replaces memory_queue (NCCL)
+            if self.rank != 0:
+                return 0, []
+            return int(sum(self.memory.append_records(t) for t in everyone)), results
+        all_recs = parallel.gather_structured(np.concatenate(recs), dst=0, device=dev)       # replaces memory_queue
         if self.rank != 0:
             return [], []
-        return records_to_moves(all_recs, game), results_to_dicts(parallel.merge_results_in_game_order(all_res))
+        return records_to_moves(all_recs, game), results
 
     def _sync_weights(self):
         """Replaces the checkpoint-file hand-off (updateworker.py:111-117 -> inference_worker.py:68-73)."""
@@ -129,12 +151,15 @@ class SelfPlayScheduler:
 
     def update(self):
         """UpdateWorker.update (updateworker.py:141-149): `updates_per_epoch` SGD steps on uniform samples."""
-        if self.rank != 0 or len(self.memory) < self.batch_size:
+        if self.rank != 0 or self.memory is None or len(self.memory) < self.batch_size:
             return None
         self.network.train()
         last = None
         for _ in range(self.updates_per_epoch):
-            loss = mcts_loss(self.network, self.memory.sample(self.batch_size))
+            if self.replay_kind == "device":
+                loss = loss_from_batch(self.network, self.memory.sample_batch(self.batch_size))
+            else:
+                loss = mcts_loss(self.network, self.memory.sample(self.batch_size))
             self.optim.zero_grad()
             loss.backward()
             self.optim.step()
@@ -146,18 +171,22 @@ class SelfPlayScheduler:
         """:213-291: initial games, then per epoch: epoch_length self-play games -> update -> weight sync -> evaluation."""
         self.network.eval()
         gen = 0
-        moves, _ = self._play(self.initial_games, evaluate=False, update=True, generation=gen)
-        for m in moves:
-            self.memory.add(m)
+        self._remember(self._play(self.initial_games, evaluate=False, update=True, generation=gen)[0])
         for epoch in range(num_epochs):
             gen += 1
             moves, results = self._play(self.epoch_length, evaluate=False, update=True, generation=gen)
-            for m in moves:
-                self.memory.add(m)
+            self._remember(moves)
+            if self.memory_step and self.rank == 0 and self.memory is not None:   # stagger_memory (updateworker.py:107-109)
+                self.memory.change_size(min(self.memory.max_size + self.memory_step, self.max_memory_size))
             self.games_played += self.epoch_length
             loss = self.update()
             self._sync_weights()
             reward = self.evaluate_policy(epoch) if self.evaluation_games else 0
             self.history.append(dict(epoch=epoch, loss=loss, self_play=parse_results(results)[0] if self.rank == 0 else None,
-                                     evaluation_reward=reward, memory=len(self.memory)))
+                                     evaluation_reward=reward, memory=len(self.memory) if self.memory is not None else 0))
         return self.history
+
+    def _remember(self, moves):
+        if self.replay_kind != "device":      # device replay: _play has already appended the records on the GPU
+            for m in moves:
+                self.memory.add(m)

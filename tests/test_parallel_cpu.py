@@ -44,6 +44,14 @@ def _worker(rank, world, port, out_dir):
     res["reward"] = [1, -1]
     all_recs = parallel.gather_structured(recs, dst=0)
     all_res = parallel.gather_structured(res, dst=0)
+    # 3b. the same gather for device-resident record rows ([n, 80] uint8 tensors; CPU tensors under gloo)
+    rows = torch.from_numpy(recs.view(np.uint8).reshape(len(recs), RECORD_DTYPE.itemsize).copy())
+    parts = parallel.gather_device_rows(rows, dst=0)
+    if rank == 0:
+        back = np.concatenate([p.numpy().reshape(-1).view(RECORD_DTYPE) for p in parts])
+        assert [len(p) for p in parts] == [3, 5] and back.tobytes() == all_recs.tobytes()
+    else:
+        assert parts is None
     tot = parallel.reduce_counters({"sims": 10 * (rank + 1), "moves": rank})
     assert tot == {"sims": 30, "moves": 1}
     if rank == 0:
