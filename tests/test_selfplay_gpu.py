@@ -196,3 +196,22 @@ def test_policy_facade_drives_reference_style_episode(swap):
     policy.reset(player=1)
     assert policy.game_index == 4 and isinstance(policy(None), int)
     policy.close()
+
+
+def test_elo_round_robin_with_native_towers_and_hardcoded_anchor():
+    """elo.py flow: register models, compare all pairs (two native towers head to head; tower vs the device-side random
+    player), accumulate under the reference's key convention, fit ratings with the anchor at 0."""
+    from self_play_reinforcement_learning_b200 import elo, nets
+    db = elo.ModelDatabase("connect4")
+    db.add_model("random", "random")
+    for i, name in enumerate(("neta", "netb")):
+        torch.manual_seed(i)
+        db.add_model(name, nets.ResidualTower(7, 6, 7, num_blocks=1).eval())
+    e = elo.Elo(db, iterations=40, seed=3)
+    e.compare_all()
+    e.compare_models("neta", "netb", num_games=7)          # odd number: accumulates, exactly 7 more games
+    assert set(db.result_shelf) == {"random__neta", "random__netb", "netb__neta"}
+    assert sum(db.result_shelf["random__neta"].values()) == 100 and sum(db.result_shelf["netb__neta"].values()) == 107
+    assert db.result_shelf["random__neta"]["losses"] > 60      # a 40-sim search beats the random player (losses: random's view)
+    ratings = e.calculate_elo()
+    assert ratings["random"] == 0 and ratings["neta"] > 100 and ratings["netb"] > 100 and db.elos()["elo"] == ratings
