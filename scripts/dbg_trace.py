@@ -1,0 +1,29 @@
+"""Per-layer clock64 trace of CTA 0 of the tower kernel (needs a library built with -DSPX_DBG_TRACE; SPX_LIB_PATH=...)."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from self_play_reinforcement_learning_b200 import nets, _lib
+from self_play_reinforcement_learning_b200.envs import boards_to_bits
+torch.manual_seed(0)
+net = nets.ResidualTower(7, 6, 7, num_blocks=20).eval()
+rng = np.random.default_rng(0)
+boards = torch.from_numpy(rng.integers(-1, 2, size=(1024, 7, 6)).astype(np.int64))
+bits = boards_to_bits(boards.cuda(), 0)
+tw = nets.NativeTower(net)
+for _ in range(5):
+    tw.forward_bits(bits[:, 0].contiguous(), bits[:, 1].contiguous())
+torch.cuda.synchronize()
+buf = np.zeros(64 * 16, np.int64)
+_lib.lib().spx_debug_trace(C.c_void_p(buf.ctypes.data))
+t = buf.reshape(64, 16)
+names = ["mma:wait_epi", "mma:go", "mma:issued", "epi:wait_acc", "epi:acc_full", "epi:t0", "epi:t1", "epi:t2", "epi:tiles_done", "epi:bias_st", "epi:fenced", "epi:signalled"]
+t0 = t[2, 1]
+for l in range(2, 8):
+    print("layer", l, {n: int(t[l, i] - t0) for i, n in enumerate(names)})
+    t0 = t[l + 1, 1] if False else t0
+d = np.diff(t[2:40, 1])
+print("layer period (cycles): mean %.0f min %d max %d" % (d.mean(), d.min(), d.max()))
+print("issue time (go -> issued): %.0f" % (t[2:40, 2] - t[2:40, 1]).mean())
+print("issued -> acc_full seen by epi: %.0f" % (t[2:40, 4] - t[2:40, 2]).mean())
+print("epi acc_full -> t0/t1/t2/tiles_done/bias/fenced/signalled:", [(t[2:40, k] - t[2:40, 4]).mean().round() for k in range(5, 12)])
+print("epi signalled -> next mma go: %.0f" % (t[3:41, 1] - t[2:40, 11]).mean())

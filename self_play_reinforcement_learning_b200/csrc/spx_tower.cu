@@ -71,9 +71,6 @@ constexpr int NUM_THREADS = EPI_WARP0 * 32 + EPI_THREADS;
 static_assert(EPI_SPLIT == 4, "epilogue column split is written for 4 parts of 32 (trunk) / 16 (head) columns");
 constexpr int FLAT = 32 * CELLS;             // 1344 inputs of each head's first Linear
 constexpr int FC_HIDDEN = 256;
-#ifndef SPX_TOWER_WCOPIES_DEFAULT
-#define SPX_TOWER_WCOPIES_DEFAULT 1
-#endif
 
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -205,6 +202,14 @@ __device__ __forceinline__ int tap_shift(int tap) { return (tap / 3 - 1) * PAD_S
 //     multicast to both CTAs' barriers; the peer relays "my half has landed" and "my epilogue is done" with remote
 //     mbarrier arrives.
 //   NCTA == 1 (SPX_TOWER_NCTA=1, fallback): every CTA is on its own (cta_group::1, M=128, 3 x 8 KB ring).
+#ifdef SPX_DBG_TRACE
+__device__ long long g_trace[64 * 16];
+#define SPX_TRACE(l, k) do { if (blockIdx.x == 0 && (l) < 64) g_trace[(l) * 16 + (k)] = clock64(); } while (0)
+#define SPX_TRACE_IF(c, l, k) do { if (c) SPX_TRACE(l, k); __syncwarp(); } while (0)
+#else
+#define SPX_TRACE(l, k) do { } while (0)
+#define SPX_TRACE_IF(c, l, k) do { } while (0)
+#endif
 template <int NCTA> struct SmemT {
     static constexpr int STAGES = NCTA * NSTAGE;
     unsigned char act[2][ACT_BYTES];
@@ -294,12 +299,8 @@ template <int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long long* __restrict__ opp_g,
              const unsigned char* __restrict__ needs, long long n_boards, int n_layers,
-             const unsigned char* __restrict__ wconv_all, unsigned long long wcopy_stride, int wcopies,
-             const float* __restrict__ bias_all, float* __restrict__ head_out) {
+             const unsigned char* __restrict__ wconv, const float* __restrict__ bias_all, float* __restrict__ head_out) {
     typedef SmemT<NCTA> Smem;
-    // every cluster streams the same weight bytes at (almost) the same time; reading them from `wcopies` replicas spreads
-    // the hot lines over that many more L2 slices
-    const unsigned char* __restrict__ wconv = wconv_all + (size_t)((blockIdx.x / NCTA) % (unsigned)wcopies) * wcopy_stride;
     constexpr int STAGES = Smem::STAGES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -401,11 +402,14 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 const unsigned b_fields = b_lbo16 << 16;
                 const unsigned kstep16 = 2u * b_lbo16;                                 // one K step of B in 16-byte units
                 const unsigned a_lo_layer = A_DESC_FIELDS | ((smem_u32(S.act[li.in_buf]) + GUARD * 16) >> 4);
+                SPX_TRACE_IF(leader, l, 0);
                 mbar_wait(&S.epi_done, lphase);   // (both CTAs:) inputs of this layer written, accumulators drained
                 tc_fence_after();
+                SPX_TRACE_IF(leader, l, 1);
                 if (l == 0) issue_layer<NCTA, 1, 1>(S, li.taps, a_lo_layer, b_fields, kstep16, idesc, tmem_base, leader, stage, sphase);
                 else issue_layer<NCTA, 2, CH / 32>(S, li.taps, a_lo_layer, b_fields, kstep16, idesc, tmem_base, leader, stage, sphase);
                 if (leader) tc_commit_t<NCTA>(&S.acc_full);
+                SPX_TRACE_IF(leader, l, 2);
                 __syncwarp();
                 lphase ^= 1u;
             }
@@ -452,8 +456,10 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 const LayerInfo li = layer_info(l, n_layers);
                 // stage the bias of layer l+2 while this layer's MMAs are still running (layer l+1's is already visible)
                 if (l + 2 < n_layers && et < CH) S.bias[(l + 2) % 3][et] = __ldg(bias_all + (size_t)(l + 2) * CH + et);
+                SPX_TRACE_IF(et == 0, l, 3);
                 mbar_wait(&S.acc_full, lphase);
                 tc_fence_after();
+                SPX_TRACE_IF(et == 0, l, 4);
                 if (li.out_buf >= 0) {
                     // trunk layer: this warp owns 128/EPI_SPLIT = 32 columns of its 32 rows, for each of the 3 row tiles
                     const int ch0 = part * (CH / EPI_SPLIT);
@@ -463,6 +469,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
 #pragma unroll
                     for (int t = 0; t < MT; ++t) {
                         tc_wait_ld();
+                        SPX_TRACE_IF(et == 0, l, 5 + t);
                         if (t + 1 < MT) tc_ld32_nowait(tcol + (unsigned)((t + 1) * 128), v[(t + 1) & 1]);
 #ifdef SPX_DBG_SKIP_EPI
                         continue;
@@ -496,7 +503,9 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                             *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
                     }
+                    SPX_TRACE_IF(et == 0, l, 8);
                     if (l + 1 < n_layers) store_bias_to_tmem(tcol, S.bias[(l + 1) % 3] + ch0);
+                    SPX_TRACE_IF(et == 0, l, 9);
                 } else {
                     // fused policy/value 1x1 head conv + BN + ReLU (modules.py:97,102) -> fp32 [board][ch*42 + cell];
                     // 64 columns: each warp owns 64/EPI_SPLIT = 16 of them
@@ -516,8 +525,10 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 tc_fence_before();
                 fence_proxy_async();
                 lphase ^= 1u;
+                SPX_TRACE_IF(et == 0, l, 10);
                 if (l + 1 < n_layers) signal_epi_done();
                 else asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+                SPX_TRACE_IF(et == 0, l, 11);
             }
         }
         // non-elected lanes of warps 0-2 and warp 3 fall through; ring/phase state persists in the role warps
@@ -673,9 +684,6 @@ struct spx_tower {
     int game, num_blocks, n_layers, A, ncta;
     size_t off_bias, off_polw, off_polb, off_w1t, off_b1, off_w2, off_b2, blob_bytes;
     unsigned char* blob;    // device copy of the packed weights
-    unsigned char* wrep;    // `wcopies` replicas of the conv-weight part of the blob (L2 hot-spot spreading)
-    size_t conv_bytes, wcopy_stride;
-    int wcopies;
     float* head_buf;        // [capacity][64*42] fp32 head-conv activations
     long long capacity;
     int sm_count;
@@ -727,15 +735,7 @@ int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
     t->off_b2 = off; off = align_up(off + 16, 256);
     t->blob_bytes = off;
     SPX_CUDA_T(cudaMalloc((void**)&t->blob, t->blob_bytes));
-    {
-        const char* e = getenv("SPX_TOWER_WCOPIES");
-        t->wcopies = e ? atoi(e) : SPX_TOWER_WCOPIES_DEFAULT;
-        if (t->wcopies < 1) t->wcopies = 1;
-        if (t->wcopies > 16) t->wcopies = 16;
-        t->conv_bytes = conv;
-        t->wcopy_stride = align_up(conv, 4096);
-        SPX_CUDA_T(cudaMalloc((void**)&t->wrep, t->wcopy_stride * (size_t)t->wcopies));
-    }
+
     int dev = 0;
     SPX_CUDA_T(cudaGetDevice(&dev));
     SPX_CUDA_T(cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -752,7 +752,6 @@ int spx_tower_ncta(spx_tower* t) { return t ? t->ncta : 0; }
 int spx_tower_destroy(spx_tower* t) {
     if (!t) return 0;
     if (t->blob) cudaFree(t->blob);
-    if (t->wrep) cudaFree(t->wrep);
     if (t->head_buf) cudaFree(t->head_buf);
     delete t;
     return 0;
@@ -763,8 +762,6 @@ int spx_tower_load(spx_tower* t, const void* dev_blob, int64_t bytes, void* stre
     if (!t || !dev_blob) return spx::set_err(SPX_E_ARG, "spx_tower_load: null argument%s", "");
     if ((size_t)bytes != t->blob_bytes) return spx::set_err(SPX_E_ARG, "spx_tower_load: blob size mismatch%s", "");
     SPX_CUDA_T(cudaMemcpyAsync(t->blob, dev_blob, t->blob_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    for (int c = 0; c < t->wcopies; ++c)
-        SPX_CUDA_T(cudaMemcpyAsync(t->wrep + (size_t)c * t->wcopy_stride, dev_blob, t->conv_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
 }
 
@@ -792,13 +789,11 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         SPX_CUDA_T(cudaLaunchKernelEx(&cfg, tower_kernel<2>, (const unsigned long long*)own, (const unsigned long long*)opp, needs_eval,
-                                      (long long)n, t->n_layers, (const unsigned char*)t->wrep, (unsigned long long)t->wcopy_stride, t->wcopies,
-                                      (const float*)(t->blob + t->off_bias), t->head_buf));
+                                      (long long)n, t->n_layers, (const unsigned char*)t->blob, (const float*)(t->blob + t->off_bias), t->head_buf));
     } else {
         const int grid = (int)(groups < t->sm_count ? groups : t->sm_count);
         tower_kernel<1><<<grid, NUM_THREADS, sizeof(SmemT<1>), st>>>((const unsigned long long*)own, (const unsigned long long*)opp, needs_eval, n,
-                                                            t->n_layers, t->wrep, (unsigned long long)t->wcopy_stride, t->wcopies,
-                                                            (const float*)(t->blob + t->off_bias), t->head_buf);
+                                                            t->n_layers, t->blob, (const float*)(t->blob + t->off_bias), t->head_buf);
     }
     spx::count_launch();
     SPX_CUDA_T(cudaGetLastError());
@@ -812,6 +807,10 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
     if (e2) SPX_CUDA_T(cudaEventRecord(e2, st));
     return 0;
 }
+
+#ifdef SPX_DBG_TRACE
+int spx_debug_trace(long long* host_out) { return (int)cudaMemcpyFromSymbol(host_out, spx::tower::g_trace, sizeof(long long) * 64 * 16); }
+#endif
 
 int spx_tower_forward(spx_tower* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n,
                       float* policy, float* value, void* stream) {
