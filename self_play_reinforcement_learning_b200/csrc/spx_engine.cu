@@ -168,6 +168,9 @@ __device__ double gamma_variate(u64 prefix, int action, double alpha) {
 #undef SPX_U
 }
 
+#ifndef SPX_PREFETCH
+#define SPX_PREFETCH "prefetch.global.L2"
+#endif
 template <int GAME> struct Ctx {
     typedef Rules<GAME> R;
     typedef NodeLayout<GAME> L;
@@ -439,40 +442,48 @@ __global__ void __launch_bounds__(128) advance_kernel(EngineDev E, const float* 
             for (;;) {
                 const char* nd = c.node(node);
                 double score = -INFINITY;
-                int ch = 0;
+                int ch = 0, n = 0;
+                double w = 0.0;
+                float p = 0.f;
+                unsigned meta = 0;
                 if (lane < A) {
-                    const double w = ((const double*)(nd + L::OFF_W))[lane];
-                    const int n = ((const int*)(nd + L::OFF_N))[lane];
-                    const float p = ((const float*)(nd + L::OFF_P))[lane];
+                    w = ((const double*)(nd + L::OFF_W))[lane];
+                    n = ((const int*)(nd + L::OFF_N))[lane];
+                    p = ((const float*)(nd + L::OFF_P))[lane];
                     ch = ((const int*)(nd + L::OFF_CHILD))[lane];
-                    const unsigned meta = *(const unsigned*)(nd + L::OFF_META);
-                    if (ch >= 0) {   // pull every expanded child towards L2 while the scores are computed (the next level is one of them)
+                    meta = *(const unsigned*)(nd + L::OFF_META);
+                }
+                // everything that does not depend on this node's statistics is computed while its loads are in flight:
+                // sqrt(N + 1) (N came with the parent edge) and the tie-break noise of this (sim, depth, lane)
+                const double sqrt_n = __dsqrt_rn((double)(N + 1));
+                const double tie = cfg.tie_mode ? __dmul_rn(0.000001, rng_uniform_from(tie_pre, (unsigned)s.sims_done, (unsigned)depth, (u64)lane)) : 0.0;
+                if (lane < A) {
+                    if (ch >= 0) {   // pull every expanded child towards the SM while the scores are computed (the next level is one of them)
                         const char* cn = c.node(ch);
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(cn));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(cn + 128));
+                        asm volatile(SPX_PREFETCH " [%0];" ::"l"(cn));
+                        asm volatile(SPX_PREFETCH " [%0];" ::"l"(cn + 128));
                     }
                     if ((meta >> lane) & 1u) {
                         const double q = n ? __ddiv_rn(w, (double)n) : 0.0;                               // :59-62 (vl = 0)
                         double p_eff = (double)p;
                         if (depth == 0) p_eff = __dadd_rn(__dmul_rn(my_noise, 0.25), __dmul_rn((double)p, 0.75));  // :64-69
-                        const double u = __ddiv_rn(__dmul_rn(__dmul_rn(4.0, p_eff), __dsqrt_rn((double)(N + 1))),
-                                                   (double)(1 + n));                                     // :71-78
+                        const double u = __ddiv_rn(__dmul_rn(__dmul_rn(4.0, p_eff), sqrt_n), (double)(1 + n));   // :71-78
                         score = __dadd_rn(__dmul_rn((double)player, q), u);                               // :80-84
                     } else score = -10000000000.0;                                                        // :346-348
-                    if (cfg.tie_mode) score = __dadd_rn(score, __dmul_rn(0.000001, rng_uniform_from(tie_pre, (unsigned)s.sims_done, (unsigned)depth, (u64)lane)));
+                    if (cfg.tie_mode) score = __dadd_rn(score, tie);
                 }
-                // np.argmax: first maximum wins
+                // np.argmax: first maximum wins (A <= 8: three butterfly rounds over 8 lanes suffice)
                 int best = lane;
                 double bs = score;
 #pragma unroll
-                for (int off = 8; off > 0; off >>= 1) {
+                for (int off = (A <= 8 ? 4 : 8); off > 0; off >>= 1) {
                     double os = __shfl_xor_sync(0xffffffffu, bs, off);
                     int ob = __shfl_xor_sync(0xffffffffu, best, off);
                     if (os > bs || (os == bs && ob < best)) { bs = os; best = ob; }
                 }
                 best = __shfl_sync(0xffffffffu, best, 0);
                 child = __shfl_sync(0xffffffffu, ch, best);
-                const int n_edge = __shfl_sync(0xffffffffu, lane < A ? ((const int*)(nd + L::OFF_N))[lane] : 0, best);
+                const int n_edge = __shfl_sync(0xffffffffu, n, best);
                 const unsigned entry = ((unsigned)node << 4) | (unsigned)best;
                 if (lane == (depth & 31)) { if (depth < 32) p0 = entry; else p1 = entry; }
                 depth += 1;
