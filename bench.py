@@ -336,12 +336,14 @@ def main():
         env_roof = _env_roofline(_lib, torch)
     if rank == 0:
         peaks = _peaks()
-        fl = flop_per_leaf(args.blocks, conv_only=True)   # the tower kernel computes the convolutions; the FC heads are heads_kernel
+        tw = getattr(ev, "tower", None)
+        fused = bool(getattr(tw, "fused_heads", False))
+        fl = flop_per_leaf(args.blocks, conv_only=not fused)   # with fused heads the tower kernel is the whole network
         roof = None
         if tower_ms:
             leaves_per_launch = evals / max(ticks, 1)
             achieved = leaves_per_launch * fl / (tower_ms / 1e3) / 1e12
-            roof = {"bound": "tensor", "kernel": "spx::tower::tower_kernel<2> (tcgen05 cta_group::2, SM pair)" if getattr(getattr(ev, "tower", None), "ncta", 2) == 2 else "spx::tower::tower_kernel<1>", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
+            roof = {"bound": "tensor", "kernel": ("spx::tower::tower_kernel<2> (tcgen05 cta_group::2, SM pair" + (", fused FC heads)" if fused else ")")) if getattr(tw, "ncta", 2) == 2 else "spx::tower::tower_kernel<1>", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
                     "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": _ncu_traffic(),
                     "peak_source": peaks["source"], "flop_per_leaf": fl, "leaves_per_launch": leaves_per_launch,
                     "kernel_ms": tower_ms, "heads_kernel_ms": heads_ms, "advance_kernel_ms": adv_ms,

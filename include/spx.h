@@ -201,6 +201,9 @@ int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out);
 int spx_tower_destroy(spx_tower* t);
 /* weight-slice layout the handle expects: 1 = single-CTA kernel, 2 = SM-pair kernel (tcgen05 cta_group::2, default) */
 int spx_tower_ncta(spx_tower* t);
+/* 1 when the fully connected heads (policy Linear + softmax, value Linear-ReLU-Linear-tanh, modules.py:99-105) run inside the
+ * tower kernel (default for the SM-pair kernel; SPX_TOWER_FUSED_HEADS=0 selects the separate heads kernel) */
+int spx_tower_fused_heads(spx_tower* t);
 int spx_tower_load(spx_tower* t, const void* dev_blob, int64_t bytes, void* stream);
 /* own/opp: dev u64[n] bitboards in the NET frame; needs_eval: dev u8[n] or NULL (all); policy dev f32[n,A]
  * (softmax), value dev f32[n] (tanh).  Rows whose needs_eval is 0 may be left untouched. */

@@ -27,3 +27,8 @@ print("issue time (go -> issued): %.0f" % (t[2:40, 2] - t[2:40, 1]).mean())
 print("issued -> acc_full seen by epi: %.0f" % (t[2:40, 4] - t[2:40, 2]).mean())
 print("epi acc_full -> t0/t1/t2/tiles_done/bias/fenced/signalled:", [(t[2:40, k] - t[2:40, 4]).mean().round() for k in range(5, 12)])
 print("epi signalled -> next mma go: %.0f" % (t[3:41, 1] - t[2:40, 11]).mean())
+L = 42
+print("head layer:", {n: int(t[L - 1, i] - t[L - 1, 1]) for i, n in enumerate(names)})
+print("FC phase (offsets from the head layer's mma:go):", dict(mma_wait=int(t[L, 0] - t[L - 1, 1]), mma_go=int(t[L, 1] - t[L - 1, 1]), mma_issued=int(t[L, 2] - t[L - 1, 1]),
+      policy_start=int(t[L, 3] - t[L - 1, 1]), policy_done=int(t[L, 4] - t[L - 1, 1]), fc_done_seen=int(t[L, 5] - t[L - 1, 1]), value_partial_done=int(t[L, 6] - t[L - 1, 1])))
+print("whole kernel (layer 0 go -> value partial done): %d cycles" % int(t[L, 6] - t[0, 1]))

@@ -71,6 +71,20 @@ constexpr int NUM_THREADS = EPI_WARP0 * 32 + EPI_THREADS;
 static_assert(EPI_SPLIT == 4, "epilogue column split is written for 4 parts of 32 (trunk) / 16 (head) columns");
 constexpr int FLAT = 32 * CELLS;             // 1344 inputs of each head's first Linear
 constexpr int FC_HIDDEN = 256;
+constexpr int FC_KSTEPS = FLAT / 16;                                   // 84 K steps of the value layer Linear(1344 -> 256)
+constexpr int FC_KSTEP_BYTES = 2 * (FC_HIDDEN / 2) * 16;               // per CTA half: [2 k-chunks][128 hidden][8] bf16 = 4 KB
+constexpr size_t FC_STREAM_BYTES = (size_t)FC_KSTEPS * 2 * FC_KSTEP_BYTES;   // fused value layer, appended to the conv stream
+// fused FC heads (SM-pair kernel): after the last trunk layer activation buffer 0 is dead and becomes a 12 x 8 KB weight
+// ring for the value layer; after the head conv buffer 1 is dead and holds the head activations
+constexpr int FC_STAGE_BYTES = 2 * FC_KSTEP_BYTES;                     // two K steps per stage (per CTA)
+constexpr int FC_STAGES = 12;
+constexpr int FC_ITERS = FC_KSTEPS / 2;                                // 42 ring stages
+constexpr int XV_OFF = 0;                                              // value activations, bf16 [168 k-chunks][8 boards][8]
+constexpr int XV_BYTES = (FLAT / 8) * 128;
+constexpr int XP_OFF = 24576;                                          // policy activations, fp32 [7 boards][1344]
+constexpr int XP_BYTES = NB * FLAT * 4;
+constexpr int FCS_OFF = 65536;                                         // fp32 scratch: logits [7][8], partial [4][16], own [16], peer [16]
+static_assert(FC_STAGES * FC_STAGE_BYTES <= ACT_BYTES && XV_OFF + XV_BYTES <= XP_OFF && XP_OFF + XP_BYTES <= FCS_OFF && FCS_OFF + 1024 <= ACT_BYTES, "fused-heads buffers");
 
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -215,6 +229,7 @@ template <int NCTA> struct SmemT {
     unsigned char act[2][ACT_BYTES];
     unsigned char wstage[STAGES][STAGE_BYTES / NCTA];
     unsigned long long full[STAGES], empty[STAGES], peer_full[STAGES], acc_full, epi_done;
+    unsigned long long fc_full[FC_STAGES], fc_empty[FC_STAGES], fc_peer_full[FC_STAGES], fc_done;   // fused FC heads
     unsigned long long own[NB], opp[NB];
     alignas(16) float bias[3][CH];   // read as float4
     unsigned tmem_base;
@@ -259,6 +274,15 @@ template <int NCTA> __device__ __forceinline__ void tc_mma_lo(unsigned d_tmem, u
                      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc) : "memory");
 }
 
+// cta_group::2 MMA with a run-time accumulate flag (the value layer starts its accumulators from zero)
+__device__ __forceinline__ void tc_mma_lo_acc2(unsigned d_tmem, unsigned a_lo, unsigned b_lo, unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void st_shared_remote_f32(void* local_addr, unsigned cta, float v) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tst.shared::cluster.f32 [ra], %2;\n\t}" ::"r"(smem_u32(local_addr)), "r"(cta), "f"(v) : "memory");
+}
+
 // All MMAs of one conv layer: taps x KPAIRS ring stages of KSTEPS K-steps x 3 row tiles.
 template <int NCTA, int KSTEPS, int KPAIRS>
 __device__ __forceinline__ void issue_layer(SmemT<NCTA>& S, int taps, unsigned a_lo_layer, unsigned b_fields, unsigned kstep16, unsigned idesc,
@@ -299,8 +323,11 @@ template <int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long long* __restrict__ opp_g,
              const unsigned char* __restrict__ needs, long long n_boards, int n_layers,
-             const unsigned char* __restrict__ wconv, const float* __restrict__ bias_all, float* __restrict__ head_out) {
+             const unsigned char* __restrict__ wconv, const float* __restrict__ bias_all, float* __restrict__ head_out,
+             int fused_in, const float* __restrict__ polw, const float* __restrict__ polb, const float* __restrict__ fc_b1,
+             const float* __restrict__ fc_w2, const float* __restrict__ fc_b2, float* __restrict__ policy_out, float* __restrict__ value_out) {
     typedef SmemT<NCTA> Smem;
+    const bool fused = NCTA == 2 && fused_in != 0;   // FC heads inside this kernel (no head_out round trip, no second launch)
     constexpr int STAGES = Smem::STAGES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -312,6 +339,8 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
         for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); mbar_init(&S.peer_full[s], 1); }
         mbar_init(&S.acc_full, 1);
         mbar_init(&S.epi_done, EPI_THREADS + (NCTA - 1));   // local epilogue threads (+ one remote arrive from the peer CTA)
+        for (int s = 0; s < FC_STAGES; ++s) { mbar_init(&S.fc_full[s], 1); mbar_init(&S.fc_empty[s], 1); mbar_init(&S.fc_peer_full[s], 1); }
+        mbar_init(&S.fc_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -333,7 +362,11 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
     const unsigned tmem_base = S.tmem_base;
 
     unsigned stage = 0, sphase = 0;   // weight ring position (producer, relay and MMA issuer walk the same sequence)
-    unsigned lphase = 0;              // per-layer barrier parity (acc_full / epi_done)
+    unsigned lphase = 0;              // per-layer parity of acc_full (n_layers, an even number, of completions per unit)
+    unsigned ephase = 0;              // parity of epi_done (one more completion per unit when the FC heads are fused)
+    unsigned fstage = 0, fphase = 0;  // FC weight ring position
+    unsigned dphase = 0;              // fc_done parity (one completion per unit)
+    bool first_unit = true;
 
     const long long n_units = (n_groups + NCTA - 1) / NCTA;      // a unit = the NCTA board groups one cluster works on together
     for (long long unit = blockIdx.x / NCTA; unit < n_units; unit += gridDim.x / NCTA) {
@@ -372,6 +405,22 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                     if (++stage == STAGES) { stage = 0; sphase ^= 1u; }
                 }
             }
+            if (fused) {
+                // value-layer weights into the dead activation buffer 0: its last readers are the MMAs of the last trunk layer
+                // (layer n_layers-2, an even index: n_layers is even, so that completion of acc_full always has parity 0; this
+                // warp is at most a ring (6 stages) ahead of the issuer, so the barrier cannot be a whole phase behind)
+                mbar_wait(&S.acc_full, 0u);
+                for (int it = 0; it < FC_ITERS; ++it) {
+                    mbar_wait(&S.fc_empty[fstage], fphase ^ 1u);
+                    if (leader) {
+                        mbar_expect_tx(&S.fc_full[fstage], FC_STAGE_BYTES);
+                        tma_bulk_g2s(S.act[0] + fstage * FC_STAGE_BYTES, wp + (size_t)crank * FC_STAGE_BYTES, FC_STAGE_BYTES, &S.fc_full[fstage]);
+                    }
+                    __syncwarp();
+                    wp += 2 * FC_STAGE_BYTES;
+                    if (++fstage == FC_STAGES) { fstage = 0; fphase ^= 1u; }
+                }
+            }
         } else if (NCTA == 2 && warp == 2 && crank == 1) {
             // ===================== peer relay: tell the leader when this CTA's half of each weight stage has landed
             const bool leader = elect_one();
@@ -389,6 +438,14 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                     if (++stage == STAGES) { stage = 0; sphase ^= 1u; }
                 }
             }
+            if (fused) {
+                for (int it = 0; it < FC_ITERS; ++it) {
+                    mbar_wait(&S.fc_full[fstage], fphase);
+                    if (leader) mbar_arrive_remote(&S.fc_peer_full[fstage], 0);
+                    __syncwarp();
+                    if (++fstage == FC_STAGES) { fstage = 0; fphase ^= 1u; }
+                }
+            }
         } else if (warp == 1 && crank == 0) {
             // ===================== MMA issuer (leader CTA): warp-uniform loop, one elected lane issues tcgen05.mma / commit.
             // This single instruction stream paces the whole kernel (6 MMAs of 64 cycles per ring stage), so descriptors
@@ -403,7 +460,8 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 const unsigned kstep16 = 2u * b_lbo16;                                 // one K step of B in 16-byte units
                 const unsigned a_lo_layer = A_DESC_FIELDS | ((smem_u32(S.act[li.in_buf]) + GUARD * 16) >> 4);
                 SPX_TRACE_IF(leader, l, 0);
-                mbar_wait(&S.epi_done, lphase);   // (both CTAs:) inputs of this layer written, accumulators drained
+                mbar_wait(&S.epi_done, ephase);   // (both CTAs:) inputs of this layer written, accumulators drained
+                ephase ^= 1u;
                 tc_fence_after();
                 SPX_TRACE_IF(leader, l, 1);
                 if (l == 0) issue_layer<NCTA, 1, 1>(S, li.taps, a_lo_layer, b_fields, kstep16, idesc, tmem_base, leader, stage, sphase);
@@ -411,7 +469,39 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 if (leader) tc_commit_t<NCTA>(&S.acc_full);
                 SPX_TRACE_IF(leader, l, 2);
                 __syncwarp();
-                lphase ^= 1u;
+            }
+            if constexpr (NCTA == 2) {
+                if (fused) {
+                    // value layer Linear(1344 -> 256) (modules.py:104): D[hidden (128 per CTA) x 16 boards (8 per CTA)] += W1 * x^T,
+                    // M=256, N=16, 84 K steps; A = weight stage (ring in buffer 0), B = the head activations (buffer 1).
+                    // Four accumulators (K step mod 4, columns 0/16/32/48) keep consecutive MMAs independent.
+                    SPX_TRACE_IF(leader, n_layers, 0);
+                    mbar_wait(&S.epi_done, ephase);   // head activations of both CTAs in place, head-conv accumulators drained
+                    ephase ^= 1u;
+                    tc_fence_after();
+                    SPX_TRACE_IF(leader, n_layers, 1);
+                    const unsigned idesc_fc = make_idesc(256, 16);
+                    const unsigned xv_lo = ((128u >> 4) << 16) | (smem_u32(S.act[1] + XV_OFF) >> 4);
+                    for (int it = 0; it < FC_ITERS; ++it) {
+                        mbar_wait(&S.fc_full[fstage], fphase);
+                        mbar_wait(&S.fc_peer_full[fstage], fphase);
+                        const unsigned a_lo = ((unsigned)(FC_KSTEP_BYTES / 2 >> 4) << 16) | (smem_u32(S.act[0] + fstage * FC_STAGE_BYTES) >> 4);
+                        if (leader) {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const int ks = 2 * it + j;
+                                tc_mma_lo_acc2(tmem_base + (unsigned)(16 * (ks & 3)), a_lo + (unsigned)(j * (FC_KSTEP_BYTES >> 4)),
+                                               xv_lo + (unsigned)(ks * (256 >> 4)), idesc_fc, ks >= 4 ? 1u : 0u);
+                            }
+                            tc_commit_t<NCTA>(&S.fc_empty[fstage]);
+                        }
+                        __syncwarp();
+                        if (++fstage == FC_STAGES) { fstage = 0; fphase ^= 1u; }
+                    }
+                    if (leader) tc_commit_t<NCTA>(&S.fc_done);
+                    SPX_TRACE_IF(leader, n_layers, 2);
+                    __syncwarp();
+                }
             }
         } else if (warp >= EPI_WARP0) {
             // ===================== epilogue warps (also write the stem input)
@@ -424,6 +514,13 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));   // also publishes the next layer's staged bias
                 if (NCTA == 2 && crank == 1 && et == 0) mbar_arrive_remote(&S.epi_done, 0);
             };
+            if (fused && !first_unit) {
+                // the previous unit's FC ring / head activations overwrote the buffers: the zero guard rows (never written by
+                // an epilogue) must read as zero again; every other row is rewritten before it is read
+                const int buf = et >> 8, chunk = (et >> 4) & 15, gr = et & 15;   // 2 buffers x 16 chunks x 16 guard rows = 512 threads
+                const int row = gr < GUARD ? gr : ROWS + gr;
+                *reinterpret_cast<uint4*>(S.act[buf] + chunk * CHUNK_BYTES + row * 16) = make_uint4(0, 0, 0, 0);
+            }
             if (et < NB) {
                 const long long gb = grp * NB + et;
                 S.own[et] = gb < n_boards ? own_g[gb] : 0ULL;
@@ -507,33 +604,123 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                     if (l + 1 < n_layers) store_bias_to_tmem(tcol, S.bias[(l + 1) % 3] + ch0);
                     SPX_TRACE_IF(et == 0, l, 9);
                 } else {
-                    // fused policy/value 1x1 head conv + BN + ReLU (modules.py:97,102) -> fp32 [board][ch*42 + cell];
-                    // 64 columns: each warp owns 64/EPI_SPLIT = 16 of them
+                    // fused policy/value 1x1 head conv + BN + ReLU (modules.py:97,102); 64 columns: each warp owns 64/EPI_SPLIT = 16.
+                    // Separate heads kernel: fp32 [board][ch*42 + cell] to global memory.  Fused FC heads: policy channels as fp32
+                    // [board][k] and value channels as bf16 in the K-major core-matrix layout [k-chunk][8 boards][8] (board 7 =
+                    // zero padding) in the dead activation buffer 1, k = channel*42 + cell (the flatten order of modules.py:98,103).
                     const int ch0 = part * (HEAD_CH / EPI_SPLIT);
+                    if (fused && et < FLAT / 8) *reinterpret_cast<uint4*>(S.act[1] + XV_OFF + et * 128 + 7 * 16) = make_uint4(0, 0, 0, 0);
 #pragma unroll
                     for (int t = 0; t < MT; ++t) {
                         unsigned v[16];
                         tc_ld16(tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(t * 128 + ch0), v);
                         const long long gb = grp * NB + board_t[t];
-                        if (real_t[t] && gb < n_boards) {
-                            float* ob = head_out + (size_t)gb * (HEAD_CH * CELLS) + cell_t[t];
+                        if (!fused) {
+                            if (real_t[t] && gb < n_boards) {
+                                float* ob = head_out + (size_t)gb * (HEAD_CH * CELLS) + cell_t[t];
 #pragma unroll
-                            for (int k = 0; k < 16; ++k) ob[(size_t)(ch0 + k) * CELLS] = fmaxf(__uint_as_float(v[k]), 0.f);
+                                for (int k = 0; k < 16; ++k) ob[(size_t)(ch0 + k) * CELLS] = fmaxf(__uint_as_float(v[k]), 0.f);
+                            }
+                        } else if (real_t[t]) {
+                            if (ch0 < 32) {
+                                float* xp = reinterpret_cast<float*>(S.act[1] + XP_OFF) + board_t[t] * FLAT + cell_t[t];
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) xp[(ch0 + k) * CELLS] = fmaxf(__uint_as_float(v[k]), 0.f);
+                            } else {
+                                unsigned char* xv = S.act[1] + XV_OFF + board_t[t] * 16;
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) {
+                                    const int kk = (ch0 - 32 + k) * CELLS + cell_t[t];
+                                    *reinterpret_cast<__nv_bfloat16*>(xv + (kk >> 3) * 128 + (kk & 7) * 2) = __float2bfloat16_rn(fmaxf(__uint_as_float(v[k]), 0.f));
+                                }
+                            }
                         }
+                        __syncwarp();
                     }
                 }
                 tc_fence_before();
                 fence_proxy_async();
                 lphase ^= 1u;
                 SPX_TRACE_IF(et == 0, l, 10);
-                if (l + 1 < n_layers) signal_epi_done();
+                if (l + 1 < n_layers || fused) signal_epi_done();
                 else asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
                 SPX_TRACE_IF(et == 0, l, 11);
             }
+            if constexpr (NCTA == 2) {
+                if (fused) {
+                    float* scr = reinterpret_cast<float*>(S.act[1] + FCS_OFF);   // logits [7][8] | partial [4][16] | own [16] | peer [16]
+                    // ---- policy head Linear(1344 -> A) + softmax (modules.py:99-100) in fp32 on the CUDA cores, while the tensor
+                    // pipe runs the value layer: one warp per (board, action) dot product
+                    const float* xp = reinterpret_cast<const float*>(S.act[1] + XP_OFF);
+                    SPX_TRACE_IF(et == 0, n_layers, 3);
+                    for (int task = warp - EPI_WARP0; task < NB * 7; task += EPI_WARPS) {
+                        const int b = task / 7, a = task - b * 7;
+                        float acc = 0.f;
+                        for (int k = lane; k < FLAT; k += 32) acc = fmaf(xp[b * FLAT + k], __ldg(polw + a * FLAT + k), acc);
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                        if (lane == 0) scr[b * 8 + a] = acc + __ldg(polb + a);
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+                    if (et < NB) {
+                        const long long gb = grp * NB + et;
+                        if (gb < n_boards && (needs == nullptr || needs[gb])) {
+                            float m = scr[et * 8];
+                            for (int a = 1; a < 7; ++a) m = fmaxf(m, scr[et * 8 + a]);
+                            float e[7], z = 0.f;
+                            for (int a = 0; a < 7; ++a) { e[a] = expf(scr[et * 8 + a] - m); z += e[a]; }
+                            for (int a = 0; a < 7; ++a) policy_out[gb * 7 + a] = e[a] / z;
+                        }
+                    }
+                    // ---- value head: relu(W1 x + b1) . w2 (+ b2, tanh after the two halves of the hidden layer met)
+                    SPX_TRACE_IF(et == 0, n_layers, 4);
+                    mbar_wait(&S.fc_done, dphase);
+                    dphase ^= 1u;
+                    tc_fence_after();
+                    SPX_TRACE_IF(et == 0, n_layers, 5);
+                    if (part == 0) {
+                        const unsigned tl = tmem_base + ((unsigned)(quarter * 32) << 16);
+                        unsigned v0[16], v1[16], v2[16], v3[16];
+                        tc_ld16(tl, v0); tc_ld16(tl + 16, v1); tc_ld16(tl + 32, v2); tc_ld16(tl + 48, v3);
+                        const int j = (int)crank * 128 + quarter * 32 + lane;      // hidden unit of this TMEM lane
+                        const float b1 = __ldg(fc_b1 + j), w2 = __ldg(fc_w2 + j);
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const float h = (__uint_as_float(v0[c]) + __uint_as_float(v1[c])) + (__uint_as_float(v2[c]) + __uint_as_float(v3[c])) + b1;
+                            float y = fmaxf(h, 0.f) * w2;
+#pragma unroll
+                            for (int off = 16; off > 0; off >>= 1) y += __shfl_xor_sync(0xffffffffu, y, off);
+                            if (lane == 0) scr[64 + quarter * 16 + c] = y;
+                        }
+                    }
+                    tc_fence_before();
+                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+                    if (et < 16) {   // column c: boards 0..7 of CTA 0, 8..15 of CTA 1; both CTAs need both halves of the hidden layer
+                        const float tot = (scr[64 + et] + scr[64 + 16 + et]) + (scr[64 + 32 + et] + scr[64 + 48 + et]);
+                        scr[128 + et] = tot;
+                        st_shared_remote_f32(&scr[144 + et], crank ^ 1u, tot);
+                    }
+                    SPX_TRACE_IF(et == 0, n_layers, 6);
+                }
+            } else {
+                (void)dphase;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
         }
         // non-elected lanes of warps 0-2 and warp 3 fall through; ring/phase state persists in the role warps
         __syncthreads();   // unit boundary: accumulators drained, buffers reusable
-        if constexpr (NCTA == 2) cluster_sync_all();
+        if constexpr (NCTA == 2) {
+            cluster_sync_all();
+            if (fused && warp == EPI_WARP0 && lane < NB) {   // both halves of the hidden layer are in: Linear(256 -> 1) + tanh (modules.py:105)
+                const float* scr = reinterpret_cast<const float*>(S.act[1] + FCS_OFF);
+                const long long gb = grp * NB + lane;
+                const int c = (int)crank * 8 + lane;
+                const float lo = crank == 0 ? scr[128 + c] : scr[144 + c], hi = crank == 0 ? scr[144 + c] : scr[128 + c];   // hidden 0..127, 128..255
+                if (gb < n_boards && (needs == nullptr || needs[gb])) value_out[gb] = tanhf((lo + hi) + __ldg(fc_b2));
+            }
+            if (fused) cluster_sync_all();   // the scratch may be overwritten by the peer in the next unit only after it was read
+        }
+        first_unit = false;
     }
 
     tc_fence_before();
@@ -681,7 +868,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ he
 
 // ================================================================================================== C ABI
 struct spx_tower {
-    int game, num_blocks, n_layers, A, ncta;
+    int game, num_blocks, n_layers, A, ncta, fused;
     size_t off_bias, off_polw, off_polb, off_w1t, off_b1, off_w2, off_b2, blob_bytes;
     unsigned char* blob;    // device copy of the packed weights
     float* head_buf;        // [capacity][64*42] fp32 head-conv activations
@@ -698,7 +885,7 @@ extern "C" {
 int64_t spx_tower_blob_bytes(int32_t game, int32_t num_blocks) {
     if (game != SPX_GAME_CONNECT4 || num_blocks < 0) return -1;
     const int A = 7, n_layers = 2 * num_blocks + 2;
-    size_t conv = (size_t)9 * 1 * KSTEP_BYTES + (size_t)num_blocks * 2 * 9 * 8 * KSTEP_BYTES + (size_t)8 * (2 * HEAD_CH * 16);
+    size_t conv = (size_t)9 * 1 * KSTEP_BYTES + (size_t)num_blocks * 2 * 9 * 8 * KSTEP_BYTES + (size_t)8 * (2 * HEAD_CH * 16) + FC_STREAM_BYTES;
     size_t off = align_up(conv, 256);
     off = align_up(off + (size_t)n_layers * CH * 4, 256);      // biases
     off = align_up(off + (size_t)A * FLAT * 4, 256);           // policy weight
@@ -723,8 +910,10 @@ int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
     {
         const char* e = getenv("SPX_TOWER_NCTA");   // 2 (default): SM-pair kernel (cta_group::2); 1: single-CTA kernel
         t->ncta = (e && e[0] == '1') ? 1 : 2;
+        const char* f = getenv("SPX_TOWER_FUSED_HEADS");   // 1 (default, SM-pair kernel only): FC heads inside the tower kernel; 0: separate heads kernel
+        t->fused = (t->ncta == 2 && !(f && f[0] == '0')) ? 1 : 0;
     }
-    size_t conv = (size_t)9 * KSTEP_BYTES + (size_t)num_blocks * 2 * 72 * KSTEP_BYTES + (size_t)8 * (2 * HEAD_CH * 16);
+    size_t conv = (size_t)9 * KSTEP_BYTES + (size_t)num_blocks * 2 * 72 * KSTEP_BYTES + (size_t)8 * (2 * HEAD_CH * 16) + FC_STREAM_BYTES;
     size_t off = align_up(conv, 256);
     t->off_bias = off; off = align_up(off + (size_t)t->n_layers * CH * 4, 256);
     t->off_polw = off; off = align_up(off + (size_t)t->A * FLAT * 4, 256);
@@ -748,6 +937,8 @@ int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
 
 /* 1 or 2: which weight-slice layout spx_tower_load expects (2 = output channels split across the SM pair) */
 int spx_tower_ncta(spx_tower* t) { return t ? t->ncta : 0; }
+/* 1 when the fully connected heads run inside the tower kernel (SM-pair kernel, default), 0 when heads_kernel follows it */
+int spx_tower_fused_heads(spx_tower* t) { return t ? t->fused : 0; }
 
 int spx_tower_destroy(spx_tower* t) {
     if (!t) return 0;
@@ -769,7 +960,7 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
                               float* policy, float* value, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2) {
     if (!t || !own || !opp || !policy || !value) return spx::set_err(SPX_E_ARG, "spx_tower_forward: null argument%s", "");
     if (n <= 0) return 0;
-    if (n > t->capacity) {
+    if (!t->fused && n > t->capacity) {   // the fused-heads kernel keeps the head activations in shared memory
         if (t->head_buf) { SPX_CUDA_T(cudaStreamSynchronize(st)); SPX_CUDA_T(cudaFree(t->head_buf)); t->head_buf = nullptr; }
         SPX_CUDA_T(cudaMalloc((void**)&t->head_buf, (size_t)n * HEAD_CH * CELLS * sizeof(float)));
         t->capacity = n;
@@ -789,15 +980,22 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         SPX_CUDA_T(cudaLaunchKernelEx(&cfg, tower_kernel<2>, (const unsigned long long*)own, (const unsigned long long*)opp, needs_eval,
-                                      (long long)n, t->n_layers, (const unsigned char*)t->blob, (const float*)(t->blob + t->off_bias), t->head_buf));
+                                      (long long)n, t->n_layers, (const unsigned char*)t->blob, (const float*)(t->blob + t->off_bias), t->head_buf,
+                                      t->fused, (const float*)(t->blob + t->off_polw), (const float*)(t->blob + t->off_polb), (const float*)(t->blob + t->off_b1),
+                                      (const float*)(t->blob + t->off_w2), (const float*)(t->blob + t->off_b2), policy, value));
     } else {
         const int grid = (int)(groups < t->sm_count ? groups : t->sm_count);
         tower_kernel<1><<<grid, NUM_THREADS, sizeof(SmemT<1>), st>>>((const unsigned long long*)own, (const unsigned long long*)opp, needs_eval, n,
-                                                            t->n_layers, t->blob, (const float*)(t->blob + t->off_bias), t->head_buf);
+                                                            t->n_layers, t->blob, (const float*)(t->blob + t->off_bias), t->head_buf,
+                                                            0, nullptr, nullptr, nullptr, nullptr, nullptr, policy, value);
     }
     spx::count_launch();
     SPX_CUDA_T(cudaGetLastError());
     if (e1) SPX_CUDA_T(cudaEventRecord(e1, st));
+    if (t->fused) {   // the FC heads ran inside the tower kernel
+        if (e2) SPX_CUDA_T(cudaEventRecord(e2, st));
+        return 0;
+    }
     heads_kernel<<<dim3((unsigned)((n + HB - 1) / HB), 2), 256, HEADS_SMEM, st>>>(
         t->head_buf, needs_eval, n, t->A, (const float*)(t->blob + t->off_polw), (const float*)(t->blob + t->off_polb),
         (const __nv_bfloat16*)(t->blob + t->off_w1t), (const float*)(t->blob + t->off_b1), (const float*)(t->blob + t->off_w2),

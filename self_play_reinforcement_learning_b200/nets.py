@@ -230,6 +230,15 @@ def _stage_blocks(w, ncta=1):
     return x.to(torch.bfloat16).reshape(-1)
 
 
+def _fc_stream(w1):
+    """fc_value.weight [256 hidden, 1344] -> the weight-ring stream of the fused value layer (SM-pair kernel): the hidden
+    units are the M rows of the MMA (128 per CTA), so every K step of 16 inputs is stored per CTA half as
+    [2 k-chunks][128 hidden][8] bf16 = 4 KB; a ring stage carries two K steps: [stage][half][2 K steps][4 KB]."""
+    HID, K = w1.shape
+    x = w1.detach().float().cpu().reshape(2, HID // 2, K // 32, 2, 2, 8)    # [half, n, stage, j, kc, e]
+    return x.permute(2, 0, 3, 4, 1, 5).contiguous().to(torch.bfloat16).reshape(-1)   # [stage, half, j, kc, n, e]
+
+
 def pack_tower_blob(module, ncta=2):
     """ResidualTower (7x6, 128 trunk channels) -> one flat uint8 tensor in the layout spx_tower_load expects."""
     m = module
@@ -256,6 +265,7 @@ def pack_tower_blob(module, ncta=2):
     wval, bval = _fold(m.conv_value, m.value_bn)
     conv_parts.append(_stage_blocks(torch.cat([wpol, wval], 0), ncta))
     biases[li, :64] = torch.cat([bpol, bval])
+    conv_parts.append(_fc_stream(m.fc_value.weight))
     f32 = lambda t: t.detach().float().cpu().contiguous()  # noqa: E731
     pieces = [torch.cat(conv_parts).view(torch.uint8),
               biases.reshape(-1).contiguous().view(torch.uint8),
@@ -285,6 +295,7 @@ class NativeTower:
         self._h = C.c_void_p()
         check(lib().spx_tower_create(game, self.num_blocks, C.byref(self._h)), "spx_tower_create")
         self.ncta = lib().spx_tower_ncta(self._h)
+        self.fused_heads = bool(lib().spx_tower_fused_heads(self._h))
         self.load(module)
 
     def load(self, module_or_blob):

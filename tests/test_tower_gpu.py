@@ -122,3 +122,37 @@ def test_two_native_towers_head_to_head_replays_in_oracle():
         p, v = tw.forward_bits(own, opp)
         assert np.array_equal(p.cpu().numpy(), np.array(logs[3][k]["policy"])) and np.array_equal(v.cpu().numpy(), np.array(logs[3][k]["value"], np.float32))
     sp.close()
+
+
+def test_fused_heads_agree_with_the_separate_heads_kernel_and_respect_the_mask(monkeypatch):
+    """The FC heads inside the tower kernel (default) vs heads_kernel after it (SPX_TOWER_FUSED_HEADS=0): same bf16 inputs,
+    fp32 accumulation in a different order -> 1e-5; the fused kernel never writes rows whose needs_eval is 0."""
+    from self_play_reinforcement_learning_b200 import nets
+    from self_play_reinforcement_learning_b200.envs import boards_to_bits
+    torch.manual_seed(4)
+    net = nets.ResidualTower(7, 6, 7, num_blocks=3).eval()
+    _randomise_bn(net)
+    n = 2100                                               # three units on some clusters: buffer reuse after the FC phase
+    bits = boards_to_bits(torch.from_numpy(_random_positions(n, 11)).cuda(), 0)
+    own, opp = bits[:, 0].contiguous(), bits[:, 1].contiguous()
+    fused = nets.NativeTower(net)
+    monkeypatch.setenv("SPX_TOWER_FUSED_HEADS", "0")
+    plain = nets.NativeTower(net)
+    monkeypatch.delenv("SPX_TOWER_FUSED_HEADS")
+    assert fused.fused_heads and not plain.fused_heads
+    pf, vf = fused.forward_bits(own, opp)
+    pp, vp = plain.forward_bits(own, opp)
+    torch.cuda.synchronize()
+    assert (pf - pp).abs().max().item() < 1e-5 and (vf - vp).abs().max().item() < 1e-5
+    need = (torch.arange(n, device="cuda") % 3 != 0).to(torch.uint8)
+    need[14:42] = 0                                        # two whole SM-pair units without work
+    for tw, (p0, v0) in ((fused, (pf, vf)), (plain, (pp, vp))):
+        p = torch.full((n, 7), -1.0, device="cuda")
+        v = torch.full((n,), -2.0, device="cuda")
+        tw.forward_bits(own, opp, needs_eval=need, policy=p, value=v)
+        torch.cuda.synchronize()
+        m = need.bool()
+        assert torch.equal(p[m], p0[m]) and torch.equal(v[m], v0[m])
+        if tw is fused:   # the separate heads kernel skips whole 16-board groups only: rows without a request are unspecified there
+            assert bool((p[~m] == -1.0).all()) and bool((v[~m] == -2.0).all())
+    fused.close(); plain.close()
