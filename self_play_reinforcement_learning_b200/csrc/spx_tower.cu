@@ -74,6 +74,7 @@ constexpr int FC_HIDDEN = 256;
 constexpr int FC_KSTEPS = FLAT / 16;                                   // 84 K steps of the value layer Linear(1344 -> 256)
 constexpr int FC_KSTEP_BYTES = 2 * (FC_HIDDEN / 2) * 16;               // per CTA half: [2 k-chunks][128 hidden][8] bf16 = 4 KB
 constexpr size_t FC_STREAM_BYTES = (size_t)FC_KSTEPS * 2 * FC_KSTEP_BYTES;   // fused value layer, appended to the conv stream
+__host__ __device__ constexpr size_t bias_slices_bytes(int num_blocks) { return (size_t)(2 * num_blocks + 1) * (2 * CH * 16) + (size_t)(2 * HEAD_CH * 16); }
 // fused FC heads (SM-pair kernel): after the last trunk layer activation buffer 0 is dead and becomes a 12 x 8 KB weight
 // ring for the value layer; after the head conv buffer 1 is dead and holds the head activations
 constexpr int FC_STAGE_BYTES = 2 * FC_KSTEP_BYTES;                     // two K steps per stage (per CTA)
@@ -231,7 +232,8 @@ template <int NCTA> struct SmemT {
     unsigned long long full[STAGES], empty[STAGES], peer_full[STAGES], acc_full, epi_done;
     unsigned long long fc_full[FC_STAGES], fc_empty[FC_STAGES], fc_peer_full[FC_STAGES], fc_done;   // fused FC heads
     unsigned long long own[NB], opp[NB];
-    alignas(16) float bias[3][CH];   // read as float4
+    alignas(16) float bias[NCTA == 1 ? 3 : 1][NCTA == 1 ? CH : 4];   // single-CTA kernel only: staged fp32 bias, read as float4
+    alignas(128) unsigned char ones[256];   // SM-pair kernel: the A operand of the bias MMA (see issue_bias)
     unsigned tmem_base;
 };
 
@@ -281,6 +283,15 @@ __device__ __forceinline__ void tc_mma_lo_acc2(unsigned d_tmem, unsigned a_lo, u
 }
 __device__ __forceinline__ void st_shared_remote_f32(void* local_addr, unsigned cta, float v) {
     asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tst.shared::cluster.f32 [ra], %2;\n\t}" ::"r"(smem_u32(local_addr)), "r"(cta), "f"(v) : "memory");
+}
+
+// SM-pair kernel: the folded-BN bias enters the accumulators through the tensor pipe instead of a tcgen05.st by the epilogue
+// warps: D = ones * bias^T with accumulate = 0 is the first MMA of every layer.  A = `ones`: ONE 8-row core matrix whose
+// rows are (1, 1, 0, ..., 0) aliased by all 16 row groups (SBO = 0) + a zero core matrix for the second k-chunk; B = a
+// [2 k-chunks][n][8] slice of the weight stream with k = 0 -> bf16(bias), k = 1 -> bf16(bias - bf16(bias)) (~16 mantissa bits).
+__device__ __forceinline__ void tc_mma_bias2(unsigned d_tmem, unsigned a_lo, unsigned b_lo, unsigned idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, 0, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %4};\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(1u << 14), "r"(DESC_HI), "r"(idesc) : "memory");
 }
 
 // All MMAs of one conv layer: taps x KPAIRS ring stages of KSTEPS K-steps x 3 row tiles.
@@ -354,6 +365,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
     }
     // zero both activation buffers once: guard rows and padding cells must read as zero forever
     for (int i = tid; i < 2 * ACT_BYTES / 16; i += NUM_THREADS) reinterpret_cast<uint4*>(S.act[0])[i] = make_uint4(0, 0, 0, 0);
+    if (tid < 16) reinterpret_cast<uint4*>(S.ones)[tid] = tid < 8 ? make_uint4(0x3F803F80u, 0, 0, 0) : make_uint4(0, 0, 0, 0);   // bf16 (1, 1, 0 x 6) x 8 rows | zeros
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -387,11 +399,23 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 const int ksteps = li.kslices >= 2 ? 2 : 1;                                   // K steps (of 16 channels) per ring stage
                 const unsigned bytes = 2u * (unsigned)li.n * 16u * (unsigned)ksteps / NCTA;   // this CTA's share of the stage
                 const int iters = li.taps * (li.kslices / ksteps);
-                for (int it = 0; it < iters; ++it) {
+                const unsigned bbytes = 2u * (unsigned)(li.n / 2) * 16u;     // one CTA's half of the layer's bias slice
+                if constexpr (NCTA == 1) wp += 2 * bbytes;                    // the single-CTA kernel seeds the bias with tcgen05.st
+                for (int it = (NCTA == 2 ? -1 : 0); it < iters; ++it) {
 #ifdef SPX_DBG_NO_TMA
                     continue;
 #endif
                     mbar_wait(&S.empty[stage], sphase ^ 1u);
+                    if (it < 0) {   // the bias slice is the first ring stage of every layer
+                        if (leader) {
+                            mbar_expect_tx(&S.full[stage], bbytes);
+                            tma_bulk_g2s(S.wstage[stage], wp + (size_t)crank * bbytes, bbytes, &S.full[stage]);
+                        }
+                        __syncwarp();
+                        wp += 2 * bbytes;
+                        if (++stage == STAGES) { stage = 0; sphase ^= 1u; }
+                        continue;
+                    }
                     if (leader) {
 #ifdef SPX_DBG_FAKE_TMA
                         mbar_arrive(&S.full[stage]);        // timing experiment: the barrier protocol without the copy
@@ -427,7 +451,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
             for (int l = 0; l < n_layers; ++l) {
                 const LayerInfo li = layer_info(l, n_layers);
                 const int ksteps = li.kslices >= 2 ? 2 : 1;
-                const int iters = li.taps * (li.kslices / ksteps);
+                const int iters = li.taps * (li.kslices / ksteps) + 1;   // + the bias slice
                 for (int it = 0; it < iters; ++it) {
 #ifdef SPX_DBG_NO_TMA
                     continue;
@@ -464,6 +488,23 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 ephase ^= 1u;
                 tc_fence_after();
                 SPX_TRACE_IF(leader, l, 1);
+                if constexpr (NCTA == 2) {
+#ifndef SPX_DBG_NO_TMA
+                    mbar_wait(&S.full[stage], sphase);
+                    mbar_wait(&S.peer_full[stage], sphase);
+#endif
+                    const unsigned bias_lo = b_fields | (smem_u32(S.wstage[stage]) >> 4);
+                    const unsigned ones_lo = ((128u >> 4) << 16) | (smem_u32(S.ones) >> 4);
+                    if (leader) {
+#pragma unroll
+                        for (int t = 0; t < MT; ++t) tc_mma_bias2(tmem_base + (unsigned)(t * 128), ones_lo, bias_lo, idesc);
+#ifndef SPX_DBG_NO_TMA
+                        tc_commit_t<NCTA>(&S.empty[stage]);
+#endif
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; sphase ^= 1u; }
+                }
                 if (l == 0) issue_layer<NCTA, 1, 1>(S, li.taps, a_lo_layer, b_fields, kstep16, idesc, tmem_base, leader, stage, sphase);
                 else issue_layer<NCTA, 2, CH / 32>(S, li.taps, a_lo_layer, b_fields, kstep16, idesc, tmem_base, leader, stage, sphase);
                 if (leader) tc_commit_t<NCTA>(&S.acc_full);
@@ -526,10 +567,14 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 S.own[et] = gb < n_boards ? own_g[gb] : 0ULL;
                 S.opp[et] = gb < n_boards ? opp_g[gb] : 0ULL;
             }
-            if (et < CH) { S.bias[0][et] = __ldg(bias_all + et); S.bias[1][et] = __ldg(bias_all + CH + et); }
+            if constexpr (NCTA == 1) {
+                if (et < CH) { S.bias[0][et] = __ldg(bias_all + et); S.bias[1][et] = __ldg(bias_all + CH + et); }
+            }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
-            store_bias_to_tmem(tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(part * (CH / EPI_SPLIT)), S.bias[0] + part * (CH / EPI_SPLIT));
-            tc_fence_before();
+            if constexpr (NCTA == 1) {
+                store_bias_to_tmem(tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(part * (CH / EPI_SPLIT)), S.bias[0] + part * (CH / EPI_SPLIT));
+                tc_fence_before();
+            }
             // preprocess (modules.py:115-125): planes (empty, own, enemy) -> channels 0..2 of buffer 0, channels 3..15 zero
             for (int row = et; row < ROWS; row += EPI_THREADS) {
                 int board, cell;
@@ -552,7 +597,9 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
             for (int l = 0; l < n_layers; ++l) {
                 const LayerInfo li = layer_info(l, n_layers);
                 // stage the bias of layer l+2 while this layer's MMAs are still running (layer l+1's is already visible)
-                if (l + 2 < n_layers && et < CH) S.bias[(l + 2) % 3][et] = __ldg(bias_all + (size_t)(l + 2) * CH + et);
+                if constexpr (NCTA == 1) {
+                    if (l + 2 < n_layers && et < CH) S.bias[(l + 2) % 3][et] = __ldg(bias_all + (size_t)(l + 2) * CH + et);
+                }
                 SPX_TRACE_IF(et == 0, l, 3);
                 mbar_wait(&S.acc_full, lphase);
                 tc_fence_after();
@@ -601,7 +648,9 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                         }
                     }
                     SPX_TRACE_IF(et == 0, l, 8);
-                    if (l + 1 < n_layers) store_bias_to_tmem(tcol, S.bias[(l + 1) % 3] + ch0);
+                    if constexpr (NCTA == 1) {
+                        if (l + 1 < n_layers) store_bias_to_tmem(tcol, S.bias[(l + 1) % 3] + ch0);
+                    }
                     SPX_TRACE_IF(et == 0, l, 9);
                 } else {
                     // fused policy/value 1x1 head conv + BN + ReLU (modules.py:97,102); 64 columns: each warp owns 64/EPI_SPLIT = 16.
@@ -885,7 +934,7 @@ extern "C" {
 int64_t spx_tower_blob_bytes(int32_t game, int32_t num_blocks) {
     if (game != SPX_GAME_CONNECT4 || num_blocks < 0) return -1;
     const int A = 7, n_layers = 2 * num_blocks + 2;
-    size_t conv = (size_t)9 * 1 * KSTEP_BYTES + (size_t)num_blocks * 2 * 9 * 8 * KSTEP_BYTES + (size_t)8 * (2 * HEAD_CH * 16) + FC_STREAM_BYTES;
+    size_t conv = (size_t)9 * 1 * KSTEP_BYTES + (size_t)num_blocks * 2 * 9 * 8 * KSTEP_BYTES + (size_t)8 * (2 * HEAD_CH * 16) + FC_STREAM_BYTES + bias_slices_bytes(num_blocks);
     size_t off = align_up(conv, 256);
     off = align_up(off + (size_t)n_layers * CH * 4, 256);      // biases
     off = align_up(off + (size_t)A * FLAT * 4, 256);           // policy weight
@@ -913,7 +962,7 @@ int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
         const char* f = getenv("SPX_TOWER_FUSED_HEADS");   // 1 (default, SM-pair kernel only): FC heads inside the tower kernel; 0: separate heads kernel
         t->fused = (t->ncta == 2 && !(f && f[0] == '0')) ? 1 : 0;
     }
-    size_t conv = (size_t)9 * KSTEP_BYTES + (size_t)num_blocks * 2 * 72 * KSTEP_BYTES + (size_t)8 * (2 * HEAD_CH * 16) + FC_STREAM_BYTES;
+    size_t conv = (size_t)9 * KSTEP_BYTES + (size_t)num_blocks * 2 * 72 * KSTEP_BYTES + (size_t)8 * (2 * HEAD_CH * 16) + FC_STREAM_BYTES + bias_slices_bytes(num_blocks);
     size_t off = align_up(conv, 256);
     t->off_bias = off; off = align_up(off + (size_t)t->n_layers * CH * 4, 256);
     t->off_polw = off; off = align_up(off + (size_t)t->A * FLAT * 4, 256);

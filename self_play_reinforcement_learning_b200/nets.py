@@ -230,6 +230,18 @@ def _stage_blocks(w, ncta=1):
     return x.to(torch.bfloat16).reshape(-1)
 
 
+def _bias_slice(b):
+    """Folded-BN bias [N] -> the first ring stage of its layer in the SM-pair kernel: the B operand of the bias MMA
+    (ones * bias^T), [half][2 k-chunks][N/2][8] bf16 with k = 0 -> bf16(b), k = 1 -> bf16(b - bf16(b)), zeros elsewhere."""
+    N = b.numel()
+    hi = b.float().to(torch.bfloat16)
+    lo = (b.float() - hi.float()).to(torch.bfloat16)
+    x = torch.zeros(2, 2, N // 2, 8, dtype=torch.bfloat16)
+    x[:, 0, :, 0] = hi.reshape(2, N // 2)
+    x[:, 0, :, 1] = lo.reshape(2, N // 2)
+    return x.reshape(-1)
+
+
 def _fc_stream(w1):
     """fc_value.weight [256 hidden, 1344] -> the weight-ring stream of the fused value layer (SM-pair kernel): the hidden
     units are the M rows of the MMA (128 per CTA), so every K step of 16 inputs is stored per CTA half as
@@ -252,17 +264,20 @@ def pack_tower_blob(module, ncta=2):
     w, b = _fold(m.conv1, m.bn1)
     wp = torch.zeros(128, 16, 3, 3)
     wp[:, :3] = w
+    conv_parts.append(_bias_slice(b))
     conv_parts.append(_stage_blocks(wp, ncta))
     biases[0] = b
     li = 1
     for blk in blocks:
         for conv, bn in ((blk.conv1, blk.bn1), (blk.conv2, blk.bn2)):
             w, b = _fold(conv, bn)
+            conv_parts.append(_bias_slice(b))
             conv_parts.append(_stage_blocks(w, ncta))
             biases[li] = b
             li += 1
     wpol, bpol = _fold(m.conv_policy, m.policy_bn)
     wval, bval = _fold(m.conv_value, m.value_bn)
+    conv_parts.append(_bias_slice(torch.cat([bpol, bval])))
     conv_parts.append(_stage_blocks(torch.cat([wpol, wval], 0), ncta))
     biases[li, :64] = torch.cat([bpol, bval])
     conv_parts.append(_fc_stream(m.fc_value.weight))
