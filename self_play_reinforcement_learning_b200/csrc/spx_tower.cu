@@ -229,7 +229,7 @@ template <int NCTA> struct SmemT {
     static constexpr int STAGES = NCTA * NSTAGE;
     unsigned char act[2][ACT_BYTES];
     unsigned char wstage[STAGES][STAGE_BYTES / NCTA];
-    unsigned long long full[STAGES], empty[STAGES], peer_full[STAGES], acc_full, epi_done;
+    unsigned long long full[STAGES], empty[STAGES], peer_full[STAGES], acc_full, epi_done[MT];   // epi_done per 128-row tile
     unsigned long long fc_full[FC_STAGES], fc_empty[FC_STAGES], fc_peer_full[FC_STAGES], fc_done;   // fused FC heads
     unsigned long long own[NB], opp[NB];
     alignas(16) float bias[NCTA == 1 ? 3 : 1][NCTA == 1 ? CH : 4];   // single-CTA kernel only: staged fp32 bias, read as float4
@@ -297,9 +297,9 @@ __device__ __forceinline__ void tc_mma_bias2(unsigned d_tmem, unsigned a_lo, uns
 // All MMAs of one conv layer: taps x KPAIRS ring stages of KSTEPS K-steps x 3 row tiles.
 template <int NCTA, int KSTEPS, int KPAIRS>
 __device__ __forceinline__ void issue_layer(SmemT<NCTA>& S, int taps, unsigned a_lo_layer, unsigned b_fields, unsigned kstep16, unsigned idesc,
-                                            unsigned tmem_base, bool leader, unsigned& stage, unsigned& sphase) {
+                                            unsigned tmem_base, bool leader, unsigned& stage, unsigned& sphase, int first_tap = 0) {
     constexpr int STAGES = SmemT<NCTA>::STAGES;
-    for (int tap = 0; tap < taps; ++tap) {
+    for (int tap = first_tap; tap < taps; ++tap) {
 #ifdef SPX_DBG_NO_SHIFT
         unsigned a_lo = a_lo_layer + 0u * (unsigned)tap;
 #else
@@ -330,6 +330,66 @@ __device__ __forceinline__ void issue_layer(SmemT<NCTA>& S, int taps, unsigned a
     }
 }
 
+// SM-pair kernel, layers with 128 input channels: bias MMAs + the FIRST tap (4 ring stages x 2 K steps x 3 tiles), issued per
+// tile as the previous layer's epilogue releases the tiles one after the other (epi_done[t]).  The first tap shifts by -8
+// rows (or 0 for the 1x1 head conv): tile t reads rows of tiles t-1 and t only, so tile 0 may start while tiles 1 and 2 are
+// still in the epilogue.  MMAs of a tile that has just become available are interleaved with the MMAs the earlier tile has
+// left (back-to-back MMAs into one accumulator run at ~150 instead of 64 cycles).  The 5 ring slots (bias slice + 4 stages)
+// stay allocated until tile 2 has used them; the remaining taps run stage-major (issue_layer, first_tap = 1).
+__device__ __forceinline__ void issue_first_tap_skewed(SmemT<2>& S, int taps, unsigned a_lo_layer, unsigned b_fields, unsigned kstep16, unsigned idesc,
+                                                       unsigned tmem_base, bool leader, unsigned& stage, unsigned& sphase, unsigned ephase) {
+    constexpr int STAGES = SmemT<2>::STAGES;
+    constexpr unsigned KSTEP_A = 2 * (CHUNK_BYTES >> 4);
+    const unsigned a_lo = a_lo_layer + (unsigned)(taps == 9 ? tap_shift(0) : 0);
+    const unsigned ones_lo = ((128u >> 4) << 16) | (smem_u32(S.ones) >> 4);
+    unsigned slot[5], b_lo[5];
+    int have = 0;
+    auto need = [&](int upto) {      // wait (whole warp) until ring stages 0..upto of this layer have landed in both CTAs
+        for (; have <= upto; ++have) {
+#ifndef SPX_DBG_NO_TMA
+            mbar_wait(&S.full[stage], sphase);
+            mbar_wait(&S.peer_full[stage], sphase);
+#endif
+            slot[have] = stage;
+            b_lo[have] = b_fields | (smem_u32(S.wstage[stage]) >> 4);
+            if (++stage == STAGES) { stage = 0; sphase ^= 1u; }
+        }
+    };
+    auto bias = [&](int t) { tc_mma_bias2(tmem_base + (unsigned)(t * 128), ones_lo, b_lo[0], idesc); };
+    auto mma = [&](int t, int s, int j) {
+        tc_mma_lo<2>(tmem_base + (unsigned)(t * 128), a_lo + (unsigned)((s * 2 + j) * KSTEP_A + t * 128), b_lo[1 + s] + (unsigned)j * kstep16, idesc);
+    };
+    auto release = [&](int i) {
+#ifndef SPX_DBG_NO_TMA
+        tc_commit_t<2>(&S.empty[slot[i]]);
+#endif
+    };
+    mbar_wait(&S.epi_done[0], ephase);
+    tc_fence_after();
+    need(2);
+    if (leader) { bias(0); mma(0, 0, 0); mma(0, 0, 1); mma(0, 1, 0); mma(0, 1, 1); }
+    __syncwarp();
+    mbar_wait(&S.epi_done[1], ephase);
+    tc_fence_after();
+    need(4);
+    if (leader) {
+        bias(1);
+        mma(1, 0, 0); mma(0, 2, 0); mma(1, 0, 1); mma(0, 2, 1);
+        mma(1, 1, 0); mma(0, 3, 0); mma(1, 1, 1); mma(0, 3, 1);
+    }
+    __syncwarp();
+    mbar_wait(&S.epi_done[2], ephase);
+    tc_fence_after();
+    if (leader) {
+        bias(2); release(0);
+        mma(2, 0, 0); mma(1, 2, 0); mma(2, 0, 1); mma(1, 2, 1); release(1);
+        mma(2, 1, 0); mma(1, 3, 0); mma(2, 1, 1); mma(1, 3, 1); release(2);
+        mma(2, 2, 0); mma(2, 2, 1); release(3);
+        mma(2, 3, 0); mma(2, 3, 1); release(4);
+    }
+    __syncwarp();
+}
+
 template <int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long long* __restrict__ opp_g,
@@ -349,7 +409,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); mbar_init(&S.peer_full[s], 1); }
         mbar_init(&S.acc_full, 1);
-        mbar_init(&S.epi_done, EPI_THREADS + (NCTA - 1));   // local epilogue threads (+ one remote arrive from the peer CTA)
+        for (int t = 0; t < MT; ++t) mbar_init(&S.epi_done[t], EPI_WARPS * NCTA);   // one arrive per epilogue warp of every CTA of the cluster
         for (int s = 0; s < FC_STAGES; ++s) { mbar_init(&S.fc_full[s], 1); mbar_init(&S.fc_empty[s], 1); mbar_init(&S.fc_peer_full[s], 1); }
         mbar_init(&S.fc_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -484,29 +544,38 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 const unsigned kstep16 = 2u * b_lbo16;                                 // one K step of B in 16-byte units
                 const unsigned a_lo_layer = A_DESC_FIELDS | ((smem_u32(S.act[li.in_buf]) + GUARD * 16) >> 4);
                 SPX_TRACE_IF(leader, l, 0);
-                mbar_wait(&S.epi_done, ephase);   // (both CTAs:) inputs of this layer written, accumulators drained
-                ephase ^= 1u;
-                tc_fence_after();
-                SPX_TRACE_IF(leader, l, 1);
+                bool skewed = false;
                 if constexpr (NCTA == 2) {
-#ifndef SPX_DBG_NO_TMA
-                    mbar_wait(&S.full[stage], sphase);
-                    mbar_wait(&S.peer_full[stage], sphase);
-#endif
-                    const unsigned bias_lo = b_fields | (smem_u32(S.wstage[stage]) >> 4);
-                    const unsigned ones_lo = ((128u >> 4) << 16) | (smem_u32(S.ones) >> 4);
-                    if (leader) {
-#pragma unroll
-                        for (int t = 0; t < MT; ++t) tc_mma_bias2(tmem_base + (unsigned)(t * 128), ones_lo, bias_lo, idesc);
-#ifndef SPX_DBG_NO_TMA
-                        tc_commit_t<NCTA>(&S.empty[stage]);
-#endif
+                    if (l > 0) {   // 128 input channels: per-tile start (the stem's input is written by all warps at once)
+                        issue_first_tap_skewed(S, li.taps, a_lo_layer, b_fields, kstep16, idesc, tmem_base, leader, stage, sphase, ephase);
+                        skewed = true;
                     }
-                    __syncwarp();
-                    if (++stage == STAGES) { stage = 0; sphase ^= 1u; }
                 }
+                if (!skewed) {
+                    for (int t = 0; t < MT; ++t) mbar_wait(&S.epi_done[t], ephase);   // (both CTAs:) inputs written, accumulators drained
+                    tc_fence_after();
+                    if constexpr (NCTA == 2) {   // bias slice = the first ring stage of the layer
+#ifndef SPX_DBG_NO_TMA
+                        mbar_wait(&S.full[stage], sphase);
+                        mbar_wait(&S.peer_full[stage], sphase);
+#endif
+                        const unsigned bias_lo = b_fields | (smem_u32(S.wstage[stage]) >> 4);
+                        const unsigned ones_lo = ((128u >> 4) << 16) | (smem_u32(S.ones) >> 4);
+                        if (leader) {
+#pragma unroll
+                            for (int t = 0; t < MT; ++t) tc_mma_bias2(tmem_base + (unsigned)(t * 128), ones_lo, bias_lo, idesc);
+#ifndef SPX_DBG_NO_TMA
+                            tc_commit_t<NCTA>(&S.empty[stage]);
+#endif
+                        }
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; sphase ^= 1u; }
+                    }
+                }
+                ephase ^= 1u;
+                SPX_TRACE_IF(leader, l, 1);
                 if (l == 0) issue_layer<NCTA, 1, 1>(S, li.taps, a_lo_layer, b_fields, kstep16, idesc, tmem_base, leader, stage, sphase);
-                else issue_layer<NCTA, 2, CH / 32>(S, li.taps, a_lo_layer, b_fields, kstep16, idesc, tmem_base, leader, stage, sphase);
+                else issue_layer<NCTA, 2, CH / 32>(S, li.taps, a_lo_layer, b_fields, kstep16, idesc, tmem_base, leader, stage, sphase, skewed ? 1 : 0);
                 if (leader) tc_commit_t<NCTA>(&S.acc_full);
                 SPX_TRACE_IF(leader, l, 2);
                 __syncwarp();
@@ -517,7 +586,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                     // M=256, N=16, 84 K steps; A = weight stage (ring in buffer 0), B = the head activations (buffer 1).
                     // Four accumulators (K step mod 4, columns 0/16/32/48) keep consecutive MMAs independent.
                     SPX_TRACE_IF(leader, n_layers, 0);
-                    mbar_wait(&S.epi_done, ephase);   // head activations of both CTAs in place, head-conv accumulators drained
+                    for (int t = 0; t < MT; ++t) mbar_wait(&S.epi_done[t], ephase);   // head activations of both CTAs in place, accumulators drained
                     ephase ^= 1u;
                     tc_fence_after();
                     SPX_TRACE_IF(leader, n_layers, 1);
@@ -550,10 +619,18 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
             const int quarter = warp & 3, part = (warp - EPI_WARP0) >> 2;   // TMEM lane quarter, column part
             // "this CTA's activations for the next layer are in place": the leader's threads arrive locally, the peer CTA
             // meets on a named barrier and sends ONE remote arrive to the leader's barrier
-            auto signal_epi_done = [&]() {
-                if (crank == 0) mbar_arrive(&S.epi_done);
-                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));   // also publishes the next layer's staged bias
-                if (NCTA == 2 && crank == 1 && et == 0) mbar_arrive_remote(&S.epi_done, 0);
+            // "tile t of this CTA is ready for the next layer" (activations written and fenced, accumulator drained): one arrive
+            // per warp on the LEADER CTA's barrier (remote from the peer CTA)
+            auto signal_tile_done = [&](int t) {
+                __syncwarp();
+                if (lane == 0) {
+                    if (crank == 0) mbar_arrive(&S.epi_done[t]);
+                    else mbar_arrive_remote(&S.epi_done[t], 0);
+                }
+            };
+            auto signal_epi_done = [&]() {   // all three tiles at once (after a CTA-wide barrier: every warp wrote to every tile)
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+                for (int t = 0; t < MT; ++t) signal_tile_done(t);
             };
             if (fused && !first_unit) {
                 // the previous unit's FC ring / head activations overwrote the buffers: the zero guard rows (never written by
@@ -599,6 +676,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 // stage the bias of layer l+2 while this layer's MMAs are still running (layer l+1's is already visible)
                 if constexpr (NCTA == 1) {
                     if (l + 2 < n_layers && et < CH) S.bias[(l + 2) % 3][et] = __ldg(bias_all + (size_t)(l + 2) * CH + et);
+                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));   // published one layer before its use
                 }
                 SPX_TRACE_IF(et == 0, l, 3);
                 mbar_wait(&S.acc_full, lphase);
@@ -615,36 +693,40 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                         tc_wait_ld();
                         SPX_TRACE_IF(et == 0, l, 5 + t);
                         if (t + 1 < MT) tc_ld32_nowait(tcol + (unsigned)((t + 1) * 128), v[(t + 1) & 1]);
-#ifdef SPX_DBG_SKIP_EPI
-                        continue;
-#endif
                         const int row = t * 128 + quarter * 32 + lane;
                         unsigned char* obase = S.act[li.out_buf] + (GUARD + row) * 16 + (ch0 >> 3) * CHUNK_BYTES;
+#ifndef SPX_DBG_SKIP_EPI
                         if (!real_t[t]) {   // padding / guard cell: must read as zero in the next layer
 #pragma unroll
                             for (int g8 = 0; g8 < 4; ++g8) *reinterpret_cast<uint4*>(obase + g8 * CHUNK_BYTES) = make_uint4(0, 0, 0, 0);
-                            continue;
-                        }
-                        const unsigned* vv = v[t & 1];
+                        } else {
+                            const unsigned* vv = v[t & 1];
 #pragma unroll
-                        for (int g8 = 0; g8 < 4; ++g8) {
-                            float y[8];   // accumulator already contains the folded-BN bias
+                            for (int g8 = 0; g8 < 4; ++g8) {
+                                float y[8];   // accumulator already contains the folded-BN bias
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) y[k] = __uint_as_float(vv[g8 * 8 + k]);
-                            uint4* dst = reinterpret_cast<uint4*>(obase + g8 * CHUNK_BYTES);
-                            if (li.residual) {  // out += identity (modules.py:37), identity lives in the output buffer
-                                const uint4 idv = *dst;
-                                const unsigned iw[4] = {idv.x, idv.y, idv.z, idv.w};
+                                for (int k = 0; k < 8; ++k) y[k] = __uint_as_float(vv[g8 * 8 + k]);
+                                uint4* dst = reinterpret_cast<uint4*>(obase + g8 * CHUNK_BYTES);
+                                if (li.residual) {  // out += identity (modules.py:37), identity lives in the output buffer
+                                    const uint4 idv = *dst;
+                                    const unsigned iw[4] = {idv.x, idv.y, idv.z, idv.w};
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    y[2 * k] += __uint_as_float(iw[k] << 16);
-                                    y[2 * k + 1] += __uint_as_float(iw[k] & 0xFFFF0000u);
+                                    for (int k = 0; k < 4; ++k) {
+                                        y[2 * k] += __uint_as_float(iw[k] << 16);
+                                        y[2 * k + 1] += __uint_as_float(iw[k] & 0xFFFF0000u);
+                                    }
                                 }
-                            }
-                            unsigned pk[4];
+                                unsigned pk[4];
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) pk[k] = relu_pack_bf16x2(y[2 * k], y[2 * k + 1]);
-                            *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                for (int k = 0; k < 4; ++k) pk[k] = relu_pack_bf16x2(y[2 * k], y[2 * k + 1]);
+                                *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                        }
+#endif
+                        if constexpr (NCTA == 2) {   // tile t is complete: the next layer may start on it (issue_first_tap_skewed)
+                            tc_fence_before();
+                            fence_proxy_async();
+                            signal_tile_done(t);
                         }
                     }
                     SPX_TRACE_IF(et == 0, l, 8);
@@ -691,7 +773,8 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 fence_proxy_async();
                 lphase ^= 1u;
                 SPX_TRACE_IF(et == 0, l, 10);
-                if (l + 1 < n_layers || fused) signal_epi_done();
+                if (NCTA == 2 && li.out_buf >= 0) { }                        // trunk layer of the SM-pair kernel: signalled tile by tile
+                else if (l + 1 < n_layers || fused) signal_epi_done();
                 else asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
                 SPX_TRACE_IF(et == 0, l, 11);
             }
