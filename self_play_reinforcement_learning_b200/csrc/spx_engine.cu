@@ -237,8 +237,11 @@ __device__ __forceinline__ int alloc_node(const Ctx<GAME>& c, TreeState& ts, u64
 }
 
 // ------------------------------------------------------------------------------------------------ the tick kernel
+#ifndef SPX_ADV_MINB
+#define SPX_ADV_MINB 8   // 64 registers: 8 CTAs (32 game warps) per SM; -8 % at 16 384 games, neutral at 1024
+#endif
 template <int GAME>
-__global__ void __launch_bounds__(128) advance_kernel(EngineDev E, const float* __restrict__ policy_in,
+__global__ void __launch_bounds__(128, SPX_ADV_MINB) advance_kernel(EngineDev E, const float* __restrict__ policy_in,
                                                       const float* __restrict__ value_in) {
     typedef Rules<GAME> R;
     typedef NodeLayout<GAME> L;
