@@ -346,7 +346,7 @@ def main():
             roof = {"bound": "tensor", "kernel": ("spx::tower::tower_kernel<2> (tcgen05 cta_group::2, SM pair" + (", fused FC heads)" if fused else ")")) if getattr(tw, "ncta", 2) == 2 else "spx::tower::tower_kernel<1>", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
                     "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": _ncu_traffic(),
                     "peak_source": peaks["source"], "flop_per_leaf": fl, "leaves_per_launch": leaves_per_launch,
-                    "kernel_ms": tower_ms, "heads_kernel_ms": heads_ms, "advance_kernel_ms": adv_ms,
+                    "kernel_ms": tower_ms, "heads_kernel_ms": None if fused else heads_ms, "advance_kernel_ms": adv_ms,
                     "kernel_share_of_step": tower_ms * ticks / max(ms, 1e-9) if world == 1 else None}
         cpu = None
         if not args.no_cpu_baseline and world == 1:

@@ -6,5 +6,5 @@ for L in "$@"; do
   python -c "
 import json
 d=json.load(open('/tmp/b.json')); r=d['roofline']
-print('$L', round(d['value']), round(d['ms_per_step'],1), 'tower', round(r['kernel_ms'],4), 'heads', round(r['heads_kernel_ms'],4), 'advance', round(r['advance_kernel_ms'],4), 'search-only', round(d['search_roofline']['advance_ms_per_launch'],4), round(d['search_roofline']['with_16384_games']['advance_ms_per_launch'],4), d['clocks']['sm_mhz'])"
+print('$L', round(d['value']), round(d['ms_per_step'],1), 'tower', round(r['kernel_ms'],4), 'heads', r['heads_kernel_ms'], 'advance', round(r['advance_kernel_ms'],4), 'search-only', round(d['search_roofline']['advance_ms_per_launch'],4), round(d['search_roofline']['with_16384_games']['advance_ms_per_launch'],4), d['clocks']['sm_mhz'])"
 done
