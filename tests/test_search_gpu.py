@@ -87,10 +87,11 @@ def test_golden_episodes():
         e.close()
 
 
-@pytest.mark.parametrize("game,n_games,sims,evaluate,two", [(0, 192, 120, False, False), (1, 256, 60, False, False),
-                                                            (0, 64, 64, True, True), (1, 64, 40, True, True),
-                                                            (0, 8, 800, False, False)])
-def test_many_games_vs_oracle(game, n_games, sims, evaluate, two):
+@pytest.mark.parametrize("game,n_games,sims,evaluate,two,strong", [(0, 192, 120, False, False, False), (1, 256, 60, False, False, False),
+                                                                   (0, 64, 64, True, True, False), (1, 64, 40, True, True, False),
+                                                                   (0, 8, 800, False, False, False), (0, 96, 100, False, False, True),
+                                                                   (1, 40, 50, True, True, True)])
+def test_many_games_vs_oracle(game, n_games, sims, evaluate, two, strong):
     """Two generations of games per slot, injected Dirichlet tables, hash nets: every game must equal the oracle."""
     from self_play_reinforcement_learning_b200.engine import HashNetEvaluator
     A = spec.GAME_DIMS[game][2]
@@ -99,7 +100,7 @@ def test_many_games_vs_oracle(game, n_games, sims, evaluate, two):
     table = rng.dirichlet([0.6] * A, size=(total, 2, 22))
     ev = HashNetEvaluator(game, 5, 9 if two else None)
     e = _engine(game=game, n_games=n_games, sims=sims, evaluator=ev, seed=99, noise_mode=1, evaluate=evaluate, two_nets=two,
-                games_target=total, max_sims_per_tick=8, move_log=False)
+                games_target=total, max_sims_per_tick=8, move_log=False, strong_play=strong)
     e.set_noise_table(table, first_game_index=0)
     e.run_until_idle(max_ticks=400000, poll_every=512)
     c = e.counters()
@@ -108,7 +109,7 @@ def test_many_games_vs_oracle(game, n_games, sims, evaluate, two):
     assert len(res) == total
     sims_total = 0
     for gi in range(total):
-        o = H.oracle_episode(game, sims, 99, gi, table[gi], evaluate=evaluate, net_seed=5, net_seed_opp=9 if two else None)
+        o = H.oracle_episode(game, sims, 99, gi, table[gi], evaluate=evaluate, net_seed=5, net_seed_opp=9 if two else None, strong_play=strong)
         sims_total += o["sims"]
         assert res[gi]["reward"] == o["reward"] and res[gi]["plies"] == len(o["moves"]), gi
         got = recs[gi]
