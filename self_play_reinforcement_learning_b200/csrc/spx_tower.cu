@@ -244,7 +244,7 @@ template <int NCTA> struct SmemT {
     static constexpr int STAGES = NCTA * NSTAGE;
     unsigned char act[2][ACT_BYTES];
     unsigned char wstage[STAGES][STAGE_BYTES / NCTA];
-    unsigned long long full[STAGES], empty[STAGES], peer_full[STAGES], acc_full, epi_done[MT];   // epi_done per 128-row tile
+    unsigned long long full[STAGES], empty[STAGES], peer_full[STAGES], acc_full[MT], epi_done[MT];   // accumulator complete / tile handed over, per 128-row tile
     unsigned long long fc_full[FC_STAGES], fc_empty[FC_STAGES], fc_peer_full[FC_STAGES], fc_done;   // fused FC heads
     unsigned long long own[NB], opp[NB];
     alignas(16) float bias[NCTA == 1 ? 3 : 1][NCTA == 1 ? CH : 4];   // single-CTA kernel only: staged fp32 bias, read as float4
@@ -328,12 +328,25 @@ __device__ __forceinline__ void issue_layer(SmemT<NCTA>& S, int taps, unsigned a
 #endif
             const unsigned b_lo = b_fields | (smem_u32(S.wstage[stage]) >> 4);
             if (leader) {
+                if (tap == taps - 1 && kp == KPAIRS - 1) {
+                    // the layer's last stage, tile by tile: accumulator t is complete (acc_full[t]) 2 * KSTEPS * (2 - t) MMAs before
+                    // the last one, so the epilogue starts on tile 0 while the tensor pipe finishes tiles 1 and 2
 #pragma unroll
-                for (int j = 0; j < KSTEPS; ++j)
+                    for (int t = 0; t < MT; ++t) {
 #pragma unroll
-                    for (int t = 0; t < MT; ++t)
-                        tc_mma_lo<NCTA>(tmem_base + (unsigned)(t * 128), a_lo + (unsigned)(j * 2 * (CHUNK_BYTES >> 4) + t * 128),
-                                        b_lo + (unsigned)j * kstep16, idesc);
+                        for (int j = 0; j < KSTEPS; ++j)
+                            tc_mma_lo<NCTA>(tmem_base + (unsigned)(t * 128), a_lo + (unsigned)(j * 2 * (CHUNK_BYTES >> 4) + t * 128),
+                                            b_lo + (unsigned)j * kstep16, idesc);
+                        tc_commit_t<NCTA>(&S.acc_full[t]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < KSTEPS; ++j)
+#pragma unroll
+                        for (int t = 0; t < MT; ++t)
+                            tc_mma_lo<NCTA>(tmem_base + (unsigned)(t * 128), a_lo + (unsigned)(j * 2 * (CHUNK_BYTES >> 4) + t * 128),
+                                            b_lo + (unsigned)j * kstep16, idesc);
+                }
 #ifndef SPX_DBG_NO_TMA
                 tc_commit_t<NCTA>(&S.empty[stage]);   // frees the weight slot (in both CTAs) once these MMAs retire
 #endif
@@ -423,7 +436,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); mbar_init(&S.peer_full[s], 1); }
-        mbar_init(&S.acc_full, 1);
+        for (int t = 0; t < MT; ++t) mbar_init(&S.acc_full[t], 1);
         for (int t = 0; t < MT; ++t) mbar_init(&S.epi_done[t], EPI_WARPS * NCTA);   // one arrive per epilogue warp of every CTA of the cluster
         for (int s = 0; s < FC_STAGES; ++s) { mbar_init(&S.fc_full[s], 1); mbar_init(&S.fc_empty[s], 1); mbar_init(&S.fc_peer_full[s], 1); }
         mbar_init(&S.fc_done, 1);
@@ -508,7 +521,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 // value-layer weights into the dead activation buffer 0: its last readers are the MMAs of the last trunk layer
                 // (layer n_layers-2, an even index: n_layers is even, so that completion of acc_full always has parity 0; this
                 // warp is at most a ring (6 stages) ahead of the issuer, so the barrier cannot be a whole phase behind)
-                mbar_wait(&S.acc_full, 0u);
+                mbar_wait(&S.acc_full[MT - 1], 0u);
                 for (int it = 0; it < FC_ITERS; ++it) {
                     mbar_wait(&S.fc_empty[fstage], fphase ^ 1u);
                     if (leader) {
@@ -591,7 +604,10 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 SPX_TRACE_IF(leader, l, 1);
                 if (l == 0) issue_layer<NCTA, 1, 1>(S, li.taps, a_lo_layer, b_fields, kstep16, idesc, tmem_base, leader, stage, sphase);
                 else issue_layer<NCTA, 2, CH / 32>(S, li.taps, a_lo_layer, b_fields, kstep16, idesc, tmem_base, leader, stage, sphase, skewed ? 1 : 0);
-                if (leader) tc_commit_t<NCTA>(&S.acc_full);
+                if (skewed && li.taps == 1) {   // the 1x1 head conv ran entirely inside issue_first_tap_skewed
+                    if (leader)
+                        for (int t = 0; t < MT; ++t) tc_commit_t<NCTA>(&S.acc_full[t]);
+                }
                 SPX_TRACE_IF(leader, l, 2);
                 __syncwarp();
             }
@@ -694,7 +710,8 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));   // published one layer before its use
                 }
                 SPX_TRACE_IF(et == 0, l, 3);
-                mbar_wait_backoff(&S.acc_full, lphase);
+                mbar_wait_backoff(&S.acc_full[0], lphase);
+                if (li.out_buf < 0) { mbar_wait(&S.acc_full[1], lphase); mbar_wait(&S.acc_full[2], lphase); }   // head layer: all tiles
                 tc_fence_after();
                 SPX_TRACE_IF(et == 0, l, 4);
                 if (li.out_buf >= 0) {
@@ -707,7 +724,11 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                     for (int t = 0; t < MT; ++t) {
                         tc_wait_ld();
                         SPX_TRACE_IF(et == 0, l, 5 + t);
-                        if (t + 1 < MT) tc_ld32_nowait(tcol + (unsigned)((t + 1) * 128), v[(t + 1) & 1]);
+                        if (t + 1 < MT) {
+                            mbar_wait(&S.acc_full[t + 1], lphase);   // complete long ago (a few MMAs after tile t)
+                            tc_fence_after();
+                            tc_ld32_nowait(tcol + (unsigned)((t + 1) * 128), v[(t + 1) & 1]);
+                        }
                         const int row = t * 128 + quarter * 32 + lane;
                         unsigned char* obase = S.act[li.out_buf] + (GUARD + row) * 16 + (ch0 >> 3) * CHUNK_BYTES;
 #ifndef SPX_DBG_SKIP_EPI
