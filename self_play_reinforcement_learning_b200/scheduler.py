@@ -172,18 +172,29 @@ class SelfPlayScheduler:
         self.network.eval()
         gen = 0
         self._remember(self._play(self.initial_games, evaluate=False, update=True, generation=gen)[0])
+        import time
+
+        def now():
+            torch.cuda.synchronize()
+            return time.time()
         for epoch in range(num_epochs):
             gen += 1
+            t0 = now()
             moves, results = self._play(self.epoch_length, evaluate=False, update=True, generation=gen)
             self._remember(moves)
+            t1 = now()
             if self.memory_step and self.rank == 0 and self.memory is not None:   # stagger_memory (updateworker.py:107-109)
                 self.memory.change_size(min(self.memory.max_size + self.memory_step, self.max_memory_size))
             self.games_played += self.epoch_length
             loss = self.update()
+            t2 = now()
             self._sync_weights()
+            t3 = now()
             reward = self.evaluate_policy(epoch) if self.evaluation_games else 0
+            t4 = now()
             self.history.append(dict(epoch=epoch, loss=loss, self_play=parse_results(results)[0] if self.rank == 0 else None,
-                                     evaluation_reward=reward, memory=len(self.memory) if self.memory is not None else 0))
+                                     evaluation_reward=reward, memory=len(self.memory) if self.memory is not None else 0,
+                                     seconds=dict(self_play=t1 - t0, update=t2 - t1, weight_sync=t3 - t2, evaluation=t4 - t3)))
         return self.history
 
     def _remember(self, moves):
