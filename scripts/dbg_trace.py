@@ -13,9 +13,10 @@ tw = nets.NativeTower(net)
 for _ in range(5):
     tw.forward_bits(bits[:, 0].contiguous(), bits[:, 1].contiguous())
 torch.cuda.synchronize()
-buf = np.zeros(64 * 16, np.int64)
+buf = np.zeros(64 * 16 + 3 * 160, np.int64)
 _lib.lib().spx_debug_trace(C.c_void_p(buf.ctypes.data))
-t = buf.reshape(64, 16)
+t = buf[:1024].reshape(64, 16)
+blk = buf[1024:].reshape(160, 3)[:148]
 names = ["mma:wait_epi", "mma:go", "mma:issued", "epi:wait_acc", "epi:acc_full", "epi:t0", "epi:t1", "epi:t2", "epi:tiles_done", "epi:bias_st", "epi:fenced", "epi:signalled"]
 t0 = t[2, 1]
 for l in range(2, 8):
@@ -32,3 +33,11 @@ print("head layer:", {n: int(t[L - 1, i] - t[L - 1, 1]) for i, n in enumerate(na
 print("FC phase (offsets from the head layer's mma:go):", dict(mma_wait=int(t[L, 0] - t[L - 1, 1]), mma_go=int(t[L, 1] - t[L - 1, 1]), mma_issued=int(t[L, 2] - t[L - 1, 1]),
       policy_start=int(t[L, 3] - t[L - 1, 1]), policy_done=int(t[L, 4] - t[L - 1, 1]), fc_done_seen=int(t[L, 5] - t[L - 1, 1]), value_partial_done=int(t[L, 6] - t[L - 1, 1])))
 print("whole kernel (layer 0 go -> value partial done): %d cycles" % int(t[L, 6] - t[0, 1]))
+print("kernel entry -> setup done: %d cycles; setup done -> layer 0 go: %d; value partial done -> exit path: %d; entry -> exit path: %d" % (
+    t[62, 1] - t[62, 0], t[0, 1] - t[62, 1], t[62, 2] - t[L, 6], t[62, 2] - t[62, 0]))
+t0 = blk[:, 0].min()
+dur = blk[:, 1] - blk[:, 0]
+print("per-CTA (globaltimer ns): first entry -> last exit %d ns; CTA duration min %d median %d max %d; entry skew max %d ns" % (
+    blk[:, 1].max() - t0, dur.min(), np.median(dur), dur.max(), (blk[:, 0] - t0).max()))
+slow = np.argsort(dur)[-6:]
+print("slowest CTAs (block, sm, ns):", [(int(b), int(blk[b, 2]), int(dur[b])) for b in slow], "fastest:", [(int(b), int(blk[b, 2]), int(dur[b])) for b in np.argsort(dur)[:4]])

@@ -233,9 +233,10 @@ __device__ __forceinline__ int tap_shift(int tap) { return (tap / 3 - 1) * PAD_S
 //     mbarrier arrives.
 //   NCTA == 1 (SPX_TOWER_NCTA=1, fallback): every CTA is on its own (cta_group::1, M=128, 3 x 8 KB ring).
 #ifdef SPX_DBG_TRACE
-__device__ long long g_trace[64 * 16];
+__device__ long long g_trace[64 * 16 + 3 * 160];   // + per-CTA {entry, exit, SM id} for the first 160 CTAs
 #define SPX_TRACE(l, k) do { if (blockIdx.x == 0 && (l) < 64) g_trace[(l) * 16 + (k)] = clock64(); } while (0)
 #define SPX_TRACE_IF(c, l, k) do { if (c) SPX_TRACE(l, k); __syncwarp(); } while (0)
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #else
 #define SPX_TRACE(l, k) do { } while (0)
 #define SPX_TRACE_IF(c, l, k) do { } while (0)
@@ -433,6 +434,10 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
     const unsigned crank = NCTA == 2 ? cluster_ctarank() : 0u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long n_groups = (n_boards + NB - 1) / NB;
+    if (tid == 0) SPX_TRACE(62, 0);
+#ifdef SPX_DBG_TRACE
+    if (tid == 0 && blockIdx.x < 160) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); g_trace[1024 + 3 * blockIdx.x] = (long long)globaltimer_ns(); g_trace[1024 + 3 * blockIdx.x + 2] = smid; }
+#endif
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); mbar_init(&S.peer_full[s], 1); }
@@ -460,6 +465,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
     if constexpr (NCTA == 2) cluster_sync_all();   // both CTAs' barriers initialised and buffers zeroed before any remote arrive / MMA
     tc_fence_after();
     const unsigned tmem_base = S.tmem_base;
+    if (tid == 0) SPX_TRACE(62, 1);
 
     unsigned stage = 0, sphase = 0;   // weight ring position (producer, relay and MMA issuer walk the same sequence)
     unsigned lphase = 0;              // per-layer parity of acc_full (n_layers, an even number, of completions per unit)
@@ -891,6 +897,10 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
         first_unit = false;
     }
 
+    if (tid == 0) SPX_TRACE(62, 2);
+#ifdef SPX_DBG_TRACE
+    if (tid == 0 && blockIdx.x < 160) g_trace[1024 + 3 * blockIdx.x + 1] = (long long)globaltimer_ns();
+#endif
     tc_fence_before();
     __syncthreads();
     if constexpr (NCTA == 2) {
@@ -1175,7 +1185,7 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
 }
 
 #ifdef SPX_DBG_TRACE
-int spx_debug_trace(long long* host_out) { return (int)cudaMemcpyFromSymbol(host_out, spx::tower::g_trace, sizeof(long long) * 64 * 16); }
+int spx_debug_trace(long long* host_out) { return (int)cudaMemcpyFromSymbol(host_out, spx::tower::g_trace, sizeof(long long) * (64 * 16 + 3 * 160)); }
 #endif
 
 int spx_tower_forward(spx_tower* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n,
