@@ -2,23 +2,30 @@
 //
 // Replaces InferenceWorker.calculate (inference_worker.py:114-119) + ResidualTower.forward
 // (games/general/modules.py:27-40,88-107): preprocess -> conv3x3 stem -> N residual blocks @128 ch ->
-// 1x1 policy/value head convs (BN folded, eval mode) in ONE persistent kernel, then the small fully
-// connected heads in a second kernel.
+// 1x1 policy/value head convs (BN folded, eval mode) -> Linear+softmax / Linear-ReLU-Linear-tanh heads in ONE
+// persistent kernel (tower_kernel<2>, the default).  DESIGN.md 3.3/3.4 has the measurements behind every choice.
 //
 // Design (B200-first):
-//   * One CTA owns 7 boards for the whole tower.  Activations never leave shared memory: two bf16
-//     ping-pong buffers of 400 rows x 128 channels (row = padded board cell, index col*7+row, 56 rows
-//     per board incl. zero guard cells, so a 3x3 tap is a constant row shift and needs no im2col).
-//   * Every conv is 9 (taps) x 8 (K slices of 16 channels) tcgen05.mma steps of M=128 rows x N=128
-//     out-channels x K=16, for 3 row tiles; A = activations read in place through a shifted
-//     no-swizzle K-major shared-memory descriptor, B = the 4 KB weight slice of that (tap, K slice),
-//     D = fp32 accumulators in TMEM (3 x 128 columns).
-//   * Weights (12.6 MB bf16 for 20 blocks, L2 resident) are pre-packed on the host in exactly the
-//     order the MMA consumes them and streamed by one producer thread with cp.async.bulk (TMA) through
-//     a 3-stage (8 KB each) mbarrier ring; each slice is loaded once per layer and reused by the 3 row tiles.
-//   * 16 epilogue warps read TMEM (tcgen05.ld 32x32b), add the folded-BN bias, the residual, apply ReLU,
-//     zero the padding rows and write bf16 rows back into the other activation buffer.
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 4..19 = epilogue.
+//   * A cluster of two CTAs (one SM pair); every CTA owns 7 boards for the whole network.  Activations never leave
+//     shared memory: two bf16 ping-pong buffers of 400 rows x 128 channels (row = padded board cell, index col*7+row,
+//     56 rows per board incl. zero guard cells, so a 3x3 tap is a constant row shift and needs no im2col).
+//   * Every conv is 9 (taps) x 8 (K slices of 16 channels) tcgen05.mma.cta_group::2 steps of M=256 (128 rows of each CTA)
+//     x N=128 out-channels x K=16, for 3 row tiles; A = activations read in place through a shifted no-swizzle K-major
+//     shared-memory descriptor, B = the weight slice of that (tap, K slice) -- each CTA stages half of it --, D = fp32
+//     accumulators in TMEM (3 x 128 columns).  The folded-BN bias is the first MMA of a layer (ones x bias^T).
+//   * Weights (13.5 MB bf16 for 20 blocks, L2 resident) are pre-packed on the host in exactly the order the MMAs consume
+//     them and streamed by one producer lane per CTA with cp.async.bulk (TMA) through a 6 x 4 KB mbarrier ring.
+//   * One elected lane of the leader CTA issues every MMA; its instruction stream paces the kernel, so descriptors are
+//     advanced with single 32-bit adds.  Layers are handed over tile by tile (epi_done[t] / acc_full[t]): the next layer's
+//     first tap starts on tile 0 while the epilogue still works on tiles 1 and 2.
+//   * 16 epilogue warps read TMEM (tcgen05.ld 32x32b.x32, double-buffered), add the residual, apply ReLU + bf16 packing,
+//     zero the padding rows and write the rows back into the other activation buffer.
+//   * FC heads in the same kernel: the value layer on tcgen05 with the roles swapped (hidden units = M, boards = N) from a
+//     second TMA ring in the dead activation buffer, the policy layer in fp32 on the epilogue warps, DSMEM exchange of the
+//     two CTAs' half sums.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warp 2 = peer relay (CTA 1), warps 4..19 = epilogue.
+// Fallbacks: tower_kernel<1> (SPX_TOWER_NCTA=1: one CTA per 7 boards, cta_group::1) and heads_kernel
+// (SPX_TOWER_FUSED_HEADS=0 or after tower_kernel<1>).  SPX_DBG_* macros build timing experiments only.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
