@@ -212,11 +212,16 @@ __host__ __device__ constexpr unsigned make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ bool row_is_cell(int row, int& board, int& cell) {
+// Which padded row is a real board cell, and which one.  Connect4 fills the 7x6 slot; a TicTacToe board (ResidualTower on
+// the 3x3 env, main.py:74 with --g tictactoe) is embedded in the corner of the same slot: cell (x, y) sits at column x, row y,
+// every other row of the slot is forced to zero by the epilogue like the padding rows, which is exactly the zero padding of
+// a 3x3 convolution.  `cell` is the flatten index of modules.py:98,103 (x * H + y), `bit` the bitboard index of the cell.
+__device__ __forceinline__ bool row_is_cell(int game, int row, int& board, int& cell, int& bit) {
     board = row / BOARD_ROWS;
     const int p = row - board * BOARD_ROWS;
     const int col = p / PAD_STRIDE, r = p - col * PAD_STRIDE;
-    cell = col * BOARD_H + r;
+    if (game == SPX_GAME_TICTACTOE) { cell = col * 3 + r; bit = cell; return col < 3 && r < 3; }
+    cell = col * BOARD_H + r; bit = p;
     return p < BOARD_W * PAD_STRIDE && r < BOARD_H;
 }
 
@@ -431,10 +436,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long long* __restrict__ opp_g,
              const unsigned char* __restrict__ needs, long long n_boards, int n_layers,
              const unsigned char* __restrict__ wconv, const float* __restrict__ bias_all, float* __restrict__ head_out,
-             int fused_in, const float* __restrict__ polw, const float* __restrict__ polb, const float* __restrict__ fc_b1,
+             int game, int fused_in, const float* __restrict__ polw, const float* __restrict__ polb, const float* __restrict__ fc_b1,
              const float* __restrict__ fc_w2, const float* __restrict__ fc_b2, float* __restrict__ policy_out, float* __restrict__ value_out) {
     typedef SmemT<NCTA> Smem;
     const bool fused = NCTA == 2 && fused_in != 0;   // FC heads inside this kernel (no head_out round trip, no second launch)
+    const int cells = game == SPX_GAME_TICTACTOE ? 9 : CELLS, n_act = game == SPX_GAME_TICTACTOE ? 9 : 7;
+    const int flat = 32 * cells, fc_iters = flat / 32;   // inputs of each head's first Linear; ring stages of the value layer
     constexpr int STAGES = Smem::STAGES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -535,7 +542,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 // (layer n_layers-2, an even index: n_layers is even, so that completion of acc_full always has parity 0; this
                 // warp is at most a ring (6 stages) ahead of the issuer, so the barrier cannot be a whole phase behind)
                 mbar_wait(&S.acc_full[MT - 1], 0u);
-                for (int it = 0; it < FC_ITERS; ++it) {
+                for (int it = 0; it < fc_iters; ++it) {
                     mbar_wait(&S.fc_empty[fstage], fphase ^ 1u);
                     if (leader) {
                         mbar_expect_tx(&S.fc_full[fstage], FC_STAGE_BYTES);
@@ -564,7 +571,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 }
             }
             if (fused) {
-                for (int it = 0; it < FC_ITERS; ++it) {
+                for (int it = 0; it < fc_iters; ++it) {
                     mbar_wait(&S.fc_full[fstage], fphase);
                     if (leader) mbar_arrive_remote(&S.fc_peer_full[fstage], 0);
                     __syncwarp();
@@ -636,7 +643,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                     SPX_TRACE_IF(leader, n_layers, 1);
                     const unsigned idesc_fc = make_idesc(256, 16);
                     const unsigned xv_lo = ((128u >> 4) << 16) | (smem_u32(S.act[1] + XV_OFF) >> 4);
-                    for (int it = 0; it < FC_ITERS; ++it) {
+                    for (int it = 0; it < fc_iters; ++it) {
                         mbar_wait(&S.fc_full[fstage], fphase);
                         mbar_wait(&S.fc_peer_full[fstage], fphase);
                         const unsigned a_lo = ((unsigned)(FC_KSTEP_BYTES / 2 >> 4) << 16) | (smem_u32(S.act[0] + fstage * FC_STAGE_BYTES) >> 4);
@@ -698,11 +705,10 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
             }
             // preprocess (modules.py:115-125): planes (empty, own, enemy) -> channels 0..2 of buffer 0, channels 3..15 zero
             for (int row = et; row < ROWS; row += EPI_THREADS) {
-                int board, cell;
-                const bool real = row_is_cell(row, board, cell);
-                const int p = row - board * BOARD_ROWS;
+                int board, cell, bit;
+                const bool real = row_is_cell(game, row, board, cell, bit);
                 unsigned o = 0, e = 0;
-                if (real) { o = (unsigned)((S.own[board] >> p) & 1ULL); e = (unsigned)((S.opp[board] >> p) & 1ULL); }
+                if (real) { o = (unsigned)((S.own[board] >> bit) & 1ULL); e = (unsigned)((S.opp[board] >> bit) & 1ULL); }
                 const unsigned emp = real ? (1u - o - e) : 0u;
                 const unsigned one = 0x3F80u;  // bf16(1.0)
                 uint4 v0 = make_uint4((emp ? one : 0u) | ((o ? one : 0u) << 16), e ? one : 0u, 0u, 0u);
@@ -714,7 +720,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
             // per-tile row bookkeeping is layer independent
             bool real_t[MT]; int board_t[MT], cell_t[MT];
 #pragma unroll
-            for (int t = 0; t < MT; ++t) real_t[t] = row_is_cell(t * 128 + quarter * 32 + lane, board_t[t], cell_t[t]);
+            for (int t = 0; t < MT; ++t) { int bit; real_t[t] = row_is_cell(game, t * 128 + quarter * 32 + lane, board_t[t], cell_t[t], bit); }
             for (int l = 0; l < n_layers; ++l) {
                 const LayerInfo li = layer_info(l, n_layers);
                 // stage the bias of layer l+2 while this layer's MMAs are still running (layer l+1's is already visible)
@@ -789,7 +795,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                     // [board][k] and value channels as bf16 in the K-major core-matrix layout [k-chunk][8 boards][8] (board 7 =
                     // zero padding) in the dead activation buffer 1, k = channel*42 + cell (the flatten order of modules.py:98,103).
                     const int ch0 = part * (HEAD_CH / EPI_SPLIT);
-                    if (fused && et < FLAT / 8) *reinterpret_cast<uint4*>(S.act[1] + XV_OFF + et * 128 + 7 * 16) = make_uint4(0, 0, 0, 0);
+                    if (fused && et < flat / 8) *reinterpret_cast<uint4*>(S.act[1] + XV_OFF + et * 128 + 7 * 16) = make_uint4(0, 0, 0, 0);
 #pragma unroll
                     for (int t = 0; t < MT; ++t) {
                         unsigned v[16];
@@ -797,20 +803,20 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                         const long long gb = grp * NB + board_t[t];
                         if (!fused) {
                             if (real_t[t] && gb < n_boards) {
-                                float* ob = head_out + (size_t)gb * (HEAD_CH * CELLS) + cell_t[t];
+                                float* ob = head_out + (size_t)gb * (HEAD_CH * cells) + cell_t[t];
 #pragma unroll
-                                for (int k = 0; k < 16; ++k) ob[(size_t)(ch0 + k) * CELLS] = fmaxf(__uint_as_float(v[k]), 0.f);
+                                for (int k = 0; k < 16; ++k) ob[(size_t)(ch0 + k) * cells] = fmaxf(__uint_as_float(v[k]), 0.f);
                             }
                         } else if (real_t[t]) {
                             if (ch0 < 32) {
-                                float* xp = reinterpret_cast<float*>(S.act[1] + XP_OFF) + board_t[t] * FLAT + cell_t[t];
+                                float* xp = reinterpret_cast<float*>(S.act[1] + XP_OFF) + board_t[t] * flat + cell_t[t];
 #pragma unroll
-                                for (int k = 0; k < 16; ++k) xp[(ch0 + k) * CELLS] = fmaxf(__uint_as_float(v[k]), 0.f);
+                                for (int k = 0; k < 16; ++k) xp[(ch0 + k) * cells] = fmaxf(__uint_as_float(v[k]), 0.f);
                             } else {
                                 unsigned char* xv = S.act[1] + XV_OFF + board_t[t] * 16;
 #pragma unroll
                                 for (int k = 0; k < 16; ++k) {
-                                    const int kk = (ch0 - 32 + k) * CELLS + cell_t[t];
+                                    const int kk = (ch0 - 32 + k) * cells + cell_t[t];
                                     *reinterpret_cast<__nv_bfloat16*>(xv + (kk >> 3) * 128 + (kk & 7) * 2) = __float2bfloat16_rn(fmaxf(__uint_as_float(v[k]), 0.f));
                                 }
                             }
@@ -829,28 +835,28 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
             }
             if constexpr (NCTA == 2) {
                 if (fused) {
-                    float* scr = reinterpret_cast<float*>(S.act[1] + FCS_OFF);   // logits [7][8] | partial [4][16] | own [16] | peer [16]
+                    float* scr = reinterpret_cast<float*>(S.act[1] + FCS_OFF);   // logits [7][9] | partial [4][16] at 64 | own [16] at 128 | peer [16] at 144
                     // ---- policy head Linear(1344 -> A) + softmax (modules.py:99-100) in fp32 on the CUDA cores, while the tensor
                     // pipe runs the value layer: one warp per (board, action) dot product
                     const float* xp = reinterpret_cast<const float*>(S.act[1] + XP_OFF);
                     SPX_TRACE_IF(et == 0, n_layers, 3);
-                    for (int task = warp - EPI_WARP0; task < NB * 7; task += EPI_WARPS) {
-                        const int b = task / 7, a = task - b * 7;
+                    for (int task = warp - EPI_WARP0; task < NB * n_act; task += EPI_WARPS) {
+                        const int b = task / n_act, a = task - b * n_act;
                         float acc = 0.f;
-                        for (int k = lane; k < FLAT; k += 32) acc = fmaf(xp[b * FLAT + k], __ldg(polw + a * FLAT + k), acc);
+                        for (int k = lane; k < flat; k += 32) acc = fmaf(xp[b * flat + k], __ldg(polw + a * flat + k), acc);
 #pragma unroll
                         for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-                        if (lane == 0) scr[b * 8 + a] = acc + __ldg(polb + a);
+                        if (lane == 0) scr[b * 9 + a] = acc + __ldg(polb + a);
                     }
                     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
                     if (et < NB) {
                         const long long gb = grp * NB + et;
                         if (gb < n_boards && (needs == nullptr || needs[gb])) {
-                            float m = scr[et * 8];
-                            for (int a = 1; a < 7; ++a) m = fmaxf(m, scr[et * 8 + a]);
-                            float e[7], z = 0.f;
-                            for (int a = 0; a < 7; ++a) { e[a] = expf(scr[et * 8 + a] - m); z += e[a]; }
-                            for (int a = 0; a < 7; ++a) policy_out[gb * 7 + a] = e[a] / z;
+                            float m = scr[et * 9];
+                            for (int a = 1; a < n_act; ++a) m = fmaxf(m, scr[et * 9 + a]);
+                            float e[SPX_MAX_ACTIONS], z = 0.f;
+                            for (int a = 0; a < n_act; ++a) { e[a] = expf(scr[et * 9 + a] - m); z += e[a]; }
+                            for (int a = 0; a < n_act; ++a) policy_out[gb * n_act + a] = e[a] / z;
                         }
                     }
                     // ---- value head: relu(W1 x + b1) . w2 (+ b2, tanh after the two halves of the hidden layer met)
@@ -1067,49 +1073,57 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 extern "C" {
 
+struct TowerLayout { int A, flat; size_t conv, off_bias, off_polw, off_polb, off_w1t, off_b1, off_w2, off_b2, bytes; };
+/* blob layout of nets.pack_tower_blob: the kernel's weight stream (per layer bias slice + conv weights, then the value layer
+ * as ring stages), then fp32 biases, policy Linear, bf16 value Linear 1, fp32 b1, w2, b2 -- every piece 256-byte aligned */
+static TowerLayout tower_layout(int game, int num_blocks) {
+    TowerLayout L;
+    const int cells = game == SPX_GAME_TICTACTOE ? 9 : CELLS, n_layers = 2 * num_blocks + 2;
+    L.A = game == SPX_GAME_TICTACTOE ? 9 : 7;
+    L.flat = 32 * cells;
+    L.conv = (size_t)9 * KSTEP_BYTES + (size_t)num_blocks * 2 * 72 * KSTEP_BYTES + (size_t)8 * (2 * HEAD_CH * 16) + bias_slices_bytes(num_blocks) +
+             (size_t)(L.flat / 16) * 2 * FC_KSTEP_BYTES;
+    size_t off = align_up(L.conv, 256);
+    L.off_bias = off; off = align_up(off + (size_t)n_layers * CH * 4, 256);
+    L.off_polw = off; off = align_up(off + (size_t)L.A * L.flat * 4, 256);
+    L.off_polb = off; off = align_up(off + 16 * 4, 256);
+    L.off_w1t = off; off = align_up(off + (size_t)L.flat * FC_HIDDEN * 2, 256);
+    L.off_b1 = off; off = align_up(off + FC_HIDDEN * 4, 256);
+    L.off_w2 = off; off = align_up(off + FC_HIDDEN * 4, 256);
+    L.off_b2 = off; off = align_up(off + 16, 256);
+    L.bytes = off;
+    return L;
+}
+
 int64_t spx_tower_blob_bytes(int32_t game, int32_t num_blocks) {
-    if (game != SPX_GAME_CONNECT4 || num_blocks < 0) return -1;
-    const int A = 7, n_layers = 2 * num_blocks + 2;
-    size_t conv = (size_t)9 * 1 * KSTEP_BYTES + (size_t)num_blocks * 2 * 9 * 8 * KSTEP_BYTES + (size_t)8 * (2 * HEAD_CH * 16) + FC_STREAM_BYTES + bias_slices_bytes(num_blocks);
-    size_t off = align_up(conv, 256);
-    off = align_up(off + (size_t)n_layers * CH * 4, 256);      // biases
-    off = align_up(off + (size_t)A * FLAT * 4, 256);           // policy weight
-    off = align_up(off + 16 * 4, 256);                         // policy bias (padded)
-    off = align_up(off + (size_t)FLAT * FC_HIDDEN * 2, 256);   // value fc1 weight [256][1344] bf16
-    off = align_up(off + FC_HIDDEN * 4, 256);                  // b1
-    off = align_up(off + FC_HIDDEN * 4, 256);                  // w2
-    off = align_up(off + 16, 256);                             // b2
-    return (int64_t)off;
+    if ((game != SPX_GAME_CONNECT4 && game != SPX_GAME_TICTACTOE) || num_blocks < 0) return -1;
+    return (int64_t)tower_layout(game, num_blocks).bytes;
 }
 
 int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
     if (!out) return spx::set_err(SPX_E_ARG, "spx_tower_create: null out%s", "");
-    if (game != SPX_GAME_CONNECT4) return spx::set_err(SPX_E_ARG, "spx_tower_create: the native tower is built for the 7x6 connect4 ResidualTower%s", "");
+    if (game != SPX_GAME_CONNECT4 && game != SPX_GAME_TICTACTOE) return spx::set_err(SPX_E_ARG, "spx_tower_create: unknown game%s", "");
     if (num_blocks < 1 || num_blocks > 64) return spx::set_err(SPX_E_ARG, "spx_tower_create: num_blocks out of range%s", "");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return spx::set_err(SPX_E_CUDA, "spx_tower_create: no CUDA device (there is no CPU fallback)%s", "");
     spx_tower* t = new (std::nothrow) spx_tower();
     if (!t) return spx::set_err(SPX_E_ARG, "spx_tower_create: out of host memory%s", "");
     memset(t, 0, sizeof(*t));
-    t->game = game; t->num_blocks = num_blocks; t->n_layers = 2 * num_blocks + 2; t->A = 7;
+    const TowerLayout L = tower_layout(game, num_blocks);
+    t->game = game; t->num_blocks = num_blocks; t->n_layers = 2 * num_blocks + 2; t->A = L.A;
     {
         const char* e = getenv("SPX_TOWER_NCTA");   // 2 (default): SM-pair kernel (cta_group::2); 1: single-CTA kernel
         t->ncta = (e && e[0] == '1') ? 1 : 2;
         const char* f = getenv("SPX_TOWER_FUSED_HEADS");   // 1 (default, SM-pair kernel only): FC heads inside the tower kernel; 0: separate heads kernel
         t->fused = (t->ncta == 2 && !(f && f[0] == '0')) ? 1 : 0;
     }
-    size_t conv = (size_t)9 * KSTEP_BYTES + (size_t)num_blocks * 2 * 72 * KSTEP_BYTES + (size_t)8 * (2 * HEAD_CH * 16) + FC_STREAM_BYTES + bias_slices_bytes(num_blocks);
-    size_t off = align_up(conv, 256);
-    t->off_bias = off; off = align_up(off + (size_t)t->n_layers * CH * 4, 256);
-    t->off_polw = off; off = align_up(off + (size_t)t->A * FLAT * 4, 256);
-    t->off_polb = off; off = align_up(off + 16 * 4, 256);
-    t->off_w1t = off; off = align_up(off + (size_t)FLAT * FC_HIDDEN * 2, 256);
-    t->off_b1 = off; off = align_up(off + FC_HIDDEN * 4, 256);
-    t->off_w2 = off; off = align_up(off + FC_HIDDEN * 4, 256);
-    t->off_b2 = off; off = align_up(off + 16, 256);
-    t->blob_bytes = off;
+    if (game == SPX_GAME_TICTACTOE && !t->fused) {
+        delete t;
+        return spx::set_err(SPX_E_ARG, "spx_tower_create: the 3x3 ResidualTower runs on the SM-pair kernel with fused heads only (unset SPX_TOWER_NCTA / SPX_TOWER_FUSED_HEADS)%s", "");
+    }
+    t->off_bias = L.off_bias; t->off_polw = L.off_polw; t->off_polb = L.off_polb; t->off_w1t = L.off_w1t;
+    t->off_b1 = L.off_b1; t->off_w2 = L.off_w2; t->off_b2 = L.off_b2; t->blob_bytes = L.bytes;
     SPX_CUDA_T(cudaMalloc((void**)&t->blob, t->blob_bytes));
-
     int dev = 0;
     SPX_CUDA_T(cudaGetDevice(&dev));
     SPX_CUDA_T(cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -1166,13 +1180,13 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
         cfg.attrs = attr; cfg.numAttrs = 1;
         SPX_CUDA_T(cudaLaunchKernelEx(&cfg, tower_kernel<2>, (const unsigned long long*)own, (const unsigned long long*)opp, needs_eval,
                                       (long long)n, t->n_layers, (const unsigned char*)t->blob, (const float*)(t->blob + t->off_bias), t->head_buf,
-                                      t->fused, (const float*)(t->blob + t->off_polw), (const float*)(t->blob + t->off_polb), (const float*)(t->blob + t->off_b1),
+                                      t->game, t->fused, (const float*)(t->blob + t->off_polw), (const float*)(t->blob + t->off_polb), (const float*)(t->blob + t->off_b1),
                                       (const float*)(t->blob + t->off_w2), (const float*)(t->blob + t->off_b2), policy, value));
     } else {
         const int grid = (int)(groups < t->sm_count ? groups : t->sm_count);
         tower_kernel<1><<<grid, NUM_THREADS, sizeof(SmemT<1>), st>>>((const unsigned long long*)own, (const unsigned long long*)opp, needs_eval, n,
                                                             t->n_layers, t->blob, (const float*)(t->blob + t->off_bias), t->head_buf,
-                                                            0, nullptr, nullptr, nullptr, nullptr, nullptr, policy, value);
+                                                            t->game, 0, nullptr, nullptr, nullptr, nullptr, nullptr, policy, value);
     }
     spx::count_launch();
     SPX_CUDA_T(cudaGetLastError());

@@ -52,7 +52,7 @@ class MCTreeSearch:
         kind = self._net_kind
         if kind == "auto":
             ok = isinstance(self.network, nets.ResidualTower) or hasattr(self.network, "residual_blocks")
-            ok = ok and self.game == _lib.GAME_CONNECT4 and getattr(self.network.conv1, "out_channels", 0) == 128
+            ok = ok and getattr(self.network.conv1, "out_channels", 0) == 128   # filter_factor 32; 7x6 and 3x3 boards are native
             kind = "tower" if ok else ("hash" if self.network is None else "torch")
             if isinstance(self.network, nets.ConvNetTicTacToe) and self.game == _lib.GAME_TICTACTOE and self.network.action_size == 9:
                 kind = "tttnet"

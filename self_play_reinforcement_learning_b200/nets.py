@@ -252,13 +252,15 @@ def _fc_stream(w1):
 
 
 def pack_tower_blob(module, ncta=2):
-    """ResidualTower (7x6, 128 trunk channels) -> one flat uint8 tensor in the layout spx_tower_load expects."""
+    """ResidualTower (128 trunk channels; the 7x6 Connect4 or the 3x3 TicTacToe board of ResidualTower.from_env) -> one flat
+    uint8 tensor in the layout spx_tower_load expects (spx_tower.cu: tower_layout)."""
     m = module
     assert hasattr(m, "residual_blocks"), "the native tower needs a ResidualTower"
-    assert m.width == 7 and m.height == 6 and m.conv1.out_channels == 128 and m.conv_policy.out_channels == 32
+    assert (m.width, m.height) in ((7, 6), (3, 3)) and m.conv1.out_channels == 128 and m.conv_policy.out_channels == 32
     blocks = list(m.residual_blocks)
     n_layers = 2 * len(blocks) + 2
-    A, FLAT, HID = m.linear_policy.out_features, 32 * 42, 256
+    A, FLAT, HID = m.linear_policy.out_features, 32 * m.width * m.height, 256
+    assert A == (7 if m.width == 7 else 9), "action_size must be the board's own (7 / 9)"
     assert m.fc_value.out_features == HID and m.linear_policy.in_features == FLAT
     conv_parts, biases = [], torch.zeros(n_layers, 128)
     w, b = _fold(m.conv1, m.bn1)
@@ -302,13 +304,16 @@ def pack_tower_blob(module, ncta=2):
 class NativeTower:
     """Handle on one spx_tower (the tcgen05 network of libspx) with weights loaded from a ResidualTower."""
 
-    def __init__(self, module, game=GAME_CONNECT4):
+    def __init__(self, module, game=None):
         if not torch.cuda.is_available():
             raise _lib.SpxError("the native tower runs on sm_100a only (no CPU fallback)")
-        self.game, self.num_blocks = game, len(module.residual_blocks)
+        board_game = GAME_CONNECT4 if (module.width, module.height) == (7, 6) else _lib.GAME_TICTACTOE
+        if game is not None and game != board_game:
+            raise ValueError("the network's board size does not match the game")
+        self.game, self.num_blocks = board_game, len(module.residual_blocks)
         self.A = module.linear_policy.out_features
         self._h = C.c_void_p()
-        check(lib().spx_tower_create(game, self.num_blocks, C.byref(self._h)), "spx_tower_create")
+        check(lib().spx_tower_create(self.game, self.num_blocks, C.byref(self._h)), "spx_tower_create")
         self.ncta = lib().spx_tower_ncta(self._h)
         self.fused_heads = bool(lib().spx_tower_fused_heads(self._h))
         self.load(module)

@@ -159,3 +159,50 @@ def test_fused_heads_agree_with_the_separate_heads_kernel_and_respect_the_mask(m
         if tw is fused:   # the separate heads kernel skips whole 16-board groups only: rows without a request are unspecified there
             assert bool((p[~m] == -1.0).all()) and bool((v[~m] == -2.0).all())
     fused.close(); plain.close()
+
+
+@pytest.mark.parametrize("blocks,n", [(1, 7), (15, 300), (15, 1100)])
+def test_tictactoe_tower_matches_fp32_reference(blocks, n):
+    """ResidualTower.from_env(TicTacToeEnv, ...) (main.py:74 with --g tictactoe): 3x3 boards embedded in the tower's board slots."""
+    from self_play_reinforcement_learning_b200 import nets
+    from self_play_reinforcement_learning_b200.envs import boards_to_bits
+    torch.manual_seed(10 + blocks)
+    net = nets.ResidualTower(3, 3, 9, num_blocks=blocks).eval()
+    _randomise_bn(net)
+    rng = np.random.default_rng(blocks)
+    boards = torch.from_numpy(rng.integers(-1, 2, size=(n, 3, 3)).astype(np.int64))
+    bits = boards_to_bits(boards.cuda(), 1)
+    tw = nets.NativeTower(net)
+    assert tw.game == 1 and tw.A == 9
+    p, v = tw.forward_bits(bits[:, 0].contiguous(), bits[:, 1].contiguous())
+    torch.cuda.synchronize()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        pr, vr = net.cuda().float().forward(boards.cuda())
+    dp, dv = (p - pr).abs().max().item(), (v - vr.reshape(-1)).abs().max().item()
+    print(f"tictactoe blocks={blocks} n={n} max|dpolicy|={dp:.3e} max|dvalue|={dv:.3e}")
+    assert p.shape == (n, 9) and torch.allclose(p.sum(1), torch.ones(n, device="cuda"), atol=1e-5)
+    assert dp < TOL_POLICY and dv < TOL_VALUE
+    perm = torch.randperm(n, device="cuda")
+    p2, v2 = tw.forward_bits(bits[perm, 0].contiguous(), bits[perm, 1].contiguous())
+    assert torch.equal(p2, p[perm]) and torch.equal(v2, v[perm])
+    tw.close()
+
+
+def test_tictactoe_selfplay_with_native_residual_tower_replays_in_oracle():
+    from self_play_reinforcement_learning_b200 import envs, nets
+    from self_play_reinforcement_learning_b200.selfplay import BatchedSelfPlay
+    from tests import helpers as H
+    torch.manual_seed(2)
+    net = nets.ResidualTower(3, 3, 9, num_blocks=2).eval()
+    n_games, sims = 24, 60
+    sp = BatchedSelfPlay(net, env=envs.TicTacToeEnv, n_games=n_games, sims=sims, net="tower", seed=8, games_target=n_games, noise_mode=0,
+                         move_log=True)
+    logs = H.run_logged(sp.engine)
+    recs, res = H.split_by_game(sp.engine.drain_records(), sp.engine.drain_results())
+    assert len(res) == n_games
+    for g in range(n_games):
+        o = H.replay_in_oracle(1, sims, 8, g, None, logs[g])
+        H.compare_game(1, sp.engine.move_log(g), recs[g], res[g], o)
+    sp.close()
