@@ -383,12 +383,8 @@ def _env_roofline(_lib, torch):
     L = _lib.lib()
     times = []
     for i, a in enumerate(acts):
-        e0, e1 = _lib.Event(), _lib.Event()
         torch.cuda.synchronize()
-        import ctypes
-        # events recorded on the launching stream around the single kernel launch
-        torch.cuda.current_stream().synchronize()
-        _lib.check(L.spx_advance_timed(None, None, None, st, None, None) if False else 0)
+        # events recorded on the launching stream (torch's current stream, passed as `st`) around the single launch
         rec = torch.cuda.Event(enable_timing=True); rec2 = torch.cuda.Event(enable_timing=True)
         rec.record()
         _lib.check(L.spx_env_step(0, n, state.data_ptr(), done.data_ptr(), a.data_ptr(), player.data_ptr(), reward.data_ptr(),

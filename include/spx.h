@@ -46,7 +46,7 @@ extern "C" {
 /* status codes written per game by spx_env_step (the reference raises instead) */
 #define SPX_ENV_OK 0
 #define SPX_ENV_GAME_OVER (-1)   /* GameOver    connect4env.py:30-31, tictactoe_env.py:24-25 */
-#define SPX_ENV_VALUE_ERROR (-2) /* ValueError  connect4env.py:36-37 (full column)           */
+#define SPX_ENV_VALUE_ERROR (-2) /* ValueError  connect4env.py:36-37 (full column); also action >= A (IndexError there) */
 #define SPX_ENV_SKIPPED (-3)     /* action < 0: slot not stepped                             */
 
 typedef struct spx_engine spx_engine;

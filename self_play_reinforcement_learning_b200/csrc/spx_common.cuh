@@ -116,6 +116,59 @@ __host__ __device__ __forceinline__ int reward_at<SPX_GAME_CONNECT4>(u64 m, int 
     return hit != 0 ? 1 : 0;
 }
 
+// Union of the four full lines (column, row, both diagonals) through Connect4 cell `bitpos` = 7*col + row; 0 for sentinel bits.
+// Run detection on `mover & c4_lines_through(cell)` equals the four per-line folds of get_reward: a line parallel to direction d
+// that does not pass through the cell meets the other three lines in at most three cells, so it cannot hold a run of four.
+__host__ __device__ inline u64 c4_lines_through(int bitpos) {
+    const int x = bitpos / 7, y = bitpos % 7;
+    if (x > 6 || y > 5) return 0;
+    u64 m = 0;
+    for (int c = 0; c < 7; ++c)
+        for (int r = 0; r < 6; ++r)
+            if (c == x || r == y || c - r == x - y || c + r == x + y) m |= 1ULL << (7 * c + r);
+    return m;
+}
+
+// Connect4 env.step for the batched kernel, branch-free and sized for the integer pipe (the scalar restatement above costs
+// ~195 ALU instructions per board and made the kernel ALU bound):  * the four line folds run on ONE masked board
+// (`lines` = shared-memory copy of c4_lines_through, 49 entries)  * the column fold runs on the 6-bit column in 32-bit registers
+// * heights < 6 of all seven columns is one 64-bit multiply that gathers the top-row bits.   Same results as env_step<CONNECT4>
+// + valid_mask<CONNECT4> bit for bit (tests/test_env_gpu.py holds the two against each other); action >= 7 reports VALUE_ERROR.
+__device__ __forceinline__ void c4_step_fast(u64& own, u64& opp, int action, int player, int done_in, const u64* __restrict__ lines,
+                                             int& reward, int& done_out, int& code, unsigned& valid) {
+    const u64 occ = own | opp;
+    const bool in_range = (unsigned)action < 7u;
+    const int sh = in_range ? 7 * action : 0;
+    const unsigned col = (unsigned)(occ >> sh) & 0x3Fu;
+    const int y = __popc(col);                                      // heights[action]
+    const bool step = in_range && !done_in && y < 6;
+    code = action < 0 ? SPX_ENV_SKIPPED : (done_in ? SPX_ENV_GAME_OVER : (step ? SPX_ENV_OK : SPX_ENV_VALUE_ERROR));
+    const int cell = sh + y;
+    // the new piece as two 32-bit halves: shl.b32 clamps (amount >= 32 gives 0), so "no step" is simply amount 64
+    const unsigned amt = step ? (unsigned)cell : 64u;
+    unsigned bit_lo, bit_hi;
+    asm("shl.b32 %0, 1, %1;" : "=r"(bit_lo) : "r"(amt));
+    asm("shl.b32 %0, 1, %1;" : "=r"(bit_hi) : "r"(amt - 32u));
+    const u64 bit = ((u64)bit_hi << 32) | bit_lo;
+    const u64 mine = player > 0 ? ~0ULL : 0ULL;                     // select by mask: folds into three-input logic ops
+    own |= bit & mine;
+    opp |= bit & ~mine;
+    const u64 m = (own & mine) | (opp & ~mine);
+    const unsigned cm = (unsigned)(m >> sh) & 0x3Fu;                // board[x, :]
+    unsigned v = cm & (cm >> 1);
+    v &= v >> 2;
+    const u64 mm = m & lines[cell];
+    u64 h = mm & (mm >> 7);   h &= h >> 14;                         // board[:, y]
+    u64 d1 = mm & (mm >> 8);  d1 &= d1 >> 16;                       // np.diagonal(board, y - x)
+    u64 d2 = mm & (mm >> 6);  d2 &= d2 >> 12;                       // np.diagonal(np.flipud(board), ...)
+    const u64 hit = h | d1 | d2;
+    reward = (step && (v | (unsigned)hit | (unsigned)(hit >> 32))) ? 1 : 0;
+    const u64 occ2 = occ | bit;
+    const u64 open_top = ~occ2 & 0x0000810204081020ULL;             // bit 7c+5 clear <=> heights[c] < 6
+    valid = (unsigned)((open_top * 0x0000001041041041ULL) >> 41) & 0x7Fu;   // bit 7c+5 -> bit c (no two partial products collide)
+    done_out = step ? (int)((reward != 0) | (__popcll(occ2) == 42)) : done_in;
+}
+
 template <int GAME>
 __host__ __device__ __forceinline__ unsigned valid_mask(u64 own, u64 opp) {
     typedef Rules<GAME> R;
@@ -136,6 +189,7 @@ __host__ __device__ __forceinline__ int env_step(u64& own, u64& opp, int action,
     typedef Rules<GAME> R;
     u64 occ = own | opp;
     int x, y;
+    if ((unsigned)action >= (unsigned)R::A) { reward = 0; done = 0; return SPX_ENV_VALUE_ERROR; }  // the reference raises IndexError
     if (GAME == SPX_GAME_CONNECT4) {
         x = action;
         y = SPX_POPC((occ >> (7 * action)) & 0x3FULL);  // heights[action]

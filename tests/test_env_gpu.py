@@ -139,3 +139,31 @@ def test_env_step_vector_and_scalar_paths_agree(game):
         for x, y in zip(ta, tu):
             assert torch.equal(x, y)
     assert bool((aligned[-1][1] == 1).any()) and bool((aligned[5][4] == -1).any() or (aligned[-1][4] == -1).any())
+
+
+@pytest.mark.parametrize("game", [0, 1])
+@pytest.mark.parametrize("n", [3, 64])
+def test_env_step_out_of_range_action_is_value_error(game, n):
+    """action >= A (IndexError in the reference) reports SPX_ENV_VALUE_ERROR and leaves the board alone, on the scalar path
+    (n = 3) and on the vector path (n = 64)."""
+    import ctypes as C
+    from self_play_reinforcement_learning_b200._lib import check, lib
+    A = spec.GAME_DIMS[game][2]
+    dev = torch.device("cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    state = torch.zeros(n, 2, dtype=torch.int64, device=dev)
+    done, reward = torch.zeros(n, dtype=torch.uint8, device=dev), torch.zeros(n, dtype=torch.int8, device=dev)
+    valid, status = torch.zeros(n, dtype=torch.int16, device=dev), torch.zeros(n, dtype=torch.int8, device=dev)
+    player = torch.ones(n, dtype=torch.int8, device=dev)
+    a = torch.full((n,), A, dtype=torch.int32, device=dev)
+    a[1] = 1_000_000
+    a[2] = 0
+    check(lib().spx_env_step(game, n, state.data_ptr(), done.data_ptr(), a.data_ptr(), player.data_ptr(), reward.data_ptr(),
+                             valid.data_ptr(), status.data_ptr(), st), "spx_env_step")
+    torch.cuda.synchronize()
+    want = torch.full((n,), -2, dtype=torch.int8, device=dev)
+    want[2] = 0
+    assert torch.equal(status, want)
+    assert int(state[2, 0]) == 1 and int(state.sum()) == 1
+    assert not bool(done.any()) and not bool(reward.any())
+    assert bool((valid == (1 << A) - 1).all() if game == 0 else (valid[0] == 0x1FF))
