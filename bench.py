@@ -397,7 +397,7 @@ def _env_roofline(_lib, torch):
     ms = sum(times) / len(times)
     peaks = _peaks()
     gbs = n * 43 / (ms / 1e3) / 1e9
-    return {"kernel": "spx::env_step_kernel_v4<connect4>", "boards": n, "bytes_per_transition": 43, "kernel_ms": ms, "achieved_GBps": gbs,
+    return {"kernel": "spx::env_step_quad_kernel<connect4>", "boards": n, "bytes_per_transition": 43, "kernel_ms": ms, "achieved_GBps": gbs,
             "peak_GBps": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"], "transitions_per_s": n / (ms / 1e3)}
 
 

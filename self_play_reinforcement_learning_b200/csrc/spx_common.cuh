@@ -169,6 +169,50 @@ __device__ __forceinline__ void c4_step_fast(u64& own, u64& opp, int action, int
     done_out = step ? (int)((reward != 0) | (__popcll(occ2) == 42)) : done_in;
 }
 
+// TicTacToe: the (up to) four lines of three through cell `a` = 3x+y as four 16-bit fields (row board[:, y], column board[x, :],
+// main diagonal if x == y, anti-diagonal if x + y == 2); an absent or shorter line is 0xFFFF, which no 9-bit board contains.
+__host__ __device__ inline u64 ttt_lines_through(int a) {
+    if (a < 0 || a > 8) return ~0ULL;
+    const int x = a / 3, y = a % 3;
+    const u64 row = 0x49ULL << y, colm = 0x7ULL << (3 * x);
+    const u64 dg = (x == y) ? 0x111ULL : 0xFFFFULL, ad = (x + y == 2) ? 0x54ULL : 0xFFFFULL;
+    return row | (colm << 16) | (dg << 32) | (ad << 48);
+}
+
+// TicTacToe env.step for the batched kernel (same results as env_step<TICTACTOE> + valid_mask<TICTACTOE>, bit for bit):
+// occupied target = silent no-op with the reward still evaluated (tictactoe_env.py:28-31), action >= 9 reports VALUE_ERROR.
+__device__ __forceinline__ void ttt_step_fast(u64& own, u64& opp, int action, int player, int done_in, const u64* __restrict__ lines,
+                                              int& reward, int& done_out, int& code, unsigned& valid) {
+    const unsigned o = (unsigned)own, e = (unsigned)opp;             // 9-bit boards
+    const bool in_range = (unsigned)action < 9u;
+    const bool step = in_range && !done_in;
+    code = action < 0 ? SPX_ENV_SKIPPED : (done_in ? SPX_ENV_GAME_OVER : (step ? SPX_ENV_OK : SPX_ENV_VALUE_ERROR));
+    const int a = in_range ? action : 0;
+    const unsigned occ = o | e;
+    const unsigned bit = (step ? (1u << a) : 0u) & ~occ;
+    const bool mine = player > 0;
+    const unsigned o2 = o | (mine ? bit : 0u), e2 = e | (mine ? 0u : bit);
+    const unsigned m = mine ? o2 : e2;
+    const u64 L = lines[a];
+    const unsigned l01 = (unsigned)L, l23 = (unsigned)(L >> 32);
+    const unsigned m2 = m | (m << 16);
+    const unsigned t01 = ~m2 & l01, t23 = ~m2 & l23;                 // a 16-bit field is 0 iff that line is complete
+    const bool win = !(t01 & 0xFFFFu) || !(t01 >> 16) || !(t23 & 0xFFFFu) || !(t23 >> 16);
+    reward = (step && win) ? 1 : 0;
+    const unsigned occ2 = o2 | e2;
+    valid = ~occ2 & 0x1FFu;
+    done_out = step ? (int)((reward != 0) | (occ2 == 0x1FFu)) : done_in;
+    own = (own & ~0x1FFULL) | o2;
+    opp = (opp & ~0x1FFULL) | e2;
+}
+
+template <int GAME>
+__device__ __forceinline__ void step_fast(u64& own, u64& opp, int action, int player, int done_in, const u64* __restrict__ lines,
+                                          int& reward, int& done_out, int& code, unsigned& valid) {
+    if (GAME == SPX_GAME_CONNECT4) c4_step_fast(own, opp, action, player, done_in, lines, reward, done_out, code, valid);
+    else ttt_step_fast(own, opp, action, player, done_in, lines, reward, done_out, code, valid);
+}
+
 template <int GAME>
 __host__ __device__ __forceinline__ unsigned valid_mask(u64 own, u64 opp) {
     typedef Rules<GAME> R;

@@ -735,59 +735,20 @@ __global__ void __launch_bounds__(256) env_step_kernel(long long n, ulonglong2* 
     }
 }
 
-// Four CONSECUTIVE boards per thread: every array is touched with one 16-byte-per-board-quad (state: 4 x 16 B) or 4/8-byte vector
-// access per thread, i.e. a warp reads/writes whole 128-byte lines of the byte-sized arrays instead of 32-byte sectors, and
-// issues 15 instead of 36 memory instructions per 4 boards.  Needs 16-byte aligned arrays (checked by the host wrapper).
+// Four CONSECUTIVE boards per thread, written for the DRAM roofline: the 64 bytes of state move as two 256-bit accesses (whole
+// 32-byte sectors per lane), every byte-sized array with ONE vector access per thread (action int4, player/done/reward/status
+// 4 x 8 bit, valid mask 4 x 16 bit), so a warp touches whole 128-byte lines; the rules are c4_step_fast / ttt_step_fast
+// (Connect4: ~80 integer-pipe instructions per board; the generic restatement of env_step_kernel needs ~195, which made the
+// first vector kernel ALU bound at 0.56 of the copy bandwidth).  Needs 32-byte aligned state and 16-byte aligned other arrays
+// (the host wrapper checks and otherwise takes the scalar kernel).
 template <int GAME>
-__global__ void __launch_bounds__(256) env_step_kernel_v4(long long n4, ulonglong2* __restrict__ state, uchar4* __restrict__ done,
-                                const int4* __restrict__ action, const char4* __restrict__ player, char4* __restrict__ reward,
-                                ushort4* __restrict__ valid, char4* __restrict__ status) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
-        ulonglong2 st[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) st[u] = state[4 * q + u];
-        const int4 a4 = action[q];
-        const uchar4 d4 = done[q];
-        const char4 p4 = player[q];
-        const int a[4] = {a4.x, a4.y, a4.z, a4.w};
-        const int d[4] = {d4.x, d4.y, d4.z, d4.w};
-        const int pl[4] = {p4.x, p4.y, p4.z, p4.w};
-        int r[4], code[4], dn[4];
-        unsigned short vm[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            r[u] = 0; code[u] = SPX_ENV_OK; dn[u] = d[u];
-            if (a[u] < 0) code[u] = SPX_ENV_SKIPPED;
-            else if (d[u]) code[u] = SPX_ENV_GAME_OVER;
-            else {
-                u64 own = st[u].x, opp = st[u].y;
-                int dd = 0;
-                code[u] = env_step<GAME>(own, opp, a[u], pl[u], r[u], dd);
-                if (code[u] == SPX_ENV_OK) { st[u].x = own; st[u].y = opp; dn[u] = dd; }
-            }
-            vm[u] = (unsigned short)valid_mask<GAME>(st[u].x, st[u].y);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) state[4 * q + u] = st[u];   // unchanged boards are rewritten with the same bytes
-        done[q] = make_uchar4((unsigned char)dn[0], (unsigned char)dn[1], (unsigned char)dn[2], (unsigned char)dn[3]);
-        reward[q] = make_char4((signed char)r[0], (signed char)r[1], (signed char)r[2], (signed char)r[3]);
-        valid[q] = make_ushort4(vm[0], vm[1], vm[2], vm[3]);
-        status[q] = make_char4((signed char)code[0], (signed char)code[1], (signed char)code[2], (signed char)code[3]);
-    }
-}
-
-// Connect4 instance of the quad kernel, written for the DRAM roofline: the 64 bytes of state of a thread's four boards move
-// as two 256-bit accesses (whole 32-byte sectors per lane), every load is issued before the first use (the asm statements
-// keep the compiler from sinking them behind the in-place stores), and the rules are c4_step_fast (~80 integer-pipe
-// instructions per board; the generic restatement needs ~195 and made the kernel ALU bound at 0.56 of the copy bandwidth).
-// Needs 32-byte aligned state and 16-byte aligned other arrays (host wrapper checks).
-__global__ void __launch_bounds__(256) env_step_c4_kernel(long long n4, ulonglong2* __restrict__ state, uchar4* __restrict__ done,
+__global__ void __launch_bounds__(256) env_step_quad_kernel(long long n4, ulonglong2* __restrict__ state, uchar4* __restrict__ done,
                                 const int4* __restrict__ action, const char4* __restrict__ player, char4* __restrict__ reward,
                                 ushort4* __restrict__ valid, char4* __restrict__ status) {
     __shared__ u64 s_lines[64];
-    if (threadIdx.x < 64) s_lines[threadIdx.x] = c4_lines_through(threadIdx.x);
+    if (threadIdx.x < 64) s_lines[threadIdx.x] = GAME == SPX_GAME_CONNECT4 ? c4_lines_through(threadIdx.x) : ttt_lines_through(threadIdx.x);
     __syncthreads();
+    // plain ld/st: .cs and L1::no_allocate variants measured the same (5.5 TB/s on 16 Mi boards)
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
         u64 own[4], opp[4];
@@ -806,17 +767,17 @@ __global__ void __launch_bounds__(256) env_step_c4_kernel(long long n4, ulonglon
             int r, dn, code;
             const int d = (d4w >> (8 * u)) & 0xFF;
             const int pl = (int)(signed char)((p4w >> (8 * u)) & 0xFF);
-            c4_step_fast(own[u], opp[u], a[u], pl, d, s_lines, r, dn, code, vm[u]);
+            step_fast<GAME>(own[u], opp[u], a[u], pl, d, s_lines, r, dn, code, vm[u]);
             dn_w |= (unsigned)dn << (8 * u);
             r_w |= (unsigned)r << (8 * u);
             code_w |= ((unsigned)code & 0xFFu) << (8 * u);
         }
         asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(sp), "l"(own[0]), "l"(opp[0]), "l"(own[1]), "l"(opp[1]) : "memory");
         asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(sp + 2), "l"(own[2]), "l"(opp[2]), "l"(own[3]), "l"(opp[3]) : "memory");
-        *reinterpret_cast<unsigned*>(done + q) = dn_w;
-        *reinterpret_cast<unsigned*>(reward + q) = r_w;
-        *reinterpret_cast<uint2*>(valid + q) = make_uint2(vm[0] | (vm[1] << 16), vm[2] | (vm[3] << 16));
-        *reinterpret_cast<unsigned*>(status + q) = code_w;
+        asm volatile("st.global.u32 [%0], %1;" :: "l"(done + q), "r"(dn_w) : "memory");
+        asm volatile("st.global.u32 [%0], %1;" :: "l"(reward + q), "r"(r_w) : "memory");
+        asm volatile("st.global.v2.u32 [%0], {%1,%2};" :: "l"(valid + q), "r"(vm[0] | (vm[1] << 16)), "r"(vm[2] | (vm[3] << 16)) : "memory");
+        asm volatile("st.global.u32 [%0], %1;" :: "l"(status + q), "r"(code_w) : "memory");
     }
 }
 
@@ -956,15 +917,14 @@ int spx_env_step(int32_t game, int64_t n, void* state, uint8_t* done, const int3
     const int block = 256;
     // vector path for the aligned bulk (4 boards per thread), scalar path for an unaligned call and for the last n % 4 boards
     const uintptr_t mis = (uintptr_t)state | (uintptr_t)done | (uintptr_t)action | (uintptr_t)player | (uintptr_t)reward | (uintptr_t)valid | (uintptr_t)status;
-    const int64_t n4 = (mis & 15) ? 0 : n / 4;
+    const int64_t n4 = ((mis & 15) || ((uintptr_t)state & 31)) ? 0 : n / 4;
     if (n4 > 0) {
-        const int grid = grid_for(n4, block);
-        if (game == SPX_GAME_CONNECT4 && ((uintptr_t)state & 31) == 0)
-            env_step_c4_kernel<<<resident_grid((const void*)env_step_c4_kernel, n4, block), block, 0, st>>>(n4, (ulonglong2*)state, (uchar4*)done, (const int4*)action, (const char4*)player, (char4*)reward, (ushort4*)valid, (char4*)status);
-        else if (game == SPX_GAME_CONNECT4)
-            env_step_kernel_v4<SPX_GAME_CONNECT4><<<grid, block, 0, st>>>(n4, (ulonglong2*)state, (uchar4*)done, (const int4*)action, (const char4*)player, (char4*)reward, (ushort4*)valid, (char4*)status);
+        if (game == SPX_GAME_CONNECT4)
+            env_step_quad_kernel<SPX_GAME_CONNECT4><<<resident_grid((const void*)env_step_quad_kernel<SPX_GAME_CONNECT4>, n4, block), block, 0, st>>>(
+                n4, (ulonglong2*)state, (uchar4*)done, (const int4*)action, (const char4*)player, (char4*)reward, (ushort4*)valid, (char4*)status);
         else
-            env_step_kernel_v4<SPX_GAME_TICTACTOE><<<grid, block, 0, st>>>(n4, (ulonglong2*)state, (uchar4*)done, (const int4*)action, (const char4*)player, (char4*)reward, (ushort4*)valid, (char4*)status);
+            env_step_quad_kernel<SPX_GAME_TICTACTOE><<<resident_grid((const void*)env_step_quad_kernel<SPX_GAME_TICTACTOE>, n4, block), block, 0, st>>>(
+                n4, (ulonglong2*)state, (uchar4*)done, (const int4*)action, (const char4*)player, (char4*)reward, (ushort4*)valid, (char4*)status);
         count_launch();
     }
     const int64_t first = 4 * n4, rest = n - first;

@@ -106,8 +106,9 @@ def test_env_full_size_property():
 
 @pytest.mark.parametrize("game", [0, 1])
 def test_env_step_vector_and_scalar_paths_agree(game):
-    """spx_env_step takes a 4-boards-per-thread vector path when every array is 16-byte aligned and a scalar path otherwise
-    (and for the last n % 4 boards): same results for the same boards, whatever the alignment and n."""
+    """spx_env_step takes the 4-boards-per-thread quad kernel (c4_step_fast / ttt_step_fast rules) when the state is 32-byte and
+    every other array 16-byte aligned, and the scalar kernel (generic rules) otherwise and for the last n % 4 boards: same
+    results for the same boards, whatever the alignment and n."""
     import ctypes as C
     from self_play_reinforcement_learning_b200._lib import check, lib
     rng = np.random.default_rng(31 + game)
