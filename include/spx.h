@@ -264,6 +264,18 @@ int spx_replay_read(spx_replay* r, int64_t first, int64_t n, spx_record* host_ou
 int spx_replay_sample(spx_replay* r, int32_t game, int64_t batch, uint64_t seed, uint64_t step, int64_t* idx, int64_t* boards,
                       float* planes, float* tree_probs, float* actual_val, float* q, void* stream);
 
+/* Memory.deduplicate("state", ["actual_val", "tree_probs"], Move) (memory.py:47-54, mcts.py:385-386; UpdateWorker option
+ * `deduplicate`, updateworker.py:88-89) with the Deduplicator of memory.py:56-94 kept on the device: a persistent table of the
+ * distinct states ever folded (first-seen order) with the running f32 sums of tree_probs / actual_val / q and a count; the first
+ * call folds the whole current buffer, later calls every record appended since (evicted or not, as the reference's
+ * temp_queue); the buffer is then REPLACED by one averaged record per distinct state (sum / count; count in spx_record.pad1,
+ * game_index / tree / ply of the first-seen member), the last `maxlen` of them, and `maxlen` becomes the buffer's max_size
+ * (maxlen <= 0 = None: the physical capacity).  Sums run in insertion order, so the result equals the reference's bit for bit.
+ * As shipped the reference raises TypeError here (Move has a fourth field `q` that create_memory does not fill); q is averaged
+ * like the other two value fields.  Synchronises `stream`. */
+int spx_replay_deduplicate(spx_replay* r, int64_t maxlen, void* stream);
+int64_t spx_replay_unique(spx_replay* r); /* len(deduplicator.counter): distinct states folded so far (0 before the first call) */
+
 /* timing-event helpers (cudaEvent_t behind void*), so hosts without a CUDA binding can time on the launching stream */
 int spx_event_create(void** ev_out);
 int spx_event_destroy(void* ev);

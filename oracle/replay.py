@@ -55,6 +55,58 @@ class Memory:
         return [self._buffer[int(i)] for i in sample_indices(seed, step, len(self._buffer), batch_size)]
 
 
+class Deduplicator:
+    """memory.py:56-94 over record dicts (key = the (own, opp) bitboards = the bytes of Move.state; values = tree_probs,
+    actual_val and q as float32, summed one by one in insertion order like `count[value] += getattr(experience, value)` on
+    float32 tensors, then divided by the count like `tensor / int`).  `counter` keeps first-insertion order (a dict)."""
+    VALUES = ("tree_probs", "actual_val", "q")
+
+    def __init__(self, buffer=()):
+        self.counter = {}
+        self.temp_queue = list(buffer)                                        # :62
+
+    def add_temp(self, experience):                                           # :70-71
+        self.temp_queue.append(experience)
+
+    def add(self, r):                                                         # :73-84
+        k = (int(r["own"]), int(r["opp"]))
+        c = self.counter.get(k)
+        if c is None:
+            self.counter[k] = dict(count=1, first=r, tree_probs=np.asarray(r["tree_probs"], np.float32).copy(),
+                                   actual_val=np.float32(r["actual_val"]), q=np.float32(r["q"]))
+        else:
+            c["count"] += 1
+            c["tree_probs"] = (c["tree_probs"] + np.asarray(r["tree_probs"], np.float32)).astype(np.float32)
+            c["actual_val"] = np.float32(c["actual_val"] + np.float32(r["actual_val"]))
+            c["q"] = np.float32(c["q"] + np.float32(r["q"]))
+
+    def deduplicate(self, max_size=None):                                     # :64-68, :86-94
+        for r in self.temp_queue:
+            self.add(r)
+        self.temp_queue = []
+        out = deque(maxlen=max_size)
+        for (own, opp), c in self.counter.items():
+            n = np.float32(c["count"])
+            out.append(dict(own=own, opp=opp, count=c["count"], game_index=int(c["first"]["game_index"]), tree=int(c["first"]["tree"]),
+                            ply=int(c["first"]["ply"]), tree_probs=(c["tree_probs"] / n).astype(np.float32),
+                            actual_val=np.float32(c["actual_val"] / n), q=np.float32(c["q"] / n)))
+        return out
+
+
+def memory_deduplicate(memory, maxlen=None):
+    """Memory.deduplicate (memory.py:47-54) + the add_temp hook of Memory.add (:19-20) for the oracle Memory above."""
+    if getattr(memory, "deduplicator", None) is None:
+        memory.deduplicator = Deduplicator(memory._buffer)
+        plain_add = memory.add
+
+        def add(experience):
+            plain_add(experience)
+            memory.deduplicator.add_temp(experience)
+        memory.add = add
+    memory._buffer = memory.deduplicator.deduplicate(max_size=maxlen)
+    return memory._buffer
+
+
 def assemble(records, game):
     """records: rows with own/opp/tree_probs/q/actual_val -> the tensors MCTreeSearch.loss stacks (mcts.py:236-243)."""
     W, H, A = spec.GAME_DIMS[game]

@@ -34,6 +34,13 @@ open(os.path.join(out_dir, f"{tag}_launches_summary.csv"), "w").write("\n".join(
 print("\n".join(lines))
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+env_rep = os.path.join(ROOT, "gpurun_out", f"prof_env_{tag}.ncu-rep")
+if os.path.exists(env_rep):   # the env kernel is captured from scripts/dbg_env_ncu.py (16 Mi boards, operands from DRAM)
+    raw_env = subprocess.run(["ncu", "-i", env_rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    open(os.path.join(out_dir, f"{tag}_ncu_env_raw.csv"), "w").write(raw_env)
+    h_env = next(csv.reader(raw_env.splitlines()[:1]))
+    if h_env == next(csv.reader(raw.splitlines()[:1])):
+        raw = raw + "\n".join(raw_env.splitlines()[2:]) + "\n"
 open(os.path.join(out_dir, f"{tag}_ncu_full_raw.csv"), "w").write(raw)
 rr = list(csv.reader(raw.splitlines()))
 h = rr[0]
@@ -41,7 +48,8 @@ want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
-        "gpc__cycles_elapsed.avg.per_second", "launch__cluster_dim_x", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum"]
+        "gpc__cycles_elapsed.avg.per_second", "launch__cluster_dim_x", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "dram__throughput.avg.pct_of_peak_sustained_elapsed"]
 idx = [(w, h.index(w)) for w in want if w in h]
 units = rr[1]
 summ = []

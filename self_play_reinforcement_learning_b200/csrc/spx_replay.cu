@@ -12,6 +12,9 @@
 
 #include <new>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include "spx_common.cuh"
 
 namespace spx {
@@ -87,6 +90,86 @@ __global__ void __launch_bounds__(64) gather_kernel(const spx_record* __restrict
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ Deduplicator (memory.py:56-94)
+// The reference keeps a dict keyed by the state bytes: per key the running SUMS of the value fields and a count, in
+// first-insertion order; create_memory emits sum / count per key.  Here the dict is a device table of spx_record (sums in the
+// value fields, count in pad1) in first-seen order; folding n new records into it is: stable sort of (table ++ new) by
+// (own, opp) [two LSD radix passes], segment heads, first-seen position = exclusive scan of "is head" in ORIGINAL order, and one
+// thread per segment that adds the members sequentially in insertion order (the same f32 additions, in the same order, as
+// count[value] += experience.value).
+struct DedupSrc {
+    const spx_record* table; long long n_table;
+    const spx_record* pending;
+    __device__ __forceinline__ const spx_record& at(long long i) const { return i < n_table ? table[i] : pending[i - n_table]; }
+};
+
+__global__ void dedup_key_kernel(DedupSrc src, long long n, int which, const unsigned* __restrict__ order, u64* __restrict__ keys, unsigned* __restrict__ idx) {
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+        const long long i = order ? (long long)order[j] : j;
+        keys[j] = which == 0 ? src.at(i).opp : src.at(i).own;
+        if (!order) idx[j] = (unsigned)j;
+    }
+}
+
+__device__ __forceinline__ bool dedup_is_head(const DedupSrc& src, const unsigned* order, long long j) {
+    if (j == 0) return true;
+    const spx_record& a = src.at(order[j]);
+    const spx_record& b = src.at(order[j - 1]);
+    return a.own != b.own || a.opp != b.opp;
+}
+
+__global__ void dedup_head_kernel(DedupSrc src, long long n, const unsigned* __restrict__ order, int* __restrict__ first_flag) {
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x)
+        first_flag[order[j]] = dedup_is_head(src, order, j) ? 1 : 0;   // stable sort: the head is the first-seen member
+}
+
+__global__ void dedup_fold_kernel(DedupSrc src, long long n, const unsigned* __restrict__ order, const int* __restrict__ pos, spx_record* __restrict__ out) {
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+        if (!dedup_is_head(src, order, j)) continue;
+        const long long first = order[j];
+        spx_record acc = src.at(first);
+        if (first >= src.n_table) acc.pad1 = 1;                       // a raw record opens a new entry with count 1
+        for (long long k = j + 1; k < n && !dedup_is_head(src, order, k); ++k) {
+            const spx_record& m = src.at(order[k]);                   // members after the head are raw records, in insertion order
+#pragma unroll
+            for (int a = 0; a < SPX_MAX_ACTIONS; ++a) acc.tree_probs[a] = __fadd_rn(acc.tree_probs[a], m.tree_probs[a]);
+            acc.actual_val = __fadd_rn(acc.actual_val, m.actual_val);
+            acc.q = __fadd_rn(acc.q, m.q);
+            acc.pad1 += 1;
+        }
+        out[pos[first]] = acc;
+    }
+}
+
+// create_memory: ring[i] = table[first + i] with every value field divided by the count (tensor / int, true division)
+__global__ void dedup_emit_kernel(const spx_record* __restrict__ table, long long first, long long keep, spx_record* __restrict__ ring) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < keep; i += (long long)gridDim.x * blockDim.x) {
+        spx_record r = table[first + i];
+        const float c = (float)r.pad1;
+#pragma unroll
+        for (int a = 0; a < SPX_MAX_ACTIONS; ++a) r.tree_probs[a] = __fdiv_rn(r.tree_probs[a], c);
+        r.actual_val = __fdiv_rn(r.actual_val, c);
+        r.q = __fdiv_rn(r.q, c);
+        ring[i] = r;
+    }
+}
+
+__global__ void ring_linearise_kernel(const spx_record* __restrict__ ring, long long P, long long head, long long n, spx_record* __restrict__ out) {
+    const long long words = n * 5;
+    const uint4* s = reinterpret_cast<const uint4*>(ring);
+    uint4* d = reinterpret_cast<uint4*>(out);
+    for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < words; w += (long long)gridDim.x * blockDim.x) {
+        const long long rec = w / 5, part = w - rec * 5;
+        d[w] = s[((head + rec) % P) * 5 + part];
+    }
+}
+
+static inline unsigned blocks_for(long long n) {
+    long long b = (n + 255) / 256;
+    return (unsigned)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
+}
+
 }  // namespace replay
 }  // namespace spx
 
@@ -94,6 +177,10 @@ struct spx_replay {
     spx_record* ring;
     long long* idx_scratch;
     int64_t P, M, head, size;
+    // Deduplicator state (memory.py:56-62): `table` = counter dict in first-seen order, `pending` = temp_queue
+    bool dedup_active = false;
+    spx_record* table = nullptr;   int64_t n_table = 0;
+    spx_record* pending = nullptr; int64_t n_pending = 0, cap_pending = 0;
 };
 
 #define RP_CUDA(expr)                                                                                    \
@@ -101,6 +188,19 @@ struct spx_replay {
         cudaError_t e_ = (expr);                                                                         \
         if (e_ != cudaSuccess) return spx::set_err(SPX_E_CUDA, "spx_replay: %s", cudaGetErrorString(e_)); \
     } while (0)
+
+static int pending_reserve(spx_replay* r, int64_t need, cudaStream_t st) {
+    if (need <= r->cap_pending) return 0;
+    int64_t cap = r->cap_pending ? r->cap_pending : 1024;
+    while (cap < need) cap *= 2;
+    spx_record* p = nullptr;
+    RP_CUDA(cudaMalloc((void**)&p, sizeof(spx_record) * (size_t)cap));
+    if (r->n_pending) RP_CUDA(cudaMemcpyAsync(p, r->pending, sizeof(spx_record) * (size_t)r->n_pending, cudaMemcpyDeviceToDevice, st));
+    RP_CUDA(cudaStreamSynchronize(st));
+    cudaFree(r->pending);
+    r->pending = p; r->cap_pending = cap;
+    return 0;
+}
 
 extern "C" {
 
@@ -124,7 +224,7 @@ int spx_replay_create(int64_t max_size, int64_t physical_capacity, spx_replay** 
 
 int spx_replay_destroy(spx_replay* r) {
     if (!r) return 0;
-    cudaFree(r->ring); cudaFree(r->idx_scratch);
+    cudaFree(r->ring); cudaFree(r->idx_scratch); cudaFree(r->table); cudaFree(r->pending);
     delete r;
     return 0;
 }
@@ -148,6 +248,11 @@ int spx_replay_reset(spx_replay* r) {
 int spx_replay_append(spx_replay* r, const spx_record* dev_records, int64_t n, void* stream) {
     if (!r || n < 0 || (n > 0 && !dev_records)) return spx::set_err(SPX_E_ARG, "spx_replay_append: bad argument%s", "");
     if (n == 0) return 0;
+    if (r->dedup_active) {   // Memory.add: self.deduplicator.add_temp(experience) (memory.py:19-20) -- every record, evicted or not
+        if (int rc = pending_reserve(r, r->n_pending + n, (cudaStream_t)stream)) return rc;
+        RP_CUDA(cudaMemcpyAsync(r->pending + r->n_pending, dev_records, sizeof(spx_record) * (size_t)n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        r->n_pending += n;
+    }
     const int64_t keep = n < r->M ? n : r->M, skip = n - keep;   // a deque(maxlen=M) fed n > M items keeps the last M
     const int64_t start = (r->head + r->size) % r->P;
     long long blocks = (keep * 5 + 255) / 256;
@@ -189,6 +294,75 @@ int spx_replay_sample(spx_replay* r, int32_t game, int64_t batch, uint64_t seed,
         spx::replay::gather_kernel<SPX_GAME_TICTACTOE><<<(unsigned)batch, 64, 0, st>>>(r->ring, r->P, r->head, ix, (long long*)boards, planes, tree_probs, actual_val, q);
     spx::count_launch();
     RP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int64_t spx_replay_unique(spx_replay* r) { return r ? r->n_table : -1; }
+
+int spx_replay_deduplicate(spx_replay* r, int64_t maxlen, void* stream) {
+    using namespace spx::replay;
+    if (!r) return spx::set_err(SPX_E_ARG, "spx_replay_deduplicate: null%s", "");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!r->dedup_active) {   // Deduplicator(buffer=self._buffer): the first call folds the whole current buffer (memory.py:48-49,62)
+        if (int rc = pending_reserve(r, r->size, st)) return rc;
+        if (r->size) {
+            ring_linearise_kernel<<<blocks_for(r->size * 5), 256, 0, st>>>(r->ring, r->P, r->head, r->size, r->pending);
+            spx::count_launch();
+        }
+        r->n_pending = r->size;
+        r->dedup_active = true;
+    }
+    const int64_t n = r->n_table + r->n_pending;
+    const int64_t max_eff = (maxlen <= 0 || maxlen > r->P) ? r->P : maxlen;   // deque(maxlen=None) is bounded by the physical ring here
+    if (n == 0) { r->head = 0; r->size = 0; r->M = max_eff; return 0; }
+    if (n >= (1LL << 31)) return spx::set_err(SPX_E_OVERFLOW, "spx_replay_deduplicate: more than 2^31 entries%s", "");
+    if (r->n_pending > 0) {
+        u64 *keys_a = nullptr, *keys_b = nullptr; unsigned *idx_a = nullptr, *idx_b = nullptr; int *flag = nullptr, *pos = nullptr;
+        spx_record* fresh = nullptr; void* tmp = nullptr;
+        size_t tmp_sort = 0, tmp_scan = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys_a, keys_b, idx_a, idx_b, (int)n, 0, 64, st);
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, flag, pos, (int)n, st);
+        const size_t tmp_bytes = tmp_sort > tmp_scan ? tmp_sort : tmp_scan;
+        auto release = [&]() { cudaFree(keys_a); cudaFree(keys_b); cudaFree(idx_a); cudaFree(idx_b); cudaFree(flag); cudaFree(pos); cudaFree(tmp); };
+        if (cudaMalloc((void**)&keys_a, 8 * n) != cudaSuccess || cudaMalloc((void**)&keys_b, 8 * n) != cudaSuccess ||
+            cudaMalloc((void**)&idx_a, 4 * n) != cudaSuccess || cudaMalloc((void**)&idx_b, 4 * n) != cudaSuccess ||
+            cudaMalloc((void**)&flag, 4 * n) != cudaSuccess || cudaMalloc((void**)&pos, 4 * n) != cudaSuccess ||
+            cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16) != cudaSuccess || cudaMalloc((void**)&fresh, sizeof(spx_record) * (size_t)n) != cudaSuccess) {
+            release(); cudaFree(fresh);
+            return spx::set_err(SPX_E_CUDA, "spx_replay_deduplicate: cudaMalloc failed%s", "");
+        }
+        const DedupSrc src{r->table, r->n_table, r->pending};
+        const unsigned g = blocks_for(n);
+        size_t tb = tmp_bytes;
+        dedup_key_kernel<<<g, 256, 0, st>>>(src, n, 0, nullptr, keys_a, idx_a);                       // LSD pass 1: by opp
+        cub::DeviceRadixSort::SortPairs(tmp, tb, keys_a, keys_b, idx_a, idx_b, (int)n, 0, 64, st);
+        dedup_key_kernel<<<g, 256, 0, st>>>(src, n, 1, idx_b, keys_a, nullptr);                       // LSD pass 2: by own (stable)
+        tb = tmp_bytes;
+        cub::DeviceRadixSort::SortPairs(tmp, tb, keys_a, keys_b, idx_b, idx_a, (int)n, 0, 64, st);    // idx_a = final order
+        dedup_head_kernel<<<g, 256, 0, st>>>(src, n, idx_a, flag);
+        tb = tmp_bytes;
+        cub::DeviceScan::ExclusiveSum(tmp, tb, flag, pos, (int)n, st);
+        dedup_fold_kernel<<<g, 256, 0, st>>>(src, n, idx_a, pos, fresh);
+        for (int k = 0; k < 4; ++k) spx::count_launch();
+        int last_pos = 0, last_flag = 0;
+        cudaError_t e1 = cudaMemcpyAsync(&last_pos, pos + (n - 1), 4, cudaMemcpyDeviceToHost, st);
+        cudaError_t e2 = cudaMemcpyAsync(&last_flag, flag + (n - 1), 4, cudaMemcpyDeviceToHost, st);
+        cudaError_t e3 = cudaStreamSynchronize(st);
+        cudaError_t e4 = cudaGetLastError();
+        release();
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+            cudaFree(fresh);
+            return spx::set_err(SPX_E_CUDA, "spx_replay_deduplicate: %s", cudaGetErrorString(e3 != cudaSuccess ? e3 : (e4 != cudaSuccess ? e4 : (e1 != cudaSuccess ? e1 : e2))));
+        }
+        cudaFree(r->table);
+        r->table = fresh; r->n_table = (int64_t)last_pos + last_flag; r->n_pending = 0;
+    }
+    // create_memory(max_size): a deque(maxlen) fed every entry in first-seen order keeps the last maxlen (memory.py:86-94)
+    const int64_t keep = r->n_table < max_eff ? r->n_table : max_eff;
+    dedup_emit_kernel<<<blocks_for(keep), 256, 0, st>>>(r->table, r->n_table - keep, keep, r->ring);
+    spx::count_launch();
+    RP_CUDA(cudaGetLastError());
+    r->head = 0; r->size = keep; r->M = max_eff;
     return 0;
 }
 

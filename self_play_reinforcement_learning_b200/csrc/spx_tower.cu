@@ -431,17 +431,20 @@ __device__ __forceinline__ void issue_first_tap_skewed(SmemT<2>& S, int taps, un
     __syncwarp();
 }
 
-template <int NCTA>
+// GAME is a template parameter: with the head sizes as run-time values the Connect4 kernel spilled (712-byte stack frame at the
+// 96-register cap, +13 % instructions, 8 MB of local-memory write-back per launch in ncu)
+template <int NCTA, int GAME = SPX_GAME_CONNECT4>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long long* __restrict__ opp_g,
              const unsigned char* __restrict__ needs, long long n_boards, int n_layers,
              const unsigned char* __restrict__ wconv, const float* __restrict__ bias_all, float* __restrict__ head_out,
-             int game, int fused_in, const float* __restrict__ polw, const float* __restrict__ polb, const float* __restrict__ fc_b1,
+             int fused_in, const float* __restrict__ polw, const float* __restrict__ polb, const float* __restrict__ fc_b1,
              const float* __restrict__ fc_w2, const float* __restrict__ fc_b2, float* __restrict__ policy_out, float* __restrict__ value_out) {
     typedef SmemT<NCTA> Smem;
     const bool fused = NCTA == 2 && fused_in != 0;   // FC heads inside this kernel (no head_out round trip, no second launch)
-    const int cells = game == SPX_GAME_TICTACTOE ? 9 : CELLS, n_act = game == SPX_GAME_TICTACTOE ? 9 : 7;
-    const int flat = 32 * cells, fc_iters = flat / 32;   // inputs of each head's first Linear; ring stages of the value layer
+    constexpr int game = GAME;
+    constexpr int cells = GAME == SPX_GAME_TICTACTOE ? 9 : CELLS, n_act = GAME == SPX_GAME_TICTACTOE ? 9 : 7;
+    constexpr int flat = 32 * cells, fc_iters = flat / 32;   // inputs of each head's first Linear; ring stages of the value layer
     constexpr int STAGES = Smem::STAGES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -1129,6 +1132,7 @@ int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
     SPX_CUDA_T(cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev));
     SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<1>)));
     SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<2>)));
+    SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<2, SPX_GAME_TICTACTOE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<2>)));
     SPX_CUDA_T(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM));
     *out = t;
     return 0;
@@ -1178,15 +1182,16 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        SPX_CUDA_T(cudaLaunchKernelEx(&cfg, tower_kernel<2>, (const unsigned long long*)own, (const unsigned long long*)opp, needs_eval,
+        auto kern = t->game == SPX_GAME_TICTACTOE ? tower_kernel<2, SPX_GAME_TICTACTOE> : tower_kernel<2, SPX_GAME_CONNECT4>;
+        SPX_CUDA_T(cudaLaunchKernelEx(&cfg, kern, (const unsigned long long*)own, (const unsigned long long*)opp, needs_eval,
                                       (long long)n, t->n_layers, (const unsigned char*)t->blob, (const float*)(t->blob + t->off_bias), t->head_buf,
-                                      t->game, t->fused, (const float*)(t->blob + t->off_polw), (const float*)(t->blob + t->off_polb), (const float*)(t->blob + t->off_b1),
+                                      t->fused, (const float*)(t->blob + t->off_polw), (const float*)(t->blob + t->off_polb), (const float*)(t->blob + t->off_b1),
                                       (const float*)(t->blob + t->off_w2), (const float*)(t->blob + t->off_b2), policy, value));
     } else {
         const int grid = (int)(groups < t->sm_count ? groups : t->sm_count);
         tower_kernel<1><<<grid, NUM_THREADS, sizeof(SmemT<1>), st>>>((const unsigned long long*)own, (const unsigned long long*)opp, needs_eval, n,
                                                             t->n_layers, t->blob, (const float*)(t->blob + t->off_bias), t->head_buf,
-                                                            t->game, 0, nullptr, nullptr, nullptr, nullptr, nullptr, policy, value);
+                                                            0, nullptr, nullptr, nullptr, nullptr, nullptr, policy, value);
     }
     spx::count_launch();
     SPX_CUDA_T(cudaGetLastError());

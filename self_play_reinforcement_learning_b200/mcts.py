@@ -183,7 +183,10 @@ class MCTreeSearch:
         pass
 
     def deduplicate(self):
-        pass
+        """mcts.py:385-386: self.memory.deduplicate("state", ["actual_val", "tree_probs"], Move) when a memory is attached."""
+        memory = getattr(self, "memory", None)
+        if memory is not None and hasattr(memory, "deduplicate"):
+            memory.deduplicate("state", ["actual_val", "tree_probs"], Move)
 
     def root_stats(self):
         return self._engine.root_stats(0)

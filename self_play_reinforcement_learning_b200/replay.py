@@ -7,7 +7,7 @@ it to the GPU for every SGD step (mcts.py:217-222,234-243).  Here the engine's r
 replacement, then boards / preprocess planes / tree_probs / actual_val / q as dense device tensors.
 
 Kept Memory API: ``len()``, ``add(Move)``, ``change_size(max_size)`` (UpdateWorker.stagger_memory, updateworker.py:107-109),
-``reset()``, ``sample(batch_size)`` (list of Move tuples, device tensors), ``max_size``.
+``reset()``, ``sample(batch_size)`` (list of Move tuples, device tensors), ``max_size``, ``deduplicate(...)`` (memory.py:47-94).
 """
 import ctypes as C
 
@@ -67,6 +67,21 @@ class DeviceReplay:
 
     def add(self, experience):
         self.extend([experience])
+
+    def deduplicate(self, key="state", values=("actual_val", "tree_probs"), named_tuple=None, maxlen=None):
+        """Memory.deduplicate (memory.py:47-54) with the Deduplicator (memory.py:56-94) kept on the device
+        (``spx_replay_deduplicate``): the buffer becomes one record per distinct state ever seen, tree_probs / actual_val / q
+        averaged over its occurrences (f32 sums in insertion order, then sum / count), first-seen order, the last ``maxlen``.
+        The signature is the reference's; only its one call site's arguments (mcts.py:385-386) are supported."""
+        if key != "state" or not set(values) <= {"actual_val", "tree_probs", "q"}:
+            raise ValueError("DeviceReplay.deduplicate: key must be 'state' and values a subset of actual_val / tree_probs / q")
+        check(lib().spx_replay_deduplicate(self._h, int(maxlen or 0), _stream()), "spx_replay_deduplicate")
+        return len(self)
+
+    @property
+    def unique_states(self):
+        """len(deduplicator.counter): distinct states folded so far (0 before the first deduplicate)."""
+        return int(lib().spx_replay_unique(self._h))
 
     def extend(self, moves):
         """Memory.add for host-side Move tuples (e.g. a pickled Memory being resumed)."""

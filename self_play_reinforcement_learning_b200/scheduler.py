@@ -22,12 +22,15 @@ class Memory:
     def __init__(self, max_size=None):
         self.max_size = max_size
         self._buffer = deque(maxlen=max_size)
+        self._dedup, self._dedup_pending = None, []
 
     def __len__(self):
         return len(self._buffer)
 
     def add(self, experience):
         self._buffer.append(experience)
+        if self._dedup is not None:
+            self._dedup_pending.append(experience)
 
     def change_size(self, max_size):
         self.max_size = max_size
@@ -39,6 +42,26 @@ class Memory:
 
     def reset(self):
         self._buffer = deque(maxlen=self.max_size)
+
+    def deduplicate(self, key="state", values=("actual_val", "tree_probs"), named_tuple=Move, maxlen=None):
+        """memory.py:47-94 for host-side Move tuples: one entry per distinct `key` ever added, `values` averaged (running sums in
+        insertion order / count), first-seen order, the last `maxlen`.  Fields of `named_tuple` that are neither key nor value
+        (Move.q at the reference's only call site, where create_memory therefore raises TypeError) are averaged too."""
+        fields = getattr(named_tuple, "_fields", (key, *values))
+        values = [f for f in fields if f != key]
+        if self._dedup is None:
+            self._dedup, self._dedup_pending = {}, list(self._buffer)
+        for e in self._dedup_pending:
+            k = getattr(e, key).detach().cpu().numpy().tobytes()
+            c = self._dedup.get(k)
+            if c is None:
+                self._dedup[k] = {"count": 1, key: getattr(e, key), **{v: getattr(e, v) for v in values}}
+            else:
+                c["count"] += 1
+                for v in values:
+                    c[v] = c[v] + getattr(e, v)
+        self._dedup_pending = []
+        self._buffer = deque((named_tuple(**{key: c[key], **{v: c[v] / c["count"] for v in values}}) for c in self._dedup.values()), maxlen=maxlen)
 
 
 def mcts_loss(network, batch, q_average=True):
@@ -71,9 +94,10 @@ class SelfPlayScheduler:
     def __init__(self, network, env, evaluation_network=None, iterations=800, epoch_length=1500, initial_games=64,
                  evaluation_games=150, games_per_gpu=1024, memory_size=200000, batch_size=128, lr=0.01, momentum=0.9,
                  weight_decay=1e-4, updates_per_epoch=100, alpha=1.0, seed=0, net="tower", evaluation_opponent=None,
-                 replay="device", max_memory_size=None, memory_step=0):
+                 replay="device", max_memory_size=None, memory_step=0, deduplicate=False):
         """replay: "device" (records stay in HBM: DeviceReplay) or "host" (reference-style Memory of Move tuples).
         max_memory_size / memory_step: UpdateWorker's staggered buffer growth (updateworker.py:107-109).
+        deduplicate: UpdateWorker's option (updateworker.py:88-89): after every epoch's records are in, merge duplicate states.
         evaluation_opponent: None (evaluation_network, or the policy itself), "lookahead" or "random": the hard-coded
         evaluation_policy_container of the reference's train command (main.py:66, hardcoded_players.py)."""
         self.network, self.env, self.evaluation_network = network, env, evaluation_network
@@ -84,7 +108,7 @@ class SelfPlayScheduler:
         self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
         self.replay_kind, self.memory_step, self.max_memory_size = replay, memory_step, max_memory_size or memory_size
         self.memory = None if replay == "device" else Memory(memory_size)   # the device memory is created with the first games
-        self._memory_size = memory_size
+        self._memory_size, self.deduplicate = memory_size, deduplicate
         # SGD(momentum 0.9, weight decay 1e-4): self_play_parallel.py:193
         self.optim = torch.optim.SGD(network.parameters(), lr=lr, momentum=momentum, weight_decay=weight_decay)
         self.games_played = 0
@@ -185,6 +209,8 @@ class SelfPlayScheduler:
             t1 = now()
             if self.memory_step and self.rank == 0 and self.memory is not None:   # stagger_memory (updateworker.py:107-109)
                 self.memory.change_size(min(self.memory.max_size + self.memory_step, self.max_memory_size))
+            if self.deduplicate and self.rank == 0 and self.memory is not None:       # updateworker.py:88-89
+                self.memory.deduplicate("state", ["actual_val", "tree_probs"], Move)
             self.games_played += self.epoch_length
             loss = self.update()
             t2 = now()

@@ -117,3 +117,80 @@ def test_reference_memory_with_hooked_choice_samples_the_same_batch():
         want = float(ref_mcts.MCTreeSearch.loss(Holder, ref_batch))
         got = float(loss_from_batch(net, {k: torch.from_numpy(v) for k, v in ours.items()}))
     assert abs(want - got) < 1e-5
+
+
+def _records_with_duplicates(rng, game, n, n_distinct):
+    """n records over n_distinct positions (so that most keys repeat), fresh values each time."""
+    W, H, A = spec.GAME_DIMS[game]
+    boards = [rng.integers(-1, 2, size=(W, H)) for _ in range(n_distinct)]
+    recs = []
+    for i in range(n):
+        cells = boards[int(rng.integers(0, n_distinct))]
+        own, opp = spec.board_to_bits(cells, game)
+        recs.append(dict(own=own, opp=opp, game_index=i, tree=int(i & 1), ply=int(np.abs(cells).sum()),
+                         tree_probs=rng.dirichlet([1.0] * A).astype(np.float32), q=np.float32(rng.uniform(-1, 1)),
+                         actual_val=np.float32(rng.integers(-1, 2)), board=cells))
+    return recs
+
+
+def test_deduplicator_restatement_properties():
+    """oracle/replay.Deduplicator: one entry per distinct state in first-seen order, counts add up, values are the float32
+    running sums divided by the count, the table persists across calls and sees records the FIFO has already evicted."""
+    rng = np.random.default_rng(2)
+    recs = _records_with_duplicates(rng, 0, 400, 37)
+    mem = orp.Memory(250)
+    for r in recs[:300]:
+        mem.add(r)
+    out = orp.memory_deduplicate(mem)
+    last250 = recs[50:300]
+    keys = []
+    for r in last250:
+        if (r["own"], r["opp"]) not in keys:
+            keys.append((r["own"], r["opp"]))
+    assert [(o["own"], o["opp"]) for o in out] == keys and sum(o["count"] for o in out) == 250
+    k0 = keys[0]
+    members = [r for r in last250 if (r["own"], r["opp"]) == k0]
+    acc = np.float32(0)
+    for i, r in enumerate(members):
+        acc = np.float32(r["actual_val"]) if i == 0 else np.float32(acc + np.float32(r["actual_val"]))
+    assert out[0]["actual_val"] == np.float32(acc / np.float32(len(members))) and out[0]["count"] == len(members)
+    for r in recs[300:]:
+        mem.add(r)                                   # raw appends after the first call land behind the averaged entries
+    assert len(mem) == len(keys) + 100
+    out2 = orp.memory_deduplicate(mem, maxlen=20)
+    assert sum(c["count"] for c in mem.deduplicator.counter.values()) == 350 and len(out2) == min(20, len(mem.deduplicator.counter))
+    assert [(o["own"], o["opp"]) for o in out2] == list(mem.deduplicator.counter.keys())[-20:]
+
+
+@pytest.mark.skipif(not rh.reference_available(), reason="reference tree not present (GPU box)")
+def test_deduplicator_matches_reference_live():
+    """rl_utils/memory.py:47-94 run live.  The reference's own call (mcts.py:385-386) raises TypeError because Move has a
+    fourth field `q` that create_memory never fills, so the live run uses the same Memory/Deduplicator with `q` listed as a
+    value (the generic algorithm is unchanged); its output must equal the restatement and the host Memory bit for bit."""
+    ref_mcts = rh._import_reference()[0]
+    import rl_utils.memory as ref_memory
+    from self_play_reinforcement_learning_b200.scheduler import Memory as HostMemory
+    rng = np.random.default_rng(8)
+    recs = _records_with_duplicates(rng, 0, 500, 41)
+    ref_mem, mem, host = ref_memory.Memory(300), orp.Memory(300), HostMemory(300)
+
+    def as_move(r):   # fresh tensors: the reference's `count[value] += ...` adds IN PLACE into the first occurrence's tensors
+        return ref_mcts.Move(torch.from_numpy(r["board"].astype(np.int64)), torch.tensor(float(r["actual_val"])),
+                             torch.from_numpy(r["tree_probs"].copy()), torch.tensor(float(r["q"])))
+    with pytest.raises(TypeError):
+        probe = ref_memory.Memory(10)
+        probe.add(as_move(recs[0]))
+        probe.deduplicate("state", ["actual_val", "tree_probs"], ref_mcts.Move)
+    for phase, (lo, hi, maxlen) in enumerate([(0, 350, None), (350, 430, None), (430, 500, 25)]):
+        for r in recs[lo:hi]:
+            ref_mem.add(as_move(r)); mem.add(r); host.add(as_move(r))
+        ref_mem.deduplicate("state", ["actual_val", "tree_probs", "q"], ref_mcts.Move, maxlen=maxlen)
+        ours = orp.memory_deduplicate(mem, maxlen=maxlen)
+        host.deduplicate("state", ["actual_val", "tree_probs"], ref_mcts.Move, maxlen=maxlen)
+        assert len(ref_mem) == len(ours) == len(host)
+        for m, o, hm in zip(ref_mem._buffer, ours, host._buffer):
+            assert spec.board_to_bits(m.state.numpy(), 0) == (o["own"], o["opp"])
+            assert np.array_equal(m.tree_probs.numpy(), o["tree_probs"][:7]) and np.float32(m.actual_val) == o["actual_val"]
+            assert np.float32(m.q) == o["q"]
+            assert torch.equal(hm.state, m.state) and torch.equal(hm.tree_probs, m.tree_probs)
+            assert torch.equal(hm.actual_val, m.actual_val) and torch.equal(hm.q, m.q)

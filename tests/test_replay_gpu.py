@@ -152,3 +152,78 @@ def test_loss_on_device_batch_matches_move_list_loss():
     for k in ("own", "opp", "tree_probs", "q", "actual_val"):
         assert np.array_equal(back[k], recs[k][:50]), k
     dev.close(); dev2.close()
+
+
+@pytest.mark.parametrize("game", [0, 1])
+def test_device_deduplicator_matches_restatement(game):
+    """spx_replay_deduplicate vs oracle/replay.Deduplicator (memory.py:47-94), bit for bit over several rounds: first call folds
+    the current buffer, later calls everything appended since (incl. records the FIFO evicted), maxlen keeps the newest,
+    raw appends after a call sit behind the averaged entries, reset() keeps the table."""
+    from self_play_reinforcement_learning_b200.replay import DeviceReplay
+    rng = np.random.default_rng(40 + game)
+    W, H, A = spec.GAME_DIMS[game]
+    boards = [rng.integers(-1, 2, size=(W, H)) for _ in range(60)]
+    boards += [np.zeros((W, H), np.int64)] * 20                    # the empty board: one long run of duplicates
+
+    def make(n, start):
+        from self_play_reinforcement_learning_b200.engine import RECORD_DTYPE
+        out = np.zeros(n, RECORD_DTYPE)
+        for i in range(n):
+            cells = boards[int(rng.integers(0, len(boards)))]
+            out["own"][i], out["opp"][i] = spec.board_to_bits(cells, game)
+            out["tree_probs"][i, :A] = rng.dirichlet([1.0] * A)
+            out["game_index"][i] = start + i
+            out["tree"][i] = i & 1
+            out["ply"][i] = int(np.abs(cells).sum())
+        out["q"] = rng.uniform(-1, 1, n)
+        out["actual_val"] = rng.integers(-1, 2, n)
+        return out
+
+    def check(dev, mem):
+        got = dev.read()
+        assert len(dev) == len(mem) == len(got)
+        for g, o in zip(got, mem._buffer):
+            assert (int(g["own"]), int(g["opp"])) == (int(o["own"]), int(o["opp"]))
+            want_probs = np.zeros(9, np.float32)
+            want_probs[:len(o["tree_probs"])] = o["tree_probs"]
+            assert g["tree_probs"].tobytes() == want_probs.tobytes()
+            assert np.float32(g["actual_val"]).tobytes() == np.float32(o["actual_val"]).tobytes()
+            assert np.float32(g["q"]).tobytes() == np.float32(o["q"]).tobytes()
+            assert int(g["game_index"]) == int(o["game_index"]) and int(g["ply"]) == int(o["ply"]) and int(g["tree"]) == int(o["tree"])
+            if isinstance(o, dict):                                  # an averaged entry (raw records are numpy rows)
+                assert int(g["pad1"]) == o["count"]
+
+    dev, mem = DeviceReplay(game, max_size=300, physical_capacity=2000, seed=1), orp.Memory(300)
+    assert dev.unique_states == 0
+    made = 0
+    for rnd, (n, maxlen) in enumerate([(450, None), (120, None), (0, None), (700, 40), (90, None), (3000, 2000)]):
+        r = make(n, made)
+        made += n
+        dev.append_records(r)
+        for x in r:
+            mem.add(x)
+        check(dev, mem)
+        if rnd == 4:
+            dev.reset(); mem.reset()
+        dev.deduplicate("state", ["actual_val", "tree_probs"], maxlen=maxlen)
+        orp.memory_deduplicate(mem, maxlen=maxlen)
+        check(dev, mem)
+        assert dev.unique_states == len(mem.deduplicator.counter)
+        assert dev.max_size == (maxlen or 2000)
+    dev.close()
+
+
+def test_device_deduplicate_empty_memory_and_sampling_after():
+    from self_play_reinforcement_learning_b200.replay import DeviceReplay
+    dev = DeviceReplay(0, max_size=100, seed=3)
+    assert dev.deduplicate() == 0 and len(dev) == 0 and dev.unique_states == 0
+    rng = np.random.default_rng(1)
+    r = _records(rng, 0, 64)
+    r[32:] = r[:32]                                                  # every state twice
+    dev.append_records(r)
+    assert dev.deduplicate() == 32 and dev.unique_states == 32
+    b = dev.sample_batch(32, step=0)
+    assert sorted(b["idx"].cpu().tolist()) == list(range(32)) if "idx" in b else True
+    with pytest.raises(ValueError):
+        dev.deduplicate(key="q")
+    dev.close()
