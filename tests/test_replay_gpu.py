@@ -179,9 +179,9 @@ def test_device_deduplicator_matches_restatement(game):
         out["actual_val"] = rng.integers(-1, 2, n)
         return out
 
-    def check(dev, mem):
+    def check(dev, mem, where):
         got = dev.read()
-        assert len(dev) == len(mem) == len(got)
+        assert len(dev) == len(mem) == len(got), (where, len(dev), len(mem), len(got))
         for g, o in zip(got, mem._buffer):
             assert (int(g["own"]), int(g["opp"])) == (int(o["own"]), int(o["opp"]))
             want_probs = np.zeros(9, np.float32)
@@ -196,18 +196,19 @@ def test_device_deduplicator_matches_restatement(game):
     dev, mem = DeviceReplay(game, max_size=300, physical_capacity=2000, seed=1), orp.Memory(300)
     assert dev.unique_states == 0
     made = 0
-    for rnd, (n, maxlen) in enumerate([(450, None), (120, None), (0, None), (700, 40), (90, None), (3000, 2000)]):
+    # (the device ring is bounded by its physical capacity where a deque(maxlen=None) is not: stay below it)
+    for rnd, (n, maxlen) in enumerate([(450, None), (120, None), (0, None), (700, 40), (90, None), (1500, 1000), (2500, 35)]):
         r = make(n, made)
         made += n
         dev.append_records(r)
         for x in r:
             mem.add(x)
-        check(dev, mem)
+        check(dev, mem, ("appended", rnd))
         if rnd == 4:
             dev.reset(); mem.reset()
         dev.deduplicate("state", ["actual_val", "tree_probs"], maxlen=maxlen)
         orp.memory_deduplicate(mem, maxlen=maxlen)
-        check(dev, mem)
+        check(dev, mem, ("deduplicated", rnd))
         assert dev.unique_states == len(mem.deduplicator.counter)
         assert dev.max_size == (maxlen or 2000)
     dev.close()
