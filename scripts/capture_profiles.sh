@@ -10,4 +10,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 250 -c 100 --csv --
 ncu --set full --clock-control none --import-source on -k 'regex:tower_kernel|advance_kernel' -s 250 -c 6 -f -o gpurun_out/prof_$TAG $B > gpurun_out/ncu_full_$TAG.log 2>&1
 python scripts/dbg_env_ncu.py > gpurun_out/env_plain_$TAG.log 2>&1 || { echo "plain env run failed"; exit 1; }
 ncu --set full --clock-control none --import-source on -k regex:env_step -s 2 -c 2 -f -o gpurun_out/prof_env_$TAG python scripts/dbg_env_ncu.py > gpurun_out/ncu_env_$TAG.log 2>&1
-tail -2 gpurun_out/ncu_full_$TAG.log gpurun_out/ncu_env_$TAG.log; cat gpurun_out/env_plain_$TAG.log
+tail -n 2 gpurun_out/ncu_full_$TAG.log; tail -n 2 gpurun_out/ncu_env_$TAG.log; cat gpurun_out/env_plain_$TAG.log

@@ -38,9 +38,8 @@ env_rep = os.path.join(ROOT, "gpurun_out", f"prof_env_{tag}.ncu-rep")
 if os.path.exists(env_rep):   # the env kernel is captured from scripts/dbg_env_ncu.py (16 Mi boards, operands from DRAM)
     raw_env = subprocess.run(["ncu", "-i", env_rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     open(os.path.join(out_dir, f"{tag}_ncu_env_raw.csv"), "w").write(raw_env)
-    h_env = next(csv.reader(raw_env.splitlines()[:1]))
-    if h_env == next(csv.reader(raw.splitlines()[:1])):
-        raw = raw + "\n".join(raw_env.splitlines()[2:]) + "\n"
+else:
+    raw_env = None
 open(os.path.join(out_dir, f"{tag}_ncu_full_raw.csv"), "w").write(raw)
 rr = list(csv.reader(raw.splitlines()))
 h = rr[0]
@@ -55,6 +54,11 @@ units = rr[1]
 summ = []
 for r in rr[2:]:
     summ.append({w: (r[i] + (" " + units[i] if units[i] else "")) for w, i in idx})
+if raw_env:   # same metrics for the env kernel (its raw page has its own column set)
+    re_ = list(csv.reader(raw_env.splitlines()))
+    he, ue = re_[0], re_[1]
+    for r in re_[2:]:
+        summ.append({w: (r[he.index(w)] + (" " + ue[he.index(w)] if ue[he.index(w)] else "")) for w in want if w in he})
 json.dump(summ, open(os.path.join(out_dir, f"{tag}_ncu_kernels.json"), "w"), indent=1)
 tw = [x for x in summ if "tower_kernel" in x["Kernel Name"]]
 if tw:
