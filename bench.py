@@ -157,7 +157,7 @@ def cpu_baseline(seconds, blocks, sims, procs=None):
     return {"sims_per_s": (s1 - s0) / dt, "positions_per_s": (m1 - m0) / dt, "cores": procs, "seconds": dt, "sims": s1 - s0}
 
 
-def run_reference(args, workload):
+def run_reference(args, workload, out=sys.stdout):
     """--impl reference: the reference's CPU implementation of the path (oracle port, kind 'port': the reference is
     pure Python and does not exist on the GPU box) on all host cores; each 'step' is a bounded time-boxed sample."""
     rank = int(os.environ.get("RANK", "0"))
@@ -183,12 +183,22 @@ def run_reference(args, workload):
             "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "positions_per_sec": sum(v["positions_per_s"] * v["seconds"] for v in vals) / tot_t,
             "wall_s": time.time() - t0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout: libraries that write to fd 1 (NCCL prints its version banner there under
+    NCCL_DEBUG=VERSION) are redirected to stderr; the returned file object is the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     args = parse()
+    out = _claim_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -198,7 +208,7 @@ def main():
                 "l2_policy": "node pools (5.4 GB/GPU) and weights (12.6 MB) are the inputs; the touched working set per step "
                              "exceeds L2 (126 MB), no flush needed", "parallelism": f"games sharded over {max(world, args.gpus)} GPU(s), no data-path collective"}
     if args.impl == "reference":
-        return run_reference(args, workload)
+        return run_reference(args, workload, out)
 
     import torch
     import torch.distributed as dist
@@ -360,7 +370,7 @@ def main():
                 "data": "synthetic", "config": workload, "positions_per_sec": moves_all / (ms / 1e3), "leaf_evals_per_sec": evals_all / (ms / 1e3),
                 "mean_select_path_len": path, "e2e": e2e, "gpu_launches": int(launches1 - launches0), "clocks": clocks,
                 "roofline": roof, "search_roofline": search, "env_roofline": env_roof, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
