@@ -164,16 +164,18 @@ def run_reference(args, workload, out=sys.stdout):
     if rank != 0:
         return
     vals, cores = [], None
+    # a "step" is a bounded time-boxed sample; the whole run stays within ~2 minutes whatever K is (>= 2 s, <= --cpu-seconds each)
+    per_step = max(2.0, min(args.cpu_seconds, 90.0 / max(args.steps, 1)))
     for _ in range(args.warmup if args.warmup < 1 else 1):
-        cpu_baseline(min(args.cpu_seconds, 5.0), args.blocks, args.sims)
+        cpu_baseline(min(per_step, 5.0), args.blocks, args.sims)
     t0 = time.time()
     for _ in range(args.steps):
-        r = cpu_baseline(args.cpu_seconds, args.blocks, args.sims)
+        r = cpu_baseline(per_step, args.blocks, args.sims)
         vals.append(r)
         cores = r["cores"]
     tot_sims = sum(v["sims"] for v in vals); tot_t = sum(v["seconds"] for v in vals)
     value = tot_sims / tot_t
-    sample = (f"{args.steps} x {args.cpu_seconds:.0f}s windows, {cores} processes x 1 thread, each playing Connect4 self-play "
+    sample = (f"{args.steps} x {per_step:.0f}s windows, {cores} processes x 1 thread, each playing Connect4 self-play "
               f"episodes (two trees, {args.sims} sims/move) with the C oracle tree + fp32 torch ResidualTower-{args.blocks} at batch 1")
     line = {"impl": "reference", "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot_t / max(args.steps, 1),
