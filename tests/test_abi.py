@@ -63,3 +63,26 @@ def test_product_package_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
                 assert "spx_oracle" not in src.replace("ox_pow_int_exact", ""), fn
+
+
+def test_hot_kernels_do_not_spill():
+    """Resource usage of the built library (cuobjdump, no GPU needed): the Connect4 tower kernel must keep its 16-byte stack frame
+    (run-time head sizes once made it spill 712 bytes per thread at the 96-register cap: -4 % throughput, found only in ncu) and
+    the quad env kernel must stay free of local memory."""
+    import re
+    import shutil
+    import subprocess
+    import pytest
+    from self_play_reinforcement_learning_b200 import _lib
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([tool, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    usage = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
+        usage[m.group(1)] = (int(m.group(2)), int(m.group(3)))
+    tower = [v for k, v in usage.items() if "tower_kernelILi2ELi0E" in k]
+    env = [v for k, v in usage.items() if "env_step_quad_kernelILi0E" in k]
+    assert tower and env, sorted(usage)
+    assert tower[0][0] <= 96 and tower[0][1] <= 64, tower
+    assert env[0][1] == 0, env
