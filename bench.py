@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bounded CPU-baseline sample per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-aux-rooflines", action="store_true", help="skip the search-only and env-kernel roofline legs (tests)")
     ap.add_argument("--max-sims-per-tick", type=int, default=8)
     return ap.parse_args()
 
@@ -204,7 +205,7 @@ def _claim_stdout():
 
 def main():
     args = parse()
-    out = _claim_stdout()
+    json_out = _claim_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -214,7 +215,7 @@ def main():
                 "l2_policy": "node pools (5.4 GB/GPU) and weights (12.6 MB) are the inputs; the touched working set per step "
                              "exceeds L2 (126 MB), no flush needed", "parallelism": f"games sharded over {max(world, args.gpus)} GPU(s), no data-path collective"}
     if args.impl == "reference":
-        return run_reference(args, workload, out)
+        return run_reference(args, workload, json_out)
 
     import torch
     import torch.distributed as dist
@@ -317,7 +318,7 @@ def main():
 
     # ---- search-only legs (hash net): HBM roofline of the search kernel at the workload's G and with 16x more trees
     search = None
-    if rank == 0 and args.net == "tower":
+    if rank == 0 and args.net == "tower" and not args.no_aux_rooflines:
         sp.close()
         peaks_s = _peaks()
 
@@ -348,7 +349,7 @@ def main():
             search["with_16384_games"] = search_leg(16384, 600)
 
     env_roof = None
-    if rank == 0 and args.net == "tower":
+    if rank == 0 and args.net == "tower" and not args.no_aux_rooflines:
         env_roof = _env_roofline(_lib, torch)
     if rank == 0:
         peaks = _peaks()
@@ -376,7 +377,7 @@ def main():
                 "data": "synthetic", "config": workload, "positions_per_sec": moves_all / (ms / 1e3), "leaf_evals_per_sec": evals_all / (ms / 1e3),
                 "mean_select_path_len": path, "e2e": e2e, "gpu_launches": int(launches1 - launches0), "clocks": clocks,
                 "roofline": roof, "search_roofline": search, "env_roofline": env_roof, "cpu_baseline": cpu}
-        print(json.dumps(line), file=out, flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
