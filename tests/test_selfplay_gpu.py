@@ -129,6 +129,29 @@ def test_scheduler_train_loop_small():
     assert set(bd) == {"first", "second"} and sum(sum(v.values()) for v in bd.values()) == 16
 
 
+@pytest.mark.parametrize("replay", ["device", "host"])
+def test_scheduler_deduplicate_option(replay):
+    """UpdateWorker(deduplicate=True) (updateworker.py:88-89): after the epoch's records are in, the memory holds one averaged
+    record per distinct position -- every game starts from the empty board, so duplicates are guaranteed -- and training still runs."""
+    from self_play_reinforcement_learning_b200 import nets
+    from self_play_reinforcement_learning_b200.scheduler import SelfPlayScheduler
+    torch.manual_seed(0)
+    net = nets.ResidualTower(7, 6, 7, num_blocks=1).cuda().eval()
+    s = SelfPlayScheduler(net, 0, iterations=20, epoch_length=24, initial_games=8, evaluation_games=0, games_per_gpu=16, batch_size=16,
+                          updates_per_epoch=3, lr=0.01, replay=replay, deduplicate=True)
+    hist = s.train_model(num_epochs=1)
+    assert np.isfinite(hist[0]["loss"])
+    if replay == "device":
+        recs = s.memory.read()
+        keys = set(zip(recs["own"].tolist(), recs["opp"].tolist()))
+        assert len(keys) == len(recs) == s.memory.unique_states and int(recs["pad1"].sum()) > len(recs)     # counts: merged records
+        empty = recs[(recs["own"] == 0) & (recs["opp"] == 0)]
+        assert len(empty) == 1 and int(empty["pad1"][0]) >= 16                                            # every game's first position
+    else:
+        states = [m.state.numpy().tobytes() for m in s.memory._buffer]
+        assert len(set(states)) == len(states) > 0
+
+
 class _StreamRandomOpponent:
     """A host-side BasePlayer (general/base_model.py:10-29) that plays the spec-stream random move -- the same rule the
     oracle's OPP_RANDOM uses, so a facade-vs-host game can be compared with ox.play_episode_vs move for move."""
