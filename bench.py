@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-aux-rooflines", action="store_true", help="skip the search-only and env-kernel roofline legs (tests)")
     ap.add_argument("--max-sims-per-tick", type=int, default=8)
+    ap.add_argument("--alpha", type=float, default=1.0, help="Dirichlet alpha of the root noise (mcts.py:135 default 1; tictactoeconfig.py:9 uses 0.15)")
     return ap.parse_args()
 
 
@@ -108,7 +109,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- CPU arm
-def _cpu_worker(idx, counters_addr_holder, blocks, sims, seed):
+def _cpu_worker(idx, counters_addr_holder, blocks, sims, seed, alpha=1.0):
     """One host core: the oracle port (C tree/env restatement + fp32 torch net, batch 1, one thread), i.e. the
     reference's direct mode (BASELINE.md 4 mode (i)): SelfPlayer.play_episode over two MCTreeSearch."""
     import ctypes as C
@@ -129,12 +130,12 @@ def _cpu_worker(idx, counters_addr_holder, blocks, sims, seed):
     pynet = ox.PyNet(0, fn)
     g = idx
     while True:
-        cfg = ox.make_cfg(0, sims, seed=seed, game_uid=g, noise_mode=2, alpha=1.0)
+        cfg = ox.make_cfg(0, sims, seed=seed, game_uid=g, noise_mode=2, alpha=alpha)
         ox.play_episode(cfg, bool(g & 1), nets=((pynet.addr, None), (pynet.addr, None)))
         g += 1 << 20
 
 
-def cpu_baseline(seconds, blocks, sims, procs=None):
+def cpu_baseline(seconds, blocks, sims, procs=None, alpha=1.0):
     """Time-boxed: `procs` processes play self-play games for `seconds`; sims and moves counted live."""
     import multiprocessing as mp
     import ctypes as C
@@ -144,7 +145,7 @@ def cpu_baseline(seconds, blocks, sims, procs=None):
     class Pair(C.Structure):
         _fields_ = [("sims", C.c_long), ("moves", C.c_long)]
     shared = [ctx.RawValue(Pair) for _ in range(procs)]
-    ps = [ctx.Process(target=_cpu_worker, args=(i, shared[i], blocks, sims, 0), daemon=True) for i in range(procs)]
+    ps = [ctx.Process(target=_cpu_worker, args=(i, shared[i], blocks, sims, 0, alpha), daemon=True) for i in range(procs)]
     for p in ps:
         p.start()
     # wait until every worker is past start-up (first simulation done), then measure a clean window
@@ -172,10 +173,10 @@ def run_reference(args, workload, out=sys.stdout):
     # a "step" is a bounded time-boxed sample; the whole run stays within ~2 minutes whatever K is (>= 2 s, <= --cpu-seconds each)
     per_step = max(2.0, min(args.cpu_seconds, 90.0 / max(args.steps, 1)))
     for _ in range(args.warmup if args.warmup < 1 else 1):
-        cpu_baseline(min(per_step, 5.0), args.blocks, args.sims)
+        cpu_baseline(min(per_step, 5.0), args.blocks, args.sims, alpha=args.alpha)
     t0 = time.time()
     for _ in range(args.steps):
-        r = cpu_baseline(per_step, args.blocks, args.sims)
+        r = cpu_baseline(per_step, args.blocks, args.sims, alpha=args.alpha)
         vals.append(r)
         cores = r["cores"]
     tot_sims = sum(v["sims"] for v in vals); tot_t = sum(v["seconds"] for v in vals)
@@ -210,7 +211,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = {"workload": f"connect4 6x7 self-play, ResidualTower-{args.blocks} random init (seed 0), {args.games} concurrent games/GPU, "
-                            f"{args.sims} sims/move, two trees per game, finished games replaced immediately",
+                            f"{args.sims} sims/move, Dirichlet alpha {args.alpha:g}, two trees per game, finished games replaced immediately",
                 "games_per_gpu": args.games, "sims_per_move": args.sims, "net": args.net, "ticks_per_step": args.ticks_per_step,
                 "l2_policy": "node pools (5.4 GB/GPU) and weights (12.6 MB) are the inputs; the touched working set per step "
                              "exceeds L2 (126 MB), no flush needed", "parallelism": f"games sharded over {max(world, args.gpus)} GPU(s), no data-path collective"}
@@ -234,7 +235,7 @@ def main():
 
     # ---- public-API object (also used for the resident-data measurement through its engine)
     sp = BatchedSelfPlay(module, game=0, n_games=G, sims=args.sims, net=args.net, seed=0, rank=rank, world=world,
-                         max_sims_per_tick=args.max_sims_per_tick)
+                         max_sims_per_tick=args.max_sims_per_tick, alpha=args.alpha)
     eng, ev = sp.engine, sp.evaluator
     blob_host = sp.packed_weights_pinned() if args.net == "tower" else None
 
@@ -367,7 +368,7 @@ def main():
                     "kernel_share_of_step": tower_ms * ticks / max(ms, 1e-9) if world == 1 else None}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            r = cpu_baseline(args.cpu_seconds, args.blocks, args.sims)
+            r = cpu_baseline(args.cpu_seconds, args.blocks, args.sims, alpha=args.alpha)
             cpu = {"value": r["sims_per_s"], "unit": "sims/s", "cores": r["cores"], "kind": "port",
                    "sample": f"{r['seconds']:.0f}s window, {r['cores']} processes x 1 thread: C oracle tree/env + fp32 torch "
                              f"ResidualTower-{args.blocks} at batch 1 (the reference's direct mode), {args.sims} sims/move",
