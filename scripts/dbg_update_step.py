@@ -5,7 +5,7 @@ import torch
 from self_play_reinforcement_learning_b200 import nets
 from self_play_reinforcement_learning_b200.replay import loss_from_batch
 
-def run(tag, channels_last=False, benchmark=False, tf32=True, graph=False, B=128, steps=30):
+def run(tag, channels_last=False, benchmark=False, tf32=True, graph=False, B=128, steps=30, amp=None):
     torch.backends.cudnn.benchmark = benchmark
     torch.backends.cudnn.allow_tf32 = tf32
     torch.backends.cuda.matmul.allow_tf32 = tf32
@@ -22,7 +22,11 @@ def run(tag, channels_last=False, benchmark=False, tf32=True, graph=False, B=128
     batch = dict(planes=planes, tree_probs=torch.softmax(torch.randn(B, 7, device="cuda", generator=g), 1),
                  actual_val=torch.randint(-1, 2, (B,), device="cuda", generator=g).float(), q=torch.rand(B, device="cuda", generator=g))
     def step():
-        loss = loss_from_batch(net, batch)
+        if amp is not None:
+            with torch.autocast("cuda", dtype=amp):
+                loss = loss_from_batch(net, batch)
+        else:
+            loss = loss_from_batch(net, batch)
         opt.zero_grad(set_to_none=False)
         loss.backward()
         opt.step()
@@ -49,9 +53,9 @@ def run(tag, channels_last=False, benchmark=False, tf32=True, graph=False, B=128
     print(f"{tag:40s} {1e3 * (time.time() - t0) / steps:7.2f} ms/step")
 
 run("default (TF32 convs, NCHW)")
-run("cudnn.benchmark", benchmark=True)
-run("channels_last", channels_last=True)
-run("channels_last + benchmark", channels_last=True, benchmark=True)
-run("default + CUDA graph", graph=True)
-run("benchmark + CUDA graph", benchmark=True, graph=True)
-run("true fp32 (no TF32)", tf32=False)
+run("bf16 autocast NCHW", amp=torch.bfloat16)
+run("bf16 autocast NCHW + benchmark", amp=torch.bfloat16, benchmark=True)
+run("bf16 autocast channels_last + benchmark", amp=torch.bfloat16, channels_last=True, benchmark=True)
+run("fp16 autocast NCHW + benchmark", amp=torch.float16, benchmark=True)
+run("batch 512 default", B=512, steps=10)
+run("batch 512 bf16 + benchmark", B=512, steps=10, amp=torch.bfloat16, benchmark=True)
