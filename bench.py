@@ -7,7 +7,7 @@ Contract (see DESIGN.md "Measurement"):
 
 Workload at N=1 = BASELINE.json configs[1]: Connect4 6x7 self-play, the repo's connect4 net
 ResidualTower(7,6,7,num_blocks=20) with random init (torch.manual_seed(0)), 1024 concurrent games per GPU,
-800 sims/move, Dirichlet alpha=1 generated on device, tie noise on, finished games replaced at once.
+800 sims/move, Dirichlet noise (--alpha, default 1) generated on device, tie noise on, finished games replaced at once.
 A "step" = 800 engine ticks (one tick = one spx_advance over all games + one batched network evaluation),
 i.e. about one searched move per game.  `value` = completed MCTS simulations per second over all ranks, device
 timed with everything resident in HBM.  `e2e` = the same metric through the package's public API with HOST
@@ -109,7 +109,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- CPU arm
-def _cpu_worker(idx, counters_addr_holder, blocks, sims, seed, alpha=1.0):
+def _cpu_worker(idx, shared, blocks, sims, seed, alpha=1.0):
     """One host core: the oracle port (C tree/env restatement + fp32 torch net, batch 1, one thread), i.e. the
     reference's direct mode (BASELINE.md 4 mode (i)): SelfPlayer.play_episode over two MCTreeSearch."""
     import ctypes as C
@@ -120,8 +120,7 @@ def _cpu_worker(idx, counters_addr_holder, blocks, sims, seed, alpha=1.0):
     from self_play_reinforcement_learning_b200 import nets
     torch.manual_seed(0)
     net = nets.ResidualTower(7, 6, 7, num_blocks=blocks).eval()
-    shared = counters_addr_holder
-    ox.lib().ox_set_live_counters(C.addressof(shared))
+    ox.lib().ox_set_live_counters(C.addressof(shared))   # the C oracle bumps (sims, moves) in this shared pair as it plays
 
     def fn(state, tree):
         with torch.no_grad():
