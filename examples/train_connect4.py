@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--evaluation-games", type=int, default=150)   # :59
     ap.add_argument("--initial-games", type=int, default=256)
     ap.add_argument("--games-per-gpu", type=int, default=1024)
+    ap.add_argument("--save-dir", default=None, help="run folder root: model-*/memory-* files as the reference writes them")
+    ap.add_argument("--resume", action="store_true", help="resume model and memory from the newest earlier run in --save-dir")
+    ap.add_argument("--amp", action="store_true", help="bf16 autocast for the SGD steps (not reference behaviour)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -38,9 +41,10 @@ def main():
     torch.manual_seed(0)
     net = nets.ResidualTower(7, 6, 7, num_blocks=args.blocks).cuda().eval()
     sched = SelfPlayScheduler(net, 0, iterations=args.iterations, epoch_length=args.epoch_length, initial_games=args.initial_games,
-                              evaluation_games=args.evaluation_games, games_per_gpu=args.games_per_gpu)
+                              evaluation_games=args.evaluation_games, games_per_gpu=args.games_per_gpu, save_dir=args.save_dir,
+                              amp=torch.bfloat16 if args.amp else None)
     t0 = time.time()
-    hist = sched.train_model(num_epochs=args.epochs)
+    hist = sched.train_model(num_epochs=args.epochs, resume_model=args.resume, resume_memory=args.resume)
     if sched.rank == 0:
         print(json.dumps({"world": world, "seconds": time.time() - t0, "history": hist}))
     if world > 1:

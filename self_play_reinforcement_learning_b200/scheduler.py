@@ -11,8 +11,12 @@ from collections import deque
 import numpy as np
 import torch
 
-from . import nets, parallel
+import datetime
+import os
+
+from . import checkpoint, nets, parallel
 from .replay import DeviceReplay, loss_from_batch
+from .envs import game_id_of
 from .selfplay import BatchedSelfPlay, Move, records_to_moves, results_to_dicts
 
 
@@ -94,9 +98,18 @@ class SelfPlayScheduler:
     def __init__(self, network, env, evaluation_network=None, iterations=800, epoch_length=1500, initial_games=64,
                  evaluation_games=150, games_per_gpu=1024, memory_size=200000, batch_size=128, lr=0.01, momentum=0.9,
                  weight_decay=1e-4, updates_per_epoch=100, alpha=1.0, seed=0, net="tower", evaluation_opponent=None,
-                 replay="device", max_memory_size=None, memory_step=0, deduplicate=False):
+                 replay="device", max_memory_size=None, memory_step=0, deduplicate=False, save_dir=None, save_memory=True,
+                 lr_patience=15, amp=None):
         """replay: "device" (records stay in HBM: DeviceReplay) or "host" (reference-style Memory of Move tuples).
         max_memory_size / memory_step: UpdateWorker's staggered buffer growth (updateworker.py:107-109).
+        save_dir: as in the reference (self_play_parallel.py:56,263-267): every epoch rank 0 writes
+        ``<save_dir>/<start_time>/model-<iso time>:<games>`` ({"model": state_dict}, updateworker.py:111-117) and, with
+        ``save_memory``, the pickled Memory of Move tuples ``memory-<iso time>:<size>`` (previous file removed, :119-139);
+        ``train_model(resume_model=, resume_memory=)`` picks up the newest files of the previous run (base_worker.py:26-62).
+        amp: None = fp32 SGD steps like the reference's UpdateWorker; torch.bfloat16 runs forward/backward under autocast
+        (12 instead of 29 ms per step of batch 128 on B200, scripts/dbg_update_step.py) -- an option, not reference behaviour.
+        lr_patience: ReduceLROnPlateau("max", patience, factor 0.5, min_lr 1e-5, cooldown 5) stepped with every epoch's
+        evaluation reward (updateworker.py:66-68,96-98).
         deduplicate: UpdateWorker's option (updateworker.py:88-89): after every epoch's records are in, merge duplicate states.
         evaluation_opponent: None (evaluation_network, or the policy itself), "lookahead" or "random": the hard-coded
         evaluation_policy_container of the reference's train command (main.py:66, hardcoded_players.py)."""
@@ -111,6 +124,10 @@ class SelfPlayScheduler:
         self._memory_size, self.deduplicate = memory_size, deduplicate
         # SGD(momentum 0.9, weight decay 1e-4): self_play_parallel.py:193
         self.optim = torch.optim.SGD(network.parameters(), lr=lr, momentum=momentum, weight_decay=weight_decay)
+        self.lr_scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(self.optim, "max", patience=lr_patience, factor=0.5,
+                                                                       min_lr=0.00001, cooldown=5)
+        self.save_dir, self.save_memory_files, self._recent_memory_file, self.amp = save_dir, save_memory, None, amp
+        self.start_time = datetime.datetime.now().isoformat()                      # self_play_parallel.py:86
         self.games_played = 0
         self.history = []
 
@@ -180,10 +197,11 @@ class SelfPlayScheduler:
         self.network.train()
         last = None
         for _ in range(self.updates_per_epoch):
-            if self.replay_kind == "device":
-                loss = loss_from_batch(self.network, self.memory.sample_batch(self.batch_size))
-            else:
-                loss = mcts_loss(self.network, self.memory.sample(self.batch_size))
+            with torch.autocast("cuda", dtype=self.amp or torch.bfloat16, enabled=self.amp is not None):
+                if self.replay_kind == "device":
+                    loss = loss_from_batch(self.network, self.memory.sample_batch(self.batch_size))
+                else:
+                    loss = mcts_loss(self.network, self.memory.sample(self.batch_size))
             self.optim.zero_grad()
             loss.backward()
             self.optim.step()
@@ -191,9 +209,55 @@ class SelfPlayScheduler:
         self.network.eval()
         return last
 
-    def train_model(self, num_epochs=10):
-        """:213-291: initial games, then per epoch: epoch_length self-play games -> update -> weight sync -> evaluation."""
+    # ------------------------------------------------------------------ on-disk state (rank 0)
+    def _host_memory(self):
+        """The replay memory as the reference's picklable object: a Memory of Move tuples (CPU tensors)."""
+        if self.replay_kind != "device":
+            return self.memory
+        m = Memory(self.memory.max_size)
+        for mv in self.memory.to_moves():
+            m.add(Move(*(t.cpu() for t in mv)))
+        return m
+
+    def save(self, games_played):
+        """UpdateWorker's {"saved_name": ...} task: save_model + save_memory (updateworker.py:84-93,111-139)."""
+        if self.rank != 0 or not self.save_dir:
+            return None
+        name = checkpoint.save_model(self.network, checkpoint.model_file_name(self.save_dir, self.start_time, games_played))
+        if self.save_memory_files and self.memory is not None:
+            self._recent_memory_file = checkpoint.save_memory(self._host_memory(), self.save_dir, self.start_time,
+                                                              previous=self._recent_memory_file)
+        return name
+
+    def resume(self, resume_model=False, resume_memory=False):
+        """BaseWorker.load_model / load_memory with prev_run=True (base_worker.py:26-42): newest files of the newest earlier run."""
+        if not self.save_dir or not os.path.isdir(self.save_dir):
+            return
+        if self.rank == 0:
+            try:
+                if resume_memory:
+                    old = checkpoint.load_memory(checkpoint.recent_save_file(self.save_dir, self.start_time, True, "memory"))
+                    moves = list(getattr(old, "_buffer", old))
+                    if self.replay_kind == "device":
+                        if self.memory is None:
+                            self.memory = DeviceReplay(game_id_of(self.env), self._memory_size, self.max_memory_size, seed=self.seed)
+                        self.memory.extend(moves)
+                    else:
+                        for m in moves:
+                            self.memory.add(m)
+                if resume_model:
+                    dev = next(self.network.parameters()).device
+                    checkpoint.load_model(self.network, checkpoint.recent_save_file(self.save_dir, self.start_time, True, "model"), map_location=dev)
+            except ValueError:      # max() of an empty list: no earlier run (the reference logs the exception and goes on)
+                pass
+        if resume_model:
+            self._sync_weights()
+
+    def train_model(self, num_epochs=10, resume_model=False, resume_memory=False):
+        """:213-291: initial games, then per epoch: epoch_length self-play games -> update -> checkpoint -> weight sync ->
+        evaluation -> LR schedule."""
         self.network.eval()
+        self.resume(resume_model, resume_memory)
         gen = 0
         self._remember(self._play(self.initial_games, evaluate=False, update=True, generation=gen)[0])
         import time
@@ -214,12 +278,16 @@ class SelfPlayScheduler:
             self.games_played += self.epoch_length
             loss = self.update()
             t2 = now()
+            saved = self.save(self.epoch_length * (epoch + 1))
             self._sync_weights()
             t3 = now()
             reward = self.evaluate_policy(epoch) if self.evaluation_games else 0
+            if self.rank == 0:
+                self.lr_scheduler.step(reward)                                         # updateworker.py:96-98
             t4 = now()
             self.history.append(dict(epoch=epoch, loss=loss, self_play=parse_results(results)[0] if self.rank == 0 else None,
                                      evaluation_reward=reward, memory=len(self.memory) if self.memory is not None else 0,
+                                     saved_model=saved, lr=self.optim.param_groups[0]["lr"],
                                      seconds=dict(self_play=t1 - t0, update=t2 - t1, weight_sync=t3 - t2, evaluation=t4 - t3)))
         return self.history
 

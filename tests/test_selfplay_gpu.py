@@ -138,7 +138,7 @@ def test_scheduler_deduplicate_option(replay):
     torch.manual_seed(0)
     net = nets.ResidualTower(7, 6, 7, num_blocks=1).cuda().eval()
     s = SelfPlayScheduler(net, 0, iterations=20, epoch_length=24, initial_games=8, evaluation_games=0, games_per_gpu=16, batch_size=16,
-                          updates_per_epoch=3, lr=0.01, replay=replay, deduplicate=True)
+                          updates_per_epoch=3, lr=0.01, replay=replay, deduplicate=True, amp=torch.bfloat16 if replay == "device" else None)
     hist = s.train_model(num_epochs=1)
     assert np.isfinite(hist[0]["loss"])
     if replay == "device":
@@ -150,6 +150,43 @@ def test_scheduler_deduplicate_option(replay):
     else:
         states = [m.state.numpy().tobytes() for m in s.memory._buffer]
         assert len(set(states)) == len(states) > 0
+
+
+@pytest.mark.parametrize("replay", ["device", "host"])
+def test_scheduler_checkpoints_and_resume(tmp_path, replay):
+    """save_dir / resume_model / resume_memory (self_play_parallel.py:213-267, updateworker.py:54-58,111-139, base_worker.py:26-62):
+    an epoch leaves model-<time>:<games> ({"model": state_dict}) and memory-<time>:<size> (pickled Memory of Move tuples) in the
+    run folder; a second run picks both up."""
+    import glob
+    import os
+    import time
+    from self_play_reinforcement_learning_b200 import checkpoint, nets
+    from self_play_reinforcement_learning_b200.scheduler import SelfPlayScheduler
+    kw = dict(iterations=20, epoch_length=12, initial_games=4, evaluation_games=4, games_per_gpu=8, batch_size=16, updates_per_epoch=2,
+              lr=0.01, replay=replay, save_dir=str(tmp_path))
+    torch.manual_seed(0)
+    net = nets.ResidualTower(7, 6, 7, num_blocks=1).cuda().eval()
+    s = SelfPlayScheduler(net, 0, **kw)
+    hist = s.train_model(num_epochs=2)
+    run = os.path.join(str(tmp_path), s.start_time)
+    models, mems = sorted(glob.glob(os.path.join(run, "model-*"))), glob.glob(os.path.join(run, "memory-*"))
+    assert [m.rsplit(":", 1)[1] for m in models] == ["12", "24"] and hist[1]["saved_model"] == models[1]
+    assert len(mems) == 1 and mems[0].endswith(":" + str(hist[1]["memory"]))          # the previous memory file was removed
+    assert set(torch.load(models[1]).keys()) == {"model"} and hist[1]["lr"] == 0.01
+    saved_moves = list(checkpoint.load_memory(mems[0])._buffer)
+    assert len(saved_moves) == hist[1]["memory"] and saved_moves[0].state.dtype == torch.int64 and tuple(saved_moves[0].state.shape) == (7, 6)
+    time.sleep(0.01)
+    torch.manual_seed(5)
+    net2 = nets.ResidualTower(7, 6, 7, num_blocks=1).cuda().eval()
+    s2 = SelfPlayScheduler(net2, 0, **kw)
+    s2.resume(resume_model=True, resume_memory=True)
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), net2.state_dict().values()))
+    assert len(s2.memory) == len(saved_moves)
+    got = s2.memory.to_moves() if replay == "device" else list(s2.memory._buffer)
+    for a, b in zip(got[:50], saved_moves[:50]):
+        assert torch.equal(a.state.cpu(), b.state) and torch.equal(a.tree_probs.cpu(), b.tree_probs) and float(a.q) == float(b.q)
+    s3 = SelfPlayScheduler(net2, 0, **{**kw, "save_dir": str(tmp_path / "nothing_here")})
+    s3.resume(resume_model=True, resume_memory=True)                                   # no earlier run: a no-op
 
 
 class _StreamRandomOpponent:
