@@ -255,13 +255,19 @@ def pack_tower_blob(module, ncta=2):
     """ResidualTower (128 trunk channels; the 7x6 Connect4 or the 3x3 TicTacToe board of ResidualTower.from_env) -> one flat
     uint8 tensor in the layout spx_tower_load expects (spx_tower.cu: tower_layout)."""
     m = module
-    assert hasattr(m, "residual_blocks"), "the native tower needs a ResidualTower"
-    assert (m.width, m.height) in ((7, 6), (3, 3)) and m.conv1.out_channels == 128 and m.conv_policy.out_channels == 32
+
+    def require(ok, what):
+        if not ok:
+            raise ValueError(f"the native tower cannot run this network ({what}); use net='torch' (nets.TorchNetEvaluator) for it")
+    require(hasattr(m, "residual_blocks"), "not a ResidualTower")
+    require((m.width, m.height) in ((7, 6), (3, 3)), f"board {m.width}x{m.height}: built for the 7x6 Connect4 and 3x3 TicTacToe boards")
+    require(m.conv1.out_channels == 128 and m.conv_policy.out_channels == 32, "filter_factor must be 32 (128 trunk channels)")
+    require(m.conv1.kernel_size == (3, 3), "default_kernel_size must be 3")
     blocks = list(m.residual_blocks)
     n_layers = 2 * len(blocks) + 2
     A, FLAT, HID = m.linear_policy.out_features, 32 * m.width * m.height, 256
-    assert A == (7 if m.width == 7 else 9), "action_size must be the board's own (7 / 9)"
-    assert m.fc_value.out_features == HID and m.linear_policy.in_features == FLAT
+    require(A == (7 if m.width == 7 else 9), "action_size must be the board's own (7 / 9)")
+    require(m.fc_value.out_features == HID and m.linear_policy.in_features == FLAT, "head sizes differ from general/modules.py:66-78")
     conv_parts, biases = [], torch.zeros(n_layers, 128)
     w, b = _fold(m.conv1, m.bn1)
     wp = torch.zeros(128, 16, 3, 3)
@@ -322,7 +328,8 @@ class NativeTower:
         """module (packed on the host, then H2D) or an already packed uint8 blob (pinned host or device tensor)."""
         blob = module_or_blob if torch.is_tensor(module_or_blob) else pack_tower_blob(module_or_blob, self.ncta)
         want = lib().spx_tower_blob_bytes(self.game, self.num_blocks)
-        assert blob.numel() == want, (blob.numel(), want)
+        if blob.numel() != want:
+            raise ValueError(f"packed weight blob has {blob.numel()} bytes, this tower ({self.num_blocks} blocks) takes {want}")
         self.blob_dev = blob.to("cuda", non_blocking=True)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         check(lib().spx_tower_load(self._h, self.blob_dev.data_ptr(), self.blob_dev.numel(), stream), "spx_tower_load")

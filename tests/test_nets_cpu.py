@@ -49,3 +49,15 @@ def test_planes_from_bits_equal_planes_from_boards():
         a = nets.board_planes(torch.from_numpy(boards), W, H)
         b = nets.bits_to_planes(torch.from_numpy(bits[:, 0]), torch.from_numpy(bits[:, 1]), game)
         assert torch.equal(a, b)
+
+
+def test_pack_tower_blob_rejects_networks_the_kernel_is_not_built_for():
+    import pytest
+    from self_play_reinforcement_learning_b200 import nets
+    with pytest.raises(ValueError, match="filter_factor"):
+        nets.pack_tower_blob(nets.ResidualTower(7, 6, 7, num_blocks=1, filter_factor=16))
+    with pytest.raises(ValueError, match="board"):
+        nets.pack_tower_blob(nets.ResidualTower(5, 4, 5, num_blocks=1))
+    with pytest.raises(ValueError, match="ResidualTower"):
+        nets.pack_tower_blob(nets.ConvNetTicTacToe(3, 3, 9))
+    assert nets.pack_tower_blob(nets.ResidualTower(7, 6, 7, num_blocks=1)).dtype.is_floating_point is False
