@@ -120,7 +120,8 @@ class SelfPlayEngine:
         """table: float64 [n_table_games, 2, table_moves, A] (host array or device tensor)."""
         t = torch.as_tensor(np.ascontiguousarray(table, dtype=np.float64) if not torch.is_tensor(table) else table)
         t = t.to(self.device, torch.float64).contiguous()
-        assert t.dim() == 4 and t.shape[1] == 2 and t.shape[3] == self.A
+        if not (t.dim() == 4 and t.shape[1] == 2 and t.shape[3] == self.A):
+            raise ValueError(f"noise table must be [n_table_games, 2, table_moves, {self.A}], got {tuple(t.shape)}")
         self._noise_table = t
         check(lib().spx_set_noise_table(self._h, t.data_ptr(), first_game_index, t.shape[0], t.shape[2]), "spx_set_noise_table")
 

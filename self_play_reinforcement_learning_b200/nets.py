@@ -420,7 +420,8 @@ def pack_tttnet_blob(module):
     """ConvNetTicTacToe (3x3, action_size 9) -> fp32 blob in the layout of csrc/spx_tttnet.cu: conv weights as
     [ic][tap][oc] with eval-mode BN folded, then the head convs, linear_policy, fc_value, linear_output."""
     m = module
-    assert m.width == 3 and m.height == 3 and m.linear_policy.out_features == 9 and m.conv3.out_channels == 64
+    if not (m.width == 3 and m.height == 3 and m.linear_policy.out_features == 9 and m.conv3.out_channels == 64):
+        raise ValueError("the native TicTacToe kernel runs ConvNetTicTacToe(3, 3, 9) (tictactoe/modules.py:14-53) only; use net='torch' otherwise")
     parts = []
     for conv, bn in ((m.conv1, m.bn1), (m.conv2, m.bn2), (m.conv3, m.bn3)):
         w, b = _fold(conv, bn)                                   # [oc, ic, 3, 3]
@@ -433,7 +434,8 @@ def pack_tttnet_blob(module):
               f32(m.fc_value.weight).reshape(-1), f32(m.fc_value.bias),
               f32(m.linear_output.weight).reshape(-1), f32(m.linear_output.bias)]
     blob = torch.cat([p.contiguous().reshape(-1) for p in parts]).contiguous()
-    assert blob.numel() == lib().spx_tttnet_blob_floats(), (blob.numel(), lib().spx_tttnet_blob_floats())
+    if blob.numel() != lib().spx_tttnet_blob_floats():
+        raise ValueError(f"packed TicTacToe net has {blob.numel()} floats, the kernel takes {lib().spx_tttnet_blob_floats()}")
     return blob
 
 

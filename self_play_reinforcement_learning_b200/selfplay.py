@@ -147,7 +147,8 @@ def run_tasks(network, env, tasks, result_queue=None, memory_queue=None, task_qu
         return [], []
     update = bool(tasks[0]["play"].get("update", False))
     evaluate = bool(tasks[0].get("evaluate", False))
-    assert all(bool(t["play"].get("update", False)) == update and bool(t.get("evaluate", False)) == evaluate for t in tasks)
+    if not all(bool(t["play"].get("update", False)) == update and bool(t.get("evaluate", False)) == evaluate for t in tasks):
+        raise ValueError("run_tasks: one call takes tasks of one kind (same 'update' and 'evaluate' flags), as one scheduler phase produces them")
     n_swap = sum(1 for t in tasks if t["play"].get("swap_sides", False))
     n_plain = len(tasks) - n_swap
     target = 2 * max(n_swap, n_plain)                 # even indices: swap_sides False, odd: True
