@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-aux-rooflines", action="store_true", help="skip the search-only and env-kernel roofline legs (tests)")
     ap.add_argument("--max-sims-per-tick", type=int, default=8)
+    ap.add_argument("--no-fused", action="store_true", help="launch spx_advance + the network kernel per tick instead of the fused tick kernel")
+    ap.add_argument("--fused-chunk", type=int, default=100, help="ticks per launch of the fused tick kernel")
     ap.add_argument("--alpha", type=float, default=1.0, help="Dirichlet alpha of the root noise (mcts.py:135 default 1; tictactoeconfig.py:9 uses 0.15)")
     return ap.parse_args()
 
@@ -243,9 +245,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    fused = args.net == "tower" and not args.no_fused and getattr(ev, "fused_ticks", None) is not None \
+        and ev.tower.ncta == 2 and ev.tower.fused_heads and os.environ.get("SPX_FUSED_TICK", "1") != "0"
     # ---- warm-up (untimed)
     for _ in range(max(args.warmup, 3)):
-        eng.run_ticks(T)
+        eng.run_ticks(T, fused=fused)
     barrier()
     c0 = eng.counters()
     launches0 = _lib.lib().spx_launch_count()
@@ -253,12 +257,25 @@ def main():
     if rank == 0:
         sampler.start()
 
-    # ---- timed region 1: everything resident (value); events around the dominant kernel every 8th tick
-    tower_ev, adv_ev = [], []
+    # ---- timed region 1: everything resident (value).  Default: the fused tick kernel, `--fused-chunk` ticks per launch, CUDA
+    # events around every launch (the dominant kernel IS the step).  --no-fused / other nets: one advance + one network launch
+    # per tick, events around the kernels of every 8th tick.
+    tower_ev, adv_ev, fused_ev = [], [], []
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record()
     for s in range(args.steps):
+        if fused:
+            done = 0
+            while done < T:
+                n = min(args.fused_chunk, T - done)
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                eng.run_ticks(n, fused=True, chunk=n)
+                f1.record()
+                fused_ev.append((f0, f1, n))
+                done += n
+            continue
         for t in range(T):
             if args.net == "tower" and t % 8 == 0:
                 a = (_lib.Event(), _lib.Event())
@@ -270,8 +287,8 @@ def main():
     end.record()
     barrier()
     ms = start.elapsed_time(end)
+    launches1 = _lib.lib().spx_launch_count()   # kernels launched inside the timed region (the counters read below is outside)
     c1 = eng.counters()
-    launches1 = _lib.lib().spx_launch_count()
     clocks = sampler.stop() if rank == 0 else None
     sims = c1["sims"] - c0["sims"]
     moves = c1["moves"] - c0["moves"]
@@ -287,7 +304,16 @@ def main():
         sims_all, moves_all, evals_all = float(sims), float(moves), float(evals)
     value = sims_all / (ms / 1e3)
 
-    tower_ms = heads_ms = adv_ms = None
+    tower_ms = heads_ms = adv_ms = fused_tick_ms = None
+    if fused_ev:
+        fused_tick_ms = sum(f0.elapsed_time(f1) for f0, f1, _ in fused_ev) / sum(n for _, _, n in fused_ev)   # kernel time per tick
+        # the two halves of a tick separately (explains the fused number; outside the timed region): 64 unfused, instrumented ticks
+        for _ in range(64):
+            a = (_lib.Event(), _lib.Event())
+            n3 = tuple(_lib.Event() for _ in range(3))
+            eng.tick(advance_events=a, net_events=n3)
+            adv_ev.append(a); tower_ev.append(n3)
+        torch.cuda.synchronize()
     if tower_ev:
         tower_ms = sum(e[0].elapsed_time(e[1]) for e in tower_ev) / len(tower_ev)
         heads_ms = sum(e[1].elapsed_time(e[2]) for e in tower_ev) / len(tower_ev)
@@ -302,7 +328,7 @@ def main():
         start2, end2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start2.record()
         for s in range(args.steps):
-            out = sp.play_step(T, weights_host=blob_host)   # H2D weights, T ticks, D2H records/results/counters
+            out = sp.play_step(T, weights_host=blob_host, fused=fused)   # H2D weights, T ticks, D2H records/results/counters
             h2d += out["h2d_bytes"]; d2h += out["d2h_bytes"]
         end2.record()
         barrier()
@@ -354,17 +380,24 @@ def main():
     if rank == 0:
         peaks = _peaks()
         tw = getattr(ev, "tower", None)
-        fused = bool(getattr(tw, "fused_heads", False))
-        fl = flop_per_leaf(args.blocks, conv_only=not fused)   # with fused heads the tower kernel is the whole network
+        fused_heads = bool(getattr(tw, "fused_heads", False))
+        fl = flop_per_leaf(args.blocks, conv_only=not fused_heads)   # with fused heads the tower kernel is the whole network
         roof = None
         if tower_ms:
             leaves_per_launch = evals / max(ticks, 1)
-            achieved = leaves_per_launch * fl / (tower_ms / 1e3) / 1e12
-            roof = {"bound": "tensor", "kernel": ("spx::tower::tower_kernel<2> (tcgen05 cta_group::2, SM pair" + (", fused FC heads)" if fused else ")")) if getattr(tw, "ncta", 2) == 2 else "spx::tower::tower_kernel<1>", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
-                    "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": _ncu_traffic(),
+            name = ("spx::tower::tower_kernel<2> (tcgen05 cta_group::2, SM pair" + (", fused FC heads)" if fused_heads else ")")) if getattr(tw, "ncta", 2) == 2 else "spx::tower::tower_kernel<1>"
+            k_ms = tower_ms
+            if fused_tick_ms:   # the step is ONE kernel: network + search engine; its time per tick is the denominator
+                name = "spx::tower::tower_kernel<2, connect4, ENGINE> (fused tick: tcgen05 network with fused FC heads + the per-game search state machine in the same persistent CTAs)"
+                k_ms = fused_tick_ms
+            achieved = leaves_per_launch * fl / (k_ms / 1e3) / 1e12
+            roof = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
+                    "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": _ncu_traffic(bool(fused_tick_ms)),
                     "peak_source": peaks["source"], "flop_per_leaf": fl, "leaves_per_launch": leaves_per_launch,
-                    "kernel_ms": tower_ms, "heads_kernel_ms": None if fused else heads_ms, "advance_kernel_ms": adv_ms,
-                    "kernel_share_of_step": tower_ms * ticks / max(ms, 1e-9) if world == 1 else None}
+                    "per": "tick (a fused launch runs --fused-chunk ticks; time, leaves and traffic are per tick)" if fused_tick_ms else "launch",
+                    "kernel_ms": k_ms, "heads_kernel_ms": None if fused_heads else heads_ms,
+                    "tower_kernel_ms_unfused": tower_ms, "advance_kernel_ms_unfused": adv_ms,
+                    "kernel_share_of_step": (k_ms * ticks / max(ms, 1e-9)) if world == 1 else None}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             r = cpu_baseline(args.cpu_seconds, args.blocks, args.sims, alpha=args.alpha)
@@ -375,7 +408,7 @@ def main():
         line = {"metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload, "positions_per_sec": moves_all / (ms / 1e3), "leaf_evals_per_sec": evals_all / (ms / 1e3),
-                "mean_select_path_len": path, "e2e": e2e, "gpu_launches": int(launches1 - launches0), "clocks": clocks,
+                "mean_select_path_len": path, "fused_tick_kernel": bool(fused_tick_ms), "e2e": e2e, "gpu_launches": int(launches1 - launches0), "clocks": clocks,
                 "roofline": roof, "search_roofline": search, "env_roofline": env_roof, "cpu_baseline": cpu}
         print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
@@ -427,12 +460,13 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def _ncu_traffic():
-    """dram bytes per launch of the tower kernel from the committed `ncu --set full` capture (profiles/)."""
+def _ncu_traffic(fused_tick=False):
+    """dram bytes of the dominant kernel from the committed `ncu --set full` capture (profiles/): per launch of the tower kernel,
+    or per tick of the fused tick kernel."""
     p = os.path.join(ROOT, "profiles", "tower_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p))["dram_bytes_per_launch"]
+            return json.load(open(p))["dram_bytes_per_tick_fused" if fused_tick else "dram_bytes_per_launch"]
         except Exception:
             return None
     return None

@@ -276,6 +276,13 @@ int spx_replay_sample(spx_replay* r, int32_t game, int64_t batch, uint64_t seed,
 int spx_replay_deduplicate(spx_replay* r, int64_t maxlen, void* stream);
 int64_t spx_replay_unique(spx_replay* r); /* len(deduplicator.counter): distinct states folded so far (0 before the first call) */
 
+/* The whole tick loop in ONE launch (the persistent form of `spx_advance` + `spx_tower_forward` x n_ticks): the tower kernel's
+ * CTAs also run the per-game state machine of the games whose leaves they evaluate, tick after tick, without returning to the
+ * host -- games are independent, so no grid-wide synchronisation is needed.  Same state, records and outputs as n_ticks
+ * separate ticks, bit for bit (tests/test_search_gpu.py).  policy / value: the engine's output buffers (dev f32[n_games][A],
+ * f32[n_games]) as passed to spx_advance.  Needs the SM-pair tower with fused heads, one network, same game as the engine. */
+int spx_tick_fused(spx_engine* e, spx_tower* t, int32_t n_ticks, float* policy, float* value, void* stream);
+
 /* timing-event helpers (cudaEvent_t behind void*), so hosts without a CUDA binding can time on the launching stream */
 int spx_event_create(void** ev_out);
 int spx_event_destroy(void* ev);

@@ -37,6 +37,9 @@ def smi():
 
 
 print("full tick            %.4f ms" % timed(e.tick, N), smi())
+for chunk in (8, 64, 256, 800):
+    print("fused ticks, chunk %-4d %.4f ms" % (chunk, timed(lambda: e.run_ticks(chunk, fused=True, chunk=chunk), N // chunk) / chunk), smi())
+print("full tick            %.4f ms" % timed(e.tick, N), smi())
 print("tower, loop leaves   %.4f ms" % timed(lambda: ev(e), N), smi())
 tw = ev.tower
 rng = np.random.default_rng(0)

@@ -26,7 +26,8 @@ for r in rows[1:]:
     agg[r[ik].split("(")[0]].append(v / 1000 if r[iu] == "ns" else v)
 tot = sum(sum(v) for v in agg.values())
 lines = [f"# {tag} ncu launch list summary (gpu__time_duration.sum, --clock-control none; cold-cache serialised launches: compare SHARES)",
-         "# command: python bench.py --steps 1 --warmup 3 --ticks-per-step 40 --no-cpu-baseline --no-e2e",
+         "# command: python bench.py --steps 1 --warmup 3 --ticks-per-step 40 --fused-chunk 40 --no-cpu-baseline --no-e2e",
+         "# (tower_kernel<2, 0, true> = the fused tick kernel, 40 ticks per launch; tower_kernel<2, 0, false> + advance_kernel = the 64 instrumented separate ticks)",
          "kernel,launches,mean_us,share"]
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     lines.append(f"{k},{len(v)},{sum(v) / len(v):.2f},{sum(v) / tot:.4f}")
@@ -54,19 +55,45 @@ units = rr[1]
 summ = []
 for r in rr[2:]:
     summ.append({w: (r[i] + (" " + units[i] if units[i] else "")) for w, i in idx})
+fused_rep = os.path.join(ROOT, "gpurun_out", f"prof_fused_{tag}.ncu-rep")
+FUSED_TICKS = 40   # scripts/capture_profiles.sh: --ticks-per-step 40 --fused-chunk 40
+fused_traffic = None
+if os.path.exists(fused_rep):   # the fused tick kernel: one launch = 40 ticks
+    raw_f = subprocess.run(["ncu", "-i", fused_rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    open(os.path.join(out_dir, f"{tag}_ncu_fused_raw.csv"), "w").write(raw_f)
+    rf = list(csv.reader(raw_f.splitlines()))
+    hf, uf = rf[0], rf[1]
+    for r in rf[2:]:
+        d = {w: (r[hf.index(w)] + (" " + uf[hf.index(w)] if uf[hf.index(w)] else "")) for w in want if w in hf}
+        d["ticks_per_launch"] = FUSED_TICKS
+        summ.append(d)
+
+    def _bytes(s_):
+        v, u_ = s_.split()[0], (s_.split() + [""])[1]
+        return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u_, 1)
+    tr_f = [(_bytes(x["dram__bytes_read.sum"]) + _bytes(x["dram__bytes_write.sum"])) / FUSED_TICKS for x in summ if x.get("ticks_per_launch")]
+    if tr_f:
+        fused_traffic = sum(tr_f) / len(tr_f)
 if raw_env:   # same metrics for the env kernel (its raw page has its own column set)
     re_ = list(csv.reader(raw_env.splitlines()))
     he, ue = re_[0], re_[1]
     for r in re_[2:]:
         summ.append({w: (r[he.index(w)] + (" " + ue[he.index(w)] if ue[he.index(w)] else "")) for w in want if w in he})
 json.dump(summ, open(os.path.join(out_dir, f"{tag}_ncu_kernels.json"), "w"), indent=1)
-tw = [x for x in summ if "tower_kernel" in x["Kernel Name"]]
+tw = [x for x in summ if "tower_kernel" in x["Kernel Name"] and not x.get("ticks_per_launch")]
+tpath = os.path.join(out_dir, "tower_traffic.json")
+traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
 if tw:
     def to_bytes(s):
         v, u = s.split()[0], (s.split() + [""])[1]
         return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
     tr = [to_bytes(x["dram__bytes_read.sum"]) + to_bytes(x["dram__bytes_write.sum"]) for x in tw]
-    json.dump({"dram_bytes_per_launch": sum(tr) / len(tr), "source": f"profiles/{tag}_ncu_full_raw.csv (ncu --set full, tower_kernel<2>, {len(tr)} launches)"},
-              open(os.path.join(out_dir, "tower_traffic.json"), "w"))
+    traffic["dram_bytes_per_launch"] = sum(tr) / len(tr)
+    traffic["source"] = f"profiles/{tag}_ncu_full_raw.csv (ncu --set full, tower_kernel<2>, {len(tr)} launches)"
+if fused_traffic is not None:
+    traffic["dram_bytes_per_tick_fused"] = fused_traffic
+    traffic["source_fused"] = (f"profiles/{tag}_ncu_fused_raw.csv (ncu --set full, fused tick kernel, bytes per launch / {FUSED_TICKS} ticks: the weights are "
+                               "read from DRAM once per launch and stay in L2, so are the search trees)")
+json.dump(traffic, open(tpath, "w"))
 for x in summ:
     print({k: v for k, v in x.items()})

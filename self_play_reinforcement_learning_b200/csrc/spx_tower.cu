@@ -35,7 +35,7 @@
 
 #include <new>
 
-#include "spx_common.cuh"
+#include "spx_advance.cuh"
 
 namespace spx {
 int set_err(int code, const char* fmt, const char* detail);
@@ -433,14 +433,25 @@ __device__ __forceinline__ void issue_first_tap_skewed(SmemT<2>& S, int taps, un
 
 // GAME is a template parameter: with the head sizes as run-time values the Connect4 kernel spilled (712-byte stack frame at the
 // 96-register cap, +13 % instructions, 8 MB of local-memory write-back per launch in ncu)
-template <int NCTA, int GAME = SPX_GAME_CONNECT4>
+// ENGINE = true is the fused tick kernel (spx_tick_fused): the kernel runs `n_ticks` ticks without the host; before every network
+// evaluation of a board group the first NB epilogue warps of the CTA that owns the group run the search engine's per-game state
+// machine (advance_game, spx_advance.cuh) for the group's games, i.e. consume the previous outputs and produce the next leaves.
+// Games are independent, so clusters never wait for each other: no grid-wide barrier, no launch gaps, no advance-kernel tail.
+template <int NCTA, int GAME = SPX_GAME_CONNECT4, bool ENGINE = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long long* __restrict__ opp_g,
              const unsigned char* __restrict__ needs, long long n_boards, int n_layers,
              const unsigned char* __restrict__ wconv, const float* __restrict__ bias_all, float* __restrict__ head_out,
              int fused_in, const float* __restrict__ polw, const float* __restrict__ polb, const float* __restrict__ fc_b1,
-             const float* __restrict__ fc_w2, const float* __restrict__ fc_b2, float* __restrict__ policy_out, float* __restrict__ value_out) {
+             const float* __restrict__ fc_w2, const float* __restrict__ fc_b2, float* __restrict__ policy_out, float* __restrict__ value_out,
+             const EngineDev E, const int n_ticks) {
     typedef SmemT<NCTA> Smem;
+    // leaves / needs_eval are produced inside this launch when ENGINE: read them through L2 (__ldcg), never through the
+    // read-only path the __restrict__ const parameters allow
+    auto ld_need = [&](long long gb) -> bool {
+        if constexpr (ENGINE) return __ldcg(E.needs_eval + gb) != 0;
+        else return needs == nullptr || needs[gb];
+    };
     const bool fused = NCTA == 2 && fused_in != 0;   // FC heads inside this kernel (no head_out round trip, no second launch)
     constexpr int game = GAME;
     constexpr int cells = GAME == SPX_GAME_TICTACTOE ? 9 : CELLS, n_act = GAME == SPX_GAME_TICTACTOE ? 9 : 7;
@@ -492,11 +503,23 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
     bool first_unit = true;
 
     const long long n_units = (n_groups + NCTA - 1) / NCTA;      // a unit = the NCTA board groups one cluster works on together
+    for (int tick = 0; tick < (ENGINE ? n_ticks : 1); ++tick)
     for (long long unit = blockIdx.x / NCTA; unit < n_units; unit += gridDim.x / NCTA) {
         const long long grp = NCTA * unit + crank;
+        if constexpr (ENGINE) {
+            // one warp per game of this CTA's group: outputs of the previous tick in, next leaf out (all global memory; the
+            // previous unit ended with a cluster barrier after the last output was written)
+            if (warp >= EPI_WARP0 && warp < EPI_WARP0 + NB) {
+                const long long gb = grp * NB + (warp - EPI_WARP0);
+                if (gb < n_boards) advance_game<GAME>(E, (int)gb, lane, policy_out, value_out);
+            }
+            __threadfence();
+            __syncthreads();
+            cluster_sync_all();   // the skip test below reads the peer group's needs_eval
+        }
         // cluster-uniform skip when none of the boards of this unit asked for an evaluation
-        bool any = needs == nullptr;
-        if (!any) for (int b = 0; b < NCTA * NB; ++b) { long long gb = unit * NCTA * NB + b; if (gb < n_boards && needs[gb]) any = true; }
+        bool any = !ENGINE && needs == nullptr;
+        if (!any) for (int b = 0; b < NCTA * NB; ++b) { long long gb = unit * NCTA * NB + b; if (gb < n_boards && ld_need(gb)) any = true; }
         if (!any) continue;
 
         if (warp == 0) {
@@ -695,8 +718,13 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
             }
             if (et < NB) {
                 const long long gb = grp * NB + et;
-                S.own[et] = gb < n_boards ? own_g[gb] : 0ULL;
-                S.opp[et] = gb < n_boards ? opp_g[gb] : 0ULL;
+                if constexpr (ENGINE) {
+                    S.own[et] = gb < n_boards ? __ldcg(E.leaf_own + gb) : 0ULL;
+                    S.opp[et] = gb < n_boards ? __ldcg(E.leaf_opp + gb) : 0ULL;
+                } else {
+                    S.own[et] = gb < n_boards ? own_g[gb] : 0ULL;
+                    S.opp[et] = gb < n_boards ? opp_g[gb] : 0ULL;
+                }
             }
             if constexpr (NCTA == 1) {
                 if (et < CH) { S.bias[0][et] = __ldg(bias_all + et); S.bias[1][et] = __ldg(bias_all + CH + et); }
@@ -854,7 +882,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
                     if (et < NB) {
                         const long long gb = grp * NB + et;
-                        if (gb < n_boards && (needs == nullptr || needs[gb])) {
+                        if (gb < n_boards && ld_need(gb)) {
                             float m = scr[et * 9];
                             for (int a = 1; a < n_act; ++a) m = fmaxf(m, scr[et * 9 + a]);
                             float e[SPX_MAX_ACTIONS], z = 0.f;
@@ -906,7 +934,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 const long long gb = grp * NB + lane;
                 const int c = (int)crank * 8 + lane;
                 const float lo = crank == 0 ? scr[128 + c] : scr[144 + c], hi = crank == 0 ? scr[144 + c] : scr[128 + c];   // hidden 0..127, 128..255
-                if (gb < n_boards && (needs == nullptr || needs[gb])) value_out[gb] = tanhf((lo + hi) + __ldg(fc_b2));
+                if (gb < n_boards && ld_need(gb)) value_out[gb] = tanhf((lo + hi) + __ldg(fc_b2));
             }
             if (fused) cluster_sync_all();   // the scratch may be overwritten by the peer in the next unit only after it was read
         }
@@ -1133,6 +1161,8 @@ int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
     SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<1>)));
     SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<2>)));
     SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<2, SPX_GAME_TICTACTOE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<2>)));
+    SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<2, SPX_GAME_CONNECT4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<2>)));
+    SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<2, SPX_GAME_TICTACTOE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<2>)));
     SPX_CUDA_T(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM));
     *out = t;
     return 0;
@@ -1186,12 +1216,12 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
         SPX_CUDA_T(cudaLaunchKernelEx(&cfg, kern, (const unsigned long long*)own, (const unsigned long long*)opp, needs_eval,
                                       (long long)n, t->n_layers, (const unsigned char*)t->blob, (const float*)(t->blob + t->off_bias), t->head_buf,
                                       t->fused, (const float*)(t->blob + t->off_polw), (const float*)(t->blob + t->off_polb), (const float*)(t->blob + t->off_b1),
-                                      (const float*)(t->blob + t->off_w2), (const float*)(t->blob + t->off_b2), policy, value));
+                                      (const float*)(t->blob + t->off_w2), (const float*)(t->blob + t->off_b2), policy, value, spx::EngineDev{}, 1));
     } else {
         const int grid = (int)(groups < t->sm_count ? groups : t->sm_count);
         tower_kernel<1><<<grid, NUM_THREADS, sizeof(SmemT<1>), st>>>((const unsigned long long*)own, (const unsigned long long*)opp, needs_eval, n,
                                                             t->n_layers, t->blob, (const float*)(t->blob + t->off_bias), t->head_buf,
-                                                            0, nullptr, nullptr, nullptr, nullptr, nullptr, policy, value);
+                                                            0, nullptr, nullptr, nullptr, nullptr, nullptr, policy, value, spx::EngineDev{}, 1);
     }
     spx::count_launch();
     SPX_CUDA_T(cudaGetLastError());
@@ -1213,6 +1243,34 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
 #ifdef SPX_DBG_TRACE
 int spx_debug_trace(long long* host_out) { return (int)cudaMemcpyFromSymbol(host_out, spx::tower::g_trace, sizeof(long long) * (64 * 16 + 3 * 160)); }
 #endif
+
+/* n_ticks ticks (spx_advance + network evaluation each) in ONE launch: see tower_kernel<.., ENGINE = true> */
+int spx_tick_fused(spx_engine* e, spx_tower* t, int32_t n_ticks, float* policy, float* value, void* stream) {
+    if (!e || !t || !policy || !value) return spx::set_err(SPX_E_ARG, "spx_tick_fused: null argument%s", "");
+    if (n_ticks <= 0) return 0;
+    if (t->ncta != 2 || !t->fused) return spx::set_err(SPX_E_STATE, "spx_tick_fused: needs the SM-pair tower with fused heads%s", "");
+    if (e->d.cfg.game != t->game || e->d.cfg.two_nets) return spx::set_err(SPX_E_ARG, "spx_tick_fused: one network, same game as the engine%s", "");
+    const long long n = e->d.cfg.n_games, groups = (n + NB - 1) / NB, pairs = (groups + 1) / 2, max_pairs = t->sm_count / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = sizeof(SmemT<2>);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    auto kern = t->game == SPX_GAME_TICTACTOE ? tower_kernel<2, SPX_GAME_TICTACTOE, true> : tower_kernel<2, SPX_GAME_CONNECT4, true>;
+    SPX_CUDA_T(cudaLaunchKernelEx(&cfg, kern, (const unsigned long long*)e->d.leaf_own, (const unsigned long long*)e->d.leaf_opp,
+                                  (const unsigned char*)e->d.needs_eval, n, t->n_layers, (const unsigned char*)t->blob,
+                                  (const float*)(t->blob + t->off_bias), t->head_buf, 1, (const float*)(t->blob + t->off_polw),
+                                  (const float*)(t->blob + t->off_polb), (const float*)(t->blob + t->off_b1), (const float*)(t->blob + t->off_w2),
+                                  (const float*)(t->blob + t->off_b2), policy, value, e->d, (int)n_ticks));
+    spx::count_launch();
+    SPX_CUDA_T(cudaGetLastError());
+    return 0;
+}
 
 int spx_tower_forward(spx_tower* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n,
                       float* policy, float* value, void* stream) {

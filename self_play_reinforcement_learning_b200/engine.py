@@ -145,8 +145,17 @@ class SelfPlayEngine:
         else:
             self.evaluator(self, events=net_events)
 
-    def run_ticks(self, n):
-        for _ in range(n):
+    def run_ticks(self, n, fused=True, chunk=256):
+        """n ticks.  With the native tower the whole loop runs as persistent launches of `chunk` ticks (spx_tick_fused: the
+        network CTAs also advance their games); any other evaluator, or fused=False, launches advance + evaluation per tick."""
+        fn = getattr(self.evaluator, "fused_ticks", None) if fused else None
+        done = 0
+        while fn is not None and done < n:
+            if not fn(self, min(chunk, n - done)):
+                break
+            done += min(chunk, n - done)
+            self._first = False
+        for _ in range(n - done):
             self.tick()
 
     def run_until_idle(self, max_ticks=10_000_000, poll_every=64):

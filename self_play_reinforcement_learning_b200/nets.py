@@ -14,6 +14,7 @@ Evaluators turn the engine's dense leaf batch (bitboards in the net frame) into 
                          cuDNN/cuBLAS comparison point)
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -377,6 +378,14 @@ class TowerEvaluator:
 
     def __call__(self, engine, events=None):
         self.tower.forward_bits(engine.leaf_own, engine.leaf_opp, engine.needs_eval, engine.policy, engine.value, events)
+
+    def fused_ticks(self, engine, n):
+        """n whole ticks (advance + evaluation) in one persistent launch (spx_tick_fused); False if this tower cannot."""
+        if not (self.tower.ncta == 2 and self.tower.fused_heads) or os.environ.get("SPX_FUSED_TICK", "1") == "0":
+            return False
+        check(lib().spx_tick_fused(engine._h, self.tower._h, int(n), engine.policy.data_ptr(), engine.value.data_ptr(),
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)), "spx_tick_fused")
+        return True
 
 
 class TwoTowerEvaluator:

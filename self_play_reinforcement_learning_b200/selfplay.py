@@ -98,13 +98,13 @@ class BatchedSelfPlay:
         return 0
 
     # ------------------------------------------------------------------ running
-    def play_step(self, ticks, weights_host=None):
+    def play_step(self, ticks, weights_host=None, fused=True):
         """One host-visible step: optional weight upload from (pinned) host memory, ``ticks`` engine ticks, then the
         step's records, results and counters copied back to the host."""
         h2d = 0
         if weights_host is not None:
             h2d += self.load_weights(weights_host)
-        self.engine.run_ticks(ticks)
+        self.engine.run_ticks(ticks, fused=fused)
         recs = self.engine.drain_records()
         res = self.engine.drain_results()
         cnt = self.engine.counters()

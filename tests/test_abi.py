@@ -81,7 +81,7 @@ def test_hot_kernels_do_not_spill():
     usage = {}
     for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
         usage[m.group(1)] = (int(m.group(2)), int(m.group(3)))
-    tower = [v for k, v in usage.items() if "tower_kernelILi2ELi0E" in k]
+    tower = [v for k, v in usage.items() if "tower_kernelILi2ELi0ELb0E" in k]
     env = [v for k, v in usage.items() if "env_step_quad_kernelILi0E" in k]
     assert tower and env, sorted(usage)
     assert tower[0][0] <= 96 and tower[0][1] <= 64, tower

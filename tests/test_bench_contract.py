@@ -29,10 +29,10 @@ def test_reference_arm_prints_one_json_line():
 
 @pytest.mark.gpu
 def test_gpu_arm_prints_one_json_line():
-    d = _run("--steps", "1", "--warmup", "3", "--ticks-per-step", "24", "--cpu-seconds", "2", "--no-aux-rooflines")
+    d = _run("--steps", "1", "--warmup", "3", "--ticks-per-step", "24", "--fused-chunk", "12", "--cpu-seconds", "2", "--no-aux-rooflines")
     assert BASE_KEYS | {"gpu_launches", "clocks", "roofline"} <= set(d)
     assert d["value"] > 0 and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["dtype"] == "bf16" and d["scaling"] == "weak"
-    assert d["gpu_launches"] >= 2 * 24 and d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["fused_tick_kernel"] is True and d["gpu_launches"] == 2 and d["e2e"]["value"] > 0     # 24 ticks = 2 fused launches of 12 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     r = d["roofline"]
     assert r["bound"] == "tensor" and 0 < r["frac"] < 1.2 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["unit"] == "TFLOP/s"
     c = d["cpu_baseline"]
