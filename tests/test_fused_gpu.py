@@ -8,9 +8,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _run(net, game, n_games, sims, ticks, fused, games_target, chunk):
+def _run(net, game, n_games, sims, ticks, fused, games_target, chunk, **kw):
     from self_play_reinforcement_learning_b200.selfplay import BatchedSelfPlay
-    sp = BatchedSelfPlay(net, game=game, n_games=n_games, sims=sims, net="tower", seed=3, games_target=games_target)
+    sp = BatchedSelfPlay(net, game=game, n_games=n_games, sims=sims, net="tower", seed=3, games_target=games_target, **kw)
     e = sp.engine
     e.run_ticks(ticks, fused=fused, chunk=chunk)
     torch.cuda.synchronize()
@@ -70,3 +70,16 @@ def test_fused_then_separate_then_fused_continues_the_same_games():
         outs.append((sp.engine.counters(), np.sort(sp.engine.drain_records(), order=["game_index", "tree", "ply"]).tobytes()))
         sp.close()
     assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("kw", [dict(opponent="lookahead", evaluate=True, update=False), dict(opponent="random"), dict(strong_play=True, alpha=0.15)])
+def test_fused_ticks_other_engine_modes(kw):
+    """Hard-coded opponents (hardcoded_players.py), evaluate mode (temp 1/20), strong_play, another Dirichlet alpha: the same
+    state machine runs inside the fused kernel."""
+    from self_play_reinforcement_learning_b200 import nets
+    torch.manual_seed(6)
+    net = nets.ResidualTower(7, 6, 7, num_blocks=1).eval()
+    a = _run(net, 0, 20, 30, 700, False, 40, 64, **kw)
+    b = _run(net, 0, 20, 30, 700, True, 40, 41, **kw)
+    assert a["counters"]["games_finished"] > 0 and a["counters"]["errors"] == 0
+    _same(a, b)
