@@ -194,3 +194,25 @@ def test_deduplicator_matches_reference_live():
             assert np.float32(m.q) == o["q"]
             assert torch.equal(hm.state, m.state) and torch.equal(hm.tree_probs, m.tree_probs)
             assert torch.equal(hm.actual_val, m.actual_val) and torch.equal(hm.q, m.q)
+
+
+def _golden_dedup_records(g):
+    return [dict(own=int(g["own"][i]), opp=int(g["opp"][i]), game_index=i, tree=0, ply=int(g["ply"][i]), tree_probs=g["tree_probs"][i],
+                 q=g["q"][i], actual_val=g["actual_val"][i]) for i in range(len(g["own"]))]
+
+
+def test_deduplicator_restatement_matches_reference_golden(golden_dir):
+    """tests/golden/dedup.npz was written by the unmodified reference (oracle/make_golden_dedup.py); the restatement must
+    reproduce every round bit for bit (this pin travels to the GPU box, where the reference does not exist)."""
+    g = np.load(os.path.join(golden_dir, "dedup.npz"))
+    recs = _golden_dedup_records(g)
+    mem = orp.Memory(int(g["max_size"]))
+    for p, (lo, hi, maxlen) in enumerate(g["phases"].tolist()):
+        for r in recs[lo:hi]:
+            mem.add(r)
+        out = orp.memory_deduplicate(mem, maxlen=maxlen or None)
+        assert [o["own"] for o in out] == g[f"own_{p}"].tolist() and [o["opp"] for o in out] == g[f"opp_{p}"].tolist()
+        assert np.stack([o["tree_probs"][:7] for o in out]).tobytes() == g[f"tree_probs_{p}"].tobytes()
+        assert np.array([o["actual_val"] for o in out], np.float32).tobytes() == g[f"actual_val_{p}"].tobytes()
+        assert np.array([o["q"] for o in out], np.float32).tobytes() == g[f"q_{p}"].tobytes()
+        assert len(mem.deduplicator.counter) == int(g[f"unique_{p}"])

@@ -228,3 +228,26 @@ def test_device_deduplicate_empty_memory_and_sampling_after():
     with pytest.raises(ValueError):
         dev.deduplicate(key="q")
     dev.close()
+
+
+def test_device_deduplicator_matches_reference_golden(golden_dir):
+    """spx_replay_deduplicate against tests/golden/dedup.npz (written by the unmodified reference's Memory/Deduplicator)."""
+    import os
+    from self_play_reinforcement_learning_b200.engine import RECORD_DTYPE
+    from self_play_reinforcement_learning_b200.replay import DeviceReplay
+    g = np.load(os.path.join(golden_dir, "dedup.npz"))
+    n = len(g["own"])
+    recs = np.zeros(n, RECORD_DTYPE)
+    recs["own"], recs["opp"], recs["q"], recs["actual_val"], recs["ply"] = g["own"], g["opp"], g["q"], g["actual_val"], g["ply"]
+    recs["tree_probs"][:, :7] = g["tree_probs"]
+    recs["game_index"] = np.arange(n)
+    dev = DeviceReplay(0, max_size=int(g["max_size"]), physical_capacity=1000, seed=0)
+    for p, (lo, hi, maxlen) in enumerate(g["phases"].tolist()):
+        dev.append_records(recs[lo:hi])
+        dev.deduplicate("state", ["actual_val", "tree_probs"], maxlen=maxlen or None)
+        got = dev.read()
+        assert got["own"].tolist() == g[f"own_{p}"].tolist() and got["opp"].tolist() == g[f"opp_{p}"].tolist()
+        assert np.ascontiguousarray(got["tree_probs"][:, :7]).tobytes() == g[f"tree_probs_{p}"].tobytes()
+        assert got["actual_val"].tobytes() == g[f"actual_val_{p}"].tobytes() and got["q"].tobytes() == g[f"q_{p}"].tobytes()
+        assert dev.unique_states == int(g[f"unique_{p}"])
+    dev.close()
