@@ -503,20 +503,26 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
     bool first_unit = true;
 
     const long long n_units = (n_groups + NCTA - 1) / NCTA;      // a unit = the NCTA board groups one cluster works on together
-    for (int tick = 0; tick < (ENGINE ? n_ticks : 1); ++tick)
+    for (int tick = 0; tick < (ENGINE ? n_ticks : 1); ++tick) {
+    if constexpr (ENGINE) {
+        // search phase of the tick: one warp per game of this CTA's board groups -- outputs of the previous tick in, next leaf out
+        // (all through global memory; the previous tick ended with a cluster barrier after its last output was written).  Two
+        // groups' games at a time when the cluster owns several units (more than 1036 games): 14 of the 16 epilogue warps.
+        const long long ustride = gridDim.x / NCTA;
+        for (long long unit0 = blockIdx.x / NCTA; unit0 < n_units; unit0 += 2 * ustride) {
+            const int w = warp - EPI_WARP0;
+            if (w >= 0 && w < 2 * NB) {
+                const long long unit = unit0 + (w / NB) * ustride;
+                const long long gb = (NCTA * unit + crank) * NB + (w % NB);
+                if (unit < n_units && gb < n_boards) advance_game<GAME>(E, (int)gb, lane, policy_out, value_out);
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        cluster_sync_all();   // the skip test below reads the peer group's needs_eval
+    }
     for (long long unit = blockIdx.x / NCTA; unit < n_units; unit += gridDim.x / NCTA) {
         const long long grp = NCTA * unit + crank;
-        if constexpr (ENGINE) {
-            // one warp per game of this CTA's group: outputs of the previous tick in, next leaf out (all global memory; the
-            // previous unit ended with a cluster barrier after the last output was written)
-            if (warp >= EPI_WARP0 && warp < EPI_WARP0 + NB) {
-                const long long gb = grp * NB + (warp - EPI_WARP0);
-                if (gb < n_boards) advance_game<GAME>(E, (int)gb, lane, policy_out, value_out);
-            }
-            __threadfence();
-            __syncthreads();
-            cluster_sync_all();   // the skip test below reads the peer group's needs_eval
-        }
         // cluster-uniform skip when none of the boards of this unit asked for an evaluation
         bool any = !ENGINE && needs == nullptr;
         if (!any) for (int b = 0; b < NCTA * NB; ++b) { long long gb = unit * NCTA * NB + b; if (gb < n_boards && ld_need(gb)) any = true; }
@@ -940,6 +946,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
         }
         first_unit = false;
     }
+    }   // tick
 
     if (tid == 0) SPX_TRACE(62, 2);
 #ifdef SPX_DBG_TRACE
