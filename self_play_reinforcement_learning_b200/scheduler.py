@@ -106,6 +106,8 @@ class SelfPlayScheduler:
         ``<save_dir>/<start_time>/model-<iso time>:<games>`` ({"model": state_dict}, updateworker.py:111-117) and, with
         ``save_memory``, the pickled Memory of Move tuples ``memory-<iso time>:<size>`` (previous file removed, :119-139);
         ``train_model(resume_model=, resume_memory=)`` picks up the newest files of the previous run (base_worker.py:26-62).
+        (Pickling a full 200 000-record Memory of Move tuples takes about a minute, as it does in the reference;
+        ``save_memory=False`` keeps only the model checkpoints.)
         amp: None = fp32 SGD steps like the reference's UpdateWorker; torch.bfloat16 runs forward/backward under autocast
         (12 instead of 29 ms per step of batch 128 on B200, scripts/dbg_update_step.py) -- an option, not reference behaviour.
         lr_patience: ReduceLROnPlateau("max", patience, factor 0.5, min_lr 1e-5, cooldown 5) stepped with every epoch's

@@ -43,7 +43,9 @@ def records_to_moves(records, game):
     probs = torch.from_numpy(np.ascontiguousarray(records["tree_probs"][:, :A]))
     q = torch.from_numpy(np.ascontiguousarray(records["q"]))
     val = torch.from_numpy(np.ascontiguousarray(records["actual_val"]))
-    return [Move(boards[i], val[i], probs[i], q[i]) for i in range(len(records))]
+    # every field of every Move owns its storage, like the reference's (torch.tensor(...) per record, mcts.py:282-289): a view
+    # into the batch tensors would drag the WHOLE batch along whenever one Move is pickled (memory_queue, save_memory)
+    return [Move(b.clone(), v.clone(), p.clone(), x.clone()) for b, v, p, x in zip(boards.unbind(0), val.unbind(0), probs.unbind(0), q.unbind(0))]
 
 
 def results_to_dicts(results):

@@ -42,3 +42,22 @@ def test_memory_pickle_roundtrip(tmp_path):
     assert not os.path.exists(f1) and f2.endswith(":5")
     m2 = checkpoint.load_memory(checkpoint.recent_save_file(str(tmp_path), None, False, "memory"))
     assert len(m2) == 5 and float(m2.sample(5)[0].tree_probs.sum()) > 0.99
+
+
+def test_moves_from_records_pickle_independently():
+    """records_to_moves must hand out tensors that own their storage: a Move that is a view into the batch would serialise the
+    whole batch with every record (mp queues, save_memory) -- 200 k records once meant 200 k copies of a 67 MB tensor."""
+    import pickle
+    import numpy as np
+    from self_play_reinforcement_learning_b200.engine import RECORD_DTYPE
+    from self_play_reinforcement_learning_b200.selfplay import records_to_moves
+    r = np.zeros(5000, RECORD_DTYPE)
+    r["own"] = np.arange(5000, dtype=np.uint64) & np.uint64(0x3F)
+    r["tree_probs"][:, :7] = 1 / 7
+    moves = records_to_moves(r, 0)
+    assert len(pickle.dumps(moves[17])) < 4000
+    m = Memory(10000)
+    for mv in moves:
+        m.add(mv)
+    assert len(pickle.dumps(m)) < 5000 * 4000
+    assert moves[63].state.dtype == torch.int64 and int(moves[63].state.sum()) == 6 and moves[63].state.shape == (7, 6)
