@@ -17,3 +17,12 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """libspx.so is git-ignored: on a fresh checkout the test session compiles it once (nvcc cross-compiles without a GPU).
+    Building is not a fallback -- outside the tests a missing library is an error (_lib.lib())."""
+    from self_play_reinforcement_learning_b200 import _lib, build
+    if not os.environ.get("SPX_LIB_PATH") and not os.path.exists(_lib.LIB_PATH):
+        build.build()
