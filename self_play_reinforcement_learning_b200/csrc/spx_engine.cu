@@ -561,7 +561,15 @@ int spx_drain_records_device(spx_engine* e, spx_record* dev_out, int64_t capacit
 }
 int spx_drain_results(spx_engine* e, spx_result* host_out, int64_t capacity, int64_t* n_out, void* stream) {
     if (!e || !host_out || !n_out) return set_err(SPX_E_ARG, "spx_drain_results: bad argument%s", "");
-    return drain<spx_result>(e->d.res_ring, e->d.res_count, e->d.cfg.result_capacity, host_out, capacity, n_out, (cudaStream_t)stream);
+    // results beyond the ring's capacity were not written (advance_game keeps counting): that is lost data, not a statistic
+    unsigned long long pending = 0;
+    SPX_CUDA(cudaMemcpyAsync(&pending, e->d.res_count, sizeof(pending), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    SPX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    const int rc = drain<spx_result>(e->d.res_ring, e->d.res_count, e->d.cfg.result_capacity, host_out, capacity, n_out, (cudaStream_t)stream);
+    if (rc == 0 && (int64_t)pending > e->d.cfg.result_capacity)
+        return set_err(SPX_E_OVERFLOW, "spx_drain_results: game results were lost, the result ring overflowed between two drains "
+                                       "(drain more often or raise result_capacity)%s", "");
+    return rc;
 }
 
 int spx_read_move_log(spx_engine* e, int32_t slot, spx_move_log* host_out, int32_t capacity, int32_t* n_out, void* stream) {

@@ -168,6 +168,21 @@ class SelfPlayEngine:
         raise _lib.SpxError("run_until_idle: max_ticks reached")
 
     # ------------------------------------------------------------------ readouts
+    @property
+    def safe_poll_interval(self):
+        """Ticks between two drains that cannot overflow the default rings: a ply takes at least sims / max_sims_per_tick
+        ticks and a game at least 5 plies, so 2 * sims ticks hold fewer than 4 finished games per slot."""
+        return int(max(8, min(512, 2 * self.sims)))
+
+    def check_overflow(self):
+        """Raises if records were dropped since the engine was created (the device ring was drained too rarely): training
+        data must not vanish silently.  (Lost game results make spx_drain_results itself fail.)"""
+        c = self.counters()
+        if c["records_dropped"]:
+            raise _lib.SpxError(f"{c['records_dropped']} self-play records were dropped: the record ring overflowed between two "
+                                "drains (drain more often or pass a larger record_capacity)")
+        return c
+
     def all_idle(self):
         out = C.c_int32()
         check(lib().spx_all_idle(self._h, C.byref(out), _stream_ptr()), "spx_all_idle")

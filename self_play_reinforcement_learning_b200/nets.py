@@ -165,16 +165,29 @@ class TorchNetEvaluator:
         self.modules = [module] + ([module_opp] if module_opp is not None else [])
 
     def bind(self, engine):
+        """Evaluation runs on PRIVATE copies (device, eval mode, evaluation dtype, channels_last): nn.Module.to works in place,
+        so casting the caller's module would turn the fp32 master weights it trains and checkpoints into bf16."""
+        import copy
         dev = engine.device
+        self.masters = list(self.modules)
         mods = []
-        for m in self.modules:
-            m = m.to(dev).eval()
+        for m in self.masters:
+            c = copy.deepcopy(m).to(dev).eval()
+            for p in c.parameters():
+                p.requires_grad_(False)
             if self.dtype != torch.float32:
-                m = m.to(self.dtype)
+                c = c.to(self.dtype)
             if self.channels_last:
-                m = m.to(memory_format=torch.channels_last)
-            mods.append(m)
+                c = c.to(memory_format=torch.channels_last)
+            mods.append(c)
         self.modules = mods
+
+    def refresh(self, module=None, which=0):
+        """Copies the weights of `module` (default: the master this evaluator was built from) into the evaluation copy."""
+        src = module if module is not None else self.masters[which]
+        with torch.no_grad():
+            self.modules[which].load_state_dict(src.state_dict())
+        self.modules[which].eval()
 
     @torch.no_grad()
     def forward_bits(self, own, opp, which=0):

@@ -28,6 +28,16 @@ class Memory:
         self._buffer = deque(maxlen=max_size)
         self._dedup, self._dedup_pending = None, []
 
+    def __setstate__(self, state):
+        """Unpickling (checkpoint.load_memory): files of the reference carry max_size, _buffer and `deduplicator`
+        (memory.py:9-12) -- a Deduplicator's counter / temp_queue are this class's running sums / pending list."""
+        state = dict(state)
+        d = state.pop("deduplicator", None)
+        self._dedup, self._dedup_pending = None, []
+        self.__dict__.update(state)
+        if d is not None and getattr(d, "counter", None) is not None:
+            self._dedup, self._dedup_pending = dict(d.counter), list(getattr(d, "temp_queue", ()))
+
     def __len__(self):
         return len(self._buffer)
 
@@ -66,6 +76,11 @@ class Memory:
                     c[v] = c[v] + getattr(e, v)
         self._dedup_pending = []
         self._buffer = deque((named_tuple(**{key: c[key], **{v: c[v] / c["count"] for v in values}}) for c in self._dedup.values()), maxlen=maxlen)
+
+
+class DeduplicatorState:
+    """What a pickled rl_utils.memory.Deduplicator becomes when a reference memory file is loaded here (its attributes,
+    no behaviour): Memory.__setstate__ takes over `counter` and `temp_queue`."""
 
 
 def mcts_loss(network, batch, q_average=True):
@@ -108,8 +123,12 @@ class SelfPlayScheduler:
         ``train_model(resume_model=, resume_memory=)`` picks up the newest files of the previous run (base_worker.py:26-62).
         (Pickling a full 200 000-record Memory of Move tuples takes about a minute, as it does in the reference;
         ``save_memory=False`` keeps only the model checkpoints.)
-        amp: None = fp32 SGD steps like the reference's UpdateWorker; torch.bfloat16 runs forward/backward under autocast
-        (12 instead of 29 ms per step of batch 128 on B200, scripts/dbg_update_step.py) -- an option, not reference behaviour.
+        amp: None = fp32 SGD steps; torch.float16 / torch.bfloat16 run forward/backward under autocast.  The reference's
+        UpdateWorker trains under torch.cuda.amp.autocast() (fp16, updateworker.py:146-149) and keeps running 100-step rounds
+        for as long as the epoch's self-play lasts; here exactly `updates_per_epoch` steps run after the epoch's self-play
+        (deliberate: self-play is ~100x faster, so "as long as self-play runs" would mean almost no SGD steps per game) --
+        scale `updates_per_epoch` to keep the reference's SGD-steps-per-game ratio.  The initial evaluate_policy(-1) of
+        self_play_parallel.py:244 is available as train_model(initial_evaluation=True).
         lr_patience: ReduceLROnPlateau("max", patience, factor 0.5, min_lr 1e-5, cooldown 5) stepped with every epoch's
         evaluation reward (updateworker.py:66-68,96-98).
         deduplicate: UpdateWorker's option (updateworker.py:88-89): after every epoch's records are in, merge duplicate states.
@@ -147,7 +166,7 @@ class SelfPlayScheduler:
             self.memory = DeviceReplay(sp.game, self._memory_size, self.max_memory_size, seed=self.seed)
         recs, res = [], []
         while True:
-            sp.engine.run_ticks(512)
+            sp.engine.run_ticks(sp.engine.safe_poll_interval)
             if device_replay:       # pull_from_queue without the queue: device ring -> device memory
                 r = self.memory.drain_engine(sp.engine, append=self.world == 1)
                 recs.append(r.clone() if self.world > 1 else r.shape[0])
@@ -156,6 +175,7 @@ class SelfPlayScheduler:
             res.append(sp.engine.drain_results())
             if sp.engine.all_idle():
                 break
+        sp.engine.check_overflow()
         game = sp.game
         sp.close()
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -250,17 +270,22 @@ class SelfPlayScheduler:
                 if resume_model:
                     dev = next(self.network.parameters()).device
                     checkpoint.load_model(self.network, checkpoint.recent_save_file(self.save_dir, self.start_time, True, "model"), map_location=dev)
-            except ValueError:      # max() of an empty list: no earlier run (the reference logs the exception and goes on)
-                pass
+            except (ValueError, OSError, ImportError, AttributeError) as e:
+                # no earlier run (max() of an empty list), or an unreadable file: the reference logs the exception and goes on
+                # (base_worker.py:31-42)
+                import logging
+                logging.getLogger(__name__).warning("resume: %s: %s", type(e).__name__, e)
         if resume_model:
             self._sync_weights()
 
-    def train_model(self, num_epochs=10, resume_model=False, resume_memory=False):
+    def train_model(self, num_epochs=10, resume_model=False, resume_memory=False, initial_evaluation=False):
         """:213-291: initial games, then per epoch: epoch_length self-play games -> update -> checkpoint -> weight sync ->
         evaluation -> LR schedule."""
         self.network.eval()
         self.resume(resume_model, resume_memory)
         gen = 0
+        if initial_evaluation and self.evaluation_games:     # self_play_parallel.py:244
+            self.history.append(dict(epoch=-1, evaluation_reward=self.evaluate_policy(-1)))
         self._remember(self._play(self.initial_games, evaluate=False, update=True, generation=gen)[0])
         import time
 

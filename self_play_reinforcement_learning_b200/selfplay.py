@@ -95,8 +95,8 @@ class BatchedSelfPlay:
         if self.net_kind == "tower":
             self.evaluator.load(module_or_blob)
             return int(module_or_blob.numel()) if torch.is_tensor(module_or_blob) else 0
-        if not torch.is_tensor(module_or_blob):
-            self.evaluator.modules[0].load_state_dict(module_or_blob.state_dict())
+        if not torch.is_tensor(module_or_blob) and hasattr(self.evaluator, "refresh"):
+            self.evaluator.refresh(module_or_blob)     # the evaluator holds a private (device, bf16) copy of the master module
         return 0
 
     # ------------------------------------------------------------------ running
@@ -113,10 +113,11 @@ class BatchedSelfPlay:
         d2h = recs.nbytes + res.nbytes + 80 + 16
         return {"records": recs, "results": res, "counters": cnt, "h2d_bytes": h2d, "d2h_bytes": d2h}
 
-    def play_games(self, max_ticks=50_000_000, poll_every=512):
+    def play_games(self, max_ticks=50_000_000, poll_every=None):
         """Run until every slot is idle (needs a finite games_target); returns (Move list, result dict list)."""
         recs, res = [], []
         t = 0
+        poll_every = poll_every or self.engine.safe_poll_interval
         while t < max_ticks:
             self.engine.run_ticks(poll_every)
             t += poll_every
@@ -124,6 +125,7 @@ class BatchedSelfPlay:
             res.append(self.engine.drain_results())
             if self.engine.all_idle():
                 break
+        self.engine.check_overflow()
         recs = np.concatenate(recs) if recs else np.zeros(0, RECORD_DTYPE)
         res = np.concatenate(res) if res else np.zeros(0, RESULT_DTYPE)
         order = np.argsort(res["game_index"], kind="stable")
@@ -161,11 +163,12 @@ def run_tasks(network, env, tasks, result_queue=None, memory_queue=None, task_qu
     moves_all, results_all = [], []
     recs, res = [], []
     while True:
-        sp.engine.run_ticks(512)
+        sp.engine.run_ticks(sp.engine.safe_poll_interval)
         recs.append(sp.engine.drain_records())
         res.append(sp.engine.drain_results())
         if sp.engine.all_idle():
             break
+    sp.engine.check_overflow()      # a dropped record or result would also leave task_queue.join() hanging
     recs, res = np.concatenate(recs), np.concatenate(res)
     keep_plain = set(sorted(int(i) for i in res["game_index"] if i % 2 == 0)[:n_plain])
     keep_swap = set(sorted(int(i) for i in res["game_index"] if i % 2 == 1)[:n_swap])

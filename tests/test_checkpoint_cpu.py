@@ -61,3 +61,62 @@ def test_moves_from_records_pickle_independently():
         m.add(mv)
     assert len(pickle.dumps(m)) < 5000 * 4000
     assert moves[63].state.dtype == torch.int64 and int(moves[63].state.sum()) == 6 and moves[63].state.shape == (7, 6)
+
+
+def test_memory_file_written_by_the_unmodified_reference_loads_here(golden_dir):
+    """tests/golden/ref_memory*.pkl were pickled by the reference's own rl_utils.memory.Memory (oracle/make_golden_memory.py).
+    They must open WITHOUT the reference tree (or anytree) importable, as local Memory / Move objects."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, os, torch\n"
+        "assert not any('reference' in p for p in sys.path)\n"
+        "from self_play_reinforcement_learning_b200 import checkpoint\n"
+        "from self_play_reinforcement_learning_b200.scheduler import Memory\n"
+        "from self_play_reinforcement_learning_b200.selfplay import Move\n"
+        f"m = checkpoint.load_memory(os.path.join({golden_dir!r}, 'ref_memory.pkl'))\n"
+        "assert type(m) is Memory and len(m) == 12 and m.max_size == 50 and m._buffer.maxlen == 50\n"
+        "assert all(type(x) is Move for x in m._buffer) and m._buffer[3].state.dtype == torch.int64\n"
+        "assert abs(float(m._buffer[5].q) - 5 / 16) < 1e-7 and len(m.sample(4)) == 4\n"
+        f"d = checkpoint.load_memory(os.path.join({golden_dir!r}, 'ref_memory_dedup.pkl'))\n"
+        "assert len(d) == 6 and len(d._dedup) == 5 and len(d._dedup_pending) == 1\n"
+        "d.deduplicate('state', ['actual_val', 'tree_probs'], Move)\n"      # the reference's running sums carry on
+        "assert len(d) == 5 and sorted(c['count'] for c in d._dedup.values()) == [2, 2, 2, 3, 4]\n"
+        "assert 'rl_utils' not in sys.modules and 'games' not in sys.modules and 'anytree' not in sys.modules\n"
+        "print('ok')\n")
+    import os as _os
+    root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, env={**_os.environ, "PYTHONPATH": root})
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_memory_file_written_here_carries_the_reference_class_paths(tmp_path):
+    """What save_memory writes names rl_utils.memory.Memory / games.algos.mcts.Move (and nothing of this package), so the
+    unmodified reference opens it with plain pickle.load (base_worker.py:36-42)."""
+    import pickletools
+    import sys
+    m = Memory(10)
+    for i in range(3):
+        m.add(Move(torch.full((7, 6), i, dtype=torch.int64), torch.tensor(1.0), torch.full((7,), 1 / 7), torch.tensor(0.5)))
+    f = checkpoint.save_memory(m, str(tmp_path), "run", now=datetime.datetime(2024, 1, 1))
+    assert "rl_utils" not in sys.modules and "games" not in sys.modules       # the stand-in modules are gone again
+    globs = set()
+    for op, arg, _ in pickletools.genops(open(f, "rb").read()):
+        if op.name in ("GLOBAL", "STACK_GLOBAL") and arg:
+            globs.add(arg)
+    blob = open(f, "rb").read()
+    assert b"rl_utils.memory" in blob and b"games.algos.mcts" in blob and b"self_play_reinforcement_learning_b200" not in blob
+    back = checkpoint.load_memory(f)
+    assert type(back) is Memory and len(back) == 3 and int(back._buffer[2].state[0, 0]) == 2 and back._buffer.maxlen == 10
+    # live check where the reference exists (this container): its own classes, plain pickle.load
+    from oracle import ref_harness as rh
+    if rh.reference_available():
+        import subprocess
+        code = (f"import sys; sys.path[:0] = ['/root/reference', {os.path.join(os.path.dirname(rh.__file__), '_shims')!r}]\n"
+                "import pickle, rl_utils.memory, games.algos.mcts\n"
+                f"m = pickle.load(open({f!r}, 'rb'))\n"
+                "assert type(m) is rl_utils.memory.Memory and len(m) == 3 and m.deduplicator is None and m.max_size == 10\n"
+                "assert type(m._buffer[0]) is games.algos.mcts.Move and len(m.sample(2)) == 2\n"
+                "m.add(m._buffer[0]); print('ok')\n")
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path))
+        assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

@@ -60,6 +60,26 @@ def test_record_ring_overflow_is_counted_not_written():
     e.close()
 
 
+def test_overflowing_rings_fail_loudly_on_the_host():
+    """Lost training records / game results must not vanish silently (run_tasks would hang in task_queue.join())."""
+    from self_play_reinforcement_learning_b200._lib import SpxError
+    e = _engine(n_games=16, sims=20, games_target=64, record_capacity=100, result_capacity=10)
+    e.run_ticks(6000)
+    with pytest.raises(SpxError, match="dropped"):
+        e.check_overflow()
+    with pytest.raises(SpxError, match="results were lost"):
+        e.drain_results()
+    assert len(e.drain_results()) == 0                       # the ring was reset: later drains work again
+    e.close()
+    e = _engine(game=1, n_games=8, sims=2, games_target=200)      # tiny searches: many games per slot between two drains
+    res = 0
+    while not e.all_idle():
+        e.run_ticks(e.safe_poll_interval)
+        res += len(e.drain_results())
+    assert res == 200 and e.check_overflow()["records_dropped"] == 0
+    e.close()
+
+
 @pytest.mark.parametrize("game", [0, 1])
 def test_single_game_with_finite_target_matches_oracle(game):
     e = _engine(game=game, n_games=1, sims=40, games_target=3, seed=9, move_log=True)

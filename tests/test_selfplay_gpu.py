@@ -129,6 +129,27 @@ def test_scheduler_train_loop_small():
     assert set(bd) == {"first", "second"} and sum(sum(v.values()) for v in bd.values()) == 16
 
 
+def test_scheduler_with_the_torch_evaluator_keeps_fp32_master_weights(tmp_path):
+    """A tower the native kernel is not built for (filter_factor != 32) runs through TorchNetEvaluator.  The evaluator casts a
+    PRIVATE copy to bf16: the caller's module -- the one the scheduler trains (fp32, no amp) and checkpoints -- stays fp32."""
+    from self_play_reinforcement_learning_b200 import nets
+    from self_play_reinforcement_learning_b200.scheduler import SelfPlayScheduler
+    torch.manual_seed(0)
+    net = nets.ResidualTower(7, 6, 7, num_blocks=1, filter_factor=8).cuda().eval()
+    with pytest.raises(ValueError):
+        nets.pack_tower_blob(net)
+    before = net.linear_output.weight.detach().clone()
+    s = SelfPlayScheduler(net, 0, iterations=20, epoch_length=12, initial_games=6, evaluation_games=4, games_per_gpu=8, batch_size=16,
+                          updates_per_epoch=3, lr=0.01, net="torch", save_dir=str(tmp_path), save_memory=False)
+    hist = s.train_model(num_epochs=1)
+    assert np.isfinite(hist[0]["loss"]) and not torch.equal(before, net.linear_output.weight.detach())
+    assert all(p.dtype == torch.float32 for p in net.parameters()) and all(b.dtype in (torch.float32, torch.int64) for b in net.buffers())
+    with torch.no_grad():
+        p, v = net.forward(torch.zeros(2, 7, 6, dtype=torch.int64))       # the fp32 forward still works
+    assert p.dtype == torch.float32 and tuple(p.shape) == (2, 7)
+    assert all(t.dtype != torch.bfloat16 for t in torch.load(hist[0]["saved_model"])["model"].values())
+
+
 @pytest.mark.parametrize("replay", ["device", "host"])
 def test_scheduler_deduplicate_option(replay):
     """UpdateWorker(deduplicate=True) (updateworker.py:88-89): after the epoch's records are in, the memory holds one averaged
