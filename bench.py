@@ -136,8 +136,31 @@ def _cpu_worker(idx, shared, blocks, sims, seed, alpha=1.0):
         g += 1 << 20
 
 
-def cpu_baseline(seconds, blocks, sims, procs=None, alpha=1.0):
-    """Time-boxed: `procs` processes play self-play games for `seconds`; sims and moves counted live."""
+def reference_kind():
+    """"reference": the unmodified reference staged as byte-code under oracle/_ref (oracle/build_ref.py) is importable;
+    "port": only the C/torch restatement is (the fallback the sample string then names)."""
+    from oracle import build_ref
+    return "reference" if build_ref.available() and os.environ.get("SPX_BENCH_CPU_ARM", "") != "port" else "port"
+
+
+def cpu_baseline(seconds, blocks, sims, procs=None, alpha=1.0, kind=None):
+    """Time-boxed: `procs` processes play self-play games for `seconds`; sims and moves counted live.
+    kind "reference": oracle/ref_run.py (the reference's own MCTreeSearch / SelfPlayer / ResidualTower); "port": the oracle."""
+    if (kind or reference_kind()) == "reference":
+        from oracle import ref_run
+        return dict(ref_run.time_reference(seconds, blocks, sims, procs=procs, alpha=alpha), kind="reference")
+    return dict(_cpu_baseline_port(seconds, blocks, sims, procs=procs, alpha=alpha), kind="port")
+
+
+def _sample_text(r, blocks, sims):
+    who = ("the UNMODIFIED reference (games/algos/mcts.py MCTreeSearch x 2 + selfplayworker.SelfPlayer.play_episode + "
+           f"games/general/modules.py ResidualTower-{blocks} in fp32 at batch 1, byte-compiled into oracle/_ref)") if r["kind"] == "reference" else \
+          (f"the oracle PORT (C tree/env restatement + fp32 torch ResidualTower-{blocks} at batch 1; the staged reference oracle/_ref is absent)")
+    return (f"{r['seconds']:.0f}s window, {r['cores']} processes x 1 torch thread, CUDA hidden, each looping Connect4 self-play episodes "
+            f"(two trees, {sims} sims/move) with {who}: the reference's direct mode (SURVEY.md 8d mode i)")
+
+
+def _cpu_baseline_port(seconds, blocks, sims, procs=None, alpha=1.0):
     import multiprocessing as mp
     import ctypes as C
     ctx = mp.get_context("fork")
@@ -165,8 +188,9 @@ def cpu_baseline(seconds, blocks, sims, procs=None, alpha=1.0):
 
 
 def run_reference(args, workload, out=sys.stdout):
-    """--impl reference: the reference's CPU implementation of the path (oracle port, kind 'port': the reference is
-    pure Python and does not exist on the GPU box) on all host cores; each 'step' is a bounded time-boxed sample."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores (kind "reference": the unmodified
+    reference byte-compiled into oracle/_ref; "port": the oracle restatement, only when oracle/_ref is absent); each 'step' is
+    a bounded time-boxed sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -182,13 +206,12 @@ def run_reference(args, workload, out=sys.stdout):
         cores = r["cores"]
     tot_sims = sum(v["sims"] for v in vals); tot_t = sum(v["seconds"] for v in vals)
     value = tot_sims / tot_t
-    sample = (f"{args.steps} x {per_step:.0f}s windows, {cores} processes x 1 thread, each playing Connect4 self-play "
-              f"episodes (two trees, {args.sims} sims/move) with the C oracle tree + fp32 torch ResidualTower-{args.blocks} at batch 1")
+    sample = f"{args.steps} windows: " + _sample_text(vals[-1], args.blocks, args.sims)
     line = {"impl": "reference", "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot_t / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload,
-            "cpu_baseline": {"value": value, "unit": "sims/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "sims/s", "cores": cores, "kind": vals[-1]["kind"], "sample": sample},
             "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "positions_per_sec": sum(v["positions_per_s"] * v["seconds"] for v in vals) / tot_t,
             "wall_s": time.time() - t0}
@@ -401,12 +424,11 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             r = cpu_baseline(args.cpu_seconds, args.blocks, args.sims, alpha=args.alpha)
-            cpu = {"value": r["sims_per_s"], "unit": "sims/s", "cores": r["cores"], "kind": "port",
-                   "sample": f"{r['seconds']:.0f}s window, {r['cores']} processes x 1 thread: C oracle tree/env + fp32 torch "
-                             f"ResidualTower-{args.blocks} at batch 1 (the reference's direct mode), {args.sims} sims/move",
-                   "positions_per_s": r["positions_per_s"]}
+            cpu = {"value": r["sims_per_s"], "unit": "sims/s", "cores": r["cores"], "kind": r["kind"],
+                   "sample": _sample_text(r, args.blocks, args.sims), "positions_per_s": r["positions_per_s"]}
         line = {"metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": ("f16" if getattr(getattr(ev, "tower", None), "f16", False) else "bf16") if args.net == "tower" else ("bf16" if args.net == "torch" else "f64"),
                 "data": "synthetic", "config": workload, "positions_per_sec": moves_all / (ms / 1e3), "leaf_evals_per_sec": evals_all / (ms / 1e3),
                 "mean_select_path_len": path, "fused_tick_kernel": bool(fused_tick_ms), "e2e": e2e, "gpu_launches": int(launches1 - launches0), "clocks": clocks,
                 "roofline": roof, "search_roofline": search, "env_roofline": env_roof, "cpu_baseline": cpu}

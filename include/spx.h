@@ -204,6 +204,10 @@ int spx_tower_ncta(spx_tower* t);
 /* 1 when the fully connected heads (policy Linear + softmax, value Linear-ReLU-Linear-tanh, modules.py:99-105) run inside the
  * tower kernel (default for the SM-pair kernel; SPX_TOWER_FUSED_HEADS=0 selects the separate heads kernel) */
 int spx_tower_fused_heads(spx_tower* t);
+/* 1: the conv trunk and the fused value layer compute in fp16 (default: the type the reference's GPU path computes in,
+ * torch.cuda.amp.autocast at inference_worker.py:117), 0: bf16 (SPX_TOWER_DTYPE=bf16 at spx_tower_create).  It is the element
+ * type spx_tower_load expects the weight stream in. */
+int spx_tower_f16(spx_tower* t);
 int spx_tower_load(spx_tower* t, const void* dev_blob, int64_t bytes, void* stream);
 /* own/opp: dev u64[n] bitboards in the NET frame; needs_eval: dev u8[n] or NULL (all); policy dev f32[n,A]
  * (softmax), value dev f32[n] (tanh).  Rows whose needs_eval is 0 may be left untouched. */

@@ -31,21 +31,26 @@ enum { PK_NONE = 0, PK_ROOT = 1, PK_EXPAND = 2, PK_REROOT = 3 };
 #define SPX_MAX_OWN_MOVES 22
 #define SPX_MAX_PLIES 44
 
-struct TreeState {
+struct TreeState {   // 32 bytes = two 16-byte words (ld_tree / st_tree)
     double root_w;
     int root, root_n, root_player, moves_played, node_count, n_rec;
 };
 
-struct GameState {
-    u64 env_own, env_opp;  // env frame: own = +1 = the policy (tree 0)
-    u64 game_index;
-    u64 pend_own, pend_opp;  // child state awaiting its evaluation, TREE frame
-    TreeState tree[2];
-    int phase, sub_tree, mover_tree, sims_done, ply, swap, last_action;
-    int pend_kind, pend_tree, pend_parent, pend_action, pend_depth, pend_parent_player;
-    int n_moves_logged, pad;
-    u64 cnt_sims, cnt_evals, cnt_term, cnt_path, cnt_moves, cnt_games, cnt_nodes, cnt_err;
+// One game slot.  Laid out in 16-byte groups so that advance_prefetch() moves it with a dozen 128-bit loads; advance_game()
+// keeps the fields it needs in registers (no dynamically indexed copy: the first version held `GameState s = *gp` with
+// `s.tree[T]`, a 496-byte local-memory frame on the latency-critical chain) and writes them back with 128-bit stores.
+struct alignas(16) GameState {
+    int phase, sub_tree, mover_tree, sims_done;                                  //   0
+    int ply, swap, last_action, n_moves_logged;                                  //  16
+    int pend_kind, pend_tree, pend_parent, pend_action;                          //  32  the evaluation this slot waits for
+    int pend_depth, pend_parent_player, leaf_waiting, pad1;                      //  48  leaf_waiting: emitted, not yet evaluated
+    u64 pend_own, pend_opp;                                                      //  64  its child state, TREE frame
+    u64 env_own, env_opp;                                                        //  80  env frame: own = +1 = the policy (tree 0)
+    u64 game_index, pad2;                                                        //  96
+    TreeState tree[2];                                                           // 112
+    u64 cnt_sims, cnt_evals, cnt_term, cnt_path, cnt_moves, cnt_games, cnt_nodes, cnt_err;   // 176 (updated with RED.ADD)
 };
+static_assert(sizeof(TreeState) == 32 && sizeof(GameState) == 240, "GameState layout");
 
 struct EngineDev {
     spx_config cfg;
@@ -78,32 +83,55 @@ namespace spx {
 // ------------------------------------------------------------------------------------------------ device helpers
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// n**k, correctly rounded (twin of ox_pow_int_exact): np.power(n, 1/temp) for integral 1/temp (mcts.py:100-101)
-__device__ inline double pow_int_exact(unsigned n, int k) {
+// n**k, correctly rounded (twin of ox_pow_int_exact): np.power(n, 1/temp) for integral 1/temp (mcts.py:100-101).
+// 640-bit integer in ten 64-bit limbs that stay in registers (every limb index is a compile-time constant: no local-memory
+// array); n**20 fits for every 32-bit n.  Round to nearest even on the top 53 bits.
+__host__ __device__ inline double pow_int_exact(unsigned n, int k) {
     if (k == 0) return 1.0;
     if (n == 0) return 0.0;
-    unsigned limb[40];
-    int nl = 1;
-    limb[0] = 1;
+    constexpr int NL = 10;
+    u64 l0 = 1, l1 = 0, l2 = 0, l3 = 0, l4 = 0, l5 = 0, l6 = 0, l7 = 0, l8 = 0, l9 = 0;
     for (int i = 0; i < k; ++i) {
         u64 carry = 0;
-        for (int j = 0; j < nl; ++j) { u64 t = (u64)limb[j] * n + carry; limb[j] = (unsigned)t; carry = t >> 32; }
-        if (carry) { if (nl >= 40) return INFINITY; limb[nl++] = (unsigned)carry; }
+#ifdef __CUDA_ARCH__
+#define SPX_MULADD(L) { const u64 lo = L * (u64)n, hi = __umul64hi(L, (u64)n); L = lo + carry; carry = hi + (L < lo ? 1ULL : 0ULL); }
+#else
+#define SPX_MULADD(L) { const unsigned __int128 t = (unsigned __int128)L * n + carry; L = (u64)t; carry = (u64)(t >> 64); }
+#endif
+        SPX_MULADD(l0) SPX_MULADD(l1) SPX_MULADD(l2) SPX_MULADD(l3) SPX_MULADD(l4)
+        SPX_MULADD(l5) SPX_MULADD(l6) SPX_MULADD(l7) SPX_MULADD(l8) SPX_MULADD(l9)
+#undef SPX_MULADD
+        if (carry) return INFINITY;
     }
-    int top = nl - 1;
-    while (top > 0 && limb[top] == 0) --top;
-    int hb = 31;
-    while (!((limb[top] >> hb) & 1)) --hb;
-    int nbits = top * 32 + hb + 1;
-    if (nbits <= 53) { double v = 0; for (int j = top; j >= 0; --j) v = __dadd_rn(__dmul_rn(v, 4294967296.0), (double)limb[j]); return v; }
-    int shift = nbits - 53;
-    u64 mant = 0;
-    for (int b = nbits - 1; b >= shift; --b) mant = (mant << 1) | ((limb[b / 32] >> (b % 32)) & 1u);
-    int half = (limb[(shift - 1) / 32] >> ((shift - 1) % 32)) & 1u;
-    int sticky = 0;
-    for (int b = shift - 2; b >= 0 && !sticky; --b) sticky |= (limb[b / 32] >> (b % 32)) & 1u;
-    if (half && (sticky || (mant & 1))) mant += 1;
-    return ldexp((double)mant, shift);
+    // the two top non-zero limbs (hi, lo), whether anything below them is set, and the index of the top limb
+    u64 hi = l0, lo = 0, rest = 0;
+    int top = 0;
+#define SPX_TOP(J, L, LM1, BELOW) if (L) { hi = L; lo = LM1; rest = BELOW; top = J; }
+    SPX_TOP(1, l1, l0, 0ULL)
+    SPX_TOP(2, l2, l1, l0)
+    SPX_TOP(3, l3, l2, l0 | l1)
+    SPX_TOP(4, l4, l3, l0 | l1 | l2)
+    SPX_TOP(5, l5, l4, l0 | l1 | l2 | l3)
+    SPX_TOP(6, l6, l5, l0 | l1 | l2 | l3 | l4)
+    SPX_TOP(7, l7, l6, l0 | l1 | l2 | l3 | l4 | l5)
+    SPX_TOP(8, l8, l7, l0 | l1 | l2 | l3 | l4 | l5 | l6)
+    SPX_TOP(9, l9, l8, l0 | l1 | l2 | l3 | l4 | l5 | l6 | l7)
+#undef SPX_TOP
+    (void)NL;
+#ifdef __CUDA_ARCH__
+    const int lz = __clzll((long long)hi);
+#else
+    const int lz = __builtin_clzll(hi);
+#endif
+    const int nbits = top * 64 + 64 - lz;
+    if (nbits <= 53) return (double)hi;                       // top == 0: exact
+    // normalise the 128-bit window so that its top bit is bit 127
+    const u64 nh = lz ? ((hi << lz) | (lo >> (64 - lz))) : hi, nl = lz ? (lo << lz) : lo;
+    u64 mant = nh >> 11;                                      // 53 bits
+    const int half = (int)((nh >> 10) & 1ULL);
+    const int sticky = ((nh & 0x3FFULL) | nl | rest) != 0;
+    if (half && (sticky || (mant & 1ULL))) mant += 1;         // may carry to 2^53: the scaling below is exact either way
+    return ldexp((double)mant, nbits - 53);
 }
 
 // Gamma(alpha,1) variate from the counter stream (same draw schedule as oracle gamma_variate; CUDA libm,
@@ -122,7 +150,7 @@ __device__ inline double gamma_variate(u64 prefix, int action, double alpha) {
     }
     double b = alpha - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * b);
     for (;; ++attempt) {
-        double X = sqrt(-2.0 * log(1.0 - SPX_U(0))) * cos(6.283185307179586 * SPX_U(1));
+        double X = sqrt(-2.0 * log(1.0 - SPX_U(0))) * cospi(2.0 * SPX_U(1));   // cospi: no large-argument reduction path (a local-memory table)
         double V = 1.0 + cc * X;
         if (attempt > 1000) return b;
         if (V <= 0.0) continue;
@@ -135,7 +163,7 @@ __device__ inline double gamma_variate(u64 prefix, int action, double alpha) {
 }
 
 #ifndef SPX_PREFETCH
-#define SPX_PREFETCH "prefetch.global.L2"
+#define SPX_PREFETCH "prefetch.global.L2"   // (.L1 measured: no gain -- 0.4661 vs 0.4628 ms per fused tick, within box noise)
 #endif
 template <int GAME> struct Ctx {
     typedef Rules<GAME> R;
@@ -181,7 +209,7 @@ __device__ __forceinline__ void backup_path(const Ctx<GAME>& c, unsigned p0, uns
 
 // create_children (mcts.py:103-107) for a freshly evaluated position + link from its parent edge
 template <int GAME>
-__device__ __forceinline__ int alloc_node(const Ctx<GAME>& c, TreeState& ts, u64 own, u64 opp, int player, const float* policy) {
+__device__ __forceinline__ int alloc_node(const Ctx<GAME>& c, TreeState& ts, u64 own, u64 opp, int player, float my_p) {
     typedef NodeLayout<GAME> L;
     typedef Rules<GAME> R;
     int idx = ts.node_count;
@@ -191,7 +219,7 @@ __device__ __forceinline__ int alloc_node(const Ctx<GAME>& c, TreeState& ts, u64
     if (c.lane < R::A) {
         ((double*)(nd + L::OFF_W))[c.lane] = 0.0;
         ((int*)(nd + L::OFF_N))[c.lane] = 0;
-        ((float*)(nd + L::OFF_P))[c.lane] = policy[c.lane];
+        ((float*)(nd + L::OFF_P))[c.lane] = my_p;
         ((int*)(nd + L::OFF_CHILD))[c.lane] = CHILD_UNEXPANDED;
     }
     if (c.lane == 0) {
@@ -202,100 +230,175 @@ __device__ __forceinline__ int alloc_node(const Ctx<GAME>& c, TreeState& ts, u64
     return idx;
 }
 
+// ------------------------------------------------------------------------------------------------ slot state in registers
+__device__ __forceinline__ TreeState ld_tree(const TreeState* t) {
+    const int4 x = reinterpret_cast<const int4*>(t)[0], y = reinterpret_cast<const int4*>(t)[1];
+    TreeState r;
+    r.root_w = __hiloint2double(x.y, x.x); r.root = x.z; r.root_n = x.w;
+    r.root_player = y.x; r.moves_played = y.y; r.node_count = y.z; r.n_rec = y.w;
+    return r;
+}
+__device__ __forceinline__ void st_tree(TreeState* t, const TreeState& r) {
+    reinterpret_cast<int4*>(t)[0] = make_int4(__double2loint(r.root_w), __double2hiint(r.root_w), r.root, r.root_n);
+    reinterpret_cast<int4*>(t)[1] = make_int4(r.root_player, r.moves_played, r.node_count, r.n_rec);
+}
+
+// The slot's state as advance_game wants it, loaded with 128-bit loads that every lane issues for the same addresses (one
+// transaction each).  Callers that have something to wait for (the fused tick kernel: the network outputs of this very leaf)
+// issue advance_prefetch() BEFORE the wait, so the state is in registers when the outputs arrive.
+struct AdvPre {
+    int4 a, b, c, d;
+    ulonglong2 pend;
+    u64 game_index;
+    TreeState t0, t1;
+    unsigned p0, p1;   // this lane's entries of the pending path (lane d / d + 32)
+    double noise;      // this lane's Dirichlet noise of the search in progress
+};
+template <int GAME>
+__device__ __forceinline__ AdvPre advance_prefetch(const EngineDev& E, const int g, const int lane) {
+    const GameState* gp = E.games + g;
+    const int4* q = reinterpret_cast<const int4*>(gp);
+    AdvPre r;
+    r.a = q[0]; r.b = q[1]; r.c = q[2]; r.d = q[3];
+    r.pend = reinterpret_cast<const ulonglong2*>(gp)[4];
+    r.game_index = gp->game_index;
+    r.t0 = ld_tree(&gp->tree[0]); r.t1 = ld_tree(&gp->tree[1]);
+    const unsigned* pp = E.paths + (size_t)g * SPX_MAX_PATH;
+    r.p0 = pp[lane]; r.p1 = pp[lane + 32];
+    r.noise = lane < Rules<GAME>::A ? E.noise[(size_t)g * SPX_MAX_ACTIONS + lane] : 0.0;
+    return r;
+}
+
+enum { ADV_EMITTED = 1, ADV_IDLE = 2, ADV_PARKED = 4 };   // advance_game's result; 0 = the sim budget ran out before a leaf came up
+
 // ------------------------------------------------------------------------------------------------ one game, one tick
 // One game slot's share of a tick, executed by one whole warp (all 32 lanes call it together): consume the evaluation the slot
-// asked for, run its state machine until the next network request, publish the leaf.  Called by advance_kernel (one warp per
-// game) and by the fused tick kernel of spx_tower.cu (the epilogue warps of the CTA that evaluates the game's leaf).
+// asked for (my_p = this lane's prior, v_in = the value; read by the caller), run its state machine until the next network
+// request or until `budget` simulations ended without one (terminal re-visits need no network), publish the leaf.
+// Called by advance_kernel (one warp per game) and by the fused tick kernel of spx_tower.cu.
+//   defer_leaf: the leaf will not be evaluated by the tick that follows this call (the fused kernel's shadow warp works ahead):
+//   needs_eval stays 0 and the slot is marked leaf_waiting; the next advance_game on the slot hands the leaf out instead of
+//   advancing.   count_tick: bump the engine's tick counter (slot 0 of advance_kernel).
+// Registers: only what the select loop needs stays live through the function (phase words, game index, ONE tree's TreeState,
+// this lane's noise); the pending-evaluation words, the env boards, the other tree and the counters live in the slot's
+// GameState and are read / written (lane 0; counters with RED.ADD) where the state machine touches them.
 template <int GAME>
-// (policy_in / value_in are deliberately not __restrict__: in the fused kernel they were written earlier in the same launch.)
-__device__ __forceinline__ void advance_game(const EngineDev& E, const int g, const int lane, const float* policy_in, const float* value_in) {
+__device__ __forceinline__ int advance_game(const EngineDev& E, const int g, const int lane, const AdvPre& pre, const float my_p,
+                                            const float v_in, int budget, const bool defer_leaf, const bool count_tick,
+                                            u64& out_own, u64& out_opp) {
     typedef Rules<GAME> R;
     typedef NodeLayout<GAME> L;
+    typedef unsigned long long ull;
     constexpr int A = R::A;
     Ctx<GAME> c(E, g, lane);
     GameState* gp = E.games + g;
-    GameState s = *gp;  // every lane keeps the (warp-uniform) scalar state in registers
     const spx_config& cfg = E.cfg;
-
-    bool emitted = false;
-    u64 out_own = 0, out_opp = 0;
+    out_own = 0; out_opp = 0;
+    if (pre.d.z) {   // leaf_waiting: this slot's leaf was emitted ahead of time (defer_leaf) and has not been evaluated yet
+        out_own = E.leaf_own[g]; out_opp = E.leaf_opp[g];
+        __syncwarp();
+        if (lane == 0) {
+            gp->leaf_waiting = 0;
+            E.needs_eval[g] = 1;
+            if (count_tick) atomicAdd(E.ticks, 1ULL);
+        }
+        __syncwarp();
+        return ADV_EMITTED;
+    }
+    // every lane keeps the (warp-uniform) scalar state in registers
+    int phase = pre.a.x, sub_tree = pre.a.y, mover_tree = pre.a.z, sims_done = pre.a.w;
+    int ply = pre.b.x, swap = pre.b.y, last_action = pre.b.z, n_moves_logged = pre.b.w;
+    u64 game_index = pre.game_index;
+    double my_noise = pre.noise;
+    // the tree being worked on (the one the slot touches first: both came with the prefetch); the other one stays in gp->tree[]
+    int curT = pre.c.x != PK_NONE ? pre.c.y : (phase == PH_SEARCH ? mover_tree : sub_tree);
+    TreeState ts = curT ? pre.t1 : pre.t0;
+    auto use = [&](const int T) {
+        if (curT != T) {
+            if (lane == 0) st_tree(&gp->tree[curT], ts);
+            __syncwarp();
+            ts = ld_tree(&gp->tree[T]);
+            curT = T;
+        }
+        c.use_tree(T);
+    };
+    auto count = [&](u64* counter, const int by) { if (lane == 0 && by) atomicAdd((ull*)counter, (ull)by); };   // RED.ADD: nothing to wait for
+    bool emitted = false, parked = false, consumed = false;
     int out_net = 0;
+    // the evaluation the slot will be waiting for when it emits (written to the slot in part 3)
+    int e_kind = PK_NONE, e_tree = 0, e_parent = 0, e_action = 0, e_depth = 0, e_pplayer = 0;
+    u64 e_own = 0, e_opp = 0;
 
     // ---- 1. consume the evaluation this slot asked for on the previous tick
-    if (s.pend_kind != PK_NONE) {
-        const float* pol = policy_in + (size_t)g * A;
-        const int T = s.pend_tree;
-        c.use_tree(T);
-        TreeState ts = s.tree[T];
-        if (s.pend_kind == PK_ROOT) {  // MCTreeSearch.reset (mcts.py:166-174); root.v is never read
-            int player = (T == 0) ? (s.swap ? -1 : 1) : (s.swap ? 1 : -1);  // selfplayworker.py:175-176
+    if (pre.c.x != PK_NONE) {
+        const int pend_kind = pre.c.x, T = pre.c.y, pend_parent = pre.c.z, pend_action = pre.c.w, pend_depth = pre.d.x;
+        consumed = true;
+        use(T);
+        if (pend_kind == PK_ROOT) {  // MCTreeSearch.reset (mcts.py:166-174); root.v is never read
+            int player = (T == 0) ? (swap ? -1 : 1) : (swap ? 1 : -1);  // selfplayworker.py:175-176
             ts.node_count = 0;
-            int idx = alloc_node<GAME>(c, ts, 0ULL, 0ULL, player, pol);
+            int idx = alloc_node<GAME>(c, ts, 0ULL, 0ULL, player, my_p);
             ts.root = idx; ts.root_n = 0; ts.root_w = 0.0; ts.root_player = player; ts.moves_played = 0; ts.n_rec = 0;
-            s.cnt_nodes += 1;
-            s.tree[T] = ts;
-            if (T == 0) { s.n_moves_logged = 0; if (lane == 0) { E.own_action[2 * g] = 0; E.own_action[2 * g + 1] = -1; } }
-            if (T == 0 && !cfg.opponent_kind) { s.phase = PH_RESET; s.sub_tree = 1; }
-            else { s.mover_tree = s.swap ? 1 : 0; s.phase = PH_SEARCH; s.sims_done = -1; /* -1: search not begun */ }
+            count(&gp->cnt_nodes, 1);
+            if (T == 0) { n_moves_logged = 0; if (lane == 0) { E.own_action[2 * g] = 0; E.own_action[2 * g + 1] = -1; } }
+            if (T == 0 && !cfg.opponent_kind) { phase = PH_RESET; sub_tree = 1; }
+            else { mover_tree = swap ? 1 : 0; phase = PH_SEARCH; sims_done = -1; /* -1: search not begun */ }
         } else {
             // _expand_node's network branch (mcts.py:316-320) + backup (:361 / :207)
-            const int pplayer = s.pend_parent_player;
-            int idx = alloc_node<GAME>(c, ts, s.pend_own, s.pend_opp, -pplayer, pol);
-            if (idx < 0) { s.cnt_err += 1; s.phase = PH_IDLE; }
+            const int pplayer = pre.d.y;
+            int idx = alloc_node<GAME>(c, ts, pre.pend.x, pre.pend.y, -pplayer, my_p);
+            if (idx < 0) { count(&gp->cnt_err, 1); phase = PH_IDLE; }
             else {
-                s.cnt_nodes += 1;
-                if (lane == 0) ((int*)(c.node(s.pend_parent) + L::OFF_CHILD))[s.pend_action] = idx;
-                double v = __dmul_rn((double)value_in[g], (double)pplayer);  // modules.py:112 value*player
+                count(&gp->cnt_nodes, 1);
+                if (lane == 0) ((int*)(c.node(pend_parent) + L::OFF_CHILD))[pend_action] = idx;
+                double v = __dmul_rn((double)v_in, (double)pplayer);  // modules.py:112 value*player
                 unsigned p0 = 0, p1 = 0;
-                if (s.pend_kind == PK_EXPAND) {
-                    const unsigned* pp = E.paths + (size_t)g * SPX_MAX_PATH;
-                    if (lane < s.pend_depth) p0 = pp[lane];
-                    if (lane + 32 < s.pend_depth) p1 = pp[lane + 32];
-                } else if (lane == 0) p0 = ((unsigned)s.pend_parent << 4) | (unsigned)s.pend_action;
+                if (pend_kind == PK_EXPAND) {
+                    if (lane < pend_depth) p0 = pre.p0;
+                    if (lane + 32 < pend_depth) p1 = pre.p1;
+                } else if (lane == 0) p0 = ((unsigned)pend_parent << 4) | (unsigned)pend_action;
                 __syncwarp();
-                backup_path<GAME>(c, p0, p1, s.pend_depth, v, ts);
+                backup_path<GAME>(c, p0, p1, pend_depth, v, ts);
                 __syncwarp();
-                if (s.pend_kind == PK_EXPAND) s.sims_done += 1;
+                if (pend_kind == PK_EXPAND) sims_done += 1;
                 else {  // _set_root(node) (mcts.py:209)
                     ts.root = idx; ts.root_n = 1; ts.root_w = v; ts.root_player = -pplayer;
-                    if (s.sub_tree == 0 && !cfg.opponent_kind) s.sub_tree = 1; else s.phase = PH_ENVSTEP;
+                    if (sub_tree == 0 && !cfg.opponent_kind) sub_tree = 1; else phase = PH_ENVSTEP;
                 }
             }
-            s.tree[T] = ts;
         }
-        s.pend_kind = PK_NONE;
     }
 
     // ---- 2. run the state machine until the next network request
-    int budget = cfg.max_sims_per_tick;
     while (!emitted) {
-        if (s.phase == PH_IDLE) break;
-        if (s.phase == PH_RESET) {
-            out_own = 0; out_opp = 0; out_net = cfg.two_nets ? s.sub_tree : 0;
-            s.pend_kind = PK_ROOT; s.pend_tree = s.sub_tree;
+        if (phase == PH_IDLE) break;
+        if (phase == PH_RESET) {
+            out_own = 0; out_opp = 0; out_net = cfg.two_nets ? sub_tree : 0;
+            e_kind = PK_ROOT; e_tree = sub_tree;
             emitted = true;
             break;
         }
-        if (s.phase == PH_SEARCH && s.mover_tree == 1 && cfg.opponent_kind == SPX_OPP_EXTERNAL) {
+        if (phase == PH_SEARCH && mover_tree == 1 && cfg.opponent_kind == SPX_OPP_EXTERNAL) {
             // the opposing player lives on the host (any BasePlayer): park until spx_set_external_actions delivers its move
             const int a = E.ext_action[g];
-            if (a < 0) break;
+            if (a < 0) { parked = true; break; }
             __syncwarp();
             if (lane == 0) E.ext_action[g] = -1;
-            s.last_action = a;
-            s.phase = PH_REROOT; s.sub_tree = 0;
+            last_action = a;
+            phase = PH_REROOT; sub_tree = 0;
             continue;
         }
-        if (s.phase == PH_SEARCH && s.mover_tree == 1 && cfg.opponent_kind) {
+        if (phase == PH_SEARCH && mover_tree == 1 && cfg.opponent_kind) {
             // OneStepLookahead / Random (hardcoded_players.py:15-30,45-50).  The opponent's own env holds its pieces as +1:
             // own-frame "own" = env_opp, "enemy" = env_own; self.player = +1 if swap_sides else -1 (selfplayworker.py:176),
             // so without swap_sides the reference's "can I win" pass actually tests the ENEMY's move first -- kept as is.
-            const int self_player = s.swap ? 1 : -1;
-            const unsigned vmask = valid_mask<GAME>(s.env_own, s.env_opp);
+            const int self_player = swap ? 1 : -1;
+            const u64 env_own = gp->env_own, env_opp = gp->env_opp;
+            const unsigned vmask = valid_mask<GAME>(env_own, env_opp);
             unsigned done_first = 0, done_second = 0;
             if (cfg.opponent_kind == SPX_OPP_LOOKAHEAD && lane < A && ((vmask >> lane) & 1u)) {
                 for (int pass = 0; pass < 2; ++pass) {
-                    u64 o = s.env_opp, e = s.env_own;   // opponent frame: own, enemy
+                    u64 o = env_opp, e = env_own;   // opponent frame: own, enemy
                     int r = 0, dn = 0;
                     env_step<GAME>(o, e, lane, pass == 0 ? self_player : -self_player, r, dn);
                     if (dn) { if (pass == 0) done_first = 1; else done_second = 1; }
@@ -307,46 +410,45 @@ __device__ __forceinline__ void advance_game(const EngineDev& E, const int g, co
             else if (b1) action = __ffs(b1) - 1;
             else {
                 const int n = __popc(vmask);
-                const double u = rng_uniform_from(rng_prefix(cfg.seed, s.game_index, 1, PURPOSE_OPPONENT, s.ply), 0, 0, 0);
+                const double u = rng_uniform_from(rng_prefix(cfg.seed, game_index, 1, PURPOSE_OPPONENT, ply), 0, 0, 0);
                 int idx = (int)(u * (double)n);
                 if (idx >= n) idx = n - 1;
                 unsigned m = vmask;
                 for (int i = 0; i < idx; ++i) m &= m - 1;   // drop the idx lowest legal moves
                 action = __ffs(m) - 1;
             }
-            if (E.mlog && s.n_moves_logged < SPX_MAX_PLIES) {
-                spx_move_log* ml = E.mlog + (size_t)g * SPX_MAX_PLIES + s.n_moves_logged;
+            if (E.mlog && n_moves_logged < SPX_MAX_PLIES) {
+                spx_move_log* ml = E.mlog + (size_t)g * SPX_MAX_PLIES + n_moves_logged;
                 if (lane < A) { ml->n[lane] = 0; ml->w[lane] = 0.0; ml->noise[lane] = 0.0; }
-                if (lane == 0) { ml->tree = 1; ml->ply = s.ply; ml->action = action; ml->root_n = 0; ml->root_w = 0.0; }
-                s.n_moves_logged += 1;
+                if (lane == 0) { ml->tree = 1; ml->ply = ply; ml->action = action; ml->root_n = 0; ml->root_w = 0.0; }
+                n_moves_logged += 1;
             }
-            s.last_action = action;
-            s.phase = PH_REROOT; s.sub_tree = 0;
+            last_action = action;
+            phase = PH_REROOT; sub_tree = 0;
             continue;
         }
-        if (s.phase == PH_SEARCH) {
-            const int T = s.mover_tree;
-            c.use_tree(T);
-            TreeState ts = s.tree[T];
-            if (s.sims_done < 0) {  // search(): root.add_noise() (mcts.py:323-327, 49-53)
+        if (phase == PH_SEARCH) {
+            const int T = mover_tree;
+            use(T);
+            if (sims_done < 0) {  // search(): root.add_noise() (mcts.py:323-327, 49-53)
                 double d = 1.0 / (double)A;
                 if (cfg.noise_mode == 1 && E.noise_table) {
-                    long long row = (long long)s.game_index - E.table_first;
+                    long long row = (long long)game_index - E.table_first;
                     int mv = ts.moves_played < E.table_moves ? ts.moves_played : E.table_moves - 1;
                     if (row >= 0 && row < E.table_games && lane < A)
                         d = E.noise_table[(((size_t)row * 2 + T) * E.table_moves + mv) * A + lane];
                 } else if (cfg.noise_mode == 2) {
-                    u64 pre = rng_prefix(cfg.seed, s.game_index, T, PURPOSE_GAMMA, s.ply);
-                    double gv = lane < A ? gamma_variate(pre, lane, cfg.alpha) : 0.0;
+                    u64 pre_g = rng_prefix(cfg.seed, game_index, T, PURPOSE_GAMMA, ply);
+                    double gv = lane < A ? gamma_variate(pre_g, lane, cfg.alpha) : 0.0;
                     double acc = 0.0;
                     for (int a = 0; a < A; ++a) acc = __dadd_rn(acc, shfl_d(gv, a));
                     d = __dmul_rn(gv, __ddiv_rn(1.0, acc));
                 }
                 if (lane < A) E.noise[(size_t)g * SPX_MAX_ACTIONS + lane] = d;
-                __syncwarp();
-                s.sims_done = 0;
+                my_noise = lane < A ? d : 0.0;
+                sims_done = 0;
             }
-            if (s.sims_done >= cfg.sims) {
+            if (sims_done >= cfg.sims) {
                 // ---------------- _play (mcts.py:272-299)
                 char* root = c.node(ts.root);
                 int n_a = lane < A ? ((int*)(root + L::OFF_N))[lane] : 0;
@@ -363,11 +465,16 @@ __device__ __forceinline__ void advance_game(const EngineDev& E, const int g, co
                     for (int a = 1; a < A; ++a) { int na = __shfl_sync(0xffffffffu, n_a, a); if (na > best) { best = na; action = a; } }
                 } else {
                     prob = __ddiv_rn(pw, sum);
-                    double cdf[SPX_MAX_ACTIONS], acc = 0.0;
-                    for (int a = 0; a < A; ++a) { acc = __dadd_rn(acc, shfl_d(prob, a)); cdf[a] = acc; }
-                    u64 pre = rng_prefix(cfg.seed, s.game_index, T, PURPOSE_ACTION, s.ply);
-                    double u = rng_uniform_from(pre, 0, 0, 0);
-                    for (int a = 0; a < A; ++a) if (__ddiv_rn(cdf[a], cdf[A - 1]) <= u) action = a + 1;  // searchsorted right
+                    double acc = 0.0;
+                    for (int a = 0; a < A; ++a) acc = __dadd_rn(acc, shfl_d(prob, a));
+                    const double last = acc;                                             // cdf[-1]
+                    u64 pre_a = rng_prefix(cfg.seed, game_index, T, PURPOSE_ACTION, ply);
+                    double u = rng_uniform_from(pre_a, 0, 0, 0);
+                    acc = 0.0;
+                    for (int a = 0; a < A; ++a) {   // searchsorted(cdf / cdf[-1], u, side="right") as np.random.choice does
+                        acc = __dadd_rn(acc, shfl_d(prob, a));
+                        if (__ddiv_rn(acc, last) <= u) action = a + 1;
+                    }
                     if (action >= A) action = A - 1;
                     if (cfg.emit_records && ts.n_rec < SPX_MAX_OWN_MOVES) {
                         spx_record* rec = E.temp_rec + ((size_t)g * 2 + T) * SPX_MAX_OWN_MOVES + ts.n_rec;
@@ -375,33 +482,31 @@ __device__ __forceinline__ void advance_game(const EngineDev& E, const int g, co
                         if (lane == 0) {
                             rec->own = *(u64*)(root + L::OFF_OWN);
                             rec->opp = *(u64*)(root + L::OFF_OPP);
-                            rec->game_index = s.game_index;
+                            rec->game_index = game_index;
                             rec->q = ts.root_n ? (float)__ddiv_rn(ts.root_w, (double)ts.root_n) : 0.f;  // root.q
                             rec->actual_val = 0.f;
-                            rec->tree = (uint8_t)T; rec->ply = (uint8_t)s.ply; rec->pad0 = 0; rec->pad1 = 0;
+                            rec->tree = (uint8_t)T; rec->ply = (uint8_t)ply; rec->pad0 = 0; rec->pad1 = 0;
                         }
                         ts.n_rec += 1;
                     }
                 }
-                if (E.mlog && s.n_moves_logged < SPX_MAX_PLIES) {
-                    spx_move_log* ml = E.mlog + (size_t)g * SPX_MAX_PLIES + s.n_moves_logged;
-                    if (lane < A) { ml->n[lane] = n_a; ml->w[lane] = w_a; ml->noise[lane] = E.noise[(size_t)g * SPX_MAX_ACTIONS + lane]; }
-                    if (lane == 0) { ml->tree = T; ml->ply = s.ply; ml->action = action; ml->root_n = ts.root_n; ml->root_w = ts.root_w; }
-                    s.n_moves_logged += 1;
+                if (E.mlog && n_moves_logged < SPX_MAX_PLIES) {
+                    spx_move_log* ml = E.mlog + (size_t)g * SPX_MAX_PLIES + n_moves_logged;
+                    if (lane < A) { ml->n[lane] = n_a; ml->w[lane] = w_a; ml->noise[lane] = my_noise; }
+                    if (lane == 0) { ml->tree = T; ml->ply = ply; ml->action = action; ml->root_n = ts.root_n; ml->root_w = ts.root_w; }
+                    n_moves_logged += 1;
                 }
                 ts.moves_played += 1;
-                s.cnt_moves += 1;
+                count(&gp->cnt_moves, 1);
                 if (lane == 0 && T == 0) { E.own_action[2 * g] = ts.moves_played; E.own_action[2 * g + 1] = action; }
-                s.tree[T] = ts;
-                s.last_action = action;
-                s.phase = PH_REROOT; s.sub_tree = 0;
+                last_action = action;
+                phase = PH_REROOT; sub_tree = 0;
                 continue;
             }
             if (budget <= 0) break;
             budget -= 1;
             // ---------------- search_node (mcts.py:340-367), sequential mode
-            const u64 tie_pre = rng_prefix(cfg.seed, s.game_index, T, PURPOSE_TIE, s.ply);
-            const double my_noise = lane < A ? E.noise[(size_t)g * SPX_MAX_ACTIONS + lane] : 0.0;
+            const u64 tie_pre = rng_prefix(cfg.seed, game_index, T, PURPOSE_TIE, ply);
             int node = ts.root, N = ts.root_n, player = ts.root_player, depth = 0;
             unsigned p0 = 0, p1 = 0;
             int child = 0, act = 0;
@@ -422,7 +527,7 @@ __device__ __forceinline__ void advance_game(const EngineDev& E, const int g, co
                 // everything that does not depend on this node's statistics is computed while its loads are in flight:
                 // sqrt(N + 1) (N came with the parent edge) and the tie-break noise of this (sim, depth, lane)
                 const double sqrt_n = __dsqrt_rn((double)(N + 1));
-                const double tie = cfg.tie_mode ? __dmul_rn(0.000001, rng_uniform_from(tie_pre, (unsigned)s.sims_done, (unsigned)depth, (u64)lane)) : 0.0;
+                const double tie = cfg.tie_mode ? __dmul_rn(0.000001, rng_uniform_from(tie_pre, (unsigned)sims_done, (unsigned)depth, (u64)lane)) : 0.0;
                 if (lane < A) {
                     if (ch >= 0) {   // pull every expanded child towards the SM while the scores are computed (the next level is one of them)
                         const char* cn = c.node(ch);
@@ -457,7 +562,7 @@ __device__ __forceinline__ void advance_game(const EngineDev& E, const int g, co
                 if (child < 0 || depth >= SPX_MAX_PATH) break;  // is_leaf: unexpanded or terminal (:357)
                 node = child; N = n_edge; player = -player;
             }
-            s.cnt_path += (u64)depth;
+            count(&gp->cnt_path, depth);
             // ---------------- _expand_node (mcts.py:301-321) on (node, act), mover = node.player
             const char* pnd = c.node(node);
             const u64 par_own = *(const u64*)(pnd + L::OFF_OWN), par_opp = *(const u64*)(pnd + L::OFF_OPP);
@@ -465,6 +570,7 @@ __device__ __forceinline__ void advance_game(const EngineDev& E, const int g, co
             int r = 0, done = 0;
             if (child == CHILD_UNEXPANDED) env_step<GAME>(c_own, c_opp, act, player, r, done);
             else { done = 1; r = (child == CHILD_TERM_WIN); }
+            count(&gp->cnt_sims, 1);   // (a sim that needs the network completes when its evaluation is consumed next tick)
             if (done) {
                 if (child == CHILD_UNEXPANDED && lane == 0)
                     ((int*)(c.node(node) + L::OFF_CHILD))[act] = r ? CHILD_TERM_WIN : CHILD_TERM_DRAW;
@@ -472,8 +578,8 @@ __device__ __forceinline__ void advance_game(const EngineDev& E, const int g, co
                 __syncwarp();
                 backup_path<GAME>(c, p0, p1, depth, v, ts);
                 __syncwarp();
-                s.sims_done += 1; s.cnt_sims += 1; s.cnt_term += 1;
-                s.tree[T] = ts;
+                sims_done += 1;
+                count(&gp->cnt_term, 1);
                 continue;
             }
             // needs the network: net input = child_state * parent.player (mcts.py:316, modules.py:109-112)
@@ -483,20 +589,17 @@ __device__ __forceinline__ void advance_game(const EngineDev& E, const int g, co
             unsigned* pp = E.paths + (size_t)g * SPX_MAX_PATH;
             if (lane < depth) pp[lane] = p0;
             if (lane + 32 < depth) pp[lane + 32] = p1;
-            s.pend_kind = PK_EXPAND; s.pend_tree = T; s.pend_parent = node; s.pend_action = act; s.pend_depth = depth;
-            s.pend_parent_player = player; s.pend_own = c_own; s.pend_opp = c_opp;
-            s.cnt_sims += 1;  // the sim completes when its evaluation is consumed next tick
-            s.tree[T] = ts;
+            e_kind = PK_EXPAND; e_tree = T; e_parent = node; e_action = act; e_depth = depth;
+            e_pplayer = player; e_own = c_own; e_opp = c_opp;
             emitted = true;
             break;
         }
-        if (s.phase == PH_REROOT) {
-            // play_action -> _set_node (mcts.py:188-209) on tree sub_tree with s.last_action
-            const int T = s.sub_tree, a = s.last_action;
-            c.use_tree(T);
-            TreeState ts = s.tree[T];
-            bool parked = false;
-            if (ts.root < 0) s.cnt_err += 1;  // re-rooting a finished tree: cannot happen in legal play
+        if (phase == PH_REROOT) {
+            // play_action -> _set_node (mcts.py:188-209) on tree sub_tree with last_action
+            const int T = sub_tree, a = last_action;
+            use(T);
+            bool wait_net = false;
+            if (ts.root < 0) count(&gp->cnt_err, 1);  // re-rooting a finished tree: cannot happen in legal play
             else {
                 char* root = c.node(ts.root);
                 const int n_a = ((const int*)(root + L::OFF_N))[a];
@@ -521,9 +624,9 @@ __device__ __forceinline__ void advance_game(const EngineDev& E, const int g, co
                         out_own = player > 0 ? c_own : c_opp;
                         out_opp = player > 0 ? c_opp : c_own;
                         out_net = cfg.two_nets ? T : 0;
-                        s.pend_kind = PK_REROOT; s.pend_tree = T; s.pend_parent = ts.root; s.pend_action = a; s.pend_depth = 1;
-                        s.pend_parent_player = player; s.pend_own = c_own; s.pend_opp = c_opp;
-                        parked = true;
+                        e_kind = PK_REROOT; e_tree = T; e_parent = ts.root; e_action = a; e_depth = 1;
+                        e_pplayer = player; e_own = c_own; e_opp = c_opp;
+                        wait_net = true;
                     }
                 } else {
                     ts.root_w = ((const double*)(root + L::OFF_W))[a];
@@ -532,21 +635,24 @@ __device__ __forceinline__ void advance_game(const EngineDev& E, const int g, co
                     ts.root = ch >= 0 ? ch : -1;
                 }
             }
-            s.tree[T] = ts;
-            if (parked) { emitted = true; break; }
-            if (T == 0 && !cfg.opponent_kind) s.sub_tree = 1; else s.phase = PH_ENVSTEP;
+            if (wait_net) { emitted = true; break; }
+            if (T == 0 && !cfg.opponent_kind) sub_tree = 1; else phase = PH_ENVSTEP;
             continue;
         }
-        if (s.phase == PH_ENVSTEP) {
+        if (phase == PH_ENVSTEP) {
             // env.step(a, player) in play_move (selfplayworker.py:221-224) and the episode bookkeeping (:180-190)
-            const int player = s.mover_tree == 0 ? 1 : -1;
+            const int player = mover_tree == 0 ? 1 : -1;
+            u64 env_own = gp->env_own, env_opp = gp->env_opp;
             int r = 0, done = 0;
-            const int st = env_step<GAME>(s.env_own, s.env_opp, s.last_action, player, r, done);
-            if (st != SPX_ENV_OK) { s.cnt_err += 1; done = 1; }
-            s.ply += 1;
+            const int st = env_step<GAME>(env_own, env_opp, last_action, player, r, done);
+            if (st != SPX_ENV_OK) { count(&gp->cnt_err, 1); done = 1; }
+            ply += 1;
             if (!done) {
-                s.mover_tree ^= 1;
-                s.phase = PH_SEARCH; s.sims_done = -1;
+                __syncwarp();
+                if (lane == 0) { gp->env_own = env_own; gp->env_opp = env_opp; }
+                __syncwarp();
+                mover_tree ^= 1;
+                phase = PH_SEARCH; sims_done = -1;
                 continue;
             }
             const int reward = r * player;  // get_and_play_moves: r = r * player (:218)
@@ -555,12 +661,16 @@ __device__ __forceinline__ void advance_game(const EngineDev& E, const int g, co
                 if (k < (unsigned long long)cfg.result_capacity) {
                     spx_result res;
                     memset(&res, 0, sizeof(res));
-                    res.game_index = s.game_index; res.reward = (int8_t)reward; res.swap_sides = (uint8_t)s.swap; res.plies = (uint8_t)s.ply;
+                    res.game_index = game_index; res.reward = (int8_t)reward; res.swap_sides = (uint8_t)swap; res.plies = (uint8_t)ply;
                     E.res_ring[k] = res;
                 }
             }
+            // both trees' record counts: the current tree goes back to the slot first
+            if (lane == 0) st_tree(&gp->tree[curT], ts);
+            __syncwarp();
+            const int n0 = gp->tree[0].n_rec, n1 = gp->tree[1].n_rec;
             if (cfg.emit_records) {  // push_to_queue (mcts.py:225-232): policy first (+r), then the opponent (-r)
-                const int n0 = s.tree[0].n_rec, n1 = s.tree[1].n_rec, tot = n0 + n1;
+                const int tot = n0 + n1;
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(E.rec_count, (unsigned long long)tot);
                 base = __shfl_sync(0xffffffffu, base, 0);
@@ -572,29 +682,44 @@ __device__ __forceinline__ void advance_game(const EngineDev& E, const int g, co
                     else atomicAdd(E.rec_dropped, 1ULL);
                 }
             }
-            s.cnt_games += 1;
+            count(&gp->cnt_games, 1);
             // next game on this slot (self_play_parallel.py:250-253: swap_sides = game index odd)
-            s.game_index += (u64)cfg.slot_stride;
-            s.env_own = 0; s.env_opp = 0; s.ply = 0;
-            s.swap = (int)(s.game_index & 1ULL);
-            s.tree[0].n_rec = 0; s.tree[1].n_rec = 0;
-            if ((long long)s.game_index < cfg.games_target) { s.phase = PH_RESET; s.sub_tree = 0; }
-            else s.phase = PH_IDLE;
+            game_index += (u64)cfg.slot_stride;
+            ply = 0;
+            swap = (int)(game_index & 1ULL);
+            __syncwarp();
+            if (lane == 0) { gp->env_own = 0; gp->env_opp = 0; gp->tree[0].n_rec = 0; gp->tree[1].n_rec = 0; }
+            __syncwarp();
+            ts.n_rec = 0;
+            if ((long long)game_index < cfg.games_target) { phase = PH_RESET; sub_tree = 0; }
+            else phase = PH_IDLE;
             continue;
         }
         break;
     }
 
-    if (emitted) s.cnt_evals += 1;
+    // ---- 3. write the slot back: 128-bit stores by lane 0, nothing the warp has to wait for
     __syncwarp();
     if (lane == 0) {
-        *gp = s;
+        int4* q = reinterpret_cast<int4*>(gp);
+        q[0] = make_int4(phase, sub_tree, mover_tree, sims_done);
+        q[1] = make_int4(ply, swap, last_action, n_moves_logged);
+        if (emitted) {
+            q[2] = make_int4(e_kind, e_tree, e_parent, e_action);
+            q[3] = make_int4(e_depth, e_pplayer, defer_leaf ? 1 : 0, 0);
+            reinterpret_cast<ulonglong2*>(gp)[4] = make_ulonglong2(e_own, e_opp);
+            atomicAdd((ull*)&gp->cnt_evals, 1ULL);
+        } else if (consumed) q[2] = make_int4(PK_NONE, 0, 0, 0);
+        gp->game_index = game_index;
+        st_tree(&gp->tree[curT], ts);
         E.leaf_own[g] = out_own;
         E.leaf_opp[g] = out_opp;
-        E.needs_eval[g] = emitted ? 1 : 0;
+        E.needs_eval[g] = (emitted && !defer_leaf) ? 1 : 0;
         E.net_id[g] = (unsigned char)out_net;
-        if (g == 0) *E.ticks += 1ULL;
+        if (count_tick) atomicAdd(E.ticks, 1ULL);
     }
+    __syncwarp();   // lane 0's stores are ordered before whatever any lane of this warp loads next (the next prefetch of this slot)
+    return emitted ? ADV_EMITTED : (phase == PH_IDLE ? ADV_IDLE : (parked ? ADV_PARKED : 0));
 }
 
 }  // namespace spx

@@ -46,14 +46,20 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------------------------------------ the tick kernel
 #ifndef SPX_ADV_MINB
-#define SPX_ADV_MINB 8   // 64 registers: 8 CTAs (32 game warps) per SM; -8 % at 16 384 games, neutral at 1024
+#define SPX_ADV_MINB 4   // 128 registers: advance_game needs 96 (Connect4) / 110 (TicTacToe) and must not spill on its select chain
 #endif
 template <int GAME>
 __global__ void __launch_bounds__(128, SPX_ADV_MINB) advance_kernel(EngineDev E, const float* __restrict__ policy_in,
                                                       const float* __restrict__ value_in) {
     const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     if (g >= E.cfg.n_games) return;
-    advance_game<GAME>(E, g, threadIdx.x & 31, policy_in, value_in);
+    const int lane = threadIdx.x & 31;
+    const AdvPre pre = advance_prefetch<GAME>(E, g, lane);
+    // the outputs of the evaluation this slot asked for (null before the first evaluation: nothing is pending then)
+    const float my_p = (policy_in && lane < Rules<GAME>::A) ? policy_in[(size_t)g * Rules<GAME>::A + lane] : 0.f;
+    const float v = value_in ? value_in[g] : 0.f;
+    u64 own, opp;
+    advance_game<GAME>(E, g, lane, pre, my_p, v, E.cfg.max_sims_per_tick, false, g == 0, own, opp);
 }
 
 __global__ void reset_kernel(EngineDev E) {

@@ -27,6 +27,7 @@
 // Fallbacks: tower_kernel<1> (SPX_TOWER_NCTA=1: one CTA per 7 boards, cta_group::1) and heads_kernel
 // (SPX_TOWER_FUSED_HEADS=0 or after tower_kernel<1>).  SPX_DBG_* macros build timing experiments only.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -187,10 +188,18 @@ __device__ __forceinline__ void store_bias_to_tmem(unsigned tcol, const float* b
     for (int t = 0; t < MT; ++t) tc_st32(tcol + (unsigned)(t * 128), b);
     tc_wait_st();
 }
-__device__ __forceinline__ unsigned relu_pack_bf16x2(float lo, float hi) {   // max(x,0) and round-to-nearest bf16 in one instruction
+// max(x, 0) and round-to-nearest packing of two activations in one instruction: bf16, or fp16 (F16 = true: 11 instead of 8
+// significant bits -- the reference's own GPU arithmetic is fp16 autocast, inference_worker.py:117; saturating, so that a
+// value beyond 65504 stays finite)
+template <bool F16> __device__ __forceinline__ unsigned relu_pack2(float lo, float hi) {
     unsigned r;
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    if constexpr (F16) asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
+}
+template <bool F16> __device__ __forceinline__ float2 unpack2(unsigned w) {
+    if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+    else return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
 }
 __device__ __forceinline__ void tc_ld16(unsigned taddr, unsigned (&v)[16]) {
     asm volatile(
@@ -207,9 +216,10 @@ __device__ __forceinline__ unsigned long long make_desc(unsigned saddr, unsigned
     return (unsigned long long)((saddr >> 4) & 0x3FFFu) | ((unsigned long long)((lbo >> 4) & 0x3FFFu) << 16) |
            ((unsigned long long)((sbo >> 4) & 0x3FFFu) << 32) | (1ULL << 46);
 }
-// instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
-__host__ __device__ constexpr unsigned make_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+// instruction descriptor: D=f32 (bit 4), A and B formats at bits 7 / 10 (0 = fp16, 1 = bf16), both K-major, N>>3 at bit 17,
+// M>>4 at bit 24
+__host__ __device__ constexpr unsigned make_idesc(int M, int N, bool f16 = false) {
+    return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
 }
 
 // Which padded row is a real board cell, and which one.  Connect4 fills the 7x6 slot; a TicTacToe board (ResidualTower on
@@ -249,9 +259,12 @@ __device__ long long g_trace[64 * 16 + 3 * 160];   // + per-CTA {entry, exit, SM
 #define SPX_TRACE(l, k) do { if (blockIdx.x == 0 && (l) < 64) g_trace[(l) * 16 + (k)] = clock64(); } while (0)
 #define SPX_TRACE_IF(c, l, k) do { if (c) SPX_TRACE(l, k); __syncwarp(); } while (0)
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ long long g_tt[64 * 12];   // fused tick kernel: globaltimer (ns) of 12 points of passes 20..83, CTA 0, first epilogue thread
+#define SPX_TT(k) do { if (ENGINE && blockIdx.x == 0 && tid == EPI_WARP0 * 32 && pass >= 20 && pass < 84) g_tt[(pass - 20) * 12 + (k)] = (long long)globaltimer_ns(); } while (0)
 #else
 #define SPX_TRACE(l, k) do { } while (0)
 #define SPX_TRACE_IF(c, l, k) do { } while (0)
+#define SPX_TT(k) do { } while (0)
 #endif
 template <int NCTA> struct SmemT {
     static constexpr int STAGES = NCTA * NSTAGE;
@@ -260,6 +273,13 @@ template <int NCTA> struct SmemT {
     unsigned long long full[STAGES], empty[STAGES], peer_full[STAGES], acc_full[MT], epi_done[MT];   // accumulator complete / tile handed over, per 128-row tile
     unsigned long long fc_full[FC_STAGES], fc_empty[FC_STAGES], fc_peer_full[FC_STAGES], fc_done;   // fused FC heads
     unsigned long long own[NB], opp[NB];
+    unsigned long long leaf2[8][2];     // ENGINE, fast mode: {own, opp} of slot w's next leaf, written by engine_step
+    // fused tick kernel (ENGINE): leaves / hand-over state of the CTA's games, see the ENGINE comment above tower_kernel
+    unsigned long long xbar;            // "the peer CTA's halves of my boards' hidden-layer sums have landed" (st.async complete_tx)
+    float xval[8];
+    int slot_status[8];                 // FS_* per board slot (fast mode)
+    int quit, passes_done, searches_done;
+    unsigned char need[8];
     alignas(16) float bias[NCTA == 1 ? 3 : 1][NCTA == 1 ? CH : 4];   // single-CTA kernel only: staged fp32 bias, read as float4
     alignas(128) unsigned char ones[256];   // SM-pair kernel: the A operand of the bias MMA (see issue_bias)
     unsigned tmem_base;
@@ -312,6 +332,19 @@ __device__ __forceinline__ void tc_mma_lo_acc2(unsigned d_tmem, unsigned a_lo, u
 __device__ __forceinline__ void st_shared_remote_f32(void* local_addr, unsigned cta, float v) {
     asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tst.shared::cluster.f32 [ra], %2;\n\t}" ::"r"(smem_u32(local_addr)), "r"(cta), "f"(v) : "memory");
 }
+
+// one fp32 into the peer CTA's shared memory, completing 4 bytes of the transaction count of the peer's mbarrier `bar`
+__device__ __forceinline__ void st_async_remote_f32(void* local_addr, void* bar, unsigned cta, float v) {
+    asm volatile("{\n\t.reg .b32 ra, rb;\n\tmapa.shared::cluster.u32 ra, %0, %2;\n\tmapa.shared::cluster.u32 rb, %1, %2;\n\t"
+                 "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [ra], %3, [rb];\n\t}" ::"r"(smem_u32(local_addr)), "r"(smem_u32(bar)),
+                 "r"(cta), "r"(__float_as_uint(v)) : "memory");
+}
+__device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ void st_volatile_s32(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
+// warp-uniform read of a flag another warp may be writing right now (lanes must not disagree: the callers shuffle afterwards)
+__device__ __forceinline__ int ld_flag_uniform(const int* p) { return __shfl_sync(0xffffffffu, ld_volatile_s32(p), 0); }
+
+enum { FS_FAST = 0, FS_TODO = 1, FS_DONE = 2 };   // who works on a game slot: its epilogue warp / the shadow warp (pending, finished)
 
 // SM-pair kernel: the folded-BN bias enters the accumulators through the tensor pipe instead of a tcgen05.st by the epilogue
 // warps: D = ones * bias^T with accumulate = 0 is the first MMA of every layer.  A = `ones`: ONE 8-row core matrix whose
@@ -431,27 +464,39 @@ __device__ __forceinline__ void issue_first_tap_skewed(SmemT<2>& S, int taps, un
     __syncwarp();
 }
 
+// The fused tick kernel calls the search engine through this NON-INLINED function: advance_game gets the whole 96-register
+// budget for its select loop (inlined into the epilogue code it competed with ~25 kernel-level values and ptxas spilled 60
+// registers across it); the caller saves what it keeps live around the call, once per simulation.  The leaf goes straight to
+// the two shared-memory words the network phase reads.
+template <int GAME>
+__device__ __noinline__ int engine_step(const spx::EngineDev& E, const int g, const float my_p, const float v_in, const int budget,
+                                        const int defer_leaf, unsigned long long* leaf2) {
+    const int lane = threadIdx.x & 31;
+    const spx::AdvPre pre = spx::advance_prefetch<GAME>(E, g, lane);
+    unsigned long long own, opp;
+    const int flags = spx::advance_game<GAME>(E, g, lane, pre, my_p, v_in, budget, defer_leaf != 0, false, own, opp);
+    if (leaf2 && lane == 0) { leaf2[0] = own; leaf2[1] = opp; }
+    return flags;
+}
+
 // GAME is a template parameter: with the head sizes as run-time values the Connect4 kernel spilled (712-byte stack frame at the
 // 96-register cap, +13 % instructions, 8 MB of local-memory write-back per launch in ncu)
 // ENGINE = true is the fused tick kernel (spx_tick_fused): the kernel runs `n_ticks` ticks without the host; before every network
 // evaluation of a board group the first NB epilogue warps of the CTA that owns the group run the search engine's per-game state
 // machine (advance_game, spx_advance.cuh) for the group's games, i.e. consume the previous outputs and produce the next leaves.
 // Games are independent, so clusters never wait for each other: no grid-wide barrier, no launch gaps, no advance-kernel tail.
-template <int NCTA, int GAME = SPX_GAME_CONNECT4, bool ENGINE = false>
+template <int NCTA, int GAME = SPX_GAME_CONNECT4, bool ENGINE = false, bool F16 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long long* __restrict__ opp_g,
              const unsigned char* __restrict__ needs, long long n_boards, int n_layers,
              const unsigned char* __restrict__ wconv, const float* __restrict__ bias_all, float* __restrict__ head_out,
              int fused_in, const float* __restrict__ polw, const float* __restrict__ polb, const float* __restrict__ fc_b1,
              const float* __restrict__ fc_w2, const float* __restrict__ fc_b2, float* __restrict__ policy_out, float* __restrict__ value_out,
-             const EngineDev E, const int n_ticks) {
+             const __grid_constant__ EngineDev E, const int n_ticks) {
     typedef SmemT<NCTA> Smem;
     // leaves / needs_eval are produced inside this launch when ENGINE: read them through L2 (__ldcg), never through the
     // read-only path the __restrict__ const parameters allow
-    auto ld_need = [&](long long gb) -> bool {
-        if constexpr (ENGINE) return __ldcg(E.needs_eval + gb) != 0;
-        else return needs == nullptr || needs[gb];
-    };
+    auto ld_need = [&](long long gb) -> bool { return needs == nullptr || needs[gb]; };   // plain forward (ENGINE: S.need)
     const bool fused = NCTA == 2 && fused_in != 0;   // FC heads inside this kernel (no head_out round trip, no second launch)
     constexpr int game = GAME;
     constexpr int cells = GAME == SPX_GAME_TICTACTOE ? 9 : CELLS, n_act = GAME == SPX_GAME_TICTACTOE ? 9 : 7;
@@ -473,6 +518,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
         for (int t = 0; t < MT; ++t) mbar_init(&S.epi_done[t], EPI_WARPS * NCTA);   // one arrive per epilogue warp of every CTA of the cluster
         for (int s = 0; s < FC_STAGES; ++s) { mbar_init(&S.fc_full[s], 1); mbar_init(&S.fc_empty[s], 1); mbar_init(&S.fc_peer_full[s], 1); }
         mbar_init(&S.fc_done, 1);
+        mbar_init(&S.xbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -486,7 +532,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
     }
     // zero both activation buffers once: guard rows and padding cells must read as zero forever
     for (int i = tid; i < 2 * ACT_BYTES / 16; i += NUM_THREADS) reinterpret_cast<uint4*>(S.act[0])[i] = make_uint4(0, 0, 0, 0);
-    if (tid < 16) reinterpret_cast<uint4*>(S.ones)[tid] = tid < 8 ? make_uint4(0x3F803F80u, 0, 0, 0) : make_uint4(0, 0, 0, 0);   // bf16 (1, 1, 0 x 6) x 8 rows | zeros
+    if (tid < 16) reinterpret_cast<uint4*>(S.ones)[tid] = tid < 8 ? make_uint4(F16 ? 0x3C003C00u : 0x3F803F80u, 0, 0, 0) : make_uint4(0, 0, 0, 0);   // (1, 1, 0 x 6) x 8 rows | zeros
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -503,28 +549,81 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
     bool first_unit = true;
 
     const long long n_units = (n_groups + NCTA - 1) / NCTA;      // a unit = the NCTA board groups one cluster works on together
-    for (int tick = 0; tick < (ENGINE ? n_ticks : 1); ++tick) {
+    // ---- ENGINE (fused tick kernel): who advances the games.
+    // A pass = one network evaluation of one unit.  The search of a game cannot overlap the pass that evaluates its own leaf,
+    // but it needs nothing else, so:
+    //  * a cluster that owns ONE unit (<= 1036 games per GPU) is in "fast mode": after every pass epilogue warp w (w < 7) runs ONE
+    //    simulation attempt of game w (advance_game, budget 1: consume the outputs it has just computed, select, expand) -- a few
+    //    microseconds between two passes.  Whatever does not end in a leaf (chains of terminal re-visits, which need no network)
+    //    is handed to the SHADOW WARP (warp 3), which keeps simulating during the next pass and hands the game back with its leaf.
+    //  * a cluster that owns SEVERAL units is in "shadow-all mode": the shadow warp advances the 7 games of unit u while the
+    //    tensor pipe evaluates the other units (job p needs the outputs of pass p - U only), the epilogue warps never search.
+    // All hand-overs go through shared-memory flags + fences inside the CTA; the two CTAs of a pair only exchange the hidden
+    // layer's half sums (st.async + mbarrier).  No CTA-wide or cluster-wide barrier inside the tick loop.
+    const long long ustride = gridDim.x / NCTA, unit_first = blockIdx.x / NCTA;
+    const int U = ENGINE ? (unit_first < n_units ? (int)((n_units - 1 - unit_first) / ustride + 1) : 0) : 0;
+    const bool shadow_all = ENGINE && U >= 2;
+    const int total_passes = ENGINE ? n_ticks * U : 0;
+    float my_p = 0.f, v_next = 0.f;      // epilogue warps w < NB: the outputs of the pass for game w (this lane's prior, the value)
     if constexpr (ENGINE) {
-        // search phase of the tick: one warp per game of this CTA's board groups -- outputs of the previous tick in, next leaf out
-        // (all through global memory; the previous tick ended with a cluster barrier after its last output was written).  Two
-        // groups' games at a time when the cluster owns several units (more than 1036 games): 14 of the 16 epilogue warps.
-        const long long ustride = gridDim.x / NCTA;
-        for (long long unit0 = blockIdx.x / NCTA; unit0 < n_units; unit0 += 2 * ustride) {
-            const int w = warp - EPI_WARP0;
-            if (w >= 0 && w < 2 * NB) {
-                const long long unit = unit0 + (w / NB) * ustride;
-                const long long gb = (NCTA * unit + crank) * NB + (w % NB);
-                if (unit < n_units && gb < n_boards) advance_game<GAME>(E, (int)gb, lane, policy_out, value_out);
+        if (tid < 8) { S.slot_status[tid] = FS_FAST; S.need[tid] = 0; }
+        if (tid == 0) { S.quit = 0; S.passes_done = 0; S.searches_done = 0; }
+        __syncthreads();
+        if (warp == 3) {
+            // ===================== shadow warp: simulations that need no network evaluation of the running pass
+            int p = 0, j = 0;
+            for (;;) {
+                long long gb = 0;
+                bool run = false, defer = false;
+                int budget = 0;
+                float sp = 0.f, sv = 0.f;
+                if (shadow_all) {
+                    if (p >= total_passes) break;
+                    if (j == 0) {   // job p = the leaves of pass p: needs the outputs of the same unit's previous pass (p - U)
+                        while (ld_flag_uniform(&S.passes_done) < p - U + 1) __nanosleep(200);
+                        __threadfence();
+                    }
+                    gb = (NCTA * (unit_first + (long long)(p % U) * ustride) + crank) * NB + j;
+                    run = gb < n_boards;
+                    budget = 2 * E.cfg.max_sims_per_tick;
+                    if (run) {
+                        sp = lane < n_act ? __ldcg(policy_out + gb * n_act + lane) : 0.f;
+                        sv = __ldcg(value_out + gb);
+                    }
+                } else {
+                    if (j == 0 && ld_flag_uniform(&S.quit)) break;
+                    gb = (NCTA * unit_first + crank) * NB + j;
+                    run = ld_flag_uniform(&S.slot_status[j]) == FS_TODO;
+                    if (run) __threadfence();
+                    budget = 4 * E.cfg.max_sims_per_tick;
+                    defer = true;       // the running pass does not evaluate this leaf: it waits for the next one
+                }
+                if (run) {
+                    const int flags = engine_step<GAME>(E, (int)gb, sp, sv, budget, defer ? 1 : 0, nullptr);
+                    if (!shadow_all && flags) {   // a leaf, or nothing more to do: back to the epilogue warp (0 = budget used up: go on later)
+                        __threadfence();
+                        if (lane == 0) st_volatile_s32(&S.slot_status[j], FS_DONE);
+                    }
+                }
+                __syncwarp();
+                if (++j == NB) {
+                    j = 0;
+                    if (shadow_all) { __threadfence(); if (lane == 0) st_volatile_s32(&S.searches_done, p + 1); ++p; }
+                    else __nanosleep(300);
+                }
             }
         }
-        __threadfence();
-        __syncthreads();
-        cluster_sync_all();   // the skip test below reads the peer group's needs_eval
     }
-    for (long long unit = blockIdx.x / NCTA; unit < n_units; unit += gridDim.x / NCTA) {
+    for (int tick = 0; tick < (ENGINE ? n_ticks : 1); ++tick) {
+    int ui = 0;
+    for (long long unit = blockIdx.x / NCTA; unit < n_units; unit += gridDim.x / NCTA, ++ui) {
         const long long grp = NCTA * unit + crank;
-        // cluster-uniform skip when none of the boards of this unit asked for an evaluation
-        bool any = !ENGINE && needs == nullptr;
+        const int pass = tick * U + ui;
+        (void)pass;
+        if constexpr (ENGINE) { if (warp == 3) continue; }   // the shadow warp has done its work above
+        // cluster-uniform skip when none of the boards of this unit asked for an evaluation (plain forward only: the fused tick
+        // kernel always evaluates -- agreeing on a skip would cost a cluster round trip per tick)
+        bool any = ENGINE || needs == nullptr;
         if (!any) for (int b = 0; b < NCTA * NB; ++b) { long long gb = unit * NCTA * NB + b; if (gb < n_boards && ld_need(gb)) any = true; }
         if (!any) continue;
 
@@ -618,7 +717,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
             const bool leader = elect_one();
             for (int l = 0; l < n_layers; ++l) {
                 const LayerInfo li = layer_info(l, n_layers);
-                const unsigned idesc = make_idesc(128 * NCTA, li.n);
+                const unsigned idesc = make_idesc(128 * NCTA, li.n, F16);
                 const unsigned b_lbo16 = (unsigned)li.n / NCTA;                       // (n/NCTA * 16 B) >> 4: stride between the two k-chunks
                 const unsigned b_fields = b_lbo16 << 16;
                 const unsigned kstep16 = 2u * b_lbo16;                                 // one K step of B in 16-byte units
@@ -673,7 +772,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                     ephase ^= 1u;
                     tc_fence_after();
                     SPX_TRACE_IF(leader, n_layers, 1);
-                    const unsigned idesc_fc = make_idesc(256, 16);
+                    const unsigned idesc_fc = make_idesc(256, 16, F16);
                     const unsigned xv_lo = ((128u >> 4) << 16) | (smem_u32(S.act[1] + XV_OFF) >> 4);
                     for (int it = 0; it < fc_iters; ++it) {
                         mbar_wait(&S.fc_full[fstage], fphase);
@@ -715,6 +814,51 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
                 for (int t = 0; t < MT; ++t) signal_tile_done(t);
             };
+            SPX_TT(0);
+            const int ew = warp - EPI_WARP0;                       // epilogue warp index; warps ew < NB own game slot ew in fast mode
+            const long long gbw = grp * NB + ew;
+            const bool live_w = ENGINE && ew < NB && gbw < n_boards;
+            if constexpr (ENGINE) {
+                if (!shadow_all) {
+                    // ---- fast mode: one simulation attempt of game ew between two passes (see the ENGINE comment above)
+                    if (ew < NB) {
+                        int emitted = 0;
+                        if (lane == 0) { S.leaf2[ew][0] = 0ULL; S.leaf2[ew][1] = 0ULL; }
+                        __syncwarp();
+                        if (live_w) {
+                            int st = ld_flag_uniform(&S.slot_status[ew]);
+                            if (tick == 0) {   // first pass of the launch: the previous launch's outputs come from global memory
+                                my_p = lane < n_act ? __ldcg(policy_out + gbw * n_act + lane) : 0.f;
+                                v_next = __ldcg(value_out + gbw);
+                            }
+                            if (st == FS_DONE) { __threadfence(); st = FS_FAST; }   // the shadow warp is through with this game (leaf waiting, idle or parked)
+                            if (E.cfg.reserved0 & 1) {   // timing experiment (SPX_DBG_FLAGS=1): no search at all, every pass re-evaluates the same leaf
+                                if (lane == 0) { S.leaf2[ew][0] = __ldcg(E.leaf_own + gbw); S.leaf2[ew][1] = __ldcg(E.leaf_opp + gbw); }
+                                emitted = 1;
+                            } else
+                            if (st == FS_FAST) {
+                                const int fast_budget = (E.cfg.reserved0 >> 8) & 0xFF ? (E.cfg.reserved0 >> 8) & 0xFF : E.cfg.max_sims_per_tick;   // measured: 1 loses 5 % of the leaves, 8 costs 3 us more than 1
+                                const int flags = engine_step<GAME>(E, (int)gbw, my_p, v_next, fast_budget, 0, &S.leaf2[ew][0]);
+                                emitted = flags & spx::ADV_EMITTED;
+                                if (!flags) { __threadfence(); st = FS_TODO; }   // no leaf yet and not idle: the shadow warp goes on with it
+                                if (lane == 0) st_volatile_s32(&S.slot_status[ew], st);
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) { S.own[ew] = S.leaf2[ew][0]; S.opp[ew] = S.leaf2[ew][1]; S.need[ew] = emitted ? 1 : 0; }
+                    }
+                } else if (et < NB) {
+                    // ---- shadow-all mode: the shadow warp has produced this pass's leaves (job == pass)
+                    while (ld_volatile_s32(&S.searches_done) < pass + 1) __nanosleep(100);
+                    __threadfence();
+                    const long long gb = grp * NB + et;
+                    const bool ok = gb < n_boards;
+                    S.own[et] = ok ? __ldcg(E.leaf_own + gb) : 0ULL;
+                    S.opp[et] = ok ? __ldcg(E.leaf_opp + gb) : 0ULL;
+                    S.need[et] = ok ? __ldcg(E.needs_eval + gb) : (unsigned char)0;
+                }
+            }
+            SPX_TT(1);
             if (fused && !first_unit) {
                 // the previous unit's FC ring / head activations overwrote the buffers: the zero guard rows (never written by
                 // an epilogue) must read as zero again; every other row is rewritten before it is read
@@ -722,12 +866,9 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 const int row = gr < GUARD ? gr : ROWS + gr;
                 *reinterpret_cast<uint4*>(S.act[buf] + chunk * CHUNK_BYTES + row * 16) = make_uint4(0, 0, 0, 0);
             }
-            if (et < NB) {
-                const long long gb = grp * NB + et;
-                if constexpr (ENGINE) {
-                    S.own[et] = gb < n_boards ? __ldcg(E.leaf_own + gb) : 0ULL;
-                    S.opp[et] = gb < n_boards ? __ldcg(E.leaf_opp + gb) : 0ULL;
-                } else {
+            if constexpr (!ENGINE) {
+                if (et < NB) {
+                    const long long gb = grp * NB + et;
                     S.own[et] = gb < n_boards ? own_g[gb] : 0ULL;
                     S.opp[et] = gb < n_boards ? opp_g[gb] : 0ULL;
                 }
@@ -736,6 +877,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 if (et < CH) { S.bias[0][et] = __ldg(bias_all + et); S.bias[1][et] = __ldg(bias_all + CH + et); }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+            SPX_TT(2);
             if constexpr (NCTA == 1) {
                 store_bias_to_tmem(tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(part * (CH / EPI_SPLIT)), S.bias[0] + part * (CH / EPI_SPLIT));
                 tc_fence_before();
@@ -747,13 +889,14 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 unsigned o = 0, e = 0;
                 if (real) { o = (unsigned)((S.own[board] >> bit) & 1ULL); e = (unsigned)((S.opp[board] >> bit) & 1ULL); }
                 const unsigned emp = real ? (1u - o - e) : 0u;
-                const unsigned one = 0x3F80u;  // bf16(1.0)
+                const unsigned one = F16 ? 0x3C00u : 0x3F80u;  // 1.0 in the activation type
                 uint4 v0 = make_uint4((emp ? one : 0u) | ((o ? one : 0u) << 16), e ? one : 0u, 0u, 0u);
                 *reinterpret_cast<uint4*>(S.act[0] + (GUARD + row) * 16) = v0;
                 *reinterpret_cast<uint4*>(S.act[0] + CHUNK_BYTES + (GUARD + row) * 16) = make_uint4(0, 0, 0, 0);
             }
             fence_proxy_async();
             signal_epi_done();
+            SPX_TT(3);
             // per-tile row bookkeeping is layer independent
             bool real_t[MT]; int board_t[MT], cell_t[MT];
 #pragma unroll
@@ -770,6 +913,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 if (li.out_buf < 0) { mbar_wait(&S.acc_full[1], lphase); mbar_wait(&S.acc_full[2], lphase); }   // head layer: all tiles
                 tc_fence_after();
                 SPX_TRACE_IF(et == 0, l, 4);
+                if (l == 0) SPX_TT(4);
                 if (li.out_buf >= 0) {
                     // trunk layer: this warp owns 128/EPI_SPLIT = 32 columns of its 32 rows, for each of the 3 row tiles
                     const int ch0 = part * (CH / EPI_SPLIT);
@@ -804,13 +948,14 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                                     const unsigned iw[4] = {idv.x, idv.y, idv.z, idv.w};
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) {
-                                        y[2 * k] += __uint_as_float(iw[k] << 16);
-                                        y[2 * k + 1] += __uint_as_float(iw[k] & 0xFFFF0000u);
+                                        const float2 id2 = unpack2<F16>(iw[k]);
+                                        y[2 * k] += id2.x;
+                                        y[2 * k + 1] += id2.y;
                                     }
                                 }
                                 unsigned pk[4];
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) pk[k] = relu_pack_bf16x2(y[2 * k], y[2 * k + 1]);
+                                for (int k = 0; k < 4; ++k) pk[k] = relu_pack2<F16>(y[2 * k], y[2 * k + 1]);
                                 *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             }
                         }
@@ -854,7 +999,9 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
 #pragma unroll
                                 for (int k = 0; k < 16; ++k) {
                                     const int kk = (ch0 - 32 + k) * cells + cell_t[t];
-                                    *reinterpret_cast<__nv_bfloat16*>(xv + (kk >> 3) * 128 + (kk & 7) * 2) = __float2bfloat16_rn(fmaxf(__uint_as_float(v[k]), 0.f));
+                                    const float xr = fmaxf(__uint_as_float(v[k]), 0.f);
+                                    if constexpr (F16) *reinterpret_cast<__half*>(xv + (kk >> 3) * 128 + (kk & 7) * 2) = __float2half_rn(fminf(xr, 65504.f));
+                                    else *reinterpret_cast<__nv_bfloat16*>(xv + (kk >> 3) * 128 + (kk & 7) * 2) = __float2bfloat16_rn(xr);
                                 }
                             }
                         }
@@ -872,6 +1019,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
             }
             if constexpr (NCTA == 2) {
                 if (fused) {
+                    SPX_TT(5);
                     float* scr = reinterpret_cast<float*>(S.act[1] + FCS_OFF);   // logits [7][9] | partial [4][16] at 64 | own [16] at 128 | peer [16] at 144
                     // ---- policy head Linear(1344 -> A) + softmax (modules.py:99-100) in fp32 on the CUDA cores, while the tensor
                     // pipe runs the value layer: one warp per (board, action) dot product
@@ -886,7 +1034,20 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                         if (lane == 0) scr[b * 9 + a] = acc + __ldg(polb + a);
                     }
                     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
-                    if (et < NB) {
+                    SPX_TT(6);
+                    bool had_w = false;              // ENGINE: game slot `ew` of this CTA was evaluated by this pass
+                    if constexpr (ENGINE) {
+                        had_w = live_w && S.need[ew] != 0;
+                        if (et == 0) mbar_expect_tx(&S.xbar, 32u);   // this pass's exchange: 8 floats from the peer CTA
+                        if (had_w) {   // softmax of board ew by its own warp: the same sequential fp32 arithmetic in every lane
+                            float m = scr[ew * 9];
+                            for (int a = 1; a < n_act; ++a) m = fmaxf(m, scr[ew * 9 + a]);
+                            float z = 0.f;
+                            for (int a = 0; a < n_act; ++a) z += expf(scr[ew * 9 + a] - m);
+                            my_p = lane < n_act ? expf(scr[ew * 9 + lane] - m) / z : 0.f;
+                            if (lane < n_act) policy_out[gbw * n_act + lane] = my_p;
+                        }
+                    } else if (et < NB) {
                         const long long gb = grp * NB + et;
                         if (gb < n_boards && ld_need(gb)) {
                             float m = scr[et * 9];
@@ -902,6 +1063,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                     dphase ^= 1u;
                     tc_fence_after();
                     SPX_TRACE_IF(et == 0, n_layers, 5);
+                    SPX_TT(7);
                     if (part == 0) {
                         const unsigned tl = tmem_base + ((unsigned)(quarter * 32) << 16);
                         unsigned v0[16], v1[16], v2[16], v3[16];
@@ -919,19 +1081,45 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                     }
                     tc_fence_before();
                     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+                    SPX_TT(8);
+                    if constexpr (ENGINE) {
+                        // column c: boards 0..7 of CTA 0, 8..15 of CTA 1; every CTA needs both halves of the hidden layer for ITS boards:
+                        // the half sums of the peer's boards go to the peer (st.async completes the peer's xbar), mine are summed here
+                        if (et < 8) {
+                            const int c = (int)(crank ^ 1u) * 8 + et;
+                            const float tot = (scr[64 + c] + scr[64 + 16 + c]) + (scr[64 + 32 + c] + scr[64 + 48 + c]);
+                            st_async_remote_f32(&S.xval[et], &S.xbar, crank ^ 1u, tot);
+                        }
+                        if (had_w) {
+                            const int c = (int)crank * 8 + ew;
+                            const float mine = (scr[64 + c] + scr[64 + 16 + c]) + (scr[64 + 32 + c] + scr[64 + 48 + c]);
+                            mbar_wait(&S.xbar, (unsigned)pass & 1u);
+                            const float peer = S.xval[ew];
+                            const float lo = crank == 0 ? mine : peer, hi = crank == 0 ? peer : mine;     // hidden 0..127, 128..255
+                            v_next = tanhf((lo + hi) + __ldg(fc_b2));                                     // Linear(256 -> 1) + tanh (modules.py:105)
+                            if (lane == 0) value_out[gbw] = v_next;
+                        }
+                    } else
                     if (et < 16) {   // column c: boards 0..7 of CTA 0, 8..15 of CTA 1; both CTAs need both halves of the hidden layer
                         const float tot = (scr[64 + et] + scr[64 + 16 + et]) + (scr[64 + 32 + et] + scr[64 + 48 + et]);
                         scr[128 + et] = tot;
                         st_shared_remote_f32(&scr[144 + et], crank ^ 1u, tot);
                     }
                     SPX_TRACE_IF(et == 0, n_layers, 6);
+                    SPX_TT(9);
                 }
             } else {
                 (void)dphase;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS));
+            SPX_TT(10);
+            if constexpr (ENGINE) {
+                // every output of this pass is written: the shadow warp may consume them (shadow-all mode)
+                if (shadow_all && et == 0) { __threadfence(); st_volatile_s32(&S.passes_done, pass + 1); }
+            }
         }
         // non-elected lanes of warps 0-2 and warp 3 fall through; ring/phase state persists in the role warps
+        if constexpr (!ENGINE) {
         __syncthreads();   // unit boundary: accumulators drained, buffers reusable
         if constexpr (NCTA == 2) {
             cluster_sync_all();
@@ -944,9 +1132,16 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
             }
             if (fused) cluster_sync_all();   // the scratch may be overwritten by the peer in the next unit only after it was read
         }
+        }
         first_unit = false;
     }
     }   // tick
+    if constexpr (ENGINE) {
+        if (tid == EPI_WARP0 * 32) {
+            st_volatile_s32(&S.quit, 1);                                  // fast mode: the shadow warp stops after the game it is on
+            if (blockIdx.x == 0) atomicAdd(E.ticks, (unsigned long long)n_ticks);
+        }
+    }
 
     if (tid == 0) SPX_TRACE(62, 2);
 #ifdef SPX_DBG_TRACE
@@ -974,14 +1169,20 @@ constexpr int KC = 64;                     // K chunk of the weight pipeline
 constexpr int WS_STRIDE = KC + 8;          // bf16 elements per staged weight row
 constexpr int HEADS_SMEM = HB * XS_STRIDE * 2 + 2 * FC_HIDDEN * WS_STRIDE * 2 + HB * FC_HIDDEN * 4;
 
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+template <bool F16>
+__device__ __forceinline__ void mma_16816(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+    if constexpr (F16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ head_in, const unsigned char* __restrict__ needs,
                                                     long long n_boards, int A, const float* __restrict__ pol_w,
                                                     const float* __restrict__ pol_b, const __nv_bfloat16* __restrict__ w1,
@@ -1045,8 +1246,15 @@ __global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ he
         const int b = i / (FLAT / 4), k4 = (i - b * (FLAT / 4)) * 4;
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b0 + b < n_boards) x = *reinterpret_cast<const float4*>(head_in + (size_t)(b0 + b) * (HEAD_CH * CELLS) + FLAT + k4);
-        __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
-        *reinterpret_cast<uint2*>(xs + b * XS_STRIDE + k4) = make_uint2(*reinterpret_cast<unsigned*>(&lo), *reinterpret_cast<unsigned*>(&hi));
+        unsigned plo, phi;   // the 16-bit type of the tower's weight stream (w1 is stored in it)
+        if constexpr (F16) {
+            __half2 lo = __floats2half2_rn(fminf(x.x, 65504.f), fminf(x.y, 65504.f)), hi = __floats2half2_rn(fminf(x.z, 65504.f), fminf(x.w, 65504.f));
+            plo = *reinterpret_cast<unsigned*>(&lo); phi = *reinterpret_cast<unsigned*>(&hi);
+        } else {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+            plo = *reinterpret_cast<unsigned*>(&lo); phi = *reinterpret_cast<unsigned*>(&hi);
+        }
+        *reinterpret_cast<uint2*>(xs + b * XS_STRIDE + k4) = make_uint2(plo, phi);
     }
     const int r = lane >> 2, kq = (lane & 3) * 2, n0 = warp * 32;
     float acc[4][4];
@@ -1067,7 +1275,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ he
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const __nv_bfloat16* wp = wb + nt * 8 * WS_STRIDE + kk;
-                mma_bf16_16816(acc[nt], a0, a1, a2, a3, *reinterpret_cast<const unsigned*>(wp), *reinterpret_cast<const unsigned*>(wp + 8));
+                mma_16816<F16>(acc[nt], a0, a1, a2, a3, *reinterpret_cast<const unsigned*>(wp), *reinterpret_cast<const unsigned*>(wp + 8));
             }
         }
         __syncthreads();
@@ -1097,7 +1305,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ he
 
 // ================================================================================================== C ABI
 struct spx_tower {
-    int game, num_blocks, n_layers, A, ncta, fused;
+    int game, num_blocks, n_layers, A, ncta, fused, f16;
     size_t off_bias, off_polw, off_polb, off_w1t, off_b1, off_w2, off_b2, blob_bytes;
     unsigned char* blob;    // device copy of the packed weights
     float* head_buf;        // [capacity][64*42] fp32 head-conv activations
@@ -1154,6 +1362,11 @@ int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
         t->ncta = (e && e[0] == '1') ? 1 : 2;
         const char* f = getenv("SPX_TOWER_FUSED_HEADS");   // 1 (default, SM-pair kernel only): FC heads inside the tower kernel; 0: separate heads kernel
         t->fused = (t->ncta == 2 && !(f && f[0] == '0')) ? 1 : 0;
+        // activation / weight type of the conv trunk and the fused value layer: fp16 (default: 11 significant bits, the type the
+        // reference's own GPU path computes in -- torch.cuda.amp.autocast, inference_worker.py:117) or bf16 (SPX_TOWER_DTYPE=bf16).
+        // Same tcgen05 kind::f16 instruction and rate either way; fp16 needs the SM-pair kernel.
+        const char* d = getenv("SPX_TOWER_DTYPE");
+        t->f16 = (t->ncta == 2 && !(d && (d[0] == 'b' || d[0] == 'B'))) ? 1 : 0;
     }
     if (game == SPX_GAME_TICTACTOE && !t->fused) {
         delete t;
@@ -1170,13 +1383,21 @@ int spx_tower_create(int32_t game, int32_t num_blocks, spx_tower** out) {
     SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<2, SPX_GAME_TICTACTOE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<2>)));
     SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<2, SPX_GAME_CONNECT4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<2>)));
     SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<2, SPX_GAME_TICTACTOE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<2>)));
-    SPX_CUDA_T(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM));
+    SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<2, SPX_GAME_CONNECT4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<2>)));
+    SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<2, SPX_GAME_TICTACTOE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<2>)));
+    SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<2, SPX_GAME_CONNECT4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<2>)));
+    SPX_CUDA_T(cudaFuncSetAttribute(tower_kernel<2, SPX_GAME_TICTACTOE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<2>)));
+    SPX_CUDA_T(cudaFuncSetAttribute(heads_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM));
+    SPX_CUDA_T(cudaFuncSetAttribute(heads_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM));
     *out = t;
     return 0;
 }
 
 /* 1 or 2: which weight-slice layout spx_tower_load expects (2 = output channels split across the SM pair) */
 int spx_tower_ncta(spx_tower* t) { return t ? t->ncta : 0; }
+/* 1: the conv trunk and the fused value layer compute in fp16 (default), 0: bf16 -- the type spx_tower_load expects the weight
+ * stream in (nets.pack_tower_blob(dtype=...)) */
+int spx_tower_f16(spx_tower* t) { return t ? t->f16 : 0; }
 /* 1 when the fully connected heads run inside the tower kernel (SM-pair kernel, default), 0 when heads_kernel follows it */
 int spx_tower_fused_heads(spx_tower* t) { return t ? t->fused : 0; }
 
@@ -1219,7 +1440,8 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        auto kern = t->game == SPX_GAME_TICTACTOE ? tower_kernel<2, SPX_GAME_TICTACTOE> : tower_kernel<2, SPX_GAME_CONNECT4>;
+        auto kern = t->f16 ? (t->game == SPX_GAME_TICTACTOE ? tower_kernel<2, SPX_GAME_TICTACTOE, false, true> : tower_kernel<2, SPX_GAME_CONNECT4, false, true>)
+                           : (t->game == SPX_GAME_TICTACTOE ? tower_kernel<2, SPX_GAME_TICTACTOE> : tower_kernel<2, SPX_GAME_CONNECT4>);
         SPX_CUDA_T(cudaLaunchKernelEx(&cfg, kern, (const unsigned long long*)own, (const unsigned long long*)opp, needs_eval,
                                       (long long)n, t->n_layers, (const unsigned char*)t->blob, (const float*)(t->blob + t->off_bias), t->head_buf,
                                       t->fused, (const float*)(t->blob + t->off_polw), (const float*)(t->blob + t->off_polb), (const float*)(t->blob + t->off_b1),
@@ -1237,7 +1459,8 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
         if (e2) SPX_CUDA_T(cudaEventRecord(e2, st));
         return 0;
     }
-    heads_kernel<<<dim3((unsigned)((n + HB - 1) / HB), 2), 256, HEADS_SMEM, st>>>(
+    auto hk = t->f16 ? heads_kernel<true> : heads_kernel<false>;
+    hk<<<dim3((unsigned)((n + HB - 1) / HB), 2), 256, HEADS_SMEM, st>>>(
         t->head_buf, needs_eval, n, t->A, (const float*)(t->blob + t->off_polw), (const float*)(t->blob + t->off_polb),
         (const __nv_bfloat16*)(t->blob + t->off_w1t), (const float*)(t->blob + t->off_b1), (const float*)(t->blob + t->off_w2),
         (const float*)(t->blob + t->off_b2), policy, value);
@@ -1248,6 +1471,7 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
 }
 
 #ifdef SPX_DBG_TRACE
+int spx_debug_tick_trace(long long* host_out) { return (int)cudaMemcpyFromSymbol(host_out, spx::tower::g_tt, sizeof(long long) * 64 * 12); }
 int spx_debug_trace(long long* host_out) { return (int)cudaMemcpyFromSymbol(host_out, spx::tower::g_trace, sizeof(long long) * (64 * 16 + 3 * 160)); }
 #endif
 
@@ -1268,7 +1492,8 @@ int spx_tick_fused(spx_engine* e, spx_tower* t, int32_t n_ticks, float* policy, 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    auto kern = t->game == SPX_GAME_TICTACTOE ? tower_kernel<2, SPX_GAME_TICTACTOE, true> : tower_kernel<2, SPX_GAME_CONNECT4, true>;
+    auto kern = t->f16 ? (t->game == SPX_GAME_TICTACTOE ? tower_kernel<2, SPX_GAME_TICTACTOE, true, true> : tower_kernel<2, SPX_GAME_CONNECT4, true, true>)
+                       : (t->game == SPX_GAME_TICTACTOE ? tower_kernel<2, SPX_GAME_TICTACTOE, true> : tower_kernel<2, SPX_GAME_CONNECT4, true>);
     SPX_CUDA_T(cudaLaunchKernelEx(&cfg, kern, (const unsigned long long*)e->d.leaf_own, (const unsigned long long*)e->d.leaf_opp,
                                   (const unsigned char*)e->d.needs_eval, n, t->n_layers, (const unsigned char*)t->blob,
                                   (const float*)(t->blob + t->off_bias), t->head_buf, 1, (const float*)(t->blob + t->off_polw),

@@ -6,6 +6,7 @@ SelfPlayWorker threads + InferenceProxy queues + InferenceWorker batching
 (selfplayworker.py:95-142, inference_proxy.py:21-24, inference_worker.py:61-119).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -74,6 +75,7 @@ class SelfPlayEngine:
         cfg.emit_records, cfg.max_sims_per_tick, cfg.nodes_per_tree = int(emit_records), max_sims_per_tick, nodes_per_tree
         cfg.move_log, cfg.two_nets, cfg.alpha, cfg.seed = int(move_log), int(two_nets), float(alpha), int(seed)
         cfg.opponent_kind = int(opponent_kind)
+        cfg.reserved0 = int(os.environ.get("SPX_DBG_FLAGS", "0"), 0)   # timing experiments only (csrc/spx_tower.cu)
         cfg.slot_offset = slot_offset
         cfg.slot_stride = n_games if slot_stride is None else slot_stride
         cfg.games_target = (1 << 62) if games_target is None else games_target

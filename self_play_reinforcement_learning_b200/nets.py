@@ -228,7 +228,7 @@ def _fold(conv, bn):
     return w.cpu(), b.cpu()
 
 
-def _stage_blocks(w, ncta=1):
+def _stage_blocks(w, ncta=1, dtype=torch.bfloat16):
     """[N, Cin(multiple of 16), kh, kw] -> bf16 elements in MMA consumption order: tap-major, then 16-channel K
     slices, each slice stored as [2 k-chunks][N][8] (the no-swizzle K-major core-matrix layout).
     ncta=2 (SM-pair kernel): ring stages carry two K slices (one for the 3-channel stem) and every stage is stored as
@@ -237,38 +237,47 @@ def _stage_blocks(w, ncta=1):
     ks = Cin // 16
     if ncta == 1:
         x = w.reshape(N, ks, 2, 8, KH, KW).permute(4, 5, 1, 2, 0, 3).contiguous()
-        return x.to(torch.bfloat16).reshape(-1)
+        return x.to(dtype).reshape(-1)
     per = 2 if ks >= 2 else 1                       # K slices per ring stage
     x = w.reshape(2, N // 2, ks // per, per, 2, 8, KH, KW)   # [h, n, kpair, j, kc, e, kh, kw]
     x = x.permute(6, 7, 2, 0, 3, 4, 1, 5).contiguous()       # [kh, kw, kpair, h, j, kc, n, e]
-    return x.to(torch.bfloat16).reshape(-1)
+    return x.to(dtype).reshape(-1)
 
 
-def _bias_slice(b):
+def _bias_slice(b, dtype=torch.bfloat16):
     """Folded-BN bias [N] -> the first ring stage of its layer in the SM-pair kernel: the B operand of the bias MMA
-    (ones * bias^T), [half][2 k-chunks][N/2][8] bf16 with k = 0 -> bf16(b), k = 1 -> bf16(b - bf16(b)), zeros elsewhere."""
+    (ones * bias^T), [half][2 k-chunks][N/2][8] with k = 0 -> round(b), k = 1 -> round(b - round(b)) in the stream's
+    element type (16 significant bits for bf16, 22 for fp16), zeros elsewhere."""
     N = b.numel()
-    hi = b.float().to(torch.bfloat16)
-    lo = (b.float() - hi.float()).to(torch.bfloat16)
-    x = torch.zeros(2, 2, N // 2, 8, dtype=torch.bfloat16)
+    hi = b.float().to(dtype)
+    lo = (b.float() - hi.float()).to(dtype)
+    x = torch.zeros(2, 2, N // 2, 8, dtype=dtype)
     x[:, 0, :, 0] = hi.reshape(2, N // 2)
     x[:, 0, :, 1] = lo.reshape(2, N // 2)
     return x.reshape(-1)
 
 
-def _fc_stream(w1):
+def _fc_stream(w1, dtype=torch.bfloat16):
     """fc_value.weight [256 hidden, 1344] -> the weight-ring stream of the fused value layer (SM-pair kernel): the hidden
     units are the M rows of the MMA (128 per CTA), so every K step of 16 inputs is stored per CTA half as
     [2 k-chunks][128 hidden][8] bf16 = 4 KB; a ring stage carries two K steps: [stage][half][2 K steps][4 KB]."""
     HID, K = w1.shape
     x = w1.detach().float().cpu().reshape(2, HID // 2, K // 32, 2, 2, 8)    # [half, n, stage, j, kc, e]
-    return x.permute(2, 0, 3, 4, 1, 5).contiguous().to(torch.bfloat16).reshape(-1)   # [stage, half, j, kc, n, e]
+    return x.permute(2, 0, 3, 4, 1, 5).contiguous().to(dtype).reshape(-1)   # [stage, half, j, kc, n, e]
 
 
-def pack_tower_blob(module, ncta=2):
+def pack_tower_blob(module, ncta=2, f16=None):
     """ResidualTower (128 trunk channels; the 7x6 Connect4 or the 3x3 TicTacToe board of ResidualTower.from_env) -> one flat
-    uint8 tensor in the layout spx_tower_load expects (spx_tower.cu: tower_layout)."""
+    uint8 tensor in the layout spx_tower_load expects (spx_tower.cu: tower_layout).  f16: element type of the weight stream the
+    kernel consumes (conv trunk + fused value layer) -- fp16 (True; what spx_tower_create selects unless SPX_TOWER_DTYPE=bf16)
+    or bf16; None = what a tower created now would take."""
     m = module
+    if f16 is None:
+        f16 = ncta == 2 and not os.environ.get("SPX_TOWER_DTYPE", "f16").lower().startswith("b")
+    sdt = torch.float16 if f16 else torch.bfloat16
+    _bs, _sb, _fs = _bias_slice, _stage_blocks, _fc_stream
+    _bias_slice_d = lambda b: _bs(b, sdt)                  # noqa: E731
+    _stage_blocks_d = lambda w, n: _sb(w, n, sdt)          # noqa: E731
 
     def require(ok, what):
         if not ok:
@@ -286,29 +295,29 @@ def pack_tower_blob(module, ncta=2):
     w, b = _fold(m.conv1, m.bn1)
     wp = torch.zeros(128, 16, 3, 3)
     wp[:, :3] = w
-    conv_parts.append(_bias_slice(b))
-    conv_parts.append(_stage_blocks(wp, ncta))
+    conv_parts.append(_bias_slice_d(b))
+    conv_parts.append(_stage_blocks_d(wp, ncta))
     biases[0] = b
     li = 1
     for blk in blocks:
         for conv, bn in ((blk.conv1, blk.bn1), (blk.conv2, blk.bn2)):
             w, b = _fold(conv, bn)
-            conv_parts.append(_bias_slice(b))
-            conv_parts.append(_stage_blocks(w, ncta))
+            conv_parts.append(_bias_slice_d(b))
+            conv_parts.append(_stage_blocks_d(w, ncta))
             biases[li] = b
             li += 1
     wpol, bpol = _fold(m.conv_policy, m.policy_bn)
     wval, bval = _fold(m.conv_value, m.value_bn)
-    conv_parts.append(_bias_slice(torch.cat([bpol, bval])))
-    conv_parts.append(_stage_blocks(torch.cat([wpol, wval], 0), ncta))
+    conv_parts.append(_bias_slice_d(torch.cat([bpol, bval])))
+    conv_parts.append(_stage_blocks_d(torch.cat([wpol, wval], 0), ncta))
     biases[li, :64] = torch.cat([bpol, bval])
-    conv_parts.append(_fc_stream(m.fc_value.weight))
+    conv_parts.append(_fs(m.fc_value.weight, sdt))
     f32 = lambda t: t.detach().float().cpu().contiguous()  # noqa: E731
-    pieces = [torch.cat(conv_parts).view(torch.uint8),
+    pieces = [torch.cat(conv_parts).view(torch.int16).view(torch.uint8),
               biases.reshape(-1).contiguous().view(torch.uint8),
               f32(m.linear_policy.weight).reshape(-1).view(torch.uint8),
               torch.cat([f32(m.linear_policy.bias), torch.zeros(16 - A)]).view(torch.uint8),
-              f32(m.fc_value.weight).to(torch.bfloat16).reshape(-1).view(torch.uint8),
+              f32(m.fc_value.weight).to(sdt).reshape(-1).view(torch.int16).view(torch.uint8),
               f32(m.fc_value.bias).view(torch.uint8),
               f32(m.linear_output.weight).reshape(-1).view(torch.uint8),
               torch.cat([f32(m.linear_output.bias), torch.zeros(3)]).view(torch.uint8)]
@@ -336,11 +345,12 @@ class NativeTower:
         check(lib().spx_tower_create(self.game, self.num_blocks, C.byref(self._h)), "spx_tower_create")
         self.ncta = lib().spx_tower_ncta(self._h)
         self.fused_heads = bool(lib().spx_tower_fused_heads(self._h))
+        self.f16 = bool(lib().spx_tower_f16(self._h))
         self.load(module)
 
     def load(self, module_or_blob):
         """module (packed on the host, then H2D) or an already packed uint8 blob (pinned host or device tensor)."""
-        blob = module_or_blob if torch.is_tensor(module_or_blob) else pack_tower_blob(module_or_blob, self.ncta)
+        blob = module_or_blob if torch.is_tensor(module_or_blob) else pack_tower_blob(module_or_blob, self.ncta, self.f16)
         want = lib().spx_tower_blob_bytes(self.game, self.num_blocks)
         if blob.numel() != want:
             raise ValueError(f"packed weight blob has {blob.numel()} bytes, this tower ({self.num_blocks} blocks) takes {want}")
@@ -517,5 +527,6 @@ def smoke_check():
     with torch.no_grad():
         pr, vr = net.forward(boards)
     torch.cuda.synchronize()
-    assert (p.cpu() - pr).abs().max() < 3e-2 and (v.cpu() - vr.reshape(-1)).abs().max() < 3e-2, "native tower diverges from fp32 torch"
+    tol = 1e-3 if tw.f16 else 8e-3      # two blocks: measured 4e-5 / 1e-4 (fp16), 3e-4 / 7e-4 (bf16)
+    assert (p.cpu() - pr).abs().max() < tol and (v.cpu() - vr.reshape(-1)).abs().max() < tol, "native tower diverges from fp32 torch"
     tw.close()

@@ -85,8 +85,8 @@ class BatchedSelfPlay:
     # ------------------------------------------------------------------ weights
     def packed_weights_pinned(self, module=None):
         """Packed weight blob of ``module`` (default: the construction network) in pinned host memory."""
-        ncta = self.evaluator.tower.ncta if self.net_kind == "tower" else 2
-        blob = nets.pack_tower_blob(module if module is not None else self.network, ncta)
+        tw = self.evaluator.tower if self.net_kind == "tower" else None
+        blob = nets.pack_tower_blob(module if module is not None else self.network, tw.ncta if tw else 2, tw.f16 if tw else None)
         self._pinned = blob.pin_memory()
         return self._pinned
 

@@ -66,9 +66,13 @@ def test_product_package_never_imports_the_oracle():
 
 
 def test_hot_kernels_do_not_spill():
-    """Resource usage of the built library (cuobjdump, no GPU needed): the Connect4 tower kernel must keep its 16-byte stack frame
-    (run-time head sizes once made it spill 712 bytes per thread at the 96-register cap: -4 % throughput, found only in ncu) and
-    the quad env kernel must stay free of local memory."""
+    """Resource usage of the built library (cuobjdump, no GPU needed).
+    * the plain Connect4 tower kernels keep their 16-byte stack frame (run-time head sizes once made them spill 712 bytes per
+      thread at the 96-register cap: -4 % throughput, found only in ncu);
+    * the FUSED TICK kernel -- the product kernel -- holds no per-game state in local memory: round 1 kept `GameState s = *gp`
+      with a dynamically indexed `s.tree[T]` (a 496-byte frame on the select chain).  What is left is the register save area
+      around the non-inlined engine_step call (once per simulation, outside the select loop);
+    * advance_kernel (separate-launch form of the same state machine) and the quad env kernel use no local memory at all."""
     import re
     import shutil
     import subprocess
@@ -81,8 +85,29 @@ def test_hot_kernels_do_not_spill():
     usage = {}
     for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
         usage[m.group(1)] = (int(m.group(2)), int(m.group(3)))
-    tower = [v for k, v in usage.items() if "tower_kernelILi2ELi0ELb0E" in k]
-    env = [v for k, v in usage.items() if "env_step_quad_kernelILi0E" in k]
-    assert tower and env, sorted(usage)
-    assert tower[0][0] <= 96 and tower[0][1] <= 64, tower
-    assert env[0][1] == 0, env
+
+    def find(tag):
+        hit = [v for k, v in usage.items() if tag in k]
+        assert hit, (tag, sorted(usage))
+        return hit[0]
+    for dt in ("Lb0E", "Lb1E"):                                  # bf16 / fp16 instantiations
+        plain = find("tower_kernelILi2ELi0ELb0E" + dt)
+        assert plain[0] <= 96 and plain[1] <= 64, plain
+        fused = find("tower_kernelILi2ELi0ELb1E" + dt)
+        assert fused[0] <= 96 and fused[1] <= 200, fused       # was 496 (round 1); engine_step's own frame is checked below
+    for g in ("ILi0E", "ILi1E"):
+        assert find("advance_kernel" + g)[1] == 0, usage
+    assert find("env_step_quad_kernelILi0E")[1] == 0
+    # engine_step itself (a device function: resource usage is reported with its callers) must not hold an array in local memory:
+    # ptxas -v reports "0 bytes stack frame" for it (build.py prints it with verbose=True); checked here through the SASS: no
+    # local-memory access inside the select loop = between the loop's DSQRT-class MUFU.RSQ64H and its last SHFL.BFLY
+    sass = subprocess.run([tool, "-sass", "-fun", [k for k in usage if "tower_kernelILi2ELi0ELb1ELb1E" in k][0], _lib.LIB_PATH],
+                          capture_output=True, text=True).stdout
+    ins = [(int(m.group(1), 16), m.group(2)) for m in re.finditer(r"/\*([0-9a-f]{4,6})\*/\s+([^;]+);", sass)]
+    # the select loop: sqrt(N + 1) (MUFU.RSQ64H) ... the three argmax butterfly rounds (SHFL.BFLY 0x4, 0x2, 0x1)
+    b4 = [a for a, t in ins if "SHFL.BFLY" in t and ", 0x4," in t]
+    assert b4, "argmax butterflies not found"
+    lo = max(a for a, t in ins if "MUFU.RSQ64H" in t and a < b4[0])
+    hi = max(a for a, t in ins if "SHFL.BFLY" in t and ", 0x1," in t and b4[0] < a < b4[0] + 0x400)
+    assert 0 < hi - lo < 0x1000
+    assert not [t for a, t in ins if lo <= a <= hi and ("LDL" in t or "STL" in t)], "local-memory access inside the PUCT select loop"

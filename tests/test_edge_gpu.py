@@ -76,6 +76,7 @@ def test_overflowing_rings_fail_loudly_on_the_host():
     while not e.all_idle():
         e.run_ticks(e.safe_poll_interval)
         res += len(e.drain_results())
+        e.drain_records()
     assert res == 200 and e.check_overflow()["records_dropped"] == 0
     e.close()
 
