@@ -42,7 +42,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--games", type=int, default=1024, help="concurrent games per GPU")
+    ap.add_argument("--games", type=int, default=None, help="concurrent games per GPU (default: 1024 on one GPU = BASELINE configs[1]; "
+                    "16384 / N on N > 1 GPUs = configs[2])")
+    ap.add_argument("--no-stagger", action="store_true", help="skip the quick-games phase that decorrelates the slots' game phases before warm-up")
+    ap.add_argument("--no-config4", action="store_true", help="skip the configs[3] leg (4096 head-to-head games, 400 sims/move, two towers)")
     ap.add_argument("--sims", type=int, default=800)
     ap.add_argument("--blocks", type=int, default=20)
     ap.add_argument("--net", default="tower", choices=["tower", "torch", "hash"])
@@ -234,11 +237,19 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = {"workload": f"connect4 6x7 self-play, ResidualTower-{args.blocks} random init (seed 0), {args.games} concurrent games/GPU, "
-                            f"{args.sims} sims/move, Dirichlet alpha {args.alpha:g}, two trees per game, finished games replaced immediately",
+    n_gpus = max(world, args.gpus)
+    fixed_total = args.games is None and n_gpus > 1
+    if args.games is None:   # configs[1] on one GPU; configs[2] (16384 concurrent games in total) sharded over N > 1 GPUs
+        args.games = 1024 if n_gpus == 1 else 16384 // n_gpus
+    workload = {"workload": f"connect4 6x7 self-play, ResidualTower-{args.blocks} random init (seed 0), {args.games} concurrent games/GPU"
+                            + (f" ({args.games * n_gpus} in total = BASELINE configs[2])" if n_gpus > 1 else " (BASELINE configs[1])") +
+                            f", {args.sims} sims/move, Dirichlet alpha {args.alpha:g}, two trees per game, finished games replaced immediately, "
+                            "game phases of the slots decorrelated before warm-up",
                 "games_per_gpu": args.games, "sims_per_move": args.sims, "net": args.net, "ticks_per_step": args.ticks_per_step,
-                "l2_policy": "node pools (5.4 GB/GPU) and weights (12.6 MB) are the inputs; the touched working set per step "
-                             "exceeds L2 (126 MB), no flush needed", "parallelism": f"games sharded over {max(world, args.gpus)} GPU(s), no data-path collective"}
+                "l2_policy": f"node pools ({args.games * 2 * 2.7e-3:.1f} GB/GPU) and weights (12.6 MB) are the inputs; the touched working set per step "
+                             "exceeds L2 (126 MB), no flush needed",
+                "parallelism": f"games sharded over {n_gpus} GPU(s), no data-path collective" +
+                               ("; e2e: rank 0 uploads the weights and ncclBroadcast()s them, records are gathered to rank 0 over NCCL every step" if n_gpus > 1 else "")}
     if args.impl == "reference":
         return run_reference(args, workload, json_out)
 
@@ -270,6 +281,10 @@ def main():
 
     fused = args.net == "tower" and not args.no_fused and getattr(ev, "fused_ticks", None) is not None \
         and ev.tower.ncta == 2 and ev.tower.fused_heads and os.environ.get("SPX_FUSED_TICK", "1") != "0"
+    # ---- decorrelate the slots (untimed): a few generations of quick games, so that the timed window sees the steady-state mix
+    # of game phases instead of "all games at ply k" (sims/s drifts with the phase: late plies re-visit terminal nodes for free)
+    if not args.no_stagger:
+        eng.stagger()
     # ---- warm-up (untimed)
     for _ in range(max(args.warmup, 3)):
         eng.run_ticks(T, fused=fused)
@@ -349,10 +364,44 @@ def main():
         t_sims0 = eng.counters()["sims"]
         h2d = d2h = 0
         start2, end2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        coll_ev, gathered = [], 0
+        if world > 1:
+            from self_play_reinforcement_learning_b200 import parallel
+            from self_play_reinforcement_learning_b200.replay import DeviceReplay
+            blob_dev = torch.empty(blob_host.numel(), dtype=torch.uint8, device="cuda")
+            stagebuf = DeviceReplay(0, 16, 16, seed=0)        # only its device staging area is used (drain, no append)
+            dist.broadcast(blob_dev, src=0)                   # untimed: NCCL sets up its channels on the first call of each kind
+            parallel.gather_device_rows(torch.zeros(8, 80, dtype=torch.uint8, device="cuda"), dst=0)
+            barrier()
         start2.record()
         for s in range(args.steps):
-            out = sp.play_step(T, weights_host=blob_host, fused=fused)   # H2D weights, T ticks, D2H records/results/counters
-            h2d += out["h2d_bytes"]; d2h += out["d2h_bytes"]
+            if world == 1:
+                out = sp.play_step(T, weights_host=blob_host, fused=fused)   # H2D weights, T ticks, D2H records/results/counters
+                h2d += out["h2d_bytes"]; d2h += out["d2h_bytes"]
+                continue
+            # N > 1 (north_star): rank 0 uploads the new weights once and ncclBroadcast()s them over NVLink; after the ticks every
+            # rank's records go to rank 0 over NCCL (device to device) and leave the box from there
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            if rank == 0:
+                blob_dev.copy_(blob_host, non_blocking=True); h2d += blob_host.numel()
+            e[0].record()
+            dist.broadcast(blob_dev, src=0)
+            e[1].record()
+            sp.load_weights(blob_dev)
+            eng.run_ticks(T, fused=fused)
+            rows = stagebuf.drain_engine(eng, append=False)
+            res = eng.drain_results(); cnt = eng.counters()
+            d2h += res.nbytes + 80 + 16
+            e[2].record()
+            parts = parallel.gather_device_rows(rows, dst=0)
+            e[3].record()
+            if rank == 0:
+                host = [p.cpu() for p in parts]
+                gathered += sum(int(h.shape[0]) for h in host)
+                d2h += sum(h.numel() for h in host)
+                if s == 0:
+                    _check_gathered(host, world, G)
+            coll_ev.append(e)
         end2.record()
         barrier()
         ms2 = start2.elapsed_time(end2)
@@ -364,6 +413,12 @@ def main():
             ms2, s2 = mx2[0].item(), sm2[1].item()
         e2e = {"value": s2 / (ms2 / 1e3), "unit": "sims/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                "ms_per_step": ms2 / args.steps}
+        if world > 1:
+            bc = sum(e[0].elapsed_time(e[1]) for e in coll_ev) / len(coll_ev)
+            ga = sum(e[2].elapsed_time(e[3]) for e in coll_ev) / len(coll_ev)
+            e2e["collectives_ms"] = {"weight_broadcast": bc, "record_gather": ga, "per": "step", "blob_bytes": int(blob_host.numel()),
+                                     "records_gathered_per_step": gathered / args.steps}
+            e2e["collectives_checked"] = _check_collectives(dist, parallel, blob_dev, rank, world, local_rank)
 
     # ---- search-only legs (hash net): HBM roofline of the search kernel at the workload's G and with 16x more trees
     search = None
@@ -400,6 +455,10 @@ def main():
     env_roof = None
     if rank == 0 and args.net == "tower" and not args.no_aux_rooflines:
         env_roof = _env_roofline(_lib, torch)
+    config4 = None
+    if rank == 0 and world == 1 and args.net == "tower" and not args.no_aux_rooflines and not args.no_config4:
+        sp.close()
+        config4 = _config4_leg(torch, nets, BatchedSelfPlay, args.blocks)
     if rank == 0:
         peaks = _peaks()
         tw = getattr(ev, "tower", None)
@@ -427,14 +486,101 @@ def main():
             cpu = {"value": r["sims_per_s"], "unit": "sims/s", "cores": r["cores"], "kind": r["kind"],
                    "sample": _sample_text(r, args.blocks, args.sims), "positions_per_s": r["positions_per_s"]}
         line = {"metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong" if fixed_total else "weak",   # N > 1 default: 16384 concurrent games in total at every N (configs[2])
+                "vs_baseline": None,
                 "dtype": ("f16" if getattr(getattr(ev, "tower", None), "f16", False) else "bf16") if args.net == "tower" else ("bf16" if args.net == "torch" else "f64"),
                 "data": "synthetic", "config": workload, "positions_per_sec": moves_all / (ms / 1e3), "leaf_evals_per_sec": evals_all / (ms / 1e3),
                 "mean_select_path_len": path, "fused_tick_kernel": bool(fused_tick_ms), "e2e": e2e, "gpu_launches": int(launches1 - launches0), "clocks": clocks,
-                "roofline": roof, "search_roofline": search, "env_roofline": env_roof, "cpu_baseline": cpu}
+                "roofline": roof, "search_roofline": search, "env_roofline": env_roof, "config4_head_to_head": config4, "cpu_baseline": cpu}
         print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _check_gathered(host_parts, world, games_per_rank):
+    """Every gathered record must come from the rank that owns its game (slot sharding, parallel.owner_of_game) and be a
+    well-formed Move: visit distribution sums to 1, |actual_val| <= 1, piece counts of the two sides differ by at most one."""
+    import numpy as np
+    from self_play_reinforcement_learning_b200.engine import RECORD_DTYPE
+    from self_play_reinforcement_learning_b200.parallel import owner_of_game
+    for r, part in enumerate(host_parts):
+        rec = np.frombuffer(part.numpy().tobytes(), dtype=RECORD_DTYPE)
+        if len(rec) == 0:
+            continue
+        own = owner_of_game(rec["game_index"].astype(np.int64), world, games_per_rank)
+        if not (own == r).all():
+            raise SystemExit(f"bench: records gathered from rank {r} belong to other ranks' games")
+        pop = lambda x: np.array([bin(int(v)).count("1") for v in x])   # noqa: E731
+        if not (np.abs(rec["tree_probs"].sum(1) - 1.0) < 1e-4).all() or not (np.abs(rec["actual_val"]) <= 1).all() \
+                or not (np.abs(pop(rec["own"]) - pop(rec["opp"])) <= 1).all() or (rec["own"] & rec["opp"]).any():
+            raise SystemExit(f"bench: malformed record in the gather from rank {r}")
+
+
+def _check_collectives(dist, parallel, blob_dev, rank, world, local_rank):
+    """Outside the timed region, N > 1 only (the driver's 1-GPU box skips the 2-GPU pytest): (1) every rank holds rank 0's
+    weight blob after the broadcast (64-bit checksums all-gathered and compared); (2) records of 8 hash-net games played to
+    the end on every rank with globally sharded game indices, gathered over NCCL, are byte-identical to the same games
+    replayed locally on rank 0 (the engine itself is held against the oracle by tests/)."""
+    import numpy as np
+    import torch
+    from self_play_reinforcement_learning_b200.engine import HashNetEvaluator, SelfPlayEngine, RECORD_DTYPE
+    from self_play_reinforcement_learning_b200.replay import DeviceReplay
+    n8 = blob_dev.numel() // 8
+    words = blob_dev[:n8 * 8].view(torch.int64)
+    ck = (words * (torch.arange(n8, device="cuda", dtype=torch.int64) % 251 + 1)).sum().reshape(1)   # wrapping int64 arithmetic
+    cks = [torch.zeros_like(ck) for _ in range(world)]
+    dist.all_gather(cks, ck)
+    if any(int(c.item()) != int(cks[0].item()) for c in cks):
+        raise SystemExit("bench: weight blob differs between ranks after ncclBroadcast")
+
+    def play(offset):
+        e = SelfPlayEngine(game=0, n_games=8, sims=40, evaluator=HashNetEvaluator(0, 1), seed=11, noise_mode=2,
+                           slot_offset=offset, slot_stride=8 * world, games_target=8 * world)
+        stage = DeviceReplay(0, 16, 16, seed=0)
+        rows = []
+        while True:
+            e.run_ticks(64)
+            rows.append(stage.drain_engine(e, append=False).clone())
+            e.drain_results()
+            if e.all_idle():
+                break
+        e.close()
+        return torch.cat(rows)
+    parts = parallel.gather_device_rows(play(8 * rank), dst=0)
+    if rank == 0:
+        key = lambda a: np.sort(np.frombuffer(a.cpu().numpy().tobytes(), dtype=RECORD_DTYPE), order=["game_index", "tree", "ply"]).tobytes()   # noqa: E731
+        for r in range(1, world):
+            if key(parts[r]) != key(play(8 * r)):
+                raise SystemExit(f"bench: records gathered from rank {r} differ from the same games replayed on rank 0")
+    return {"broadcast_checksum_equal_on_all_ranks": True, "gathered_records_equal_local_replay": True, "ranks": world}
+
+
+def _config4_leg(torch, nets, BatchedSelfPlay, blocks, games=4096, sims=400, ticks=600):
+    """BASELINE configs[3]: elo.py head-to-head evaluation, two random-init ResidualTower nets, 4096 games, 400 sims/move
+    (evaluate mode, no records), both towers native; leaves are partitioned by owning network on the device."""
+    torch.manual_seed(0)
+    a = nets.ResidualTower(7, 6, 7, num_blocks=blocks).eval()
+    torch.manual_seed(1)
+    b = nets.ResidualTower(7, 6, 7, num_blocks=blocks).eval()
+    sp = BatchedSelfPlay(a, game=0, n_games=games, sims=sims, net="tower", evaluation_network=b, evaluate=True, update=False, seed=0)
+    sp.engine.stagger()
+    sp.engine.run_ticks(sims)
+    torch.cuda.synchronize()
+    c0 = sp.engine.counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sp.engine.run_ticks(ticks)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    c1 = sp.engine.counters()
+    out = {"workload": f"{games} head-to-head games, {sims} sims/move, evaluate mode, two native ResidualTower-{blocks}", "ticks": ticks,
+           "sims_per_s": (c1["sims"] - c0["sims"]) / (ms / 1e3), "moves_per_s": (c1["moves"] - c0["moves"]) / (ms / 1e3),
+           "games_per_s": (c1["games_finished"] - c0["games_finished"]) / (ms / 1e3), "ms_per_tick": ms / ticks,
+           "leaf_evals_per_tick": (c1["leaf_evals"] - c0["leaf_evals"]) / ticks}
+    sp.close()
+    return out
 
 
 def _env_roofline(_lib, torch):

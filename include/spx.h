@@ -180,6 +180,9 @@ int64_t spx_device_bytes(spx_engine* e);
 /* (re)start with a new global index for slot 0 and a new games_target (the per-game Policy facade starts every
  * episode this way: one game, then the slot idles) */
 int spx_restart(spx_engine* e, int64_t slot_offset, int64_t games_target, void* stream);
+/* change the simulations per move (MCTreeSearch.iterations, mcts.py:131) for all following launches; at most the value
+ * the engine was created with (the node pool is sized for it).  Searches in progress run on to the new count. */
+int spx_set_sims(spx_engine* e, int32_t sims);
 /* SPX_OPP_EXTERNAL: deliver the opposing player's moves, dev i32[n_games] (-1 = none for that slot).  Replaces
  * opposing_policy(s) + policy.play_action(a, -player) in SelfPlayer.get_and_play_moves (selfplayworker.py:206-224). */
 int spx_set_external_actions(spx_engine* e, const int32_t* actions, void* stream);

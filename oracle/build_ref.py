@@ -20,18 +20,19 @@ REFERENCE_ROOT = "/root/reference"
 REF_DIR = os.path.join(_HERE, "_ref")
 SHIMS = os.path.join(_HERE, "_shims")
 PACKAGES = ("games", "rl_utils")
+SUFFIX = ".refpyc"   # not ".pyc": snapshot tools (the GPU runner among them) drop *.pyc / __pycache__ as build litter
 STAMP = os.path.join(REF_DIR, "BUILT_FROM")
 
 
 def available():
     """True when the staged reference can be imported (this container after build(); the GPU box via the snapshot)."""
-    return os.path.exists(os.path.join(REF_DIR, "games", "algos", "mcts.pyc"))
+    return os.path.exists(os.path.join(REF_DIR, "games", "algos", "mcts" + SUFFIX))
 
 
 def build(force=False):
     if not os.path.isdir(os.path.join(REFERENCE_ROOT, "games")):
         return REF_DIR if available() else None          # GPU box: use what travelled
-    tag = f"{REFERENCE_ROOT} python {sys.version_info[0]}.{sys.version_info[1]} magic {py_compile.importlib.util.MAGIC_NUMBER.hex()}"
+    tag = f"{SUFFIX} {REFERENCE_ROOT} python {sys.version_info[0]}.{sys.version_info[1]} magic {py_compile.importlib.util.MAGIC_NUMBER.hex()}"
     if not force and available() and os.path.exists(STAMP) and open(STAMP).read() == tag:
         return REF_DIR
     shutil.rmtree(REF_DIR, ignore_errors=True)
@@ -42,7 +43,7 @@ def build(force=False):
             rel = os.path.relpath(dirpath, REFERENCE_ROOT)
             for fn in files:
                 if fn.endswith(".py"):
-                    out = os.path.join(REF_DIR, rel, fn[:-3] + ".pyc")
+                    out = os.path.join(REF_DIR, rel, fn[:-3] + SUFFIX)
                     os.makedirs(os.path.dirname(out), exist_ok=True)
                     # dfile: the path shown in tracebacks stays the reference's own
                     py_compile.compile(os.path.join(dirpath, fn), cfile=out, dfile=os.path.join(REFERENCE_ROOT, rel, fn), doraise=True,
@@ -54,7 +55,19 @@ def build(force=False):
 
 
 def import_paths():
-    """sys.path entries (in order) that make `import games.algos.mcts` resolve to the staged reference."""
+    """sys.path entries (in order) that make `import games.algos.mcts` resolve to the staged reference.  Also registers the
+    path hook that loads the staged byte-code files (a sourceless loader for SUFFIX, consulted for oracle/_ref only)."""
+    import importlib.machinery as m
+    if not getattr(import_paths, "_hooked", False):
+        file_hook = m.FileFinder.path_hook((m.SourcelessFileLoader, [SUFFIX]))
+
+        def ref_hook(path):
+            if not os.path.abspath(path).startswith(REF_DIR):
+                raise ImportError("not the staged reference")
+            return file_hook(path)
+        sys.path_hooks.insert(0, ref_hook)
+        sys.path_importer_cache.clear()
+        import_paths._hooked = True
     return [REF_DIR, SHIMS]
 
 

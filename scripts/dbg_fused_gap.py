@@ -17,7 +17,8 @@ torch.manual_seed(0)
 net = nets.ResidualTower(7, 6, 7, num_blocks=20).eval()
 sp = BatchedSelfPlay(net, game=0, n_games=G, sims=800, net="tower", seed=0)
 e, ev = sp.engine, sp.evaluator
-e.run_ticks(3000, chunk=100)
+e.stagger()   # steady-state mix of game phases
+e.run_ticks(1600, chunk=100)
 torch.cuda.synchronize()
 
 
@@ -43,5 +44,6 @@ for rep in range(2):
     c1 = e.counters()
     out["leaves_per_tick"] = (c1["leaf_evals"] - c0["leaf_evals"]) / 3000
     out["sims_per_tick"] = (c1["sims"] - c0["sims"]) / 3000
-    out["tower_back_to_back_ms"] = timed(lambda: tower_only(3000), 3000)
+    if os.environ.get("SPX_GAP_TOWER", "1") != "0":
+        out["tower_back_to_back_ms"] = timed(lambda: tower_only(3000), 3000)
 print(os.environ.get("SPX_DBG_FLAGS", "0"), G, out, flush=True)

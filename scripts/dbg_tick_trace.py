@@ -16,7 +16,8 @@ torch.manual_seed(0)
 net = nets.ResidualTower(7, 6, 7, num_blocks=20).eval()
 sp = BatchedSelfPlay(net, game=0, n_games=G, sims=800, net="tower", seed=0)
 e = sp.engine
-e.run_ticks(4000, chunk=100)
+e.stagger()
+e.run_ticks(2000, chunk=100)
 torch.cuda.synchronize()
 e.run_ticks(100, chunk=100)
 torch.cuda.synchronize()

@@ -54,7 +54,7 @@ EXPORTS = ["spx_last_error", "spx_version", "spx_launch_count", "spx_env_step", 
            "spx_counters_read", "spx_all_idle", "spx_device_bytes", "spx_pending_tree", "spx_tower_blob_bytes",
            "spx_tower_create", "spx_tower_destroy", "spx_tower_ncta", "spx_tower_fused_heads", "spx_tower_f16", "spx_tower_load", "spx_tower_forward", "spx_tower_forward_timed", "spx_partition_leaves", "spx_scatter_outputs", "spx_tttnet_blob_floats", "spx_tttnet_create", "spx_tttnet_destroy",
            "spx_tttnet_load", "spx_tttnet_forward",
-           "spx_advance_timed", "spx_restart", "spx_set_external_actions", "spx_slot_status", "spx_event_create", "spx_event_destroy", "spx_event_elapsed_ms",
+           "spx_advance_timed", "spx_restart", "spx_set_sims", "spx_set_external_actions", "spx_slot_status", "spx_event_create", "spx_event_destroy", "spx_event_elapsed_ms",
            "spx_replay_create", "spx_replay_destroy", "spx_replay_size", "spx_replay_max_size", "spx_replay_change_size", "spx_replay_reset",
            "spx_drain_records_device", "spx_replay_append", "spx_replay_read", "spx_replay_sample", "spx_replay_deduplicate", "spx_replay_unique", "spx_tick_fused"]
 
@@ -91,6 +91,7 @@ def lib():
         L.spx_all_idle.argtypes = [vp, C.POINTER(i32), vp]
         L.spx_pending_tree.argtypes = [vp, vp, vp]
         L.spx_restart.argtypes = [vp, i64, i64, vp]
+        L.spx_set_sims.argtypes = [vp, i32]
         L.spx_set_external_actions.argtypes = [vp, vp, vp]
         L.spx_slot_status.argtypes = [vp, vp, vp]
         L.spx_tower_blob_bytes.restype = C.c_int64

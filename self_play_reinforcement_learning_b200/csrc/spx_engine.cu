@@ -646,6 +646,16 @@ int spx_restart(spx_engine* e, int64_t slot_offset, int64_t games_target, void* 
     return spx_reset(e, stream);
 }
 
+int spx_set_sims(spx_engine* e, int32_t sims) {
+    if (!e) return set_err(SPX_E_ARG, "spx_set_sims: null engine%s", "");
+    const int mm = e->d.cfg.game == SPX_GAME_TICTACTOE ? 9 : 42;
+    // the node pool was sized for the simulations per move the engine was created with (it can never overflow)
+    if (sims < 1 || (long long)(sims + 1) * ((mm + 1) / 2) + mm + 2 > (long long)e->d.nodes_per_tree)
+        return set_err(SPX_E_ARG, "spx_set_sims: sims must be in [1, the value the node pool was sized for]%s", "");
+    e->d.cfg.sims = sims;   // read by the next launch (the config travels by value); searches in progress simply run on to the new count
+    return 0;
+}
+
 __global__ void set_external_kernel(EngineDev E, const int* actions) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < E.cfg.n_games && actions[g] >= 0) E.ext_action[g] = actions[g];

@@ -118,6 +118,28 @@ class SelfPlayEngine:
         check(lib().spx_reset(self._h, _stream_ptr()), "spx_reset")
         self._first = True
 
+    def set_sims(self, sims):
+        """Simulations per move (MCTreeSearch.iterations) for the launches that follow; at most the creation-time value."""
+        check(lib().spx_set_sims(self._h, int(sims)), "spx_set_sims")
+        self.sims = int(sims)
+
+    def stagger(self, generations=3, sims=2):
+        """Decorrelate the slots' game phases: play `generations` rounds of quick games (`sims` simulations per move) so that
+        the slots sit at different plies of different games, then restore the configured simulation count.  Benchmarks call this
+        once before warm-up: all slots otherwise start their first game together and throughput drifts with the game phase
+        (early plies have no terminal nodes, late plies many)."""
+        full = self.sims
+        self.set_sims(min(int(sims), full))
+        max_moves = self.W * self.H
+        # records/results of the quick games are discarded in bounded chunks (the rings must not overflow)
+        ticks, chunk = int(generations * max_moves * (self.sims + 2)), int(max(8, min(512, 2 * self.sims)))
+        done = 0
+        while done < ticks:
+            self.run_ticks(chunk, chunk=chunk)
+            self.drain_records(); self.drain_results()
+            done += chunk
+        self.set_sims(full)
+
     def set_noise_table(self, table, first_game_index=0):
         """table: float64 [n_table_games, 2, table_moves, A] (host array or device tensor)."""
         t = torch.as_tensor(np.ascontiguousarray(table, dtype=np.float64) if not torch.is_tensor(table) else table)
