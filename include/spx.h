@@ -297,6 +297,42 @@ int spx_event_elapsed_ms(void* ev_start, void* ev_end, float* ms_out); /* synchr
 /* spx_advance with events before/after (HBM roofline of the search kernel) */
 int spx_advance_timed(spx_engine* e, const float* policy, const float* value, void* stream, void* ev_start, void* ev_end);
 
+/* ---------------------------------------------------------------- the SGD step on the device
+ * Replaces MCTreeSearch.loss + update_from_memory (mcts.py:234-270) as UpdateWorker.update runs them (updateworker.py:141-149,
+ * network.train(): BatchNorm on batch statistics, Dropout(0.5) on both head activations, general/modules.py:88-107) with
+ * torch.optim.SGD(momentum, weight_decay) (self_play_parallel.py:193) for ResidualTower(7, 6, 7, num_blocks, filter_factor 32)
+ * on Connect4 boards.  Convolutions run on tcgen05 in TF32 (fp32 storage and master weights), everything else in fp32.
+ * Parameter vector = the tensors of ResidualTower.named_parameters() in order, flattened (general/modules.py:42-75); running
+ * statistics = per BatchNorm in module order, running_mean[C] then running_var[C]. */
+typedef struct spx_trainer spx_trainer;
+int spx_train_create(int32_t num_blocks, int32_t batch, spx_trainer** out);
+int spx_train_destroy(spx_trainer* t);
+int64_t spx_train_param_count(spx_trainer* t);
+int64_t spx_train_running_count(spx_trainer* t);
+/* copy parameters / running statistics in (dev pointers, either may be NULL) and rebuild the packed weights;
+ * reset_momentum != 0 clears the momentum buffers (a fresh optimizer) */
+int spx_train_set_state(spx_trainer* t, const float* dev_params, const float* dev_running, int32_t reset_momentum, void* stream);
+/* what: 0 parameters, 1 running statistics, 2 gradients of the last step, 3 momentum buffers -> dev_out */
+int spx_train_get_state(spx_trainer* t, int32_t what, float* dev_out, void* stream);
+/* One update_from_memory step on a batch in device memory: planes f32[B][3][7][6] (modules.py:115-125, as
+ * spx_replay_sample writes them), tree_probs f32[B][7], target f32[B] (actual_val, + q when q_average: mcts.py:243-244),
+ * dropout_mask u8[B][2][1344] keep-masks (policy head, value head) or NULL (drawn from (seed, step)); apply_update 0 =
+ * forward + backward only.  loss_out (dev, 3 floats or NULL): total, value term, policy term. */
+int spx_train_step(spx_trainer* t, const float* planes, const float* tree_probs, const float* target, const uint8_t* dropout_mask,
+                   uint64_t seed, uint64_t step, float lr, float momentum, float weight_decay, int32_t apply_update,
+                   float* loss_out, void* stream);
+/* train-mode network outputs of the last step: probs f32[B][7], value f32[B] (dev, either may be NULL) */
+int spx_train_outputs(spx_trainer* t, float* dev_probs, float* dev_value, void* stream);
+/* test hook: device pointer / size of an internal plane tensor [C/4][rows][4] (rows = 16 + 56 * batch padded to 16 boards;
+ * row = 8 + 56 * board + 7 * col + row_in_col).  which: 0 input, 1 conv output of `layer`, 2 activation of `layer`, 3/4 head conv
+ * output / activation, 5/6 trunk gradient ping-pong, 7 conv-output gradient, 8 head conv-output gradient, 9 head activation
+ * gradient, 10 identity-branch gradient */
+int spx_train_debug_planes(spx_trainer* t, int32_t which, int32_t layer, float** dev_ptr, int64_t* n_floats, int32_t* rows);
+/* test hook: the backward-weights kernel alone on caller-provided bf16 plane tensors [C/8][rows][8] (x 128 channels, dy N channels,
+ * `rows` rows incl. the 16 guard rows); partial_out f32 [S][taps][128 ci][N co]; descriptor strides < 0 = the product's */
+int spx_train_debug_wgrad(const void* x, const void* dy, int32_t N, int32_t taps, int32_t rows, int32_t S, float* partial_out,
+                          int32_t a_lbo, int32_t a_sbo, int32_t b_lbo, int32_t b_sbo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libspx.so")
-SOURCES = ["spx_engine.cu", "spx_tower.cu", "spx_tttnet.cu", "spx_replay.cu"]
+SOURCES = ["spx_engine.cu", "spx_tower.cu", "spx_tttnet.cu", "spx_replay.cu", "spx_train.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
