@@ -459,6 +459,9 @@ def main():
     if rank == 0 and world == 1 and args.net == "tower" and not args.no_aux_rooflines and not args.no_config4:
         sp.close()
         config4 = _config4_leg(torch, nets, BatchedSelfPlay, args.blocks)
+    train_leg = None
+    if rank == 0 and world == 1 and args.net == "tower" and not args.no_aux_rooflines and not args.no_config4:
+        train_leg = _train_leg(torch, nets, args.blocks)
     if rank == 0:
         peaks = _peaks()
         tw = getattr(ev, "tower", None)
@@ -492,7 +495,7 @@ def main():
                 "dtype": ("f16" if getattr(getattr(ev, "tower", None), "f16", False) else "bf16") if args.net == "tower" else ("bf16" if args.net == "torch" else "f64"),
                 "data": "synthetic", "config": workload, "positions_per_sec": moves_all / (ms / 1e3), "leaf_evals_per_sec": evals_all / (ms / 1e3),
                 "mean_select_path_len": path, "fused_tick_kernel": bool(fused_tick_ms), "e2e": e2e, "gpu_launches": int(launches1 - launches0), "clocks": clocks,
-                "roofline": roof, "search_roofline": search, "env_roofline": env_roof, "config4_head_to_head": config4, "cpu_baseline": cpu}
+                "roofline": roof, "search_roofline": search, "env_roofline": env_roof, "config4_head_to_head": config4, "train_step": train_leg, "cpu_baseline": cpu}
         print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -581,6 +584,56 @@ def _config4_leg(torch, nets, BatchedSelfPlay, blocks, games=4096, sims=400, tic
            "leaf_evals_per_tick": (c1["leaf_evals"] - c0["leaf_evals"]) / ticks}
     sp.close()
     return out
+
+
+def _train_leg(torch, nets, blocks, batch=128, steps=100):
+    """BASELINE configs[4]'s training half: UpdateWorker.update = 100 SGD steps of batch 128 (updateworker.py:141-149) with the native
+    step (csrc/spx_train.cu; synthetic batch resident in HBM), next to PyTorch autograd + torch.optim.SGD on the same module
+    (stock settings: TF32 convolutions) for scale."""
+    from self_play_reinforcement_learning_b200.train import DeviceTrainer
+    torch.manual_seed(0)
+    net = nets.ResidualTower(7, 6, 7, num_blocks=blocks).cuda()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    boards = torch.randint(-1, 2, (batch, 7, 6), generator=g, device="cuda")
+    planes = torch.stack([(boards == 0), (boards == 1), (boards == -1)], 1).float()
+    probs = torch.softmax(torch.randn(batch, 7, generator=g, device="cuda"), 1)
+    target = torch.rand(batch, generator=g, device="cuda") * 2 - 1
+    tr = DeviceTrainer(net, batch_size=batch)
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+    l0 = _lib_launches()
+    ms = timed(lambda: tr.step(planes, probs, target), steps)
+    launches = (_lib_launches() - l0) // (steps + 3)
+    loss = tr.step(planes, probs, target).tolist()
+    tr.close()
+    net.train()
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+
+    def torch_step():
+        p, v = net.forward_planes(planes)
+        l = torch.nn.functional.mse_loss(v.view(-1), target) - (p.log() * probs).sum() / batch
+        opt.zero_grad(); l.backward(); opt.step()
+    ms_torch = timed(torch_step, 10)
+    flop = 3 * batch * flop_per_leaf(blocks)     # forward + backward-data + backward-weights
+    return {"workload": f"{steps} SGD steps, batch {batch}, ResidualTower-{blocks}, train mode (batch-statistics BatchNorm, Dropout 0.5), SGD momentum 0.9 wd 1e-4",
+            "ms_per_step": ms, "steps_per_s": 1e3 / ms, "ms_per_100_steps": 100 * ms, "kernels_per_step": int(launches), "tflops": flop / (ms / 1e3) / 1e12,
+            "loss": loss, "dtype": "tf32 (forward, backward-data) / bf16 (backward-weights) tensor-core GEMMs, fp32 elsewhere",
+            "torch_autograd_ms_per_step": ms_torch, "speedup_vs_torch_autograd": ms_torch / ms}
+
+
+def _lib_launches():
+    from self_play_reinforcement_learning_b200 import _lib
+    return int(_lib.lib().spx_launch_count())
 
 
 def _env_roofline(_lib, torch):

@@ -1,0 +1,28 @@
+"""Times the device training step (20 blocks, batch 128) -- run under ncu for the per-kernel launch list."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from self_play_reinforcement_learning_b200 import nets  # noqa: E402
+from self_play_reinforcement_learning_b200.train import DeviceTrainer  # noqa: E402
+from tests import train_ref as R  # noqa: E402
+
+blocks = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 50
+torch.manual_seed(0)
+net = nets.ResidualTower(7, 6, 7, num_blocks=blocks).cuda()
+planes, probs, target, _ = R.make_batch(B)
+tr = DeviceTrainer(net, batch_size=B)
+for _ in range(3):
+    tr.step(planes, probs, target)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(n):
+    tr.step(planes, probs, target)
+b.record()
+torch.cuda.synchronize()
+print("ms per step", a.elapsed_time(b) / n)

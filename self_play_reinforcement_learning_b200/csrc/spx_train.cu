@@ -54,7 +54,7 @@ typedef unsigned long long ull;
 constexpr int CH = 128, HEAD = 64, CELLS = 42, BOARD_ROWS = 56, GUARD = 8, TILE = 128, AROWS = TILE + 2 * GUARD;
 constexpr int FLAT = 32 * CELLS, HID = 256, NA = 7;
 constexpr int PIECE = AROWS * 16;            // bytes of one 4-channel chunk of an activation tile (144 rows x 16 B)
-constexpr int RING_STAGES = 4, STAGE_MAX = 32768;
+constexpr int RING_STAGES = 8, STAGE_MAX = 16384, NC = 64;   // weight ring; output channels per CTA of the conv kernel
 constexpr float BN_EPS = 1e-5f, BN_MOM = 0.1f;
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -136,7 +136,7 @@ struct Seg2 {
 // ------------------------------------------------------------------------------------------------ conv forward / backward-data
 struct ConvP {
     const float* in; int in_chunks;     // planes of the input tensor, K / 4
-    const float* w; int taps, ks_per_tap;   // packed weights [tap][kstep][2 k-chunks][N][4], K / 8 K-steps per tap
+    const float* w; int taps, ks_per_tap;   // packed weights [N / 64 halves][tap][kstep][2 k-chunks][64][4], K / 8 K-steps per tap
     int N;                              // output channels (64 or 128)
     float* out;                         // planes, N / 4 chunks
     Seg2 bias; int has_bias;
@@ -150,15 +150,15 @@ __global__ void __launch_bounds__(256, 1) conv_tf32_kernel(const ConvP p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* atile = smem;
     unsigned char* ring = smem + (CH / 4) * PIECE;
-    ull* bars = reinterpret_cast<ull*>(ring + RING_STAGES * STAGE_MAX);   // full[4] empty[4] abar accbar
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 12);
+    ull* bars = reinterpret_cast<ull*>(ring + RING_STAGES * STAGE_MAX);   // full[8] empty[8] abar accbar
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 20);
     int* realrow = reinterpret_cast<int*>(ring + RING_STAGES * STAGE_MAX + 256);
-    ull* full = bars; ull* empty = bars + 4; ull* abar = bars + 8; ull* accbar = bars + 9;
+    ull* full = bars; ull* empty = bars + RING_STAGES; ull* abar = bars + 2 * RING_STAGES; ull* accbar = abar + 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x, r0 = tile * TILE;      // tile row m <-> global row r0 + GUARD + m; A-tile row a <-> global row r0 + a
-    const int N = p.N;
+    const int N = p.N, n0 = blockIdx.y * NC;            // this CTA computes output channels [n0, n0 + 64)
     const int ks_stage = p.ks_per_tap < 8 ? p.ks_per_tap : 8, stages_per_tap = p.ks_per_tap / ks_stage, total = p.taps * stages_per_tap;
-    const unsigned stage_bytes = (unsigned)(ks_stage * 2 * N * 16);
+    const unsigned stage_bytes = (unsigned)(ks_stage * 2 * NC * 16);
 
     if (tid == 0) {
         for (int i = 0; i < RING_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256, 1) conv_tf32_kernel(const ConvP p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid < TILE) { int b, cell; realrow[tid] = row_real(r0 + GUARD + tid, p.B, b, cell) ? 1 : 0; }
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256, 1) conv_tf32_kernel(const ConvP p) {
         mbar_expect_tx(abar, (unsigned)(p.in_chunks * PIECE));
         for (int c = 0; c < p.in_chunks; ++c)
             tma_bulk_g2s(atile + c * PIECE, p.in + ((size_t)c * p.Rg + r0) * 4, PIECE, abar);
-        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.w);
+        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.w) + (size_t)blockIdx.y * total * stage_bytes;   // this half's slices
         for (int i = 0; i < total; ++i) {
             const int slot = i % RING_STAGES;
             if (i >= RING_STAGES) mbar_wait(&empty[slot], (unsigned)((i / RING_STAGES - 1) & 1));
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256, 1) conv_tf32_kernel(const ConvP p) {
         }
     } else if (warp == 1 && lane == 0) {
         // ---- MMA issuer
-        const unsigned idesc = make_idesc_tf32(TILE, N, false);
+        const unsigned idesc = make_idesc_tf32(TILE, NC, false);
         mbar_wait(abar, 0);
         for (int i = 0; i < total; ++i) {
             const int slot = i % RING_STAGES;
@@ -200,20 +200,21 @@ __global__ void __launch_bounds__(256, 1) conv_tf32_kernel(const ConvP p) {
             for (int ks = 0; ks < ks_stage; ++ks) {
                 const int kk = half * ks_stage + ks;
                 const ull adesc = make_desc(smem_u32(atile) + (unsigned)(2 * kk * PIECE + (GUARD + shift) * 16), PIECE, 128);
-                const ull bdesc = make_desc(smem_u32(ring + slot * STAGE_MAX) + (unsigned)(ks * 2 * N * 16), (unsigned)(N * 16), 128);
+                const ull bdesc = make_desc(smem_u32(ring + slot * STAGE_MAX) + (unsigned)(ks * 2 * NC * 16), (unsigned)(NC * 16), 128);
                 tc_mma_tf32(tmem, adesc, bdesc, idesc, (i | ks) != 0 ? 1u : 0u);
             }
             tc_commit(&empty[slot]);
         }
         tc_commit(accbar);
     } else if (warp >= 4) {
-        // ---- epilogue: TMEM -> shared staging [128 rows][N + 1] (reuses the weight ring once every MMA has retired)
+        // ---- epilogue: TMEM -> shared staging [128 rows][64 + 1] (reuses the weight ring once every MMA has retired)
         const int et = tid - 128;                 // TMEM lane == tile row
         float* st = reinterpret_cast<float*>(ring);
-        const int ld = N + 1;
+        constexpr int ld = NC + 1;
         mbar_wait(accbar, 0);
         tc_fence_after();
-        for (int cg = 0; cg < N / 32; ++cg) {
+#pragma unroll
+        for (int cg = 0; cg < NC / 32; ++cg) {
             float v[32];
             tc_ld32(tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(cg * 32), v);
 #pragma unroll
@@ -221,31 +222,38 @@ __global__ void __launch_bounds__(256, 1) conv_tf32_kernel(const ConvP p) {
         }
         tc_fence_before();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        // pass 1, thread = channel: bias, padding rows -> 0, per-tile BatchNorm sums over the real rows
-        if (et < N) {
-            const float bv = p.has_bias ? *p.bias.at(et) : 0.f;
+        // pass 1, two threads per channel (64 rows each): bias, padding rows -> 0, per-tile BatchNorm sums over the real rows
+        {
+            const int c = et & (NC - 1), hrow = et >> 6;
+            const float bv = p.has_bias ? *p.bias.at(n0 + c) : 0.f;
             float s = 0.f, sq = 0.f;
-            for (int m = 0; m < TILE; ++m) {
-                float v = st[m * ld + et] + bv;
+            for (int m = hrow * 64; m < hrow * 64 + 64; ++m) {
+                float v = st[m * ld + c] + bv;
                 if (!realrow[m]) v = 0.f;
                 else { s += v; sq = fmaf(v, v, sq); }
-                st[m * ld + et] = v;
+                st[m * ld + c] = v;
             }
-            if (p.stat) { p.stat[((size_t)tile * 2) * N + et] = s; p.stat[((size_t)tile * 2 + 1) * N + et] = sq; }
+            float* red = st + TILE * ld;          // [2 row halves][2 stats][64]
+            red[(hrow * 2) * NC + c] = s; red[(hrow * 2 + 1) * NC + c] = sq;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (p.stat && et < NC) {
+            const float* red = st + TILE * ld;
+            p.stat[((size_t)tile * 2) * N + n0 + et] = red[et] + red[2 * NC + et];
+            p.stat[((size_t)tile * 2 + 1) * N + n0 + et] = red[NC + et] + red[3 * NC + et];
+        }
         // pass 2, thread = row: planes out (16 B per row and chunk, coalesced over rows)
-        for (int idx = et; idx < TILE * (N / 4); idx += 128) {
+        for (int idx = et; idx < TILE * (NC / 4); idx += 128) {
             const int m = idx & (TILE - 1), ch = idx >> 7;
             float4 v = make_float4(st[m * ld + 4 * ch], st[m * ld + 4 * ch + 1], st[m * ld + 4 * ch + 2], st[m * ld + 4 * ch + 3]);
-            const size_t o = (size_t)ch * p.Rg + r0 + GUARD + m;
+            const size_t o = (size_t)(n0 / 4 + ch) * p.Rg + r0 + GUARD + m;
             if (p.add && realrow[m]) { const float4 a = reinterpret_cast<const float4*>(p.add)[o]; v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
             reinterpret_cast<float4*>(p.out)[o] = v;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ backward-weights
@@ -375,20 +383,42 @@ __device__ __forceinline__ void store_bf16x4(__nv_bfloat16* planes, int ch, int 
     *reinterpret_cast<uint2*>(planes + ((size_t)(ch >> 1) * Rg + g) * 8 + (ch & 1) * 4) = w;
 }
 
+// The three BatchNorm kernels run on a grid of (row tiles, N / 16) blocks: a block owns 128 rows x 16 channels (4 plane chunks;
+// thread = row x chunk pair), so that a 5376-row tensor is spread over a few hundred blocks instead of 56.
+constexpr int BN_CG = 16;    // channels per block
+
+// per-channel totals of the per-tile partial sums part[tile][2][N] for the block's 16 channels, in fp64 and in a fixed order
+// (8 tile subsets per (stat, channel) pair, then the subsets in order): tot[0][c] / tot[1][c]
+__device__ __forceinline__ void bn_totals(const float* __restrict__ part, int tiles, int N, int c0, double (*tot)[BN_CG]) {
+    __shared__ double sub[8][2 * BN_CG];
+    const int tid = threadIdx.x, cs = tid & 31, subset = tid >> 5, stat = cs >> 4, c = cs & 15;
+    double acc = 0.0;
+    for (int t = subset; t < tiles; t += 8) acc += (double)part[((size_t)t * 2 + stat) * N + c0 + c];
+    sub[subset][cs] = acc;
+    __syncthreads();
+    if (tid < 2 * BN_CG) {
+        double a2 = 0.0;
+        for (int k = 0; k < 8; ++k) a2 += sub[k][tid];
+        tot[tid >> 4][tid & 15] = a2;
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) bn_fwd_kernel(const BnP p) {
-    __shared__ float sc[CH], sh[CH];
-    const int tid = threadIdx.x, N = p.N, r0 = blockIdx.x * TILE;
-    if (tid < N) {
-        double s = 0.0, sq = 0.0;
-        for (int t = 0; t < p.tiles; ++t) { s += (double)p.stat[((size_t)t * 2) * N + tid]; sq += (double)p.stat[((size_t)t * 2 + 1) * N + tid]; }
-        const double mean = s / p.n_real, var = fmax(sq / p.n_real - mean * mean, 0.0);
+    __shared__ double tot[2][BN_CG];
+    __shared__ float sc[BN_CG], sh[BN_CG];
+    const int tid = threadIdx.x, N = p.N, r0 = blockIdx.x * TILE, c0 = blockIdx.y * BN_CG;
+    bn_totals(p.stat, p.tiles, N, c0, tot);
+    if (tid < BN_CG) {
+        const int c = c0 + tid;
+        const double mean = tot[0][tid] / p.n_real, var = fmax(tot[1][tid] / p.n_real - mean * mean, 0.0);
         const float invstd = (float)(1.0 / sqrt(var + (double)BN_EPS));
-        const float gm = *p.gamma.at(tid), bt = *p.beta.at(tid);
+        const float gm = *p.gamma.at(c), bt = *p.beta.at(c);
         sc[tid] = gm * invstd;
         sh[tid] = bt - (float)mean * gm * invstd;
         if (blockIdx.x == 0) {
-            p.mean[tid] = (float)mean; p.invstd[tid] = invstd;
-            float* rm = p.rmean.at(tid); float* rv = p.rvar.at(tid);     // nn.BatchNorm2d: momentum 0.1, unbiased variance in the running estimate
+            p.mean[c] = (float)mean; p.invstd[c] = invstd;
+            float* rm = p.rmean.at(c); float* rv = p.rvar.at(c);     // nn.BatchNorm2d: momentum 0.1, unbiased variance in the running estimate
             *rm = (1.f - BN_MOM) * *rm + BN_MOM * (float)mean;
             *rv = (1.f - BN_MOM) * *rv + BN_MOM * (float)(var * (double)p.n_real / (double)(p.n_real - 1));
         }
@@ -397,13 +427,15 @@ __global__ void __launch_bounds__(256) bn_fwd_kernel(const BnP p) {
     const int m = tid & (TILE - 1), g = r0 + GUARD + m;
     int b, cell;
     const bool real = row_real(g, p.B, b, cell);
-    for (int ch = tid >> 7; ch < N / 4; ch += 2) {
+#pragma unroll
+    for (int k2 = 0; k2 < 2; ++k2) {
+        const int lc = (tid >> 7) + 2 * k2, ch = (c0 >> 2) + lc;      // local / global plane chunk
         const size_t o = (size_t)ch * p.Rg + g;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (real) {
             const float4 y = reinterpret_cast<const float4*>(p.y)[o];
-            v.x = fmaf(y.x, sc[4 * ch], sh[4 * ch]); v.y = fmaf(y.y, sc[4 * ch + 1], sh[4 * ch + 1]);
-            v.z = fmaf(y.z, sc[4 * ch + 2], sh[4 * ch + 2]); v.w = fmaf(y.w, sc[4 * ch + 3], sh[4 * ch + 3]);
+            v.x = fmaf(y.x, sc[4 * lc], sh[4 * lc]); v.y = fmaf(y.y, sc[4 * lc + 1], sh[4 * lc + 1]);
+            v.z = fmaf(y.z, sc[4 * lc + 2], sh[4 * lc + 2]); v.w = fmaf(y.w, sc[4 * lc + 3], sh[4 * lc + 3]);
             if (p.res) { const float4 r = reinterpret_cast<const float4*>(p.res)[o]; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
         }
@@ -412,16 +444,16 @@ __global__ void __launch_bounds__(256) bn_fwd_kernel(const BnP p) {
     }
 }
 
-// dz = g * (a > 0); per-tile sums of dz and dz * xhat per channel
+// dz = g * (a > 0); per-tile sums of dz and dz * xhat per channel (warp shuffles, then the block's 4 warps per chunk pair in order)
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnP p) {
-    __shared__ float acc[2][CH];
-    const int tid = threadIdx.x, N = p.N, r0 = blockIdx.x * TILE, lane = tid & 31;
-    if (tid < CH) { acc[0][tid] = 0.f; acc[1][tid] = 0.f; }
-    __syncthreads();
+    __shared__ float wsum[8][2][8];      // [warp][stat][channel within the warp's two chunks]
+    const int tid = threadIdx.x, N = p.N, r0 = blockIdx.x * TILE, c0 = blockIdx.y * BN_CG, lane = tid & 31, warp = tid >> 5;
     const int m = tid & (TILE - 1), g = r0 + GUARD + m;
     int b, cell;
     const bool real = row_real(g, p.B, b, cell);
-    for (int ch = tid >> 7; ch < N / 4; ch += 2) {
+#pragma unroll
+    for (int k2 = 0; k2 < 2; ++k2) {
+        const int lc = (tid >> 7) + 2 * k2, ch = (c0 >> 2) + lc;
         const size_t o = (size_t)ch * p.Rg + g;
         float d[4] = {0.f, 0.f, 0.f, 0.f}, dx[4] = {0.f, 0.f, 0.f, 0.f};
         if (real) {
@@ -440,30 +472,40 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnP p) {
         }
         if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { atomicAdd(&acc[0][4 * ch + k], d[k]); atomicAdd(&acc[1][4 * ch + k], dx[k]); }
+            for (int k = 0; k < 4; ++k) { wsum[warp][0][4 * k2 + k] = d[k]; wsum[warp][1][4 * k2 + k] = dx[k]; }
         }
     }
     __syncthreads();
-    if (tid < N) { p.part[((size_t)blockIdx.x * 2) * N + tid] = acc[0][tid]; p.part[((size_t)blockIdx.x * 2 + 1) * N + tid] = acc[1][tid]; }
+    if (tid < 2 * BN_CG) {
+        // channel lc4 = local channel 0..15 = chunk lc (0..3) * 4 + k; chunk lc belongs to thread half (lc & 1) and k2 = lc >> 1; warps 4*half .. 4*half + 3
+        const int stat = tid >> 4, lc4 = tid & 15, lc = lc4 >> 2, k = lc4 & 3, half = lc & 1, k2 = lc >> 1;
+        float acc = 0.f;
+        for (int w = 0; w < 4; ++w) acc += wsum[4 * half + w][stat][4 * k2 + k];
+        p.part[((size_t)blockIdx.x * 2 + stat) * N + c0 + lc4] = acc;
+    }
 }
 
 // dy = gamma * invstd * (dz - mean(dz) - xhat * mean(dz * xhat));  dgamma = sum dz * xhat, dbeta = sum dz, dbias = 0 (exactly:
 // a per-channel constant added before training-mode BatchNorm does not change its output)
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnP p) {
-    __shared__ float m1[CH], m2[CH], sc[CH];
-    const int tid = threadIdx.x, N = p.N, r0 = blockIdx.x * TILE;
-    if (tid < N) {
-        double s1 = 0.0, s2 = 0.0;
-        for (int t = 0; t < p.tiles; ++t) { s1 += (double)p.part[((size_t)t * 2) * N + tid]; s2 += (double)p.part[((size_t)t * 2 + 1) * N + tid]; }
-        m1[tid] = (float)(s1 / p.n_real); m2[tid] = (float)(s2 / p.n_real);
-        sc[tid] = *p.gamma.at(tid) * p.invstd[tid];
-        if (blockIdx.x == 0) { *p.dgamma.at(tid) = (float)s2; *p.dbeta.at(tid) = (float)s1; *p.dbias.at(tid) = 0.f; }
+    __shared__ double tot[2][BN_CG];
+    __shared__ float m1[BN_CG], m2[BN_CG], sc[BN_CG], mu[BN_CG], is[BN_CG];
+    const int tid = threadIdx.x, N = p.N, r0 = blockIdx.x * TILE, c0 = blockIdx.y * BN_CG;
+    bn_totals(p.part, p.tiles, N, c0, tot);
+    if (tid < BN_CG) {
+        const int c = c0 + tid;
+        m1[tid] = (float)(tot[0][tid] / p.n_real); m2[tid] = (float)(tot[1][tid] / p.n_real);
+        mu[tid] = p.mean[c]; is[tid] = p.invstd[c];
+        sc[tid] = *p.gamma.at(c) * is[tid];
+        if (blockIdx.x == 0) { *p.dgamma.at(c) = (float)tot[1][tid]; *p.dbeta.at(c) = (float)tot[0][tid]; *p.dbias.at(c) = 0.f; }
     }
     __syncthreads();
     const int m = tid & (TILE - 1), g = r0 + GUARD + m;
     int b, cell;
     const bool real = row_real(g, p.B, b, cell);
-    for (int ch = tid >> 7; ch < N / 4; ch += 2) {
+#pragma unroll
+    for (int k2 = 0; k2 < 2; ++k2) {
+        const int lc = (tid >> 7) + 2 * k2, ch = (c0 >> 2) + lc;
         const size_t o = (size_t)ch * p.Rg + g;
         float4 out = make_float4(0.f, 0.f, 0.f, 0.f), dzv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (real) {
@@ -472,9 +514,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnP p) {
             float r[4], dz[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int c = 4 * ch + k;
+                const int c = 4 * lc + k;
                 dz[k] = av[k] > 0.f ? gv[k] : 0.f;
-                const float xh = (yv[k] - p.mean[c]) * p.invstd[c];
+                const float xh = (yv[k] - mu[c]) * is[c];
                 r[k] = sc[c] * (dz[k] - m1[c] - xh * m2[c]);
             }
             out = make_float4(r[0], r[1], r[2], r[3]);
@@ -647,22 +689,24 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
     p[i] = fmaf(-lr, mm, p[i]);
 }
 
-// conv weights W[co][ci][tap] (two tensors split over co for the fused head conv) -> the two packed forms conv_tf32_kernel reads:
-//   forward  wf[tap][ks][kc][n = co][i]  = W[co][ci = 8 ks + 4 kc + i][tap]           (K = CINP input channels, zero beyond CIN)
-//   backward wb[tap][ks][kc][n = ci][i]  = W[co = 8 ks + 4 kc + i][ci][taps - 1 - tap] (K = COUT, N = CINP; absent for the stem)
+// conv weights W[co][ci][tap] (two tensors split over co for the fused head conv) -> the two packed forms conv_tf32_kernel reads
+// (a CTA computes 64 output channels, so the slices of each half are contiguous):
+//   forward  wf[co / 64][tap][ks][kc][co % 64][i] = W[co][ci = 8 ks + 4 kc + i][tap]             (K = CINP input channels, zero beyond CIN)
+//   backward wb[ci / 64][tap][ks][kc][ci % 64][i] = W[co = 8 ks + 4 kc + i][ci][taps - 1 - tap]   (K = COUT, N = CINP; absent for the stem)
 __global__ void pack_conv_kernel(const float* __restrict__ w0, const float* __restrict__ w1, int split, int COUT, int CIN, int CINP, int taps, float* wf, float* wb) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nf = taps * CINP * COUT;
-    if (i < nf) {
-        const int q = i & 3, n = (i >> 2) % COUT, kc = ((i >> 2) / COUT) & 1, ks = ((i >> 2) / COUT / 2) % (CINP / 8), tap = i / (CINP * COUT);
-        const int ci = 8 * ks + 4 * kc + q, co = n;
+    if (i >= taps * CINP * COUT) return;
+    const int q = i & 3, n64 = (i >> 2) & 63, kc = (i >> 8) & 1;
+    {
+        const int KS = CINP / 8, r = i >> 9, ks = r % KS, tap = (r / KS) % taps, half = r / (KS * taps);
+        const int ci = 8 * ks + 4 * kc + q, co = half * 64 + n64;
         float v = 0.f;
         if (ci < CIN) v = co < split ? w0[((size_t)co * CIN + ci) * taps + tap] : w1[((size_t)(co - split) * CIN + ci) * taps + tap];
         wf[i] = v;
     }
-    if (wb && i < taps * COUT * CINP) {
-        const int q = i & 3, n = (i >> 2) % CINP, kc = ((i >> 2) / CINP) & 1, ks = ((i >> 2) / CINP / 2) % (COUT / 8), tap = i / (COUT * CINP);
-        const int co = 8 * ks + 4 * kc + q, ci = n, t = taps - 1 - tap;
+    if (wb) {
+        const int KS = COUT / 8, r = i >> 9, ks = r % KS, tap = (r / KS) % taps, half = r / (KS * taps);
+        const int co = 8 * ks + 4 * kc + q, ci = half * 64 + n64, t = taps - 1 - tap;
         wb[i] = co < split ? w0[((size_t)co * CIN + ci) * taps + t] : w1[((size_t)(co - split) * CIN + ci) * taps + t];
     }
 }
@@ -865,7 +909,7 @@ static Seg2 seg(float* p) { Seg2 s; s.p0 = p; s.p1 = p; s.split = 1 << 30; retur
 static Seg2 seg2(float* p0, float* p1) { Seg2 s; s.p0 = p0; s.p1 = p1; s.split = 32; return s; }
 
 static void launch_conv(const ConvP& p, int tiles, cudaStream_t st) {
-    conv_tf32_kernel<<<tiles, 256, CONV_SMEM, st>>>(p);
+    conv_tf32_kernel<<<dim3(tiles, p.N / NC), 256, CONV_SMEM, st>>>(p);
     spx::count_launch();
 }
 
@@ -900,7 +944,7 @@ int spx_train_step(spx_trainer* t, const float* planes, const float* tree_probs,
         bp.mean = t->mean + (size_t)l * CH; bp.invstd = t->invstd + (size_t)l * CH;
         bp.a16 = t->a16 + (size_t)l * (CH / 8) * Rg * 8;
         bp.N = CH; bp.B = B; bp.Rg = Rg; bp.tiles = tiles; bp.n_real = t->n_real;
-        bn_fwd_kernel<<<tiles, 256, 0, st>>>(bp);
+        bn_fwd_kernel<<<dim3(tiles, bp.N / BN_CG), 256, 0, st>>>(bp);
         spx::count_launch();
     }
     const float* a_last = t->a + (size_t)(L - 1) * t->plane128;
@@ -914,7 +958,7 @@ int spx_train_step(spx_trainer* t, const float* planes, const float* tree_probs,
         bp.rmean = seg2(t->running + t->pol_rs, t->running + t->val_rs); bp.rvar = seg2(t->running + t->pol_rs + 32, t->running + t->val_rs + 32);
         bp.mean = t->mean + (size_t)L * CH; bp.invstd = t->invstd + (size_t)L * CH;
         bp.N = HEAD; bp.B = B; bp.Rg = Rg; bp.tiles = tiles; bp.n_real = t->n_real;
-        bn_fwd_kernel<<<tiles, 256, 0, st>>>(bp);
+        bn_fwd_kernel<<<dim3(tiles, bp.N / BN_CG), 256, 0, st>>>(bp);
         spx::count_launch();
     }
     HeadP hp; memset(&hp, 0, sizeof(hp));
@@ -937,8 +981,8 @@ int spx_train_step(spx_trainer* t, const float* planes, const float* tree_probs,
         bp.gamma = seg2(P + t->pol_g, P + t->val_g); bp.mean = t->mean + (size_t)L * CH; bp.invstd = t->invstd + (size_t)L * CH;
         bp.dgamma = seg2(G + t->pol_g, G + t->val_g); bp.dbeta = seg2(G + t->pol_be, G + t->val_be); bp.dbias = seg2(G + t->pol_b, G + t->val_b);
         bp.N = HEAD; bp.B = B; bp.Rg = Rg; bp.tiles = tiles; bp.n_real = t->n_real;
-        bn_bwd_reduce_kernel<<<tiles, 256, 0, st>>>(bp);
-        bn_bwd_apply_kernel<<<tiles, 256, 0, st>>>(bp);
+        bn_bwd_reduce_kernel<<<dim3(tiles, bp.N / BN_CG), 256, 0, st>>>(bp);
+        bn_bwd_apply_kernel<<<dim3(tiles, bp.N / BN_CG), 256, 0, st>>>(bp);
         spx::count_launch(); spx::count_launch();
         WgP wp; wp.x = t->a16 + (size_t)(L - 1) * (CH / 8) * Rg * 8; wp.dy = t->dy16; wp.N = HEAD; wp.taps = 1; wp.partial = t->partial; wp.Rg = Rg; wp.nchunks = tiles; wg_default_strides(wp);
         wgrad_kernel<<<dim3(t->S, 1), 256, WG_SMEM, st>>>(wp);
@@ -960,8 +1004,8 @@ int spx_train_step(spx_trainer* t, const float* planes, const float* tree_probs,
         bp.gamma = seg(P + c.gamma); bp.mean = t->mean + (size_t)l * CH; bp.invstd = t->invstd + (size_t)l * CH;
         bp.dgamma = seg(G + c.gamma); bp.dbeta = seg(G + c.beta); bp.dbias = seg(G + c.b);
         bp.N = CH; bp.B = B; bp.Rg = Rg; bp.tiles = tiles; bp.n_real = t->n_real;
-        bn_bwd_reduce_kernel<<<tiles, 256, 0, st>>>(bp);
-        bn_bwd_apply_kernel<<<tiles, 256, 0, st>>>(bp);
+        bn_bwd_reduce_kernel<<<dim3(tiles, bp.N / BN_CG), 256, 0, st>>>(bp);
+        bn_bwd_apply_kernel<<<dim3(tiles, bp.N / BN_CG), 256, 0, st>>>(bp);
         spx::count_launch(); spx::count_launch();
         if (l == 0) {
             const int splits = t->S, rows_per = (t->R + splits - 1) / splits;

@@ -3,8 +3,9 @@ GPU engine -- same epoch structure, same result bookkeeping, same loss, with the
 checkpoint-file weight hand-off replaced by one BatchedSelfPlay per GPU and an NCCL weight broadcast.
 
 Row (f1)/(f2) of SURVEY.md 8: records flow engine -> device replay memory (replay.DeviceReplay, csrc/spx_replay.cu) ->
-sampled training batch without touching the host; the forward/backward itself is PyTorch autograd on rank 0 (the
-reference trains in one UpdateWorker, updateworker.py:141-149) and is not part of the measured hot path.
+sampled training batch -> the hand-written SGD step (train.DeviceTrainer, csrc/spx_train.cu) without touching the host, on
+rank 0 (the reference trains in one UpdateWorker, updateworker.py:141-149).  Networks the native step is not built for
+(filter_factor != 32, other boards) and the host replay memory train with PyTorch autograd (trainer="torch").
 """
 from collections import deque
 
@@ -114,7 +115,7 @@ class SelfPlayScheduler:
                  evaluation_games=150, games_per_gpu=1024, memory_size=200000, batch_size=128, lr=0.01, momentum=0.9,
                  weight_decay=1e-4, updates_per_epoch=100, alpha=1.0, seed=0, net="tower", evaluation_opponent=None,
                  replay="device", max_memory_size=None, memory_step=0, deduplicate=False, save_dir=None, save_memory=True,
-                 lr_patience=15, amp=None):
+                 lr_patience=15, amp=None, trainer="auto"):
         """replay: "device" (records stay in HBM: DeviceReplay) or "host" (reference-style Memory of Move tuples).
         max_memory_size / memory_step: UpdateWorker's staggered buffer growth (updateworker.py:107-109).
         save_dir: as in the reference (self_play_parallel.py:56,263-267): every epoch rank 0 writes
@@ -123,7 +124,10 @@ class SelfPlayScheduler:
         ``train_model(resume_model=, resume_memory=)`` picks up the newest files of the previous run (base_worker.py:26-62).
         (Pickling a full 200 000-record Memory of Move tuples takes about a minute, as it does in the reference;
         ``save_memory=False`` keeps only the model checkpoints.)
-        amp: None = fp32 SGD steps; torch.float16 / torch.bfloat16 run forward/backward under autocast.  The reference's
+        trainer: "device" = the native SGD step (train.DeviceTrainer: TF32 / bf16 tensor-core convolutions, fp32 master weights,
+        momentum buffers on the device), "torch" = PyTorch autograd with torch.optim.SGD, "auto" = "device" whenever the network
+        is one it is built for and the replay memory is on the device.
+        amp (trainer="torch" only): None = fp32 SGD steps; torch.float16 / torch.bfloat16 run forward/backward under autocast.  The reference's
         UpdateWorker trains under torch.cuda.amp.autocast() (fp16, updateworker.py:146-149) and keeps running 100-step rounds
         for as long as the epoch's self-play lasts; here exactly `updates_per_epoch` steps run after the epoch's self-play
         (deliberate: self-play is ~100x faster, so "as long as self-play runs" would mean almost no SGD steps per game) --
@@ -148,6 +152,14 @@ class SelfPlayScheduler:
         self.lr_scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(self.optim, "max", patience=lr_patience, factor=0.5,
                                                                        min_lr=0.00001, cooldown=5)
         self.save_dir, self.save_memory_files, self._recent_memory_file, self.amp = save_dir, save_memory, None, amp
+        from . import train as _train
+        if trainer not in ("auto", "device", "torch"):
+            raise ValueError("trainer must be 'auto', 'device' or 'torch'")
+        can = replay == "device" and _train.supports(network)
+        if trainer == "device" and not can:
+            raise ValueError("trainer='device' needs replay='device' and a ResidualTower(7, 6, 7, filter_factor=32)")
+        self.trainer_kind = "device" if (trainer == "device" or (trainer == "auto" and can)) else "torch"
+        self._trainer, self._momentum, self._weight_decay = None, momentum, weight_decay
         self.start_time = datetime.datetime.now().isoformat()                      # self_play_parallel.py:86
         self.games_played = 0
         self.history = []
@@ -216,6 +228,16 @@ class SelfPlayScheduler:
         """UpdateWorker.update (updateworker.py:141-149): `updates_per_epoch` SGD steps on uniform samples."""
         if self.rank != 0 or self.memory is None or len(self.memory) < self.batch_size:
             return None
+        if self.trainer_kind == "device":
+            from .train import DeviceTrainer
+            if self._trainer is None:     # parameters, running statistics and momentum buffers stay on the device between epochs
+                self._trainer = DeviceTrainer(self.network, batch_size=self.batch_size, lr=self.optim.param_groups[0]["lr"],
+                                              momentum=self._momentum, weight_decay=self._weight_decay, seed=self.seed)
+            loss = None
+            for _ in range(self.updates_per_epoch):
+                loss = self._trainer.step_from_batch(self.memory.sample_batch(self.batch_size), lr=self.optim.param_groups[0]["lr"])
+            self._trainer.store(self.network)     # the module is what the evaluators pack and the checkpoints save
+            return float(loss[0])
         self.network.train()
         last = None
         for _ in range(self.updates_per_epoch):
@@ -270,6 +292,8 @@ class SelfPlayScheduler:
                 if resume_model:
                     dev = next(self.network.parameters()).device
                     checkpoint.load_model(self.network, checkpoint.recent_save_file(self.save_dir, self.start_time, True, "model"), map_location=dev)
+                    if self._trainer is not None:          # the device copies follow the module (a fresh optimizer, as in the reference)
+                        self._trainer.load(self.network, reset_momentum=True)
             except (ValueError, OSError, ImportError, AttributeError) as e:
                 # no earlier run (max() of an empty list), or an unreadable file: the reference logs the exception and goes on
                 # (base_worker.py:31-42)

@@ -122,9 +122,11 @@ def test_scheduler_train_loop_small():
     before = net.linear_output.weight.detach().clone()
     s = SelfPlayScheduler(net, 0, iterations=30, epoch_length=16, initial_games=8, evaluation_games=6, games_per_gpu=16, batch_size=32,
                           updates_per_epoch=5, lr=0.01)
+    assert s.trainer_kind == "device"        # the native SGD step (csrc/spx_train.cu) is the default for the reference's tower
     hist = s.train_model(num_epochs=1)
     assert len(hist) == 1 and hist[0]["memory"] > 16 * 7 and np.isfinite(hist[0]["loss"])
     assert not torch.equal(before, net.linear_output.weight.detach())
+    assert int(net.bn1.num_batches_tracked) == 5 and net.conv1.weight.dtype == torch.float32 and not net.training
     total, bd = s.compare_models()
     assert set(bd) == {"first", "second"} and sum(sum(v.values()) for v in bd.values()) == 16
 
