@@ -46,6 +46,7 @@ def parse():
                     "16384 / N on N > 1 GPUs = configs[2])")
     ap.add_argument("--no-stagger", action="store_true", help="skip the quick-games phase that decorrelates the slots' game phases before warm-up")
     ap.add_argument("--no-config4", action="store_true", help="skip the configs[3] leg (4096 head-to-head games, 400 sims/move, two towers)")
+    ap.add_argument("--no-config5", action="store_true", help="skip the configs[4] leg (one epoch of the full loop: self-play, SGD, weight refresh, evaluation)")
     ap.add_argument("--sims", type=int, default=800)
     ap.add_argument("--blocks", type=int, default=20)
     ap.add_argument("--net", default="tower", choices=["tower", "torch", "hash"])
@@ -462,6 +463,9 @@ def main():
     train_leg = None
     if rank == 0 and world == 1 and args.net == "tower" and not args.no_aux_rooflines and not args.no_config4:
         train_leg = _train_leg(torch, nets, args.blocks)
+    config5 = None
+    if rank == 0 and world == 1 and args.net == "tower" and not args.no_aux_rooflines and not args.no_config5:
+        config5 = _config5_leg(torch, nets, args.blocks, args.sims)
     if rank == 0:
         peaks = _peaks()
         tw = getattr(ev, "tower", None)
@@ -495,7 +499,7 @@ def main():
                 "dtype": ("f16" if getattr(getattr(ev, "tower", None), "f16", False) else "bf16") if args.net == "tower" else ("bf16" if args.net == "torch" else "f64"),
                 "data": "synthetic", "config": workload, "positions_per_sec": moves_all / (ms / 1e3), "leaf_evals_per_sec": evals_all / (ms / 1e3),
                 "mean_select_path_len": path, "fused_tick_kernel": bool(fused_tick_ms), "e2e": e2e, "gpu_launches": int(launches1 - launches0), "clocks": clocks,
-                "roofline": roof, "search_roofline": search, "env_roofline": env_roof, "config4_head_to_head": config4, "train_step": train_leg, "cpu_baseline": cpu}
+                "roofline": roof, "search_roofline": search, "env_roofline": env_roof, "config4_head_to_head": config4, "train_step": train_leg, "config5_epoch": config5, "cpu_baseline": cpu}
         print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -629,6 +633,29 @@ def _train_leg(torch, nets, blocks, batch=128, steps=100):
             "ms_per_step": ms, "steps_per_s": 1e3 / ms, "ms_per_100_steps": 100 * ms, "kernels_per_step": int(launches), "tflops": flop / (ms / 1e3) / 1e12,
             "loss": loss, "dtype": "tf32 (forward, backward-data) / bf16 (backward-weights) tensor-core GEMMs, fp32 elsewhere",
             "torch_autograd_ms_per_step": ms_torch, "speedup_vs_torch_autograd": ms_torch / ms}
+
+
+def _config5_leg(torch, nets, blocks, sims, games=1024):
+    """BASELINE configs[4] on this GPU: ONE epoch of the reference's loop (self_play_parallel.py:213-291) through
+    scheduler.SelfPlayScheduler -- `games` initial games fill the device replay memory, then an epoch of `games` self-play games
+    (records stay on the device), 100 native SGD steps of batch 128, the weight refresh and 128 evaluation games against the
+    hard-coded OneStepLookahead opponent (main.py:66).  Every game phase is bound by the LATENCY of one game (~36 plies x 800
+    ticks), not by throughput; seconds per phase are the scheduler's own (device-synchronised) clock."""
+    from self_play_reinforcement_learning_b200.scheduler import SelfPlayScheduler
+    torch.manual_seed(0)
+    net = nets.ResidualTower(7, 6, 7, num_blocks=blocks).cuda().eval()
+    s = SelfPlayScheduler(net, 0, iterations=sims, epoch_length=games, initial_games=games, evaluation_games=128, games_per_gpu=1024,
+                          batch_size=128, updates_per_epoch=100, evaluation_opponent="lookahead", save_dir=None)
+    import time
+    t0 = time.time()
+    h = s.train_model(num_epochs=1)[0]
+    torch.cuda.synchronize()
+    wall = time.time() - t0
+    sec = h["seconds"]
+    return {"workload": f"{games} initial + {games} self-play games ({sims} sims/move), 100 SGD steps of batch 128 (native step), weight refresh, "
+                        "128 evaluation games vs OneStepLookahead; one GPU", "seconds": sec, "wall_s_incl_initial_games": wall,
+            "records_in_memory": h["memory"], "loss": h["loss"], "evaluation_reward": h["evaluation_reward"], "trainer": s.trainer_kind,
+            "self_play_games_per_s": games / sec["self_play"]}
 
 
 def _lib_launches():

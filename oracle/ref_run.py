@@ -12,6 +12,13 @@ import sys
 import time
 
 
+import ctypes as _C
+
+
+class Pair(_C.Structure):   # live counters of one worker (module level: a spawned child has to unpickle it)
+    _fields_ = [("sims", _C.c_long), ("moves", _C.c_long)]
+
+
 def _worker(idx, shared, blocks, sims, alpha):
     os.environ["CUDA_VISIBLE_DEVICES"] = ""        # mcts.py:18 picks cuda when available: this arm is the HOST-CPU reference
     import tempfile
@@ -61,11 +68,12 @@ def time_reference(seconds, blocks, sims, procs=None, alpha=1.0):
     """`procs` processes (default: every host core) for `seconds`; returns sims/s and positions/s counted live."""
     import ctypes as C
     import multiprocessing as mp
-    ctx = mp.get_context("fork")
+    # spawn, not fork: the GPU arm of bench.py calls this with CUDA already initialised in the parent, and the reference picks its
+    # device at import time (mcts.py:18) -- a forked child would inherit "cuda is available" and die in .to(device); a spawned
+    # child starts clean and hides the GPUs before it imports torch
+    ctx = mp.get_context("spawn")
     procs = procs or len(os.sched_getaffinity(0))
 
-    class Pair(C.Structure):
-        _fields_ = [("sims", C.c_long), ("moves", C.c_long)]
     shared = [ctx.RawValue(Pair) for _ in range(procs)]
     ps = [ctx.Process(target=_worker, args=(i, shared[i], blocks, sims, alpha), daemon=True) for i in range(procs)]
     for p in ps:

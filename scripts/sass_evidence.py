@@ -2,7 +2,7 @@
 """Counts the Blackwell-native SASS mnemonics per kernel of libspx.so (cuobjdump -sass; runs here, no GPU): usage sass_evidence.py <tag>"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1e"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2a"
 lib = os.path.join(ROOT, "self_play_reinforcement_learning_b200", "libspx.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 cols = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "SYNCS", "HMMA", "LDGSTS", "SHFL", "DFMA|DMUL|DADD", "LDG.256|STG.256", "LDL|STL"]
@@ -28,7 +28,8 @@ for ln in sass.splitlines():
         c["LDG.256|STG.256"] += 1
     elif base in ("LDL", "STL"):
         c["LDL|STL"] += 1
-want = ["advance_kernel", "tower_kernel", "heads_kernel", "tttnet_kernel", "env_step_quad_kernel", "env_step_kernel"]
+want = ["advance_kernel", "tower_kernel", "heads_kernel", "tttnet_kernel", "env_step_quad_kernel", "env_step_kernel", "conv_tf32_kernel", "wgrad_kernel",
+        "bn_fwd_kernel", "bn_bwd"]
 lines = [f"# {tag} SASS evidence (cuobjdump -sass libspx.so): Blackwell-native instructions per kernel",
          "# UTCHMMA = tcgen05.mma, UTCBAR = tcgen05.commit, LDTM/STTM = tcgen05.ld/st, UBLKCP = cp.async.bulk (TMA), SYNCS = mbarrier, HMMA = mma.sync, "
          "LDGSTS = cp.async, LDG.256 = 256-bit global access, LDL|STL = local-memory (spill) traffic",

@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1b"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2a"
 launches = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
 rep = os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
 out_dir = os.path.join(ROOT, "profiles")
@@ -26,7 +26,7 @@ for r in rows[1:]:
     agg[r[ik].split("(")[0]].append(v / 1000 if r[iu] == "ns" else v)
 tot = sum(sum(v) for v in agg.values())
 lines = [f"# {tag} ncu launch list summary (gpu__time_duration.sum, --clock-control none; cold-cache serialised launches: compare SHARES)",
-         "# command: python bench.py --steps 1 --warmup 3 --ticks-per-step 40 --fused-chunk 40 --no-cpu-baseline --no-e2e",
+         "# command: python bench.py --steps 1 --warmup 3 --ticks-per-step 40 --fused-chunk 40 --no-cpu-baseline --no-e2e --no-stagger --no-config4",
          "# (tower_kernel<2, 0, true> = the fused tick kernel, 40 ticks per launch; tower_kernel<2, 0, false> + advance_kernel = the 64 instrumented separate ticks)",
          "kernel,launches,mean_us,share"]
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
@@ -79,6 +79,35 @@ if raw_env:   # same metrics for the env kernel (its raw page has its own column
     he, ue = re_[0], re_[1]
     for r in re_[2:]:
         summ.append({w: (r[he.index(w)] + (" " + ue[he.index(w)] if ue[he.index(w)] else "")) for w in want if w in he})
+# the SGD step on the device: launch list of scripts/dbg_train_time.py (all launches of the process: 3 warm + 2 timed steps) and the full
+# capture of the two tcgen05 GEMM kernels
+tl = os.path.join(ROOT, "gpurun_out", f"train_launches_{tag}.csv")
+if os.path.exists(tl):
+    rows_t = [r for r in csv.reader(open(tl)) if len(r) > 5]
+    ht = rows_t[0]
+    jk, jv, ju = ht.index("Kernel Name"), ht.index("Metric Value"), ht.index("Metric Unit")
+    agg_t = collections.defaultdict(list)
+    for r in rows_t[1:]:
+        try:
+            v = float(r[jv].replace(",", ""))
+        except ValueError:
+            continue
+        agg_t[r[jk].split("(")[0]].append(v / 1000 if r[ju] == "ns" else v)
+    tot_t = sum(sum(v) for v in agg_t.values())
+    lt = [f"# {tag} ncu launch list of the device SGD step (python scripts/dbg_train_time.py 20 128 2: ResidualTower-20, batch 128, 5 steps incl. warm-up;",
+          "# gpu__time_duration.sum, --clock-control none; cold-cache serialised launches: compare SHARES)", "kernel,launches,mean_us,share"]
+    for k, v in sorted(agg_t.items(), key=lambda kv: -sum(kv[1])):
+        lt.append(f"{k},{len(v)},{sum(v) / len(v):.2f},{sum(v) / tot_t:.4f}")
+    open(os.path.join(out_dir, f"{tag}_train_launches_summary.csv"), "w").write("\n".join(lt) + "\n")
+    print("\n".join(lt))
+train_rep = os.path.join(ROOT, "gpurun_out", f"prof_train_{tag}.ncu-rep")
+if os.path.exists(train_rep):
+    raw_t = subprocess.run(["ncu", "-i", train_rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    open(os.path.join(out_dir, f"{tag}_ncu_train_raw.csv"), "w").write(raw_t)
+    rt = list(csv.reader(raw_t.splitlines()))
+    hq, uq = rt[0], rt[1]
+    for r in rt[2:]:
+        summ.append({w: (r[hq.index(w)] + (" " + uq[hq.index(w)] if uq[hq.index(w)] else "")) for w in want if w in hq})
 json.dump(summ, open(os.path.join(out_dir, f"{tag}_ncu_kernels.json"), "w"), indent=1)
 tw = [x for x in summ if "tower_kernel" in x["Kernel Name"] and not x.get("ticks_per_launch")]
 tpath = os.path.join(out_dir, "tower_traffic.json")
