@@ -19,7 +19,7 @@ class Cfg(C.Structure):
     _fields_ = [("game", C.c_int), ("sims", C.c_int), ("evaluate", C.c_int), ("strong_play", C.c_int),
                 ("tie_mode", C.c_int), ("noise_mode", C.c_int), ("alpha", C.c_double),
                 ("seed", C.c_uint64), ("game_uid", C.c_uint64),
-                ("noise_table", C.POINTER(C.c_double)), ("table_moves", C.c_int)]
+                ("noise_table", C.POINTER(C.c_double)), ("table_moves", C.c_int), ("threads", C.c_int)]
 
 
 class Record(C.Structure):
@@ -116,8 +116,9 @@ def hashnet_bits(own, opp, A, net_seed=0):
 
 
 def make_cfg(game, sims, seed=0, game_uid=0, evaluate=False, strong_play=False, tie_mode=1, noise_table=None,
-             noise_mode=None, alpha=1.0):
+             noise_mode=None, alpha=1.0, threads=1):
     cfg = Cfg()
+    cfg.threads = threads
     cfg.game, cfg.sims, cfg.evaluate, cfg.strong_play = game, sims, int(evaluate), int(strong_play)
     cfg.tie_mode, cfg.alpha, cfg.seed, cfg.game_uid = tie_mode, alpha, seed, game_uid
     keep = None

@@ -120,17 +120,80 @@ class HashNet:
         return [float(x) for x in p], float(v) * player
 
 
+def _coop_search(mcts, tree, K):
+    """The reference's threaded search (mcts.py:328-331: ThreadPoolExecutor(thread_count) runs `iterations` search_node tasks)
+    under ONE forced, legal interleaving: K real threads run the UNMODIFIED ``MCTreeSearch.search_node``; exactly one of them
+    runs at a time; a worker keeps taking tasks until it blocks inside ``self.network(...)`` (the InferenceProxy round trip),
+    then the next worker runs; when all K have blocked (or run out of tasks) the answers come back and worker 0 resumes, ...
+    Locks (``child_node.lock``, held across the network call) and virtual losses are the reference's own."""
+    import threading
+    N = tree.iterations
+    state = {"next": 0, "cur": 0}
+    turn = [threading.Semaphore(0) for _ in range(K)]
+    back = threading.Semaphore(0)
+    status = ["run"] * K
+    real_net = tree.network
+    errors = []
+
+    class YieldingNet:
+        def __call__(self, *a, **kw):
+            out = real_net(*a, **kw)          # evaluated now, delivered when the worker is resumed
+            k = state["cur"]
+            status[k] = "blocked"
+            back.release()
+            turn[k].acquire()
+            status[k] = "run"
+            return out
+
+    def worker(k):
+        turn[k].acquire()
+        try:
+            while state["next"] < N:
+                CTX.sim = state["next"]
+                CTX.depth = 0
+                state["next"] += 1
+                mcts.MCTreeSearch.search_node(tree)
+        except BaseException as e:       # noqa: BLE001 -- reported by the scheduler thread
+            errors.append(e)
+        status[k] = "done"
+        back.release()
+
+    threads = [threading.Thread(target=worker, args=(k,), daemon=True) for k in range(K)]
+    tree.network = YieldingNet()
+    try:
+        for th in threads:
+            th.start()
+        active = list(range(K))
+        while active:
+            for k in list(active):
+                state["cur"] = k
+                turn[k].release()
+                back.acquire()
+                if status[k] == "done":
+                    active.remove(k)
+    finally:
+        tree.network = real_net
+    if errors:
+        raise errors[0]
+
+
 def _make_tree_class(mcts):
     class TracedTree(mcts.MCTreeSearch):
         """MCTreeSearch that keeps CTX in sync and logs per-move root statistics."""
         tree_id = 0
         move_log = None
+        coop_threads = 1     # > 1: the threaded search under the cooperative schedule of _coop_search
 
         def search(self):
             CTX.tree = self.tree_id
             CTX.ply = int(np.sum(np.abs(self.root_node.state)))
             CTX.sim = -1
             CTX.moves_played = self.moves_played
+            if self.coop_threads > 1:     # search() of mcts.py:323-338 with the executor replaced by the forced schedule
+                self.root_node.add_noise()
+                _coop_search(mcts, self, self.coop_threads)
+                self.root_node.remove_noise()
+                return None
             return super().search()
 
         def search_node(self):
@@ -159,7 +222,7 @@ def _env_cls(game):
 
 
 def run_search(game, sims, seed=0, game_uid=0, tie_mode=1, noise=None, net_seed=0, prefix=(),
-               alpha=1, network=None, strong_play=False):
+               alpha=1, network=None, strong_play=False, threads=1):
     """Fresh MCTreeSearch (root player +1), optional ``prefix`` of (action, player) play_action
     calls, then one ``search()``.  Returns root child n, w, valid, root n, w, q."""
     mcts, _, _, _ = _import_reference()
@@ -170,6 +233,7 @@ def run_search(game, sims, seed=0, game_uid=0, tie_mode=1, noise=None, net_seed=
     with hooked():
         t = Tree(net, _env_cls(game), iterations=sims, thread_count=1, alpha=alpha, strong_play=strong_play)
         t.tree_id = 0
+        t.coop_threads = threads
         for a, pl in prefix:
             t.play_action(a, pl)
         if noise is not None:
@@ -183,7 +247,7 @@ def run_search(game, sims, seed=0, game_uid=0, tie_mode=1, noise=None, net_seed=
 
 
 def run_episode(game, sims, seed=0, game_uid=0, swap_sides=False, evaluate=False, tie_mode=1,
-                noise_table=None, net_seed=0, net_seed_opp=None, alpha=1, strong_play=False):
+                noise_table=None, net_seed=0, net_seed_opp=None, alpha=1, strong_play=False, threads=1):
     """One ``SelfPlayer.play_episode(swap_sides, update=True)`` with two traced trees
     (selfplayworker.py:67-90,172-194).  ``noise_table``: float64 [2][max_moves][A] or None."""
     mcts, SelfPlayer, _, _ = _import_reference()
@@ -201,6 +265,7 @@ def run_episode(game, sims, seed=0, game_uid=0, swap_sides=False, evaluate=False
                      alpha=alpha, strong_play=strong_play)
             t.tree_id = tid
             t.move_log = move_log
+            t.coop_threads = threads
             t.train(False) if hasattr(t.network, "train") else None
             t.evaluate(evaluate)
             trees.append(t)

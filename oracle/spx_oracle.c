@@ -211,6 +211,7 @@ typedef struct {
     uint64_t seed, game_uid;
     const double* noise_table; /* [2][table_moves][A] */
     int table_moves;
+    int threads;    /* <= 1: sequential search; K > 1: K cooperative workers with virtual loss (mcts.py:328-331) */
 } ox_cfg;
 
 typedef struct {
@@ -220,6 +221,7 @@ typedef struct {
     int noise_active;   /* :33 */
     int player, valid;  /* :38,39 */
     int virtual_loss;   /* :43 */
+    int locked;         /* :47 lock.locked() (threaded search only) */
     int parent;         /* index or -1 */
     int first_child;    /* index of A consecutive children or -1 (anytree children) */
     int has_state;
@@ -428,10 +430,106 @@ static void search_node(ox_tree* t, int ply, uint32_t sim) {
     t->path_len_sum += depth;
 }
 
+/* ---- threaded search (mcts.py:328-331: ThreadPoolExecutor(thread_count) runs `iterations` search_node tasks) restated as ONE
+ * legal interleaving of those threads, the cooperative round-robin schedule: worker 0 runs search_node tasks until it blocks in
+ * a network call (a task that needs none -- terminal leaf, or the "all states in use" return -- completes and the worker takes
+ * the next task), then worker 1, ..., worker K-1; the K pending evaluations come back together; worker 0 resumes (create_children,
+ * backup, virtual loss removed, lock released) and runs on, then worker 1, ...  until all tasks are done.  While a worker waits
+ * it holds the lock of the child it expands (mcts.py:358,362), so `valid` is false for it (:86-88), and its virtual losses stay
+ * on the path (:345).  tests/golden/threaded.json holds the unmodified reference run under exactly this schedule. */
+typedef struct {
+    int waiting;                     /* blocked in the network call of `child` */
+    int node_list[OX_MAX_MOVES + 2], depth;
+    int parent, action, child;
+    float probs[OX_MAX_A]; double v; uint8_t valid[OX_MAX_A];
+    int8_t child_state[OX_MAX_CELLS];
+} ox_worker;
+
+/* one search_node task of worker w up to its network call; returns 1 if it blocks there, 0 if the task completed */
+static int worker_run_task(ox_tree* t, ox_worker* w, int ply, uint32_t sim) {
+    int node = t->root;
+    w->depth = 0;
+    for (;;) {
+        w->node_list[w->depth] = node;
+        t->nodes[node].virtual_loss += 1;
+        double scores[OX_MAX_A]; int all_bad = 1;
+        for (int a = 0; a < t->A; ++a) {
+            const ox_node* c = &t->nodes[t->nodes[node].first_child + a];
+            scores[a] = (c->valid && !c->locked) ? node_select_prob(t, c) : -10000000000.0;   /* valid: mcts.py:86-88 */
+            if (!(scores[a] < -100000)) all_bad = 0;
+        }
+        if (all_bad) return 0; /* mcts.py:349-354: the task ends, virtual loss deliberately NOT removed */
+        int best = 0; double best_s = 0;
+        for (int a = 0; a < t->A; ++a) {
+            double noise = t->cfg.tie_mode ? ox_rng_uniform(t->cfg.seed, t->cfg.game_uid, t->tree_id, OX_PURPOSE_TIE, ply, sim, (uint32_t)w->depth, (uint64_t)a) : 0.0;
+            double s = scores[a] + (0.000001 * noise);
+            if (a == 0 || s > best_s) { best = a; best_s = s; }
+        }
+        int child = t->nodes[node].first_child + best;
+        w->depth++;
+        if (t->nodes[child].first_child < 0) { /* is_leaf */
+            t->nodes[child].locked = 1;                                   /* :358 */
+            ox_env env; ox_env_reset(&env, t->cfg.game);                 /* _expand_node :301-321 up to the network call */
+            ox_env_set_state(&env, t->nodes[node].state);
+            int r = 0, done = 0, player = t->nodes[node].player;
+            ox_env_step(&env, best, player, &r, &done);
+            r = r * player;
+            t->path_len_sum += w->depth;
+            if (done) {
+                double v;
+                if (t->cfg.strong_play) {
+                    int num_steps = 1; for (int i = 0; i < t->cells; ++i) num_steps += abs(t->nodes[node].state[i]);
+                    v = (1.18 - ((double)(9 * num_steps) / 350.0)) * (double)r;
+                } else v = (double)r;
+                memcpy(t->nodes[child].state, env.board, (size_t)t->cells); t->nodes[child].has_state = 1;
+                node_backup(t, child, v); t->nodes[child].v = v;
+                t->nodes[child].locked = 0;
+                for (int i = 0; i < w->depth; ++i) t->nodes[w->node_list[i]].virtual_loss -= 1;
+                return 0;
+            }
+            call_network(t, env.board, player, w->probs, &w->v);          /* the answer is consumed when the worker resumes */
+            ox_env_valid_moves(&env, w->valid);
+            memcpy(w->child_state, env.board, (size_t)t->cells);
+            w->parent = node; w->action = best; w->child = child; w->waiting = 1;
+            return 1;
+        }
+        node = child;
+    }
+}
+
+static void worker_resume(ox_tree* t, ox_worker* w) {   /* _expand_node after the network call, backup, unlock, virtual loss removed */
+    create_children(t, w->child, w->probs, w->valid);
+    memcpy(t->nodes[w->child].state, w->child_state, (size_t)t->cells); t->nodes[w->child].has_state = 1;
+    node_backup(t, w->child, w->v); t->nodes[w->child].v = w->v;
+    t->nodes[w->child].locked = 0;
+    for (int i = 0; i < w->depth; ++i) t->nodes[w->node_list[i]].virtual_loss -= 1;
+    w->waiting = 0;
+}
+
+static void search_threaded(ox_tree* t, int ply) {
+    const int K = t->cfg.threads;
+    ox_worker* ws = (ox_worker*)calloc((size_t)K, sizeof(ox_worker));
+    int next_task = 0, any = 1;
+    while (any) {
+        any = 0;
+        for (int k = 0; k < K; ++k) {
+            ox_worker* w = &ws[k];
+            if (w->waiting) { worker_resume(t, w); t->sims_done++; if (g_live) g_live[0]++; }
+            while (!w->waiting && next_task < t->cfg.sims) {
+                const uint32_t sim = (uint32_t)next_task++;
+                if (!worker_run_task(t, w, ply, sim)) { t->sims_done++; if (g_live) g_live[0]++; }
+            }
+            if (w->waiting) any = 1;
+        }
+    }
+    free(ws);
+}
+
 void ox_tree_search(ox_tree* t) { /* mcts.py:323-338 */
     add_noise(t);
     int ply = root_ply(t);
-    for (int i = 0; i < t->cfg.sims; ++i) { search_node(t, ply, (uint32_t)i); t->sims_done++; if (g_live) g_live[0]++; }
+    if (t->cfg.threads > 1) search_threaded(t, ply);
+    else for (int i = 0; i < t->cfg.sims; ++i) { search_node(t, ply, (uint32_t)i); t->sims_done++; if (g_live) g_live[0]++; }
     remove_noise(t);
 }
 

@@ -129,3 +129,43 @@ def test_hardcoded_opponent_episodes_match_reference(golden_dir):
         assert o["reward"] == e["reward"]
         assert [[m["tree"], m["ply"], m["action"]] for m in o["moves"]] == e["moves"]
         assert o["final_state"].tolist() == e["final_state"]
+
+
+def test_threaded_search_matches_reference_under_the_cooperative_schedule(golden_dir):
+    """MCTreeSearch(thread_count=K) behind an InferenceProxy (mcts.py:328-331: virtual loss, per-child locks, the "all states
+    in use" return): the unmodified reference run with its K threads forced into the cooperative round-robin interleaving
+    (oracle/ref_harness._coop_search -> tests/golden/threaded.json) vs the C restatement of that schedule, bit for bit."""
+    with open(os.path.join(golden_dir, "threaded.json")) as f:
+        g = json.load(f)
+    assert len(g["searches"]) >= 10 and len(g["episodes"]) >= 6
+    for c in g["searches"]:
+        noise = np.array([[[unhex(x) for x in c["noise"]]] * 64], np.float64)
+        cfg = ox.make_cfg(c["game"], c["sims"], seed=c["seed"], game_uid=c["game_uid"], noise_table=noise, strong_play=c["strong_play"],
+                          threads=c["threads"])
+        t = ox.Tree(cfg, hash_seed=c["net_seed"])
+        t.reset(1)
+        for a, _pl in c["prefix"]:
+            t.play_action(a)
+        t.search()
+        o = t.root_stats()
+        assert o["n"].tolist() == c["n"], c["name"]
+        assert o["w"].tolist() == [unhex(x) for x in c["w"]], c["name"]
+        assert o["root_n"] == c["root_n"] and o["root_w"] == unhex(c["root_w"]) and o["q"] == unhex(c["q"]), c["name"]
+    for e in g["episodes"]:
+        table = np.array([[[unhex(x) for x in row] for row in t] for t in e["noise_table"]], np.float64)
+        cfg = ox.make_cfg(e["game"], e["sims"], seed=e["seed"], game_uid=e["game_uid"], evaluate=e["evaluate"], noise_table=table,
+                          threads=e["threads"])
+        o = ox.play_episode(cfg, e["swap"], net_seed=e["net_seed"], net_seed_opp=e["net_seed_opp"])
+        assert o["reward"] == e["reward"] and len(o["moves"]) == len(e["moves"])
+        for a, b in zip(o["moves"], e["moves"]):
+            assert (a["tree"], a["ply"], a["action"], a["root_n"]) == (b["tree"], b["ply"], b["action"], b["root_n"])
+            assert a["n"] == b["n"] and a["w"] == [unhex(x) for x in b["w"]] and a["root_w"] == unhex(b["root_w"])
+        assert len(o["records"]) == len(e["records"])
+        for a, b in zip(o["records"], e["records"]):
+            assert a["state"].tolist() == b["state"] and a["actual_val"] == b["actual_val"] and a["q"] == np.float32(unhex(b["q"]))
+            got, want = a["tree_probs"], np.array([unhex(x) for x in b["tree_probs"]], np.float32)
+            if e["evaluate"]:
+                assert np.all(np.abs(got - want) <= np.spacing(np.maximum(np.abs(want), np.float32(1e-30))))
+            else:
+                assert np.array_equal(got, want)
+        assert o["final_state"].tolist() == e["final_state"]
