@@ -52,7 +52,7 @@ extern "C" {
 typedef struct spx_engine spx_engine;
 
 /* Mirrors MCTreeSearch.__init__ kwargs (mcts.py:119-136), MCNode constants x=0.25, cpuct=4
- * (mcts.py:24-26) are fixed.  thread_count is always 1 (sequential search: the parity target). */
+ * (mcts.py:24-26) are fixed.  thread_count = search_threads (default 1: the sequential search). */
 typedef struct spx_config {
     int32_t game;              /* SPX_GAME_*                                                        */
     int32_t n_games;           /* concurrent game slots on this device (two trees per game)         */
@@ -75,6 +75,11 @@ typedef struct spx_config {
     int64_t games_target;      /* games with index < target are played, then the slot idles         */
     int64_t record_capacity;   /* Move records buffered on device between drains                    */
     int64_t result_capacity;   /* game results buffered on device between drains                    */
+    int32_t search_threads;    /* MCTreeSearch(thread_count=K) behind an InferenceProxy, mcts.py:132,328-331: 0/1 = the
+                                * sequential search; K in 2..16 = K search_node tasks in flight per tree with virtual loss and
+                                * per-child locks, under the cooperative round-robin schedule.  The leaf batch
+                                * then has n_games * K slots (slot of worker k of game g = g * K + k).                  */
+    int32_t reserved1;
 } spx_config;
 
 /* One Move record (mcts.py:17,282-289 + :230): state in the tree's own frame, tree_probs, q, and

@@ -22,7 +22,7 @@ class Config(C.Structure):
                 ("move_log", C.c_int32), ("two_nets", C.c_int32), ("opponent_kind", C.c_int32), ("reserved0", C.c_int32),
                 ("alpha", C.c_double), ("seed", C.c_uint64),
                 ("slot_offset", C.c_int64), ("slot_stride", C.c_int64), ("games_target", C.c_int64),
-                ("record_capacity", C.c_int64), ("result_capacity", C.c_int64)]
+                ("record_capacity", C.c_int64), ("result_capacity", C.c_int64), ("search_threads", C.c_int32), ("reserved1", C.c_int32)]
 
 
 class Record(C.Structure):

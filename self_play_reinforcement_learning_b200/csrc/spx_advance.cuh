@@ -21,12 +21,13 @@ template <int GAME> struct NodeLayout {
     static constexpr int OFF_OWN = 20 * A + 4;
     static constexpr int OFF_OPP = OFF_OWN + 8;
     static constexpr int SIZE = ((OFF_OPP + 8 + 31) / 32) * 32;
+    static constexpr int VLS = A <= 8 ? 8 : 16;   // entries per node of the virtual-loss side array (threaded search)
     static_assert(OFF_OWN % 8 == 0, "bitboards must be 8-byte aligned");
 };
 
 enum { CHILD_UNEXPANDED = -1, CHILD_TERM_DRAW = -2, CHILD_TERM_WIN = -3 };
 enum { PH_IDLE = 0, PH_RESET = 1, PH_SEARCH = 2, PH_REROOT = 3, PH_ENVSTEP = 4 };
-enum { PK_NONE = 0, PK_ROOT = 1, PK_EXPAND = 2, PK_REROOT = 3 };
+enum { PK_NONE = 0, PK_ROOT = 1, PK_EXPAND = 2, PK_REROOT = 3, PK_THREADS = 4 };   // PK_THREADS: the pending evaluations are the workers' (threaded search)
 #define SPX_MAX_PATH 64
 #define SPX_MAX_OWN_MOVES 22
 #define SPX_MAX_PLIES 44
@@ -46,15 +47,29 @@ struct alignas(16) GameState {
     int pend_depth, pend_parent_player, leaf_waiting, pad1;                      //  48  leaf_waiting: emitted, not yet evaluated
     u64 pend_own, pend_opp;                                                      //  64  its child state, TREE frame
     u64 env_own, env_opp;                                                        //  80  env frame: own = +1 = the policy (tree 0)
-    u64 game_index, pad2;                                                        //  96
+    u64 game_index; int root_vl[2];                                              //  96  root_vl: MCNode.virtual_loss of the two roots (threaded search)
     TreeState tree[2];                                                           // 112
     u64 cnt_sims, cnt_evals, cnt_term, cnt_path, cnt_moves, cnt_games, cnt_nodes, cnt_err;   // 176 (updated with RED.ADD)
 };
 static_assert(sizeof(TreeState) == 32 && sizeof(GameState) == 240, "GameState layout");
 
+// One worker thread of the threaded search (MCTreeSearch(thread_count = K), mcts.py:328-331): idle, or blocked in the network
+// call of the child (parent, action) it expands -- whose lock it holds -- with its select path in wpaths[g][k][].
+struct alignas(16) Worker {
+    int kind, parent, action, depth;      // kind: PK_NONE idle / PK_EXPAND waiting for its evaluation
+    int pplayer, pad0, pad1, pad2;
+    u64 own, opp;                         // the child's state, tree frame
+};
+static_assert(sizeof(Worker) == 48, "Worker layout");
+#define SPX_LOCK_SHIFT 17                 // node meta: bits 0..8 valid moves, bit 16 player, bits 17..25 "child is locked" (mcts.py:47,86-88)
+
 struct EngineDev {
     spx_config cfg;
     int nodes_per_tree;
+    int K;                 // leaf slots per game: 1, or cfg.search_threads (slot of worker k of game g = g * K + k)
+    Worker* workers;       // [G][K]                       (K > 1)
+    unsigned* wpaths;      // [G][K][SPX_MAX_PATH]         (K > 1)
+    unsigned short* vlpool;  // [G][2][nodes_per_tree][8 or 16]: MCNode.virtual_loss of a node's children (K > 1)
     GameState* games;
     char* pool;
     unsigned* paths;       // [G][SPX_MAX_PATH]  node<<4 | action
@@ -171,9 +186,11 @@ template <int GAME> struct Ctx {
     const EngineDev& E;
     int g, lane;
     char* tbase;  // node pool of the tree currently worked on
-    __device__ Ctx(const EngineDev& e, int g_, int lane_) : E(e), g(g_), lane(lane_), tbase(nullptr) {}
+    unsigned short* vbase;   // its virtual-loss side array (threaded search only)
+    __device__ Ctx(const EngineDev& e, int g_, int lane_) : E(e), g(g_), lane(lane_), tbase(nullptr), vbase(nullptr) {}
     __device__ __forceinline__ void use_tree(int t) {
         tbase = E.pool + ((size_t)g * 2 + t) * (size_t)E.nodes_per_tree * L::SIZE;
+        if (E.vlpool) vbase = E.vlpool + ((size_t)g * 2 + t) * (size_t)E.nodes_per_tree * L::VLS;
     }
     __device__ __forceinline__ char* node(int idx) const { return tbase + (size_t)idx * L::SIZE; }
 };
@@ -227,6 +244,7 @@ __device__ __forceinline__ int alloc_node(const Ctx<GAME>& c, TreeState& ts, u64
         *(u64*)(nd + L::OFF_OWN) = own;
         *(u64*)(nd + L::OFF_OPP) = opp;
     }
+    if (c.vbase && c.lane < L::VLS) c.vbase[(size_t)idx * L::VLS + c.lane] = 0;   // fresh MCNodes: virtual_loss = 0 (mcts.py:43)
     return idx;
 }
 
@@ -269,6 +287,174 @@ __device__ __forceinline__ AdvPre advance_prefetch(const EngineDev& E, const int
     return r;
 }
 
+// ------------------------------------------------------------------------------------------------ threaded search, one tick
+// MCTreeSearch.search with thread_count = K behind an InferenceProxy (mcts.py:328-331) under the cooperative round-robin schedule
+// (tests/golden/threaded.json holds the unmodified reference forced into it): worker k
+// resumes with the evaluation it was blocked on (create_children, backup, virtual loss removed, lock released), then runs
+// search_node tasks until it blocks in the next network call; tasks that need none (terminal leaf, "all states in use") complete
+// on the spot.  select_prob sees the other workers' virtual losses ((w - vl) / (n + vl), sqrt(parent.n + parent.vl), 1 + n + vl:
+// mcts.py:59-78) and skips locked children (:86-88).  Leaf of worker k -> leaf slot g * K + k.  Returns true when every task
+// has run and no worker is waiting.  One warp; `ts` / `root_vl` are the searching tree's state (registers of the caller).
+template <int GAME>
+__device__ __noinline__ bool search_round_threaded(const EngineDev& E, Ctx<GAME>& c, GameState* gp, const int g, const int lane, const int T,
+                                                   TreeState& ts, int& root_vl, int& sims_started, const u64 game_index, const int ply,
+                                                   const double my_noise, const float* __restrict__ policy_in, const float* __restrict__ value_in) {
+    typedef Rules<GAME> R;
+    typedef NodeLayout<GAME> L;
+    typedef unsigned long long ull;
+    constexpr int A = R::A;
+    const spx_config& cfg = E.cfg;
+    const int K = E.K, ls = g * K;
+    const u64 tie_pre = rng_prefix(cfg.seed, game_index, T, PURPOSE_TIE, ply);
+    unsigned short* vlp = c.vbase;
+    auto count = [&](u64* counter, const int by) { if (lane == 0 && by) atomicAdd((ull*)counter, (ull)by); };
+    // virtual loss of the nodes of a finished task's node_list: the root and the inner nodes (children reached by edges 0 .. depth-2)
+    auto remove_vl = [&](const unsigned p0, const unsigned p1, const int depth) {
+        root_vl -= 1;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int d = lane + 32 * half;
+            if (d < depth - 1) {
+                const unsigned e = half ? p1 : p0;
+                unsigned short* pv = vlp + (size_t)(e >> 4) * L::VLS + (e & 15u);
+                *pv = (unsigned short)(*pv - 1);
+            }
+        }
+    };
+    int waiting = 0;
+    for (int k = 0; k < K; ++k) {
+        Worker* wk = E.workers + (size_t)ls + k;
+        unsigned* wp = E.wpaths + ((size_t)ls + k) * SPX_MAX_PATH;
+        if (wk->kind == PK_EXPAND) {
+            // ---- resume: _expand_node after the network call (mcts.py:316-320), backup, remove_virtual_loss, lock.release (:360-364)
+            const int parent = wk->parent, action = wk->action, depth = wk->depth, pplayer = wk->pplayer;
+            const u64 own = wk->own, opp = wk->opp;
+            const float my_p = lane < A ? policy_in[((size_t)ls + k) * A + lane] : 0.f;
+            const double v = __dmul_rn((double)value_in[ls + k], (double)pplayer);
+            const int idx = alloc_node<GAME>(c, ts, own, opp, -pplayer, my_p);
+            if (idx < 0) count(&gp->cnt_err, 1);
+            count(&gp->cnt_nodes, 1);
+            if (lane == 0) {
+                char* pn = c.node(parent);
+                if (idx >= 0) ((int*)(pn + L::OFF_CHILD))[action] = idx;
+                *(unsigned*)(pn + L::OFF_META) &= ~(1u << (SPX_LOCK_SHIFT + action));
+                wk->kind = PK_NONE;
+            }
+            const unsigned p0 = lane < depth ? wp[lane] : 0u, p1 = lane + 32 < depth ? wp[lane + 32] : 0u;
+            __syncwarp();
+            backup_path<GAME>(c, p0, p1, depth, v, ts);
+            remove_vl(p0, p1, depth);
+            __syncwarp();
+        }
+        bool blocked = false;
+        while (!blocked && sims_started < cfg.sims) {
+            const int sim = sims_started++;
+            // ---------------- search_node (mcts.py:340-367) with virtual loss
+            int node = ts.root, N = ts.root_n, player = ts.root_player, depth = 0;
+            root_vl += 1;
+            int VL = root_vl;
+            unsigned p0 = 0, p1 = 0;
+            int child = 0, act = 0;
+            bool all_bad = false;
+            unsigned meta_u = 0;
+            for (;;) {
+                const char* nd = c.node(node);
+                double score = -INFINITY, w = 0.0;
+                int ch = 0, n = 0, vl = 0;
+                float p = 0.f;
+                unsigned meta = 0;
+                if (lane < A) {
+                    w = ((const double*)(nd + L::OFF_W))[lane];
+                    n = ((const int*)(nd + L::OFF_N))[lane];
+                    p = ((const float*)(nd + L::OFF_P))[lane];
+                    ch = ((const int*)(nd + L::OFF_CHILD))[lane];
+                    meta = *(const unsigned*)(nd + L::OFF_META);
+                    vl = (int)vlp[(size_t)node * L::VLS + lane];
+                }
+                const double sqrt_n = __dsqrt_rn((double)(N + VL));
+                const double tie = cfg.tie_mode ? __dmul_rn(0.000001, rng_uniform_from(tie_pre, (unsigned)sim, (unsigned)depth, (u64)lane)) : 0.0;
+                bool ok = false;
+                if (lane < A) {
+                    ok = ((meta >> lane) & 1u) && !((meta >> (SPX_LOCK_SHIFT + lane)) & 1u);                 // valid: :86-88
+                    if (ok) {
+                        const int n_eff = n + vl;
+                        const double q = n_eff ? __ddiv_rn(__dsub_rn(w, (double)vl), (double)n_eff) : 0.0;      // :59-62
+                        double p_eff = (double)p;
+                        if (depth == 0) p_eff = __dadd_rn(__dmul_rn(my_noise, 0.25), __dmul_rn((double)p, 0.75));
+                        const double u = __ddiv_rn(__dmul_rn(__dmul_rn(4.0, p_eff), sqrt_n), (double)(1 + n + vl));   // :71-78
+                        score = __dadd_rn(__dmul_rn((double)player, q), u);
+                    } else score = -10000000000.0;
+                }
+                if (!__ballot_sync(0xffffffffu, lane < A && !(score < -100000.0))) { all_bad = true; break; }   // :349-354 "all states in use"
+                if (lane < A && cfg.tie_mode) score = __dadd_rn(score, tie);
+                int best = lane;
+                double bs = score;
+#pragma unroll
+                for (int off = (A <= 8 ? 4 : 8); off > 0; off >>= 1) {
+                    const double os = __shfl_xor_sync(0xffffffffu, bs, off);
+                    const int ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    if (os > bs || (os == bs && ob < best)) { bs = os; best = ob; }
+                }
+                best = __shfl_sync(0xffffffffu, best, 0);
+                child = __shfl_sync(0xffffffffu, ch, best);
+                const int n_edge = __shfl_sync(0xffffffffu, n, best), vl_edge = __shfl_sync(0xffffffffu, vl, best);
+                meta_u = __shfl_sync(0xffffffffu, meta, 0);
+                const unsigned entry = ((unsigned)node << 4) | (unsigned)best;
+                if (lane == (depth & 31)) { if (depth < 32) p0 = entry; else p1 = entry; }
+                depth += 1;
+                act = best;
+                if (child < 0 || depth >= SPX_MAX_PATH) break;
+                // descend: the child joins node_list, its virtual loss goes up before ITS children are scored (:344-345)
+                if (lane == 0) vlp[(size_t)node * L::VLS + best] = (unsigned short)(vl_edge + 1);
+                __syncwarp();
+                node = child; N = n_edge; VL = vl_edge + 1; player = -player;
+            }
+            if (all_bad) { count(&gp->cnt_sims, 1); continue; }   // the task is over; its virtual losses stay (as in the reference)
+            count(&gp->cnt_path, depth);
+            // ---------------- the leaf (node, act): lock (:358), _expand_node (:301-321)
+            char* pnd = c.node(node);
+            if (lane == 0) *(unsigned*)(pnd + L::OFF_META) = meta_u | (1u << (SPX_LOCK_SHIFT + act));
+            const u64 par_own = *(const u64*)(pnd + L::OFF_OWN), par_opp = *(const u64*)(pnd + L::OFF_OPP);
+            u64 c_own = par_own, c_opp = par_opp;
+            int r = 0, done = 0;
+            if (child == CHILD_UNEXPANDED) env_step<GAME>(c_own, c_opp, act, player, r, done);
+            else { done = 1; r = (child == CHILD_TERM_WIN); }
+            count(&gp->cnt_sims, 1);
+            if (done) {
+                const double v = terminal_value(cfg.strong_play, r * player, par_own, par_opp);
+                __syncwarp();
+                if (lane == 0) {
+                    if (child == CHILD_UNEXPANDED) ((int*)(pnd + L::OFF_CHILD))[act] = r ? CHILD_TERM_WIN : CHILD_TERM_DRAW;
+                    *(unsigned*)(pnd + L::OFF_META) = meta_u;      // lock.release
+                }
+                __syncwarp();
+                backup_path<GAME>(c, p0, p1, depth, v, ts);
+                remove_vl(p0, p1, depth);
+                __syncwarp();
+                count(&gp->cnt_term, 1);
+                continue;
+            }
+            // blocks in self.network(s, parent.player): the leaf goes to slot ls + k, the worker keeps lock and virtual losses
+            if (lane < depth) wp[lane] = p0;
+            if (lane + 32 < depth) wp[lane + 32] = p1;
+            if (lane == 0) {
+                wk->kind = PK_EXPAND; wk->parent = node; wk->action = act; wk->depth = depth; wk->pplayer = player;
+                wk->own = c_own; wk->opp = c_opp;
+                E.leaf_own[ls + k] = player > 0 ? c_own : c_opp;
+                E.leaf_opp[ls + k] = player > 0 ? c_opp : c_own;
+                E.needs_eval[ls + k] = 1;
+                E.net_id[ls + k] = (unsigned char)(cfg.two_nets ? T : 0);
+                atomicAdd((ull*)&gp->cnt_evals, 1ULL);
+            }
+            __syncwarp();
+            blocked = true;
+        }
+        if (blocked) waiting += 1;
+        else if (lane == 0) E.needs_eval[ls + k] = 0;
+    }
+    return waiting == 0 && sims_started >= cfg.sims;
+}
+
 enum { ADV_EMITTED = 1, ADV_IDLE = 2, ADV_PARKED = 4 };   // advance_game's result; 0 = the sim budget ran out before a leaf came up
 
 // ------------------------------------------------------------------------------------------------ one game, one tick
@@ -282,10 +468,11 @@ enum { ADV_EMITTED = 1, ADV_IDLE = 2, ADV_PARKED = 4 };   // advance_game's resu
 // Registers: only what the select loop needs stays live through the function (phase words, game index, ONE tree's TreeState,
 // this lane's noise); the pending-evaluation words, the env boards, the other tree and the counters live in the slot's
 // GameState and are read / written (lane 0; counters with RED.ADD) where the state machine touches them.
-template <int GAME>
+template <int GAME, bool THREADED = false>
 __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, const int lane, const AdvPre& pre, const float my_p,
                                             const float v_in, int budget, const bool defer_leaf, const bool count_tick,
-                                            u64& out_own, u64& out_opp) {
+                                            u64& out_own, u64& out_opp, const float* __restrict__ policy_in = nullptr,
+                                            const float* __restrict__ value_in = nullptr) {
     typedef Rules<GAME> R;
     typedef NodeLayout<GAME> L;
     typedef unsigned long long ull;
@@ -293,13 +480,16 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
     Ctx<GAME> c(E, g, lane);
     GameState* gp = E.games + g;
     const spx_config& cfg = E.cfg;
+    const int ls = THREADED ? g * E.K : g;   // leaf slot of the slot's single evaluations (THREADED: worker 0's)
+    bool threads_wait = false;               // THREADED: the workers of the search in progress hold the pending evaluations
+    int search_root_vl = 0;                  // THREADED: root.virtual_loss left behind by the search that has just finished
     out_own = 0; out_opp = 0;
     if (pre.d.z) {   // leaf_waiting: this slot's leaf was emitted ahead of time (defer_leaf) and has not been evaluated yet
-        out_own = E.leaf_own[g]; out_opp = E.leaf_opp[g];
+        out_own = E.leaf_own[ls]; out_opp = E.leaf_opp[ls];
         __syncwarp();
         if (lane == 0) {
             gp->leaf_waiting = 0;
-            E.needs_eval[g] = 1;
+            E.needs_eval[ls] = 1;
             if (count_tick) atomicAdd(E.ticks, 1ULL);
         }
         __syncwarp();
@@ -330,7 +520,8 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
     u64 e_own = 0, e_opp = 0;
 
     // ---- 1. consume the evaluation this slot asked for on the previous tick
-    if (pre.c.x != PK_NONE) {
+    if (THREADED && pre.c.x == PK_THREADS) consumed = true;   // the workers consume theirs inside the search round below
+    else if (pre.c.x != PK_NONE) {
         const int pend_kind = pre.c.x, T = pre.c.y, pend_parent = pre.c.z, pend_action = pre.c.w, pend_depth = pre.d.x;
         consumed = true;
         use(T);
@@ -339,6 +530,7 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
             ts.node_count = 0;
             int idx = alloc_node<GAME>(c, ts, 0ULL, 0ULL, player, my_p);
             ts.root = idx; ts.root_n = 0; ts.root_w = 0.0; ts.root_player = player; ts.moves_played = 0; ts.n_rec = 0;
+            if (THREADED && lane == 0) gp->root_vl[T] = 0;
             count(&gp->cnt_nodes, 1);
             if (T == 0) { n_moves_logged = 0; if (lane == 0) { E.own_action[2 * g] = 0; E.own_action[2 * g + 1] = -1; } }
             if (T == 0 && !cfg.opponent_kind) { phase = PH_RESET; sub_tree = 1; }
@@ -362,6 +554,7 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
                 __syncwarp();
                 if (pend_kind == PK_EXPAND) sims_done += 1;
                 else {  // _set_root(node) (mcts.py:209)
+                    if (THREADED && lane == 0) gp->root_vl[T] = (int)c.vbase[(size_t)pend_parent * L::VLS + pend_action];   // the child MCNode keeps its virtual_loss
                     ts.root = idx; ts.root_n = 1; ts.root_w = v; ts.root_player = -pplayer;
                     if (sub_tree == 0 && !cfg.opponent_kind) sub_tree = 1; else phase = PH_ENVSTEP;
                 }
@@ -448,6 +641,15 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
                 my_noise = lane < A ? d : 0.0;
                 sims_done = 0;
             }
+            if constexpr (THREADED) {
+                // thread_count = K: one round of the cooperative schedule per tick; sims_done counts the tasks STARTED
+                int rvl = gp->root_vl[T];
+                const bool finished = search_round_threaded<GAME>(E, c, gp, g, lane, T, ts, rvl, sims_done, game_index, ply, my_noise, policy_in, value_in);
+                __syncwarp();
+                if (lane == 0) gp->root_vl[T] = rvl;
+                if (!finished) { threads_wait = true; e_tree = T; emitted = true; break; }
+                search_root_vl = rvl;
+            }
             if (sims_done >= cfg.sims) {
                 // ---------------- _play (mcts.py:272-299)
                 char* root = c.node(ts.root);
@@ -483,7 +685,9 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
                             rec->own = *(u64*)(root + L::OFF_OWN);
                             rec->opp = *(u64*)(root + L::OFF_OPP);
                             rec->game_index = game_index;
-                            rec->q = ts.root_n ? (float)__ddiv_rn(ts.root_w, (double)ts.root_n) : 0.f;  // root.q
+                            // root.q (mcts.py:59-62): (w - virtual_loss) / (n + virtual_loss); the sequential search leaves virtual_loss = 0
+                            const int q_den = ts.root_n + search_root_vl;
+                            rec->q = q_den ? (float)__ddiv_rn(__dsub_rn(ts.root_w, (double)search_root_vl), (double)q_den) : 0.f;
                             rec->actual_val = 0.f;
                             rec->tree = (uint8_t)T; rec->ply = (uint8_t)ply; rec->pad0 = 0; rec->pad1 = 0;
                         }
@@ -632,6 +836,7 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
                     ts.root_w = ((const double*)(root + L::OFF_W))[a];
                     ts.root_n = n_a;
                     ts.root_player = -ts.root_player;
+                    if (THREADED && lane == 0) gp->root_vl[T] = (int)c.vbase[(size_t)ts.root * L::VLS + a];   // the child MCNode keeps its virtual_loss
                     ts.root = ch >= 0 ? ch : -1;
                 }
             }
@@ -704,7 +909,8 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
         int4* q = reinterpret_cast<int4*>(gp);
         q[0] = make_int4(phase, sub_tree, mover_tree, sims_done);
         q[1] = make_int4(ply, swap, last_action, n_moves_logged);
-        if (emitted) {
+        if (threads_wait) q[2] = make_int4(PK_THREADS, e_tree, 0, 0);    // the leaf slots were written by the search round
+        else if (emitted) {
             q[2] = make_int4(e_kind, e_tree, e_parent, e_action);
             q[3] = make_int4(e_depth, e_pplayer, defer_leaf ? 1 : 0, 0);
             reinterpret_cast<ulonglong2*>(gp)[4] = make_ulonglong2(e_own, e_opp);
@@ -712,12 +918,15 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
         } else if (consumed) q[2] = make_int4(PK_NONE, 0, 0, 0);
         gp->game_index = game_index;
         st_tree(&gp->tree[curT], ts);
-        E.leaf_own[g] = out_own;
-        E.leaf_opp[g] = out_opp;
-        E.needs_eval[g] = (emitted && !defer_leaf) ? 1 : 0;
-        E.net_id[g] = (unsigned char)out_net;
+        if (!threads_wait) {
+            E.leaf_own[ls] = out_own;
+            E.leaf_opp[ls] = out_opp;
+            E.needs_eval[ls] = (emitted && !defer_leaf) ? 1 : 0;
+            E.net_id[ls] = (unsigned char)out_net;
+        }
         if (count_tick) atomicAdd(E.ticks, 1ULL);
     }
+    if (THREADED && !threads_wait && lane >= 1 && lane < E.K) E.needs_eval[ls + lane] = 0;   // single evaluations use worker 0's slot
     __syncwarp();   // lane 0's stores are ordered before whatever any lane of this warp loads next (the next prefetch of this slot)
     return emitted ? ADV_EMITTED : (phase == PH_IDLE ? ADV_IDLE : (parked ? ADV_PARKED : 0));
 }

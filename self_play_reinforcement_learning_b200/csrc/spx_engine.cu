@@ -62,6 +62,20 @@ __global__ void __launch_bounds__(128, SPX_ADV_MINB) advance_kernel(EngineDev E,
     advance_game<GAME>(E, g, lane, pre, my_p, v, E.cfg.max_sims_per_tick, false, g == 0, own, opp);
 }
 
+// the same tick for an engine created with search_threads = K > 1 (leaf slot of worker k of game g = g * K + k)
+template <int GAME>
+__global__ void __launch_bounds__(128, 2) advance_kernel_threaded(EngineDev E, const float* __restrict__ policy_in, const float* __restrict__ value_in) {
+    const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (g >= E.cfg.n_games) return;
+    const int lane = threadIdx.x & 31;
+    const AdvPre pre = advance_prefetch<GAME>(E, g, lane);
+    const size_t ls = (size_t)g * E.K;
+    const float my_p = (policy_in && lane < Rules<GAME>::A) ? policy_in[ls * Rules<GAME>::A + lane] : 0.f;
+    const float v = value_in ? value_in[ls] : 0.f;
+    u64 own, opp;
+    advance_game<GAME, true>(E, g, lane, pre, my_p, v, E.cfg.max_sims_per_tick, false, g == 0, own, opp, policy_in, value_in);
+}
+
 __global__ void reset_kernel(EngineDev E) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= E.cfg.n_games) return;
@@ -72,7 +86,11 @@ __global__ void reset_kernel(EngineDev E) {
     s.phase = ((long long)s.game_index < E.cfg.games_target) ? PH_RESET : PH_IDLE;
     s.tree[0].root = s.tree[1].root = -1;
     E.games[g] = s;
-    E.leaf_own[g] = 0; E.leaf_opp[g] = 0; E.needs_eval[g] = 0; E.net_id[g] = 0;
+    for (int k = 0; k < E.K; ++k) {
+        const size_t l = (size_t)g * E.K + k;
+        E.leaf_own[l] = 0; E.leaf_opp[l] = 0; E.needs_eval[l] = 0; E.net_id[l] = 0;
+        if (E.workers) memset(&E.workers[l], 0, sizeof(Worker));
+    }
     E.ext_action[g] = -1; E.own_action[2 * g] = 0; E.own_action[2 * g + 1] = -1;
     if (g == 0) { *E.rec_count = 0; *E.res_count = 0; *E.rec_dropped = 0; *E.ticks = 0; }
 }
@@ -409,6 +427,8 @@ int spx_create(const spx_config* cfg, spx_engine** out) {
     EngineDev& d = e->d;
     d.cfg = *cfg;
     if (d.cfg.max_sims_per_tick < 1) d.cfg.max_sims_per_tick = 1;
+    if (cfg->search_threads < 0 || cfg->search_threads > 16) return set_err(SPX_E_ARG, "spx_create: search_threads must be in [0, 16]%s", "");
+    d.K = cfg->search_threads > 1 ? cfg->search_threads : 1;
     if (d.cfg.record_capacity < 1) d.cfg.record_capacity = 1;
     if (d.cfg.result_capacity < 1) d.cfg.result_capacity = 1;
     const int mm = max_moves_of(cfg->game);
@@ -440,10 +460,15 @@ int spx_create(const spx_config* cfg, spx_engine** out) {
     SPX_ALLOC(d.res_count, unsigned long long, 1);
     SPX_ALLOC(d.rec_dropped, unsigned long long, 1);
     SPX_ALLOC(d.ticks, unsigned long long, 1);
-    SPX_ALLOC(d.leaf_own, u64, G);
-    SPX_ALLOC(d.leaf_opp, u64, G);
-    SPX_ALLOC(d.needs_eval, unsigned char, G);
-    SPX_ALLOC(d.net_id, unsigned char, G);
+    SPX_ALLOC(d.leaf_own, u64, G * d.K);
+    SPX_ALLOC(d.leaf_opp, u64, G * d.K);
+    SPX_ALLOC(d.needs_eval, unsigned char, G * d.K);
+    SPX_ALLOC(d.net_id, unsigned char, G * d.K);
+    if (d.K > 1) {   // threaded search: worker contexts, their select paths, MCNode.virtual_loss of every node's children
+        SPX_ALLOC(d.workers, Worker, G * d.K);
+        SPX_ALLOC(d.wpaths, unsigned, G * d.K * SPX_MAX_PATH);
+        SPX_ALLOC(d.vlpool, unsigned short, G * 2 * (size_t)d.nodes_per_tree * (cfg->game == SPX_GAME_TICTACTOE ? 16 : 8));
+    }
     SPX_ALLOC(d.ext_action, int, G);
     SPX_ALLOC(d.own_action, int, 2 * G);
 #undef SPX_ALLOC
@@ -456,7 +481,7 @@ int spx_destroy(spx_engine* e) {
     if (!e) return 0;
     EngineDev& d = e->d;
     void* ptrs[] = {d.games, d.pool, d.paths, d.noise, d.temp_rec, d.mlog, d.rec_ring, d.res_ring, d.rec_count, d.res_count,
-                    d.rec_dropped, d.ticks, d.leaf_own, d.leaf_opp, d.needs_eval, d.net_id, d.ext_action, d.own_action};
+                    d.rec_dropped, d.ticks, d.leaf_own, d.leaf_opp, d.needs_eval, d.net_id, d.ext_action, d.own_action, d.workers, d.wpaths, d.vlpool};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete e;
     return 0;
@@ -479,7 +504,10 @@ int spx_set_noise_table(spx_engine* e, const double* table, int64_t first_game_i
 int spx_advance(spx_engine* e, const float* policy, const float* value, void* stream) {
     if (!e) return set_err(SPX_E_ARG, "spx_advance: null engine%s", "");
     const int block = 128, grid = (e->d.cfg.n_games * 32 + block - 1) / block;
-    if (e->d.cfg.game == SPX_GAME_CONNECT4) advance_kernel<SPX_GAME_CONNECT4><<<grid, block, 0, (cudaStream_t)stream>>>(e->d, policy, value);
+    if (e->d.K > 1) {   // threaded search: K leaf slots per game
+        if (e->d.cfg.game == SPX_GAME_CONNECT4) advance_kernel_threaded<SPX_GAME_CONNECT4><<<grid, block, 0, (cudaStream_t)stream>>>(e->d, policy, value);
+        else advance_kernel_threaded<SPX_GAME_TICTACTOE><<<grid, block, 0, (cudaStream_t)stream>>>(e->d, policy, value);
+    } else if (e->d.cfg.game == SPX_GAME_CONNECT4) advance_kernel<SPX_GAME_CONNECT4><<<grid, block, 0, (cudaStream_t)stream>>>(e->d, policy, value);
     else advance_kernel<SPX_GAME_TICTACTOE><<<grid, block, 0, (cudaStream_t)stream>>>(e->d, policy, value);
     count_launch();
     SPX_CUDA(cudaGetLastError());

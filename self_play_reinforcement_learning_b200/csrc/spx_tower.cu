@@ -1481,6 +1481,7 @@ int spx_tick_fused(spx_engine* e, spx_tower* t, int32_t n_ticks, float* policy, 
     if (n_ticks <= 0) return 0;
     if (t->ncta != 2 || !t->fused) return spx::set_err(SPX_E_STATE, "spx_tick_fused: needs the SM-pair tower with fused heads%s", "");
     if (e->d.cfg.game != t->game || e->d.cfg.two_nets) return spx::set_err(SPX_E_ARG, "spx_tick_fused: one network, same game as the engine%s", "");
+    if (e->d.K > 1) return spx::set_err(SPX_E_STATE, "spx_tick_fused: engines with search_threads > 1 tick with spx_advance + the network forward%s", "");
     const long long n = e->d.cfg.n_games, groups = (n + NB - 1) / NB, pairs = (groups + 1) / 2, max_pairs = t->sm_count / 2;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

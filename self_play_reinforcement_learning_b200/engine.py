@@ -51,7 +51,7 @@ class HashNetEvaluator:
         self.engine = engine
 
     def __call__(self, engine, events=None):
-        check(lib().spx_hashnet_forward(self.game, engine.n_games, engine.leaf_own.data_ptr(), engine.leaf_opp.data_ptr(),
+        check(lib().spx_hashnet_forward(self.game, engine.n_leaves, engine.leaf_own.data_ptr(), engine.leaf_opp.data_ptr(),
                                         engine.needs_eval.data_ptr(), engine.net_id.data_ptr(), self.seed0, self.seed1,
                                         engine.policy.data_ptr(), engine.value.data_ptr(), _stream_ptr()),
               "spx_hashnet_forward")
@@ -63,7 +63,10 @@ class SelfPlayEngine:
     def __init__(self, game, n_games, sims, evaluator, *, evaluate=False, strong_play=False, alpha=1.0, seed=0,
                  tie_mode=1, noise_mode=2, emit_records=True, max_sims_per_tick=8, nodes_per_tree=0, move_log=False,
                  two_nets=False, opponent_kind=0, slot_offset=0, slot_stride=None, games_target=None, record_capacity=None,
-                 result_capacity=None):
+                 result_capacity=None, search_threads=1):
+        """search_threads: MCTreeSearch(thread_count=K) behind an InferenceProxy (mcts.py:132,328-331; the reference's default is 4):
+        K search_node tasks in flight per tree with virtual loss and per-child locks, under the cooperative round-robin
+        schedule.  1 = the sequential search.  With K > 1 the leaf batch has n_games * K rows."""
         if not torch.cuda.is_available():
             raise _lib.SpxError("SelfPlayEngine needs a CUDA device (B200); there is no CPU fallback")
         self.game, self.n_games, self.sims = game, int(n_games), int(sims)
@@ -75,6 +78,9 @@ class SelfPlayEngine:
         cfg.emit_records, cfg.max_sims_per_tick, cfg.nodes_per_tree = int(emit_records), max_sims_per_tick, nodes_per_tree
         cfg.move_log, cfg.two_nets, cfg.alpha, cfg.seed = int(move_log), int(two_nets), float(alpha), int(seed)
         cfg.opponent_kind = int(opponent_kind)
+        cfg.search_threads = int(search_threads)
+        self.search_threads = max(1, int(search_threads))
+        self.n_leaves = int(n_games) * self.search_threads
         cfg.reserved0 = int(os.environ.get("SPX_DBG_FLAGS", "0"), 0)   # timing experiments only (csrc/spx_tower.cu)
         cfg.slot_offset = slot_offset
         cfg.slot_stride = n_games if slot_stride is None else slot_stride
@@ -87,12 +93,13 @@ class SelfPlayEngine:
         check(lib().spx_create(C.byref(cfg), C.byref(self._h)), "spx_create")
         own, opp, need, nid = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
         check(lib().spx_leaf_batch(self._h, C.byref(own), C.byref(opp), C.byref(need), C.byref(nid)), "spx_leaf_batch")
-        self.leaf_own = _view(own.value, (n_games,), "<i8", self.device)
-        self.leaf_opp = _view(opp.value, (n_games,), "<i8", self.device)
-        self.needs_eval = _view(need.value, (n_games,), "|u1", self.device)
-        self.net_id = _view(nid.value, (n_games,), "|u1", self.device)
-        self.policy = torch.zeros(n_games, self.A, dtype=torch.float32, device=self.device)
-        self.value = torch.zeros(n_games, dtype=torch.float32, device=self.device)
+        nl = self.n_leaves
+        self.leaf_own = _view(own.value, (nl,), "<i8", self.device)
+        self.leaf_opp = _view(opp.value, (nl,), "<i8", self.device)
+        self.needs_eval = _view(need.value, (nl,), "|u1", self.device)
+        self.net_id = _view(nid.value, (nl,), "|u1", self.device)
+        self.policy = torch.zeros(nl, self.A, dtype=torch.float32, device=self.device)
+        self.value = torch.zeros(nl, dtype=torch.float32, device=self.device)
         self._noise_table = None
         self._first = True
         self.evaluator = evaluator
@@ -172,7 +179,7 @@ class SelfPlayEngine:
     def run_ticks(self, n, fused=True, chunk=256):
         """n ticks.  With the native tower the whole loop runs as persistent launches of `chunk` ticks (spx_tick_fused: the
         network CTAs also advance their games); any other evaluator, or fused=False, launches advance + evaluation per tick."""
-        fn = getattr(self.evaluator, "fused_ticks", None) if fused else None
+        fn = getattr(self.evaluator, "fused_ticks", None) if (fused and self.search_threads == 1) else None
         done = 0
         while fn is not None and done < n:
             if not fn(self, min(chunk, n - done)):

@@ -420,7 +420,7 @@ class TwoTowerEvaluator:
         self.tower = self.towers[0]
 
     def bind(self, engine):
-        n, dev, A = engine.n_games, engine.device, engine.A
+        n, dev, A = engine.n_leaves, engine.device, engine.A
         self.own2 = torch.zeros(2, n, dtype=torch.int64, device=dev)
         self.opp2 = torch.zeros(2, n, dtype=torch.int64, device=dev)
         self.needs2 = torch.zeros(2, n, dtype=torch.uint8, device=dev)
@@ -432,7 +432,7 @@ class TwoTowerEvaluator:
         self.towers[which].load(module_or_blob)
 
     def __call__(self, engine, events=None):
-        n = engine.n_games
+        n = engine.n_leaves
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         check(lib().spx_partition_leaves(n, engine.leaf_own.data_ptr(), engine.leaf_opp.data_ptr(), engine.needs_eval.data_ptr(),
                                          engine.net_id.data_ptr(), self.own2.data_ptr(), self.opp2.data_ptr(), self.needs2.data_ptr(),

@@ -47,9 +47,9 @@ def compare_game(game, engine_moves, engine_records, engine_result, oracle_ep, e
 
 
 def oracle_episode(game, sims, seed, game_index, noise_table, evaluate=False, strong_play=False, net_seed=0,
-                   net_seed_opp=None, tie_mode=1):
+                   net_seed_opp=None, tie_mode=1, threads=1):
     cfg = ox.make_cfg(game, sims, seed=seed, game_uid=game_index, evaluate=evaluate, strong_play=strong_play,
-                      noise_table=noise_table, tie_mode=tie_mode)
+                      noise_table=noise_table, tie_mode=tie_mode, threads=threads)
     return ox.play_episode(cfg, bool(game_index & 1), net_seed=net_seed, net_seed_opp=net_seed_opp)
 
 
