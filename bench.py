@@ -652,10 +652,30 @@ def _config5_leg(torch, nets, blocks, sims, games=1024):
     torch.cuda.synchronize()
     wall = time.time() - t0
     sec = h["seconds"]
-    return {"workload": f"{games} initial + {games} self-play games ({sims} sims/move), 100 SGD steps of batch 128 (native step), weight refresh, "
-                        "128 evaluation games vs OneStepLookahead; one GPU", "seconds": sec, "wall_s_incl_initial_games": wall,
-            "records_in_memory": h["memory"], "loss": h["loss"], "evaluation_reward": h["evaluation_reward"], "trainer": s.trainer_kind,
-            "self_play_games_per_s": games / sec["self_play"]}
+    out = {"workload": f"{games} initial + {games} self-play games ({sims} sims/move), 100 SGD steps of batch 128 (native step), weight refresh, "
+                       "128 evaluation games vs OneStepLookahead; one GPU", "seconds": sec, "wall_s_incl_initial_games": wall,
+           "records_in_memory": h["memory"], "loss": h["loss"], "evaluation_reward": h["evaluation_reward"], "trainer": s.trainer_kind,
+           "self_play_games_per_s": games / sec["self_play"]}
+    # the reference's own epoch size on 8 GPUs is 1500 / 8 = 188 games per GPU: far fewer games than leaf slots, so the phase is
+    # bound by the latency of one game.  thread_count = 4 (the reference's default behind its InferenceProxy: virtual loss, 4
+    # simulations in flight per tree) makes a move take 200 ticks of 752 leaves instead of 800 ticks of 188.
+    from self_play_reinforcement_learning_b200.selfplay import BatchedSelfPlay
+    small = {}
+    for K in (1, 4):
+        sp = BatchedSelfPlay(net, game=0, n_games=188, sims=sims, net="tower", seed=5, games_target=188, search_threads=K)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        while True:
+            sp.engine.run_ticks(sp.engine.safe_poll_interval)
+            sp.engine.drain_records(); sp.engine.drain_results()
+            if sp.engine.all_idle():
+                break
+        torch.cuda.synchronize()
+        small[f"thread_count_{K}"] = time.time() - t0
+        sp.close()
+    out["self_play_188_games_seconds"] = small
+    out["self_play_188_games_speedup_with_4_threads"] = small["thread_count_1"] / small["thread_count_4"]
+    return out
 
 
 def _lib_launches():

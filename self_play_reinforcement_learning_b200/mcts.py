@@ -37,7 +37,9 @@ class MCTreeSearch:
         self.env = env() if callable(env) else env
         self.alpha, self.strong_play, self.q_average = alpha, strong_play, q_average
         self.temperature_cutoff, self.batch_size, self.min_memory, self.update_nn = temperature_cutoff, batch_size, min_memory, update_nn
-        self.thread_count = 1          # the engine is the sequential search (the reference's deterministic mode)
+        # the reference searches with thread_count threads only behind an InferenceProxy (mcts.py:154,328); called directly -- as this
+        # object is -- it is the sequential search.  BatchedSelfPlay / SelfPlayScheduler(search_threads=K) run the threaded search.
+        self.thread_count = 1
         self.memory_queue, self.memory = memory_queue, Memory(memory_size)
         self.evaluating = False
         self.seed, self._net_kind, self._net_dtype, self._noise_mode = seed, net, net_dtype, noise_mode

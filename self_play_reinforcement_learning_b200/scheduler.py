@@ -115,7 +115,7 @@ class SelfPlayScheduler:
                  evaluation_games=150, games_per_gpu=1024, memory_size=200000, batch_size=128, lr=0.01, momentum=0.9,
                  weight_decay=1e-4, updates_per_epoch=100, alpha=1.0, seed=0, net="tower", evaluation_opponent=None,
                  replay="device", max_memory_size=None, memory_step=0, deduplicate=False, save_dir=None, save_memory=True,
-                 lr_patience=15, amp=None, trainer="auto"):
+                 lr_patience=15, amp=None, trainer="auto", search_threads=1):
         """replay: "device" (records stay in HBM: DeviceReplay) or "host" (reference-style Memory of Move tuples).
         max_memory_size / memory_step: UpdateWorker's staggered buffer growth (updateworker.py:107-109).
         save_dir: as in the reference (self_play_parallel.py:56,263-267): every epoch rank 0 writes
@@ -124,6 +124,8 @@ class SelfPlayScheduler:
         ``train_model(resume_model=, resume_memory=)`` picks up the newest files of the previous run (base_worker.py:26-62).
         (Pickling a full 200 000-record Memory of Move tuples takes about a minute, as it does in the reference;
         ``save_memory=False`` keeps only the model checkpoints.)
+        search_threads: thread_count of the policies' MCTreeSearch (mcts.py:132: 4 in the reference, behind its InferenceProxy): K
+        simulations in flight per tree with virtual loss, a move takes iterations / K ticks (BatchedSelfPlay); 1 = sequential.
         trainer: "device" = the native SGD step (train.DeviceTrainer: TF32 / bf16 tensor-core convolutions, fp32 master weights,
         momentum buffers on the device), "torch" = PyTorch autograd with torch.optim.SGD, "auto" = "device" whenever the network
         is one it is built for and the replay memory is on the device.
@@ -160,6 +162,7 @@ class SelfPlayScheduler:
             raise ValueError("trainer='device' needs replay='device' and a ResidualTower(7, 6, 7, filter_factor=32)")
         self.trainer_kind = "device" if (trainer == "device" or (trainer == "auto" and can)) else "torch"
         self._trainer, self._momentum, self._weight_decay = None, momentum, weight_decay
+        self.search_threads = int(search_threads)
         self.start_time = datetime.datetime.now().isoformat()                      # self_play_parallel.py:86
         self.games_played = 0
         self.history = []
@@ -172,7 +175,8 @@ class SelfPlayScheduler:
         sp = BatchedSelfPlay(self.network, env=self.env, n_games=G, sims=self.iterations, net=self.net,
                              evaluation_network=self.evaluation_network if evaluate else None, evaluate=evaluate, update=update,
                              alpha=self.alpha, seed=self.seed + 7919 * generation, rank=self.rank, world=self.world,
-                             games_target=n_games_total, opponent=self.evaluation_opponent if evaluate else None)
+                             games_target=n_games_total, opponent=self.evaluation_opponent if evaluate else None,
+                             search_threads=self.search_threads)
         device_replay = update and self.replay_kind == "device"
         if device_replay and self.memory is None:
             self.memory = DeviceReplay(sp.game, self._memory_size, self.max_memory_size, seed=self.seed)
