@@ -32,7 +32,9 @@ def main():
     ap.add_argument("--save-dir", default=None, help="run folder root: model-*/memory-* files as the reference writes them")
     ap.add_argument("--resume", action="store_true", help="resume model and memory from the newest earlier run in --save-dir")
     ap.add_argument("--no-save-memory", action="store_true", help="with --save-dir: write only the model checkpoints, not the pickled replay memory")
-    ap.add_argument("--amp", action="store_true", help="bf16 autocast for the SGD steps (not reference behaviour)")
+    ap.add_argument("--amp", action="store_true", help="with --trainer torch: bf16 autocast for the SGD steps")
+    ap.add_argument("--trainer", default="auto", choices=["auto", "device", "torch"], help="device: the native SGD step (csrc/spx_train.cu)")
+    ap.add_argument("--threads", type=int, default=1, help="thread_count of the searches (the reference's default behind its InferenceProxy is 4)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -43,7 +45,8 @@ def main():
     net = nets.ResidualTower(7, 6, 7, num_blocks=args.blocks).cuda().eval()
     sched = SelfPlayScheduler(net, 0, iterations=args.iterations, epoch_length=args.epoch_length, initial_games=args.initial_games,
                               evaluation_games=args.evaluation_games, games_per_gpu=args.games_per_gpu, save_dir=args.save_dir,
-                              save_memory=not args.no_save_memory, amp=torch.bfloat16 if args.amp else None)
+                              save_memory=not args.no_save_memory, amp=torch.bfloat16 if args.amp else None, trainer=args.trainer,
+                              search_threads=args.threads)
     t0 = time.time()
     hist = sched.train_model(num_epochs=args.epochs, resume_model=args.resume, resume_memory=args.resume)
     if sched.rank == 0:
