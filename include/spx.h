@@ -333,6 +333,8 @@ int spx_train_outputs(spx_trainer* t, float* dev_probs, float* dev_value, void* 
  * output / activation, 5/6 trunk gradient ping-pong, 7 conv-output gradient, 8 head conv-output gradient, 9 head activation
  * gradient, 10 identity-branch gradient */
 int spx_train_debug_planes(spx_trainer* t, int32_t which, int32_t layer, float** dev_ptr, int64_t* n_floats, int32_t* rows);
+/* test hook: dev buffer of 8 int64 receiving clock64() at 8 points of CTA 0 of every conv kernel launch (NULL: off) */
+int spx_train_debug_trace(long long* dev_trace);
 /* test hook: the backward-weights kernel alone on caller-provided bf16 plane tensors [C/8][rows][8] (x 128 channels, dy N channels,
  * `rows` rows incl. the 16 guard rows); partial_out f32 [S][taps][128 ci][N co]; descriptor strides < 0 = the product's */
 int spx_train_debug_wgrad(const void* x, const void* dy, int32_t N, int32_t taps, int32_t rows, int32_t S, float* partial_out,

@@ -26,3 +26,15 @@ for _ in range(n):
 b.record()
 torch.cuda.synchronize()
 print("ms per step", a.elapsed_time(b) / n)
+
+# where a conv_tf32_kernel launch goes: clock64 of CTA 0 at 8 points (the last launch of a step = the stem's backward... no: the last conv
+# launch of a step is the backward-data conv of layer 1)
+from self_play_reinforcement_learning_b200._lib import lib  # noqa: E402
+tb = torch.zeros(8, dtype=torch.int64, device="cuda")
+lib().spx_train_debug_trace(tb.data_ptr())
+tr.step(planes, probs, target)
+torch.cuda.synchronize()
+lib().spx_train_debug_trace(None)
+t = tb.cpu().numpy()
+names = ["start", "setup done", "producer issued all", "A tile landed", "all MMAs issued", "accumulators complete", "TMEM->smem done", "epilogue done"]
+print("conv kernel CTA 0 (cycles since start):", {n: int(t[i] - t[0]) for i, n in enumerate(names)})

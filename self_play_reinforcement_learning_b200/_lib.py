@@ -58,7 +58,7 @@ EXPORTS = ["spx_last_error", "spx_version", "spx_launch_count", "spx_env_step", 
            "spx_replay_create", "spx_replay_destroy", "spx_replay_size", "spx_replay_max_size", "spx_replay_change_size", "spx_replay_reset",
            "spx_drain_records_device", "spx_replay_append", "spx_replay_read", "spx_replay_sample", "spx_replay_deduplicate", "spx_replay_unique", "spx_tick_fused",
            "spx_train_create", "spx_train_destroy", "spx_train_param_count", "spx_train_running_count", "spx_train_set_state", "spx_train_get_state",
-           "spx_train_step", "spx_train_outputs", "spx_train_debug_planes", "spx_train_debug_wgrad"]
+           "spx_train_step", "spx_train_outputs", "spx_train_debug_planes", "spx_train_debug_wgrad", "spx_train_debug_trace"]
 
 _lib = None
 
@@ -140,6 +140,7 @@ def lib():
         L.spx_train_get_state.argtypes = [vp, i32, vp, vp]
         L.spx_train_step.argtypes = [vp, vp, vp, vp, vp, u64, u64, C.c_float, C.c_float, C.c_float, i32, vp, vp]
         L.spx_train_outputs.argtypes = [vp, vp, vp, vp]
+        L.spx_train_debug_trace.argtypes = [vp]
         L.spx_train_debug_wgrad.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp]
         L.spx_train_debug_planes.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i32)]
         L.spx_event_create.argtypes = [C.POINTER(vp)]

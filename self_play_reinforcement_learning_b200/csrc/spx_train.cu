@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -72,10 +73,23 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// the same copy delivered to the same shared-memory offset (and mbarrier) of every CTA of the cluster named in `mask`
+__device__ __forceinline__ void tma_bulk_g2s_mc(void* dst, const void* src, unsigned bytes, void* bar, unsigned short mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(void* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// completion of this thread's MMAs -> the same mbarrier in every CTA of the cluster named in `mask`
+__device__ __forceinline__ void tc_commit_mc(void* bar, unsigned short mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(unsigned d_tmem, ull adesc, ull bdesc, unsigned idesc, unsigned accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
@@ -83,6 +97,19 @@ __device__ __forceinline__ void tc_mma_tf32(unsigned d_tmem, ull adesc, ull bdes
 __device__ __forceinline__ void tc_mma_f16(unsigned d_tmem, ull adesc, ull bdesc, unsigned idesc, unsigned accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// the same MMAs with the descriptors passed as (low word, constant high word): the issuing thread advances a descriptor with ONE
+// 32-bit add (low word = LBO >> 4 << 16 | address >> 4; high word = SBO >> 4 | version bit) -- the issue loop is a single
+// thread's instruction stream and paces the kernel otherwise (measured: 129 cycles per MMA with make_desc in the loop)
+__device__ __forceinline__ void tc_mma_tf32_lo(unsigned d_tmem, unsigned a_lo, unsigned a_hi, unsigned b_lo, unsigned b_hi, unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_lo(unsigned d_tmem, unsigned a_lo, unsigned a_hi, unsigned b_lo, unsigned b_hi, unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ unsigned desc_lo(unsigned saddr, unsigned lbo) { return ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ unsigned desc_hi(unsigned sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14); }
 __device__ __forceinline__ void tc_ld32(unsigned taddr, float (&v)[32]) {
     unsigned r[32];
     asm volatile(
@@ -143,7 +170,10 @@ struct ConvP {
     const float* add;                   // optional planes added on real rows (skip-connection gradient)
     float* stat;                        // optional [tiles][2][N]: per-tile sum / sum of squares over real rows
     int B, Rg;
+    long long* trace;                   // debug: clock64 at 8 points of CTA 0 (null in production)
 };
+#define SPX_CT(k) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[k] = clock64(); } while (0)
+constexpr int CONV_CLUSTER = 1;   // SPX_CONV_CLUSTER=7: seven row tiles share one multicast weight stream (measured slower, see below)
 constexpr int CONV_SMEM = (CH / 4) * PIECE + RING_STAGES * STAGE_MAX + 256 + TILE * 4;
 
 __global__ void __launch_bounds__(256, 1) conv_tf32_kernel(const ConvP p) {
@@ -159,21 +189,31 @@ __global__ void __launch_bounds__(256, 1) conv_tf32_kernel(const ConvP p) {
     const int N = p.N, n0 = blockIdx.y * NC;            // this CTA computes output channels [n0, n0 + 64)
     const int ks_stage = p.ks_per_tap < 8 ? p.ks_per_tap : 8, stages_per_tap = p.ks_per_tap / ks_stage, total = p.taps * stages_per_tap;
     const unsigned stage_bytes = (unsigned)(ks_stage * 2 * NC * 16);
+    // Optional (SPX_CONV_CLUSTER=7): the CTAs of a cluster work on consecutive row tiles of the SAME 64 output channels, i.e. they
+    // consume the same weight stream: stage i is fetched once, by CTA i % CL, and multicast into every CTA's ring slot; a slot is
+    // refilled when the MMAs of ALL CTAs have released it.  Measured: the kernel's own time does not change (it is not bound by
+    // the 33 MB of L2 -> SM weight reads per layer) and the step gets SLOWER, 3.82 -> 5.05 ms: a 7-CTA cluster needs 7 free SMs of
+    // one GPC at once, which serialises the tails of the ~340 short dependent kernels.  Default: no clusters (CL = 1).
+    const unsigned crank = cluster_ctarank(), CL = cluster_nctarank();
+    const unsigned short cmask = (unsigned short)((1u << CL) - 1u);
+    if (tid == 0) SPX_CT(0);
 
     if (tid == 0) {
-        for (int i = 0; i < RING_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < RING_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
         mbar_init(abar, 1); mbar_init(accbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid < TILE) { int b, cell; realrow[tid] = row_real(r0 + GUARD + tid, p.B, b, cell) ? 1 : 0; }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();      // every CTA's barriers are initialised before any multicast copy / commit can reach them
     tc_fence_after();
     const unsigned tmem = *tmem_slot;
+    if (tid == 0) SPX_CT(1);
 
     if (warp == 0 && lane == 0) {
         // ---- TMA producer: the activation tile (one 2304-byte piece per 4-channel chunk), then the weight stages in MMA order
@@ -183,29 +223,47 @@ __global__ void __launch_bounds__(256, 1) conv_tf32_kernel(const ConvP p) {
         const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.w) + (size_t)blockIdx.y * total * stage_bytes;   // this half's slices
         for (int i = 0; i < total; ++i) {
             const int slot = i % RING_STAGES;
-            if (i >= RING_STAGES) mbar_wait(&empty[slot], (unsigned)((i / RING_STAGES - 1) & 1));
-            mbar_expect_tx(&full[slot], stage_bytes);
-            tma_bulk_g2s(ring + slot * STAGE_MAX, wsrc + (size_t)i * stage_bytes, stage_bytes, &full[slot]);
+            if (i >= RING_STAGES) mbar_wait(&empty[slot], (unsigned)((i / RING_STAGES - 1) & 1));   // released by all CL CTAs
+            mbar_expect_tx(&full[slot], stage_bytes);                                                // every CTA arms its own barrier
+            if ((unsigned)i % CL == crank)
+                tma_bulk_g2s_mc(ring + slot * STAGE_MAX, wsrc + (size_t)i * stage_bytes, stage_bytes, &full[slot], cmask);
         }
+        SPX_CT(2);
     } else if (warp == 1 && lane == 0) {
         // ---- MMA issuer
+        // consecutive MMAs go to FOUR accumulators in turn (K split four ways, summed by the epilogue): back-to-back MMAs into one
+        // accumulator wait for each other (~150 instead of ~35 cycles each), and every layer issues >= 8 of them
         const unsigned idesc = make_idesc_tf32(TILE, NC, false);
+        const unsigned hi = desc_hi(128);                                                     // SBO = 128 B for both operands
+        const unsigned a_lo0 = desc_lo(smem_u32(atile) + GUARD * 16, PIECE);                  // tile row 0, K-step 0, no shift
+        const unsigned b_lo0 = desc_lo(smem_u32(ring), NC * 16);
+        constexpr unsigned A_KSTEP = (2 * PIECE) >> 4, B_KSTEP = (2 * NC * 16) >> 4, B_SLOT = STAGE_MAX >> 4;
+        unsigned mm = 0;
         mbar_wait(abar, 0);
+        SPX_CT(3);
         for (int i = 0; i < total; ++i) {
             const int slot = i % RING_STAGES;
             mbar_wait(&full[slot], (unsigned)((i / RING_STAGES) & 1));
             tc_fence_after();
             const int tap = i / stages_per_tap, half = i - tap * stages_per_tap;
-            const int shift = tap_shift(p.taps, tap);
-            for (int ks = 0; ks < ks_stage; ++ks) {
-                const int kk = half * ks_stage + ks;
-                const ull adesc = make_desc(smem_u32(atile) + (unsigned)(2 * kk * PIECE + (GUARD + shift) * 16), PIECE, 128);
-                const ull bdesc = make_desc(smem_u32(ring + slot * STAGE_MAX) + (unsigned)(ks * 2 * NC * 16), (unsigned)(NC * 16), 128);
-                tc_mma_tf32(tmem, adesc, bdesc, idesc, (i | ks) != 0 ? 1u : 0u);
+            unsigned a_lo = a_lo0 + (unsigned)tap_shift(p.taps, tap) + (unsigned)(half * ks_stage) * A_KSTEP;   // a row is one 16-byte address unit
+            unsigned b_lo = b_lo0 + (unsigned)slot * B_SLOT;
+            if (ks_stage == 8) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    tc_mma_tf32_lo(tmem + (mm & 3u) * NC, a_lo, hi, b_lo, hi, idesc, mm >= 4u ? 1u : 0u);
+                    ++mm; a_lo += A_KSTEP; b_lo += B_KSTEP;
+                }
+            } else {
+                for (int ks = 0; ks < ks_stage; ++ks) {
+                    tc_mma_tf32_lo(tmem + (mm & 3u) * NC, a_lo, hi, b_lo, hi, idesc, mm >= 4u ? 1u : 0u);
+                    ++mm; a_lo += A_KSTEP; b_lo += B_KSTEP;
+                }
             }
-            tc_commit(&empty[slot]);
+            tc_commit_mc(&empty[slot], cmask);
         }
         tc_commit(accbar);
+        SPX_CT(4);
     } else if (warp >= 4) {
         // ---- epilogue: TMEM -> shared staging [128 rows][64 + 1] (reuses the weight ring once every MMA has retired)
         const int et = tid - 128;                 // TMEM lane == tile row
@@ -213,24 +271,34 @@ __global__ void __launch_bounds__(256, 1) conv_tf32_kernel(const ConvP p) {
         constexpr int ld = NC + 1;
         mbar_wait(accbar, 0);
         tc_fence_after();
+        if (et == 0) SPX_CT(5);
 #pragma unroll
         for (int cg = 0; cg < NC / 32; ++cg) {
-            float v[32];
-            tc_ld32(tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(cg * 32), v);
+            float v[32], u[32];
+            const unsigned tl = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(cg * 32);
+            tc_ld32(tl, v);
+#pragma unroll
+            for (int a = 1; a < 4; ++a) {          // the four K-split accumulators, summed in a fixed order
+                tc_ld32(tl + (unsigned)(a * NC), u);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += u[j];
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) st[et * ld + cg * 32 + j] = v[j];
         }
         tc_fence_before();
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) SPX_CT(6);
         // pass 1, two threads per channel (64 rows each): bias, padding rows -> 0, per-tile BatchNorm sums over the real rows
         {
             const int c = et & (NC - 1), hrow = et >> 6;
             const float bv = p.has_bias ? *p.bias.at(n0 + c) : 0.f;
             float s = 0.f, sq = 0.f;
+#pragma unroll 8
             for (int m = hrow * 64; m < hrow * 64 + 64; ++m) {
                 float v = st[m * ld + c] + bv;
                 if (!realrow[m]) v = 0.f;
-                else { s += v; sq = fmaf(v, v, sq); }
+                s += v; sq = fmaf(v, v, sq);          // padding rows contribute exact zeros
                 st[m * ld + c] = v;
             }
             float* red = st + TILE * ld;          // [2 row halves][2 stats][64]
@@ -242,18 +310,31 @@ __global__ void __launch_bounds__(256, 1) conv_tf32_kernel(const ConvP p) {
             p.stat[((size_t)tile * 2) * N + n0 + et] = red[et] + red[2 * NC + et];
             p.stat[((size_t)tile * 2 + 1) * N + n0 + et] = red[NC + et] + red[3 * NC + et];
         }
-        // pass 2, thread = row: planes out (16 B per row and chunk, coalesced over rows)
-        for (int idx = et; idx < TILE * (NC / 4); idx += 128) {
-            const int m = idx & (TILE - 1), ch = idx >> 7;
-            float4 v = make_float4(st[m * ld + 4 * ch], st[m * ld + 4 * ch + 1], st[m * ld + 4 * ch + 2], st[m * ld + 4 * ch + 3]);
-            const size_t o = (size_t)(n0 / 4 + ch) * p.Rg + r0 + GUARD + m;
-            if (p.add && realrow[m]) { const float4 a = reinterpret_cast<const float4*>(p.add)[o]; v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
-            reinterpret_cast<float4*>(p.out)[o] = v;
+        // pass 2, thread = row: planes out (16 B per row and chunk, coalesced over rows); the optional skip-gradient loads of
+        // four chunks are issued together before they are used (one L2 round trip per four chunks instead of one each)
+        {
+            const int m = et;     // 128 threads = 128 rows; 16 chunks each
+            const bool addr = p.add && realrow[m];
+            const size_t o0 = (size_t)(n0 / 4) * p.Rg + r0 + GUARD + m;
+#pragma unroll
+            for (int c4 = 0; c4 < NC / 4; c4 += 4) {
+                float4 a[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a[k] = addr ? reinterpret_cast<const float4*>(p.add)[o0 + (size_t)(c4 + k) * p.Rg] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ch = c4 + k;
+                    const float4 v = make_float4(st[m * ld + 4 * ch] + a[k].x, st[m * ld + 4 * ch + 1] + a[k].y, st[m * ld + 4 * ch + 2] + a[k].z, st[m * ld + 4 * ch + 3] + a[k].w);
+                    reinterpret_cast<float4*>(p.out)[o0 + (size_t)ch * p.Rg] = v;
+                }
+            }
         }
+        if (et == 0) SPX_CT(7);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem) : "memory");
+    if (CL > 1) cluster_sync_all();      // no CTA leaves while another one may still signal its barriers
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ backward-weights
@@ -275,7 +356,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const WgP p) {
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N, S = gridDim.x, s = blockIdx.x;
-    const int ntap = p.taps == 9 ? 3 : 1, tap0 = blockIdx.y * 3;
+    const int ntap = p.taps == 9 ? 3 : 1, tap0 = blockIdx.y * 3, nsub = ntap == 1 ? 4 : 1;   // accumulators per tap
     if (tid == 0) {
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -299,14 +380,23 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const WgP p) {
             for (int c = 0; c < N / 8; ++c) tma_bulk_g2s(dt + c * TILE * 16, p.dy + ((size_t)c * p.Rg + (size_t)j * TILE + GUARD) * 8, TILE * 16, &bars[0]);
             mbar_wait(&bars[0], (unsigned)(it & 1));
             tc_fence_after();
-            for (int t = 0; t < ntap; ++t) {
-                const int shift = tap_shift(p.taps, tap0 + t);
+            // consecutive MMAs alternate between independent accumulators (back-to-back MMAs into one accumulator wait for each
+            // other): the three taps of the group, or -- one tap only (1x1 head conv) -- four K-split accumulators summed by the epilogue
+            {
+                const unsigned a_hi = desc_hi((unsigned)p.a_sbo), b_hi = desc_hi((unsigned)p.b_sbo);
+                const unsigned a_lo0 = desc_lo(smem_u32(xt) + GUARD * 16, (unsigned)p.a_lbo), b_lo0 = desc_lo(smem_u32(dt), (unsigned)p.b_lbo);
+                unsigned sh[3];
+                for (int t = 0; t < ntap; ++t) sh[t] = (unsigned)tap_shift(p.taps, tap0 + t);
+                // A[ci][k = row] and B[co][k = row], both MN-major: 8 channels per 16 B, chunk stride = SBO, rows 16 B apart, the two
+                // groups of 8 rows of one K = 16 step LBO = 128 B apart; a K step advances both start addresses by 16 rows
+#pragma unroll
                 for (int kk = 0; kk < TILE / 16; ++kk) {
-                    // A[ci][k = row] and B[co][k = row], both MN-major: 8 channels per 16 B, chunk stride = SBO, rows 16 B apart,
-                    // the two groups of 8 rows of one K = 16 step LBO = 128 B apart
-                    const ull adesc = make_desc(smem_u32(xt) + (unsigned)((GUARD + shift + 16 * kk) * 16), (unsigned)p.a_lbo, (unsigned)p.a_sbo);
-                    const ull bdesc = make_desc(smem_u32(dt) + (unsigned)(16 * kk * 16), (unsigned)p.b_lbo, (unsigned)p.b_sbo);
-                    tc_mma_f16(tmem + (unsigned)(t * N), adesc, bdesc, idesc, (it | kk) != 0 ? 1u : 0u);
+                    for (int t = 0; t < ntap; ++t) {
+                        const int sub = ntap == 1 ? (kk & 3) : 0;
+                        const bool first = it == 0 && (ntap == 1 ? kk < 4 : kk == 0);
+                        tc_mma_f16_lo(tmem + (unsigned)((t * nsub + sub) * N), a_lo0 + sh[t] + (unsigned)(16 * kk), a_hi, b_lo0 + (unsigned)(16 * kk), b_hi, idesc,
+                                      first ? 0u : 1u);
+                    }
                 }
             }
             tc_commit(&bars[1]);
@@ -319,8 +409,14 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const WgP p) {
         for (int t = 0; t < ntap; ++t) {
             float* dst = p.partial + (((size_t)s * p.taps + tap0 + t) * CH + ci) * N;
             for (int cg = 0; cg < N / 32; ++cg) {
-                float v[32];
-                tc_ld32(tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(t * N + cg * 32), v);
+                float v[32], u[32];
+                const unsigned tl = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(t * nsub * N + cg * 32);
+                tc_ld32(tl, v);
+                for (int a = 1; a < nsub; ++a) {
+                    tc_ld32(tl + (unsigned)(a * N), u);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += u[j];
+                }
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) reinterpret_cast<float4*>(dst + cg * 32)[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
@@ -905,11 +1001,26 @@ int spx_train_debug_wgrad(const void* x, const void* dy, int32_t N, int32_t taps
     return 0;
 }
 
+static long long* g_conv_trace = nullptr;
+/* test hook: device buffer of 8 int64 that receives clock64() at 8 points of CTA 0 of every conv_tf32_kernel launch (NULL: off) */
+int spx_train_debug_trace(long long* dev_trace) { g_conv_trace = dev_trace; return 0; }
+
 static Seg2 seg(float* p) { Seg2 s; s.p0 = p; s.p1 = p; s.split = 1 << 30; return s; }
 static Seg2 seg2(float* p0, float* p1) { Seg2 s; s.p0 = p0; s.p1 = p1; s.split = 32; return s; }
 
-static void launch_conv(const ConvP& p, int tiles, cudaStream_t st) {
-    conv_tf32_kernel<<<dim3(tiles, p.N / NC), 256, CONV_SMEM, st>>>(p);
+static void launch_conv(const ConvP& p0, int tiles, cudaStream_t st) {
+    ConvP p = p0;
+    p.trace = g_conv_trace;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(tiles, p.N / NC); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = CONV_SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;      // 1, or 7 consecutive row tiles (the tile count is a multiple of 7) sharing the weight stream
+    static int cl = 0;
+    if (!cl) { const char* e = getenv("SPX_CONV_CLUSTER"); cl = e ? atoi(e) : CONV_CLUSTER; if (cl != 1 && cl != 7) cl = CONV_CLUSTER; }
+    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, conv_tf32_kernel, p);
     spx::count_launch();
 }
 
