@@ -140,3 +140,39 @@ def test_threaded_with_the_tower_network():
         H.compare_records_and_result(game, recs[g], res[g], o)
     assert e.counters()["errors"] == 0
     e.close()
+
+
+@pytest.mark.parametrize("game,kind", [(0, 1), (1, 2)])
+def test_threaded_search_against_hardcoded_opponents(game, kind):
+    """Evaluation games (evaluate mode, no records) of a thread_count = 4 policy against OneStepLookahead / Random: move for move
+    and root statistics against the oracle."""
+    from oracle import oracle as ox
+    from self_play_reinforcement_learning_b200.engine import HashNetEvaluator
+    n_games, sims, K = 32, 36, 4
+    e = _engine(game=game, n_games=n_games, sims=sims, evaluator=HashNetEvaluator(game, 4), seed=21, noise_mode=0, evaluate=True,
+                emit_records=False, opponent_kind=kind, games_target=n_games, move_log=True, search_threads=K)
+    e.run_until_idle(max_ticks=200000, poll_every=256)
+    _, res = H.split_by_game(e.drain_records(), e.drain_results())
+    assert len(res) == n_games and e.counters()["errors"] == 0
+    for g in range(n_games):
+        cfg = ox.make_cfg(game, sims, seed=21, game_uid=g, evaluate=True, threads=K)
+        o = ox.play_episode_vs(cfg, bool(g & 1), kind, net_seed=4)
+        ml = e.move_log(g)
+        assert res[g]["reward"] == o["reward"] and res[g]["plies"] == len(o["moves"]), g
+        assert [(m["tree"], m["ply"], m["action"]) for m in ml] == [(m["tree"], m["ply"], m["action"]) for m in o["moves"]], g
+        for a, b in zip(ml, o["moves"]):
+            if a["tree"] == 0:
+                assert a["n"] == list(b["n"]) and a["w"] == list(b["w"]) and a["root_n"] == b["root_n"]
+    e.close()
+
+
+def test_scheduler_epoch_with_four_search_threads():
+    """The full loop (self-play -> native SGD step -> evaluation) with thread_count = 4 searches, toy sizes."""
+    from self_play_reinforcement_learning_b200 import nets
+    from self_play_reinforcement_learning_b200.scheduler import SelfPlayScheduler
+    torch.manual_seed(0)
+    net = nets.ResidualTower(7, 6, 7, num_blocks=1).cuda().eval()
+    s = SelfPlayScheduler(net, 0, iterations=32, epoch_length=16, initial_games=8, evaluation_games=6, games_per_gpu=16, batch_size=32,
+                          updates_per_epoch=3, lr=0.01, search_threads=4, evaluation_opponent="lookahead")
+    hist = s.train_model(num_epochs=1)
+    assert len(hist) == 1 and hist[0]["memory"] > 16 * 7 and np.isfinite(hist[0]["loss"]) and s.trainer_kind == "device"
