@@ -142,6 +142,15 @@ __host__ __device__ constexpr unsigned make_idesc_bf16_mn(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
 }
 
+// Programmatic dependent launch: every kernel of the step is launched with programmaticStreamSerialization, so its CTAs are
+// scheduled while the previous kernel of the stream is still draining; pdl_sync() lets the NEXT kernel start the same way and then
+// waits until the previous grid has completed and its memory is visible.  (A step is ~340 kernels of ~10 us: the launch gaps were
+// ~15 % of it.)  Must run before the first access to anything an earlier kernel wrote.
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ geometry
 // global row g (0 .. Rg-1) of a plane tensor: 8 guard rows, then 56 rows per board (cell (col, row) at col*7 + row), 8 guard rows
 __device__ __forceinline__ bool row_real(int g, int B, int& b, int& cell) {
@@ -177,6 +186,7 @@ constexpr int CONV_CLUSTER = 1;   // SPX_CONV_CLUSTER=7: seven row tiles share o
 constexpr int CONV_SMEM = (CH / 4) * PIECE + RING_STAGES * STAGE_MAX + 256 + TILE * 4;
 
 __global__ void __launch_bounds__(256, 1) conv_tf32_kernel(const ConvP p) {
+    pdl_sync();
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* atile = smem;
     unsigned char* ring = smem + (CH / 4) * PIECE;
@@ -349,6 +359,7 @@ struct WgP {
 constexpr int WG_SMEM = (CH / 8) * PIECE + (CH / 8) * TILE * 16 + 256;
 
 __global__ void __launch_bounds__(256, 1) wgrad_kernel(const WgP p) {
+    pdl_sync();
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* xt = smem;                               // 16 chunks x 144 rows x 16 B
     unsigned char* dt = smem + (CH / 8) * PIECE;            // N/8 chunks x 128 rows x 16 B
@@ -430,6 +441,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const WgP p) {
 // grad[(co * CIN + ci) * taps + tap] = sum_s partial[((s * taps + tap) * CINP + ci) * N + co]   (PyTorch [co][ci][kh][kw]);
 // channels >= split go to a second tensor (the value head conv)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int S, int taps, int CINP, int CIN, int N, float* g0, float* g1, int split) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= taps * CIN * N) return;
     const int co = i % N, ci = (i / N) % CIN, tap = i / (N * CIN);
@@ -441,6 +453,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int S, in
 
 // stem backward-weights on the CUDA cores (3 input planes): partial[s][tap][ci < 3][co]
 __global__ void stem_wgrad_kernel(const float* __restrict__ x0, const float* __restrict__ dy, float* partial, int Rg, int R, int rows_per_split) {
+    pdl_sync();
     const int tap = blockIdx.y, s = blockIdx.x, co = threadIdx.x;
     const int shift = tap_shift(9, tap);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
@@ -501,6 +514,7 @@ __device__ __forceinline__ void bn_totals(const float* __restrict__ part, int ti
 }
 
 __global__ void __launch_bounds__(256) bn_fwd_kernel(const BnP p) {
+    pdl_sync();
     __shared__ double tot[2][BN_CG];
     __shared__ float sc[BN_CG], sh[BN_CG];
     const int tid = threadIdx.x, N = p.N, r0 = blockIdx.x * TILE, c0 = blockIdx.y * BN_CG;
@@ -542,6 +556,7 @@ __global__ void __launch_bounds__(256) bn_fwd_kernel(const BnP p) {
 
 // dz = g * (a > 0); per-tile sums of dz and dz * xhat per channel (warp shuffles, then the block's 4 warps per chunk pair in order)
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnP p) {
+    pdl_sync();
     __shared__ float wsum[8][2][8];      // [warp][stat][channel within the warp's two chunks]
     const int tid = threadIdx.x, N = p.N, r0 = blockIdx.x * TILE, c0 = blockIdx.y * BN_CG, lane = tid & 31, warp = tid >> 5;
     const int m = tid & (TILE - 1), g = r0 + GUARD + m;
@@ -584,6 +599,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnP p) {
 // dy = gamma * invstd * (dz - mean(dz) - xhat * mean(dz * xhat));  dgamma = sum dz * xhat, dbeta = sum dz, dbias = 0 (exactly:
 // a per-channel constant added before training-mode BatchNorm does not change its output)
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnP p) {
+    pdl_sync();
     __shared__ double tot[2][BN_CG];
     __shared__ float m1[BN_CG], m2[BN_CG], sc[BN_CG], mu[BN_CG], is[BN_CG];
     const int tid = threadIdx.x, N = p.N, r0 = blockIdx.x * TILE, c0 = blockIdx.y * BN_CG;
@@ -627,6 +643,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnP p) {
 // ------------------------------------------------------------------------------------------------ input planes
 // planes [B][3][7][6] (preprocess, general/modules.py:115-125) -> X0: chunk 0 = (empty, own, enemy, 0), chunk 1 = 0
 __global__ void input_kernel(const float* __restrict__ planes, float* x0, int B, int Rg) {
+    pdl_sync();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= Rg) return;
     int b, cell;
@@ -661,6 +678,7 @@ struct HeadP {
 };
 
 __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadP p) {
+    pdl_sync();
     __shared__ float xs[2][FLAT];
     __shared__ float logit[8], red[8];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -719,6 +737,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadP p) {
 
 // gradient w.r.t. the head activations (through the Linear layers and Dropout), scattered into the gradient planes
 __global__ void __launch_bounds__(256) head_bwd_x_kernel(const HeadP p) {
+    pdl_sync();
     __shared__ float dh[HID], dl[8];
     const int b = blockIdx.x, tid = threadIdx.x;
     dh[tid] = p.dh1[(size_t)b * HID + tid];
@@ -743,6 +762,7 @@ struct FcGradP {
     int B;
 };
 __global__ void __launch_bounds__(256) fc_wgrad_kernel(const FcGradP p) {
+    pdl_sync();
     const int i = blockIdx.x * 256 + threadIdx.x;
     const int n_w1 = HID * FLAT, n_wp = NA * FLAT;
     if (i < n_w1) {
@@ -777,6 +797,7 @@ __global__ void __launch_bounds__(256) fc_wgrad_kernel(const FcGradP p) {
 // ------------------------------------------------------------------------------------------------ SGD + weight packing
 // torch.optim.SGD(momentum, weight_decay), dampening 0, no Nesterov: g += wd * p; buf = mu * buf + g; p -= lr * buf
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, long long n, float lr, float mu, float wd) {
+    pdl_sync();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float gg = fmaf(wd, p[i], g[i]);
@@ -790,6 +811,7 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
 //   forward  wf[co / 64][tap][ks][kc][co % 64][i] = W[co][ci = 8 ks + 4 kc + i][tap]             (K = CINP input channels, zero beyond CIN)
 //   backward wb[ci / 64][tap][ks][kc][ci % 64][i] = W[co = 8 ks + 4 kc + i][ci][taps - 1 - tap]   (K = COUT, N = CINP; absent for the stem)
 __global__ void pack_conv_kernel(const float* __restrict__ w0, const float* __restrict__ w1, int split, int COUT, int CIN, int CINP, int taps, float* wf, float* wb) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= taps * CINP * COUT) return;
     const int q = i & 3, n64 = (i >> 2) & 63, kc = (i >> 8) & 1;
@@ -806,7 +828,8 @@ __global__ void pack_conv_kernel(const float* __restrict__ w0, const float* __re
         wb[i] = co < split ? w0[((size_t)co * CIN + ci) * taps + t] : w1[((size_t)(co - split) * CIN + ci) * taps + t];
     }
 }
-__global__ void transpose_w1_kernel(const float* __restrict__ w1, float* w1t) {   // [256][1344] -> [1344][256]
+__global__ void transpose_w1_kernel(const float* __restrict__ w1, float* w1t) {
+    pdl_sync();   // [256][1344] -> [1344][256]
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < HID * FLAT) { const int j = i / FLAT, k = i - j * FLAT; w1t[(size_t)k * HID + j] = w1[i]; }
 }
@@ -816,6 +839,21 @@ __global__ void transpose_w1_kernel(const float* __restrict__ w1, float* w1t) { 
 
 // ================================================================================================ host side
 using namespace spx::train;
+
+// every kernel of the trainer goes through here: programmatic stream serialization (see pdl_sync) + the launch counter
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    spx::count_launch();
+}
+
 
 struct ConvLayer {
     size_t w, b, gamma, beta;     // offsets into the flat parameter vector
@@ -918,14 +956,11 @@ static int repack(spx_trainer* t, cudaStream_t st) {
     for (int l = 0; l < t->L; ++l) {
         const int cin = l == 0 ? 3 : CH, cinp = l == 0 ? 8 : CH;
         const int n = 9 * cinp * CH;
-        pack_conv_kernel<<<(n + 255) / 256, 256, 0, st>>>(t->params + t->conv[l].w, nullptr, CH, CH, cin, cinp, 9, t->wf + (size_t)l * 9 * CH * CH,
+        launch_k(pack_conv_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, t->params + t->conv[l].w, nullptr, CH, CH, cin, cinp, 9, t->wf + (size_t)l * 9 * CH * CH,
                                                              l == 0 ? nullptr : t->wb + (size_t)l * 9 * CH * CH);
-        spx::count_launch();
     }
-    pack_conv_kernel<<<(CH * HEAD + 255) / 256, 256, 0, st>>>(t->params + t->pol_w, t->params + t->val_w, 32, HEAD, CH, CH, 1, t->whf, t->whb);
-    spx::count_launch();
-    transpose_w1_kernel<<<(HID * FLAT + 255) / 256, 256, 0, st>>>(t->params + t->fc_w, t->w1t);
-    spx::count_launch();
+    launch_k(pack_conv_kernel, dim3((unsigned)((CH * HEAD + 255) / 256)), dim3(256), 0, st, t->params + t->pol_w, t->params + t->val_w, 32, HEAD, CH, CH, 1, t->whf, t->whb);
+    launch_k(transpose_w1_kernel, dim3((unsigned)((HID * FLAT + 255) / 256)), dim3(256), 0, st, t->params + t->fc_w, t->w1t);
     SPX_CUDA_R(cudaGetLastError());
     t->packed = true;
     return 0;
@@ -995,8 +1030,7 @@ int spx_train_debug_wgrad(const void* x, const void* dy, int32_t N, int32_t taps
     WgP wp; wp.x = (const __nv_bfloat16*)x; wp.dy = (const __nv_bfloat16*)dy; wp.N = N; wp.taps = taps; wp.partial = partial_out; wp.Rg = rows; wp.nchunks = (rows - 16) / TILE;
     wg_default_strides(wp);
     if (a_lbo >= 0) { wp.a_lbo = a_lbo; wp.a_sbo = a_sbo; wp.b_lbo = b_lbo; wp.b_sbo = b_sbo; }
-    wgrad_kernel<<<dim3(S, taps == 9 ? 3 : 1), 256, WG_SMEM, (cudaStream_t)stream>>>(wp);
-    spx::count_launch();
+    launch_k(wgrad_kernel, dim3(S, taps == 9 ? 3 : 1), dim3(256), WG_SMEM, (cudaStream_t)stream, wp);
     SPX_CUDA_R(cudaGetLastError());
     return 0;
 }
@@ -1014,12 +1048,14 @@ static void launch_conv(const ConvP& p0, int tiles, cudaStream_t st) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(tiles, p.N / NC); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = CONV_SMEM; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     attr[0].id = cudaLaunchAttributeClusterDimension;      // 1, or 7 consecutive row tiles (the tile count is a multiple of 7) sharing the weight stream
     static int cl = 0;
     if (!cl) { const char* e = getenv("SPX_CONV_CLUSTER"); cl = e ? atoi(e) : CONV_CLUSTER; if (cl != 1 && cl != 7) cl = CONV_CLUSTER; }
     attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = 2;
     cudaLaunchKernelEx(&cfg, conv_tf32_kernel, p);
     spx::count_launch();
 }
@@ -1037,8 +1073,7 @@ int spx_train_step(spx_trainer* t, const float* planes, const float* tree_probs,
     cudaStream_t st = (cudaStream_t)stream;
     const int L = t->L, B = t->B, Rg = t->Rg, tiles = t->tiles;
     float* P = t->params; float* G = t->grads;
-    input_kernel<<<(Rg + 255) / 256, 256, 0, st>>>(planes, t->x0, B, Rg);
-    spx::count_launch();
+    launch_k(input_kernel, dim3((unsigned)((Rg + 255) / 256)), dim3(256), 0, st, planes, t->x0, B, Rg);
     // ---------------- forward
     for (int l = 0; l < L; ++l) {
         const ConvLayer& c = t->conv[l];
@@ -1055,8 +1090,7 @@ int spx_train_step(spx_trainer* t, const float* planes, const float* tree_probs,
         bp.mean = t->mean + (size_t)l * CH; bp.invstd = t->invstd + (size_t)l * CH;
         bp.a16 = t->a16 + (size_t)l * (CH / 8) * Rg * 8;
         bp.N = CH; bp.B = B; bp.Rg = Rg; bp.tiles = tiles; bp.n_real = t->n_real;
-        bn_fwd_kernel<<<dim3(tiles, bp.N / BN_CG), 256, 0, st>>>(bp);
-        spx::count_launch();
+        launch_k(bn_fwd_kernel, dim3(tiles, bp.N / BN_CG), dim3(256), 0, st, bp);
     }
     const float* a_last = t->a + (size_t)(L - 1) * t->plane128;
     {   // fused policy | value 1x1 head conv + its two BatchNorms + ReLU (modules.py:97,102)
@@ -1069,37 +1103,30 @@ int spx_train_step(spx_trainer* t, const float* planes, const float* tree_probs,
         bp.rmean = seg2(t->running + t->pol_rs, t->running + t->val_rs); bp.rvar = seg2(t->running + t->pol_rs + 32, t->running + t->val_rs + 32);
         bp.mean = t->mean + (size_t)L * CH; bp.invstd = t->invstd + (size_t)L * CH;
         bp.N = HEAD; bp.B = B; bp.Rg = Rg; bp.tiles = tiles; bp.n_real = t->n_real;
-        bn_fwd_kernel<<<dim3(tiles, bp.N / BN_CG), 256, 0, st>>>(bp);
-        spx::count_launch();
+        launch_k(bn_fwd_kernel, dim3(tiles, bp.N / BN_CG), dim3(256), 0, st, bp);
     }
     HeadP hp; memset(&hp, 0, sizeof(hp));
     hp.ah = t->ah; hp.mask_in = dropout_mask; hp.mask = t->mask; hp.xd = t->xd; hp.wp = P + t->lp_w; hp.bp = P + t->lp_b; hp.w1t = t->w1t; hp.b1 = P + t->fc_b;
     hp.w1 = P + t->fc_w; hp.w2 = P + t->lo_w; hp.b2 = P + t->lo_b; hp.tree_probs = tree_probs; hp.target = target; hp.probs = t->probs; hp.value = t->value;
     hp.h1 = t->h1; hp.dlogit = t->dlogit; hp.du = t->du; hp.dh1 = t->dh1; hp.lossb = t->lossb; hp.gah = t->gah; hp.seed = seed; hp.step = step; hp.B = B; hp.Rg = Rg;
-    head_fwd_kernel<<<B, 256, 0, st>>>(hp);
-    spx::count_launch();
+    launch_k(head_fwd_kernel, dim3((unsigned)(B)), dim3(256), 0, st, hp);
     // ---------------- backward: heads
-    head_bwd_x_kernel<<<B, 256, 0, st>>>(hp);
-    spx::count_launch();
+    launch_k(head_bwd_x_kernel, dim3((unsigned)(B)), dim3(256), 0, st, hp);
     FcGradP fg; fg.xd = t->xd; fg.dh1 = t->dh1; fg.dlogit = t->dlogit; fg.du = t->du; fg.h1 = t->h1; fg.lossb = t->lossb;
     fg.g_w1 = G + t->fc_w; fg.g_b1 = G + t->fc_b; fg.g_wp = G + t->lp_w; fg.g_bp = G + t->lp_b; fg.g_w2 = G + t->lo_w; fg.g_b2 = G + t->lo_b;
     fg.loss_out = t->loss; fg.B = B;
-    fc_wgrad_kernel<<<(HID * FLAT + NA * FLAT + HID + NA + 1 + 255) / 256, 256, 0, st>>>(fg);
-    spx::count_launch();
+    launch_k(fc_wgrad_kernel, dim3((unsigned)((HID * FLAT + NA * FLAT + HID + NA + 1 + 255) / 256)), dim3(256), 0, st, fg);
     {
         BnP bp; memset(&bp, 0, sizeof(bp));
         bp.y = t->yh; bp.a = t->ah; bp.g = t->gah; bp.dy = t->dyh; bp.dy16 = t->dy16; bp.skip = nullptr; bp.part = t->part;
         bp.gamma = seg2(P + t->pol_g, P + t->val_g); bp.mean = t->mean + (size_t)L * CH; bp.invstd = t->invstd + (size_t)L * CH;
         bp.dgamma = seg2(G + t->pol_g, G + t->val_g); bp.dbeta = seg2(G + t->pol_be, G + t->val_be); bp.dbias = seg2(G + t->pol_b, G + t->val_b);
         bp.N = HEAD; bp.B = B; bp.Rg = Rg; bp.tiles = tiles; bp.n_real = t->n_real;
-        bn_bwd_reduce_kernel<<<dim3(tiles, bp.N / BN_CG), 256, 0, st>>>(bp);
-        bn_bwd_apply_kernel<<<dim3(tiles, bp.N / BN_CG), 256, 0, st>>>(bp);
-        spx::count_launch(); spx::count_launch();
+        launch_k(bn_bwd_reduce_kernel, dim3(tiles, bp.N / BN_CG), dim3(256), 0, st, bp);
+        launch_k(bn_bwd_apply_kernel, dim3(tiles, bp.N / BN_CG), dim3(256), 0, st, bp);
         WgP wp; wp.x = t->a16 + (size_t)(L - 1) * (CH / 8) * Rg * 8; wp.dy = t->dy16; wp.N = HEAD; wp.taps = 1; wp.partial = t->partial; wp.Rg = Rg; wp.nchunks = tiles; wg_default_strides(wp);
-        wgrad_kernel<<<dim3(t->S, 1), 256, WG_SMEM, st>>>(wp);
-        spx::count_launch();
-        wgrad_reduce_kernel<<<(CH * HEAD + 255) / 256, 256, 0, st>>>(t->partial, t->S, 1, CH, CH, HEAD, G + t->pol_w, G + t->val_w, 32);
-        spx::count_launch();
+        launch_k(wgrad_kernel, dim3(t->S, 1), dim3(256), WG_SMEM, st, wp);
+        launch_k(wgrad_reduce_kernel, dim3((unsigned)((CH * HEAD + 255) / 256)), dim3(256), 0, st, t->partial, t->S, 1, CH, CH, HEAD, G + t->pol_w, G + t->val_w, 32);
         ConvP cp; memset(&cp, 0, sizeof(cp));    // gradient w.r.t. the trunk output: dyh (64 channels) x W^T
         cp.in = t->dyh; cp.in_chunks = HEAD / 4; cp.w = t->whb; cp.taps = 1; cp.ks_per_tap = HEAD / 8; cp.N = CH; cp.out = t->g0; cp.has_bias = 0; cp.bias = seg(nullptr);
         cp.B = B; cp.Rg = Rg;
@@ -1115,22 +1142,17 @@ int spx_train_step(spx_trainer* t, const float* planes, const float* tree_probs,
         bp.gamma = seg(P + c.gamma); bp.mean = t->mean + (size_t)l * CH; bp.invstd = t->invstd + (size_t)l * CH;
         bp.dgamma = seg(G + c.gamma); bp.dbeta = seg(G + c.beta); bp.dbias = seg(G + c.b);
         bp.N = CH; bp.B = B; bp.Rg = Rg; bp.tiles = tiles; bp.n_real = t->n_real;
-        bn_bwd_reduce_kernel<<<dim3(tiles, bp.N / BN_CG), 256, 0, st>>>(bp);
-        bn_bwd_apply_kernel<<<dim3(tiles, bp.N / BN_CG), 256, 0, st>>>(bp);
-        spx::count_launch(); spx::count_launch();
+        launch_k(bn_bwd_reduce_kernel, dim3(tiles, bp.N / BN_CG), dim3(256), 0, st, bp);
+        launch_k(bn_bwd_apply_kernel, dim3(tiles, bp.N / BN_CG), dim3(256), 0, st, bp);
         if (l == 0) {
             const int splits = t->S, rows_per = (t->R + splits - 1) / splits;
-            stem_wgrad_kernel<<<dim3(splits, 9), CH, 0, st>>>(t->x0, t->dy, t->partial, Rg, t->R, rows_per);
-            spx::count_launch();
-            wgrad_reduce_kernel<<<(9 * 3 * CH + 255) / 256, 256, 0, st>>>(t->partial, splits, 9, 3, 3, CH, G + c.w, G + c.w, 1 << 30);
-            spx::count_launch();
+            launch_k(stem_wgrad_kernel, dim3(splits, 9), dim3(CH), 0, st, t->x0, t->dy, t->partial, Rg, t->R, rows_per);
+            launch_k(wgrad_reduce_kernel, dim3((unsigned)((9 * 3 * CH + 255) / 256)), dim3(256), 0, st, t->partial, splits, 9, 3, 3, CH, G + c.w, G + c.w, 1 << 30);
             break;
         }
         WgP wp; wp.x = t->a16 + (size_t)(l - 1) * (CH / 8) * Rg * 8; wp.dy = t->dy16; wp.N = CH; wp.taps = 9; wp.partial = t->partial; wp.Rg = Rg; wp.nchunks = tiles; wg_default_strides(wp);
-        wgrad_kernel<<<dim3(t->S, 3), 256, WG_SMEM, st>>>(wp);
-        spx::count_launch();
-        wgrad_reduce_kernel<<<(9 * CH * CH + 255) / 256, 256, 0, st>>>(t->partial, t->S, 9, CH, CH, CH, G + c.w, G + c.w, 1 << 30);
-        spx::count_launch();
+        launch_k(wgrad_kernel, dim3(t->S, 3), dim3(256), WG_SMEM, st, wp);
+        launch_k(wgrad_reduce_kernel, dim3((unsigned)((9 * CH * CH + 255) / 256)), dim3(256), 0, st, t->partial, t->S, 9, CH, CH, CH, G + c.w, G + c.w, 1 << 30);
         ConvP cp; memset(&cp, 0, sizeof(cp));
         cp.in = t->dy; cp.in_chunks = CH / 4; cp.w = t->wb + (size_t)l * 9 * CH * CH; cp.taps = 9; cp.ks_per_tap = CH / 8; cp.N = CH; cp.out = gnext;
         cp.has_bias = 0; cp.bias = seg(nullptr); cp.add = first ? t->skip : nullptr; cp.B = B; cp.Rg = Rg;
@@ -1139,8 +1161,7 @@ int spx_train_step(spx_trainer* t, const float* planes, const float* tree_probs,
     }
     if (loss_out) SPX_CUDA_R(cudaMemcpyAsync(loss_out, t->loss, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (apply_update) {
-        sgd_kernel<<<(unsigned)((t->n_params + 255) / 256), 256, 0, st>>>(P, G, t->mom, (long long)t->n_params, lr, momentum, weight_decay);
-        spx::count_launch();
+        launch_k(sgd_kernel, dim3((unsigned)((unsigned)((t->n_params + 255) / 256))), dim3(256), 0, st, P, G, t->mom, (long long)t->n_params, lr, momentum, weight_decay);
         if (repack(t, st)) return SPX_E_CUDA;
     }
     SPX_CUDA_R(cudaGetLastError());
