@@ -156,6 +156,37 @@ def cpu_baseline(seconds, blocks, sims, procs=None, alpha=1.0, kind=None):
     return dict(_cpu_baseline_port(seconds, blocks, sims, procs=procs, alpha=alpha), kind="port")
 
 
+def cpu_baseline_as_shipped(seconds, blocks, sims):
+    """SURVEY.md 8(d) mode (ii): the unmodified reference's own multi-process path (SelfPlayScheduler.compare_models: SelfPlayWorker
+    processes with 8 threaded games each + one InferenceWorker batching the network on the CPU, spawn) -- oracle/ref_run_shipped.py in
+    a subprocess with a hard time limit; network evaluations per second.  None when the staged reference is absent; an error
+    string instead of a number when the run fails (the reference swallows its workers' exceptions)."""
+    if reference_kind() != "reference":
+        return None
+    try:
+        import signal
+        # its own session: whatever happens, the whole tree of reference worker processes goes away with it
+        p = subprocess.Popen([sys.executable, "-m", "oracle.ref_run_shipped", str(seconds), str(blocks), str(sims)], cwd=ROOT,
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, start_new_session=True)
+        try:
+            out, _ = p.communicate(timeout=420)
+        finally:
+            try:
+                os.killpg(p.pid, signal.SIGKILL)
+            except OSError:
+                pass
+        lines = [ln for ln in out.splitlines() if ln.startswith("{")]
+        d = json.loads(lines[-1])
+        if "error" in d:
+            return {"error": d["error"]}
+        return {"leaf_evals_per_s": d["leaf_evals_per_s"], "unit": "network evaluations/s", "processes": d["processes"], "threads_per_worker": d["threads_per_worker"],
+                "thread_count": d["thread_count"], "seconds": d["seconds"],
+                "what": "SelfPlayScheduler.compare_models as shipped (self_play_parallel.py:355-379): SelfPlayWorker processes + one InferenceWorker "
+                        "on the CPU, requests answered by the InferenceWorker per second (inference_worker.py:112)"}
+    except Exception as e:      # noqa: BLE001 -- a reported baseline must not take the bench down
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def _sample_text(r, blocks, sims):
     who = ("the UNMODIFIED reference (games/algos/mcts.py MCTreeSearch x 2 + selfplayworker.SelfPlayer.play_episode + "
            f"games/general/modules.py ResidualTower-{blocks} in fp32 at batch 1, byte-compiled into oracle/_ref)") if r["kind"] == "reference" else \
@@ -219,6 +250,7 @@ def run_reference(args, workload, out=sys.stdout):
             "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "positions_per_sec": sum(v["positions_per_s"] * v["seconds"] for v in vals) / tot_t,
             "wall_s": time.time() - t0}
+    line["cpu_baseline"]["as_shipped"] = cpu_baseline_as_shipped(min(per_step, 20.0), args.blocks, args.sims)
     print(json.dumps(line), file=out, flush=True)
 
 
@@ -493,7 +525,8 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             r = cpu_baseline(args.cpu_seconds, args.blocks, args.sims, alpha=args.alpha)
             cpu = {"value": r["sims_per_s"], "unit": "sims/s", "cores": r["cores"], "kind": r["kind"],
-                   "sample": _sample_text(r, args.blocks, args.sims), "positions_per_s": r["positions_per_s"]}
+                   "sample": _sample_text(r, args.blocks, args.sims), "positions_per_s": r["positions_per_s"],
+                   "as_shipped": cpu_baseline_as_shipped(min(args.cpu_seconds, 20.0), args.blocks, args.sims) if not args.no_aux_rooflines else None}
         line = {"metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong" if fixed_total else "weak",   # N > 1 default: 16384 concurrent games in total at every N (configs[2])
