@@ -36,3 +36,19 @@ def test_memory_fifo_and_sampling():
     assert len(m) == 5 and sorted(m.sample(5)) == [3, 4, 5, 6, 7]
     m.change_size(3)
     assert len(m) == 3 and sorted(m.sample(3)) == [5, 6, 7]
+
+
+def test_training_reference_formula_reproduces_the_golden_loss(golden_dir):
+    """tests/train_ref.torch_loss -- the autograd reference the device SGD step (csrc/spx_train.cu) is held against -- is the
+    reference's MCTreeSearch.loss (mcts.py:234-252): with the network in eval mode and every Dropout unit kept-and-unscaled it
+    reproduces the loss value the unmodified reference computed for the golden batch (q_average: target = actual_val + q)."""
+    from tests import train_ref as R
+    g = np.load(os.path.join(golden_dir, "nets.npz"))
+    torch.manual_seed(3)
+    net = R.patch_dropout(nets.ResidualTower(7, 6, 7, num_blocks=2)).eval()
+    boards = torch.from_numpy(g["loss_states"].astype(np.int64))
+    planes = torch.stack([(boards == 0), (boards == 1), (boards == -1)], 1).float()
+    half = torch.full((16, 2, 1344), 0.5)            # FixedDropout computes x * keep * 2: keep = 0.5 is the identity (eval-mode Dropout)
+    with torch.no_grad():
+        loss, *_ = R.torch_loss(net, planes, torch.from_numpy(g["loss_probs"]), torch.from_numpy(g["loss_val"] + g["loss_q"]), half)
+    assert abs(float(loss) - float(g["loss_value"][0])) < 1e-5

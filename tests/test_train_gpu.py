@@ -183,3 +183,32 @@ def test_hundred_steps_of_batch_128_take_under_a_second():
     print("100 steps of batch 128, 20 blocks:", ms, "ms")
     assert ms < 1000.0
     tr.close()
+
+
+def test_step_on_the_golden_loss_batch(golden_dir):
+    """The batch of the reference's golden loss fixture (tests/golden/nets.npz: states, tree_probs, actual_val, q written by the
+    unmodified reference; target = actual_val + q, mcts.py:243-244) through one device step in train mode vs autograd on the same
+    module (tests/test_scheduler_cpu.py ties that autograd formula to the reference's own loss value)."""
+    import os
+    import numpy as np
+    from self_play_reinforcement_learning_b200.train import DeviceTrainer
+    g = np.load(os.path.join(golden_dir, "nets.npz"))
+    boards = torch.from_numpy(g["loss_states"].astype(np.int64)).cuda()
+    planes = torch.stack([(boards == 0), (boards == 1), (boards == -1)], 1).float()
+    probs = torch.from_numpy(g["loss_probs"]).cuda()
+    target = torch.from_numpy(g["loss_val"] + g["loss_q"]).cuda()
+    mask = (torch.rand(16, 2, 1344, generator=torch.Generator().manual_seed(1)) < 0.5).to(torch.uint8).cuda()
+    torch.manual_seed(3)
+    net = R.patch_dropout(nets.ResidualTower(7, 6, 7, num_blocks=2)).cuda().train()
+    ref64 = R.patch_dropout(nets.ResidualTower(7, 6, 7, num_blocks=2))
+    ref64.load_state_dict({k: v for k, v in net.state_dict().items()}, strict=False)
+    ref64 = ref64.cuda().double().train()
+    tr = DeviceTrainer(net, batch_size=16)
+    out = tr.step(planes, probs, target, dropout_mask=mask, apply_update=False).cpu()
+    loss64, lv64, lp64, _, _ = R.torch_loss(ref64, planes.double(), probs.double(), target.double(), mask)
+    loss64.backward()
+    assert abs(out[0].item() - loss64.item()) < 2e-3 * abs(loss64.item()) and abs(out[1].item() - lv64.item()) < 2e-3 and abs(out[2].item() - lp64.item()) < 2e-3
+    gflat = DeviceTrainer.unflatten(tr.gradients_flat(), net)
+    errs = {n: _rel(gflat[n], p.grad) for n, p in ref64.named_parameters() if p.grad.norm() > 1e-6}
+    assert max(errs.values()) < 1e-1, errs
+    tr.close()
