@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--no-aux-rooflines", action="store_true", help="skip the search-only and env-kernel roofline legs (tests)")
     ap.add_argument("--max-sims-per-tick", type=int, default=8)
     ap.add_argument("--no-fused", action="store_true", help="launch spx_advance + the network kernel per tick instead of the fused tick kernel")
-    ap.add_argument("--fused-chunk", type=int, default=100, help="ticks per launch of the fused tick kernel")
+    ap.add_argument("--fused-chunk", type=int, default=400, help="ticks per launch of the fused tick kernel")
     ap.add_argument("--alpha", type=float, default=1.0, help="Dirichlet alpha of the root noise (mcts.py:135 default 1; tictactoeconfig.py:9 uses 0.15)")
     return ap.parse_args()
 

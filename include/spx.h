@@ -294,6 +294,14 @@ int64_t spx_replay_unique(spx_replay* r); /* len(deduplicator.counter): distinct
  * separate ticks, bit for bit (tests/test_search_gpu.py).  policy / value: the engine's output buffers (dev f32[n_games][A],
  * f32[n_games]) as passed to spx_advance.  Needs the SM-pair tower with fused heads, one network, same game as the engine. */
 int spx_tick_fused(spx_engine* e, spx_tower* t, int32_t n_ticks, float* policy, float* value, void* stream);
+/* The same launch, work-conserving: the reference's workers are independent processes that take games off a shared task queue and
+ * never wait for each other (self_play_parallel.py:236-253, selfplayworker.py:105-161).  Here the launch holds a budget of
+ * n_ticks x ceil(n_games / 14) network passes; every SM pair draws its next tick from that budget when it gets there, so a pair
+ * whose games search longer between two evaluations (chains of terminal re-visits) runs fewer ticks instead of making 73 other
+ * pairs wait at the end of the launch.  A game's records and results do not depend on how many ticks a launch gives it (every game
+ * is replayed bit for bit either way); only the number of ticks per game per launch is no longer exactly n_ticks.  The tick counter
+ * advances by n_ticks. */
+int spx_tick_fused_balanced(spx_engine* e, spx_tower* t, int32_t n_ticks, float* policy, float* value, void* stream);
 
 /* timing-event helpers (cudaEvent_t behind void*), so hosts without a CUDA binding can time on the launching stream */
 int spx_event_create(void** ev_out);

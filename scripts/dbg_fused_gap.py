@@ -22,13 +22,26 @@ e.run_ticks(1600, chunk=100)
 torch.cuda.synchronize()
 
 
-def timed(fn, n):
+import subprocess
+import threading
+lines = []
+proc = subprocess.Popen(["nvidia-smi", "--id=0", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-lms", "100"],
+                        stdout=subprocess.PIPE, text=True)
+threading.Thread(target=lambda: [lines.append(l) for l in proc.stdout], daemon=True).start()
+clk = {}
+
+
+def timed(fn, n, tag=None):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    lines.clear()
     a.record()
     fn()
     b.record()
     torch.cuda.synchronize()
+    mhz = sorted(float(l.split(",")[0]) for l in lines if "," in l)
+    if tag and mhz:
+        clk[tag] = mhz[len(mhz) // 2]
     return a.elapsed_time(b) / n
 
 
@@ -40,10 +53,11 @@ def tower_only(n):
 out = {}
 for rep in range(2):
     c0 = e.counters()
-    out["fused_ms_per_tick"] = timed(lambda: e.run_ticks(3000, chunk=100), 3000)
+    out["fused_ms_per_tick"] = timed(lambda: e.run_ticks(3000, chunk=100), 3000, "fused_mhz")
     c1 = e.counters()
     out["leaves_per_tick"] = (c1["leaf_evals"] - c0["leaf_evals"]) / 3000
     out["sims_per_tick"] = (c1["sims"] - c0["sims"]) / 3000
     if os.environ.get("SPX_GAP_TOWER", "1") != "0":
-        out["tower_back_to_back_ms"] = timed(lambda: tower_only(3000), 3000)
-print(os.environ.get("SPX_DBG_FLAGS", "0"), G, out, flush=True)
+        out["tower_back_to_back_ms"] = timed(lambda: tower_only(3000), 3000, "tower_mhz")
+print(os.environ.get("SPX_DBG_FLAGS", "0"), G, out, clk, flush=True)
+proc.terminate()

@@ -56,7 +56,7 @@ EXPORTS = ["spx_last_error", "spx_version", "spx_launch_count", "spx_env_step", 
            "spx_tttnet_load", "spx_tttnet_forward",
            "spx_advance_timed", "spx_restart", "spx_set_sims", "spx_set_external_actions", "spx_slot_status", "spx_event_create", "spx_event_destroy", "spx_event_elapsed_ms",
            "spx_replay_create", "spx_replay_destroy", "spx_replay_size", "spx_replay_max_size", "spx_replay_change_size", "spx_replay_reset",
-           "spx_drain_records_device", "spx_replay_append", "spx_replay_read", "spx_replay_sample", "spx_replay_deduplicate", "spx_replay_unique", "spx_tick_fused",
+           "spx_drain_records_device", "spx_replay_append", "spx_replay_read", "spx_replay_sample", "spx_replay_deduplicate", "spx_replay_unique", "spx_tick_fused", "spx_tick_fused_balanced",
            "spx_train_create", "spx_train_destroy", "spx_train_param_count", "spx_train_running_count", "spx_train_set_state", "spx_train_get_state",
            "spx_train_step", "spx_train_outputs", "spx_train_debug_planes", "spx_train_debug_wgrad", "spx_train_debug_trace"]
 
@@ -127,6 +127,7 @@ def lib():
         L.spx_replay_read.argtypes = [vp, i64, i64, vp, vp]
         L.spx_replay_sample.argtypes = [vp, i32, i64, u64, u64, vp, vp, vp, vp, vp, vp, vp]
         L.spx_tick_fused.argtypes = [vp, vp, i32, vp, vp, vp]
+        L.spx_tick_fused_balanced.argtypes = [vp, vp, i32, vp, vp, vp]
         L.spx_replay_deduplicate.argtypes = [vp, i64, vp]
         L.spx_replay_unique.restype = C.c_int64
         L.spx_replay_unique.argtypes = [vp]

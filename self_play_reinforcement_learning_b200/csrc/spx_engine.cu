@@ -459,7 +459,7 @@ int spx_create(const spx_config* cfg, spx_engine** out) {
     SPX_ALLOC(d.rec_count, unsigned long long, 1);
     SPX_ALLOC(d.res_count, unsigned long long, 1);
     SPX_ALLOC(d.rec_dropped, unsigned long long, 1);
-    SPX_ALLOC(d.ticks, unsigned long long, 1);
+    SPX_ALLOC(d.ticks, unsigned long long, 2);   // [0] ticks run, [1] pass tickets of the running work-conserving launch (spx_tick_fused_balanced)
     SPX_ALLOC(d.leaf_own, u64, G * d.K);
     SPX_ALLOC(d.leaf_opp, u64, G * d.K);
     SPX_ALLOC(d.needs_eval, unsigned char, G * d.K);

@@ -260,7 +260,7 @@ __device__ long long g_trace[64 * 16 + 3 * 160];   // + per-CTA {entry, exit, SM
 #define SPX_TRACE_IF(c, l, k) do { if (c) SPX_TRACE(l, k); __syncwarp(); } while (0)
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ long long g_tt[64 * 12];   // fused tick kernel: globaltimer (ns) of 12 points of passes 20..83, CTA 0, first epilogue thread
-#define SPX_TT(k) do { if (ENGINE && blockIdx.x == 0 && tid == EPI_WARP0 * 32 && pass >= 20 && pass < 84) g_tt[(pass - 20) * 12 + (k)] = (long long)globaltimer_ns(); } while (0)
+#define SPX_TT(k) do { if (ENGINE && blockIdx.x == 0 && tid == EPI_WARP0 * 32 && pass >= 20 && pass < 84) g_tt[(pass - 20) * 12 + (k)] = (long long)clock64(); } while (0)
 #else
 #define SPX_TRACE(l, k) do { } while (0)
 #define SPX_TRACE_IF(c, l, k) do { } while (0)
@@ -279,6 +279,7 @@ template <int NCTA> struct SmemT {
     float xval[8];
     int slot_status[8];                 // FS_* per board slot (fast mode)
     int quit, passes_done, searches_done;
+    int go;                             // ENGINE: ticks known to exist | GO_FINAL (no more after those), see "work-conserving launches"
     unsigned char need[8];
     alignas(16) float bias[NCTA == 1 ? 3 : 1][NCTA == 1 ? CH : 4];   // single-CTA kernel only: staged fp32 bias, read as float4
     alignas(128) unsigned char ones[256];   // SM-pair kernel: the A operand of the bias MMA (see issue_bias)
@@ -339,6 +340,10 @@ __device__ __forceinline__ void st_async_remote_f32(void* local_addr, void* bar,
                  "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [ra], %3, [rb];\n\t}" ::"r"(smem_u32(local_addr)), "r"(smem_u32(bar)),
                  "r"(cta), "r"(__float_as_uint(v)) : "memory");
 }
+__device__ __forceinline__ void st_shared_remote_s32(void* local_addr, unsigned cta, int v) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tst.volatile.shared::cluster.s32 [ra], %2;\n\t}" ::"r"(smem_u32(local_addr)), "r"(cta), "r"(v) : "memory");
+}
+constexpr int GO_FINAL = 0x40000000;
 __device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 __device__ __forceinline__ void st_volatile_s32(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
 // warp-uniform read of a flag another warp may be writing right now (lanes must not disagree: the callers shuffle afterwards)
@@ -492,7 +497,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
              const unsigned char* __restrict__ wconv, const float* __restrict__ bias_all, float* __restrict__ head_out,
              int fused_in, const float* __restrict__ polw, const float* __restrict__ polb, const float* __restrict__ fc_b1,
              const float* __restrict__ fc_w2, const float* __restrict__ fc_b2, float* __restrict__ policy_out, float* __restrict__ value_out,
-             const __grid_constant__ EngineDev E, const int n_ticks) {
+             const __grid_constant__ EngineDev E, const int n_ticks, const long long pass_budget) {
     typedef SmemT<NCTA> Smem;
     // leaves / needs_eval are produced inside this launch when ENGINE: read them through L2 (__ldcg), never through the
     // read-only path the __restrict__ const parameters allow
@@ -563,11 +568,12 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
     const long long ustride = gridDim.x / NCTA, unit_first = blockIdx.x / NCTA;
     const int U = ENGINE ? (unit_first < n_units ? (int)((n_units - 1 - unit_first) / ustride + 1) : 0) : 0;
     const bool shadow_all = ENGINE && U >= 2;
-    const int total_passes = ENGINE ? n_ticks * U : 0;
     float my_p = 0.f, v_next = 0.f;      // epilogue warps w < NB: the outputs of the pass for game w (this lane's prior, the value)
     if constexpr (ENGINE) {
         if (tid < 8) { S.slot_status[tid] = FS_FAST; S.need[tid] = 0; }
-        if (tid == 0) { S.quit = 0; S.passes_done = 0; S.searches_done = 0; }
+        // work-conserving launches (pass_budget >= 0, spx_tick_fused_balanced): tick 0 exists for every cluster; whether tick t + 1
+        // exists is decided at the start of tick t by a ticket drawn from the launch's budget of passes (E.ticks[1]), see below
+        if (tid == 0) { S.quit = 0; S.passes_done = 0; S.searches_done = 0; S.go = U == 0 ? GO_FINAL : pass_budget >= 0 ? 1 : (n_ticks | GO_FINAL); }
         __syncthreads();
         if (warp == 3) {
             // ===================== shadow warp: simulations that need no network evaluation of the running pass
@@ -578,7 +584,11 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 int budget = 0;
                 float sp = 0.f, sv = 0.f;
                 if (shadow_all) {
-                    if (p >= total_passes) break;
+                    if (j == 0 && p % U == 0) {   // first job of tick p / U: does that tick exist?
+                        int w;
+                        for (;;) { w = ld_flag_uniform(&S.go); if (p / U < (w & (GO_FINAL - 1)) || (w & GO_FINAL)) break; __nanosleep(200); }
+                        if (p / U >= (w & (GO_FINAL - 1))) break;
+                    }
                     if (j == 0) {   // job p = the leaves of pass p: needs the outputs of the same unit's previous pass (p - U)
                         while (ld_flag_uniform(&S.passes_done) < p - U + 1) __nanosleep(200);
                         __threadfence();
@@ -598,6 +608,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                     budget = 4 * E.cfg.max_sims_per_tick;
                     defer = true;       // the running pass does not evaluate this leaf: it waits for the next one
                 }
+                if (run && shadow_all && (E.cfg.reserved0 & 1)) run = false;   // timing experiment (SPX_DBG_FLAGS=1): no search, the same leaves again
                 if (run) {
                     const int flags = engine_step<GAME>(E, (int)gb, sp, sv, budget, defer ? 1 : 0, nullptr);
                     if (!shadow_all && flags) {   // a leaf, or nothing more to do: back to the epilogue warp (0 = budget used up: go on later)
@@ -614,13 +625,20 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
             }
         }
     }
-    for (int tick = 0; tick < (ENGINE ? n_ticks : 1); ++tick) {
+    // warps without a role in the tick loop (and the shadow warp, whose loop is above) go straight to the final barrier
+    const bool has_role = warp == 0 || (warp == 1 && crank == 0) || (NCTA == 2 && warp == 2 && crank == 1) || warp >= EPI_WARP0;
+    bool go_final = false;               // decider thread: the last tick of this cluster is known
+    for (int tick = 0; ENGINE ? has_role : tick < 1; ++tick) {
+    if constexpr (ENGINE) {   // does tick `tick` exist?  (exact launches: S.go = n_ticks | GO_FINAL from the start)
+        int w;
+        for (;;) { w = ld_flag_uniform(&S.go); if (tick < (w & (GO_FINAL - 1)) || (w & GO_FINAL)) break; __nanosleep(100); }
+        if (tick >= (w & (GO_FINAL - 1))) break;
+    }
     int ui = 0;
     for (long long unit = blockIdx.x / NCTA; unit < n_units; unit += gridDim.x / NCTA, ++ui) {
         const long long grp = NCTA * unit + crank;
         const int pass = tick * U + ui;
         (void)pass;
-        if constexpr (ENGINE) { if (warp == 3) continue; }   // the shadow warp has done its work above
         // cluster-uniform skip when none of the boards of this unit asked for an evaluation (plain forward only: the fused tick
         // kernel always evaluates -- agreeing on a skip would cost a cluster round trip per tick)
         bool any = ENGINE || needs == nullptr;
@@ -859,6 +877,17 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                 }
             }
             SPX_TT(1);
+            // work-conserving launch: one thread of the leader CTA (an epilogue warp that owns no game) draws the ticket for the
+            // cluster's NEXT tick now and publishes the answer after the preprocess below -- the atomic's latency is off every
+            // critical path, and every role warp of both CTAs finds the answer long before it gets to the top of that tick
+            long long tk_prev = 0;
+            bool tk_asked = false;
+            if constexpr (ENGINE) {
+                if (pass_budget >= 0 && ui == 0 && crank == 0 && ew == NB && lane == 0 && !go_final) {
+                    tk_prev = (long long)atomicAdd(E.ticks + 1, (unsigned long long)U);
+                    tk_asked = true;
+                }
+            }
             if (fused && !first_unit) {
                 // the previous unit's FC ring / head activations overwrote the buffers: the zero guard rows (never written by
                 // an epilogue) must read as zero again; every other row is rewritten before it is read
@@ -897,6 +926,15 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
             fence_proxy_async();
             signal_epi_done();
             SPX_TT(3);
+            if constexpr (ENGINE) {
+                if (tk_asked) {
+                    const bool ok = tk_prev + U <= pass_budget;
+                    const int w = ok ? tick + 2 : ((tick + 1) | GO_FINAL);
+                    go_final = !ok;
+                    st_volatile_s32(&S.go, w);
+                    if constexpr (NCTA == 2) st_shared_remote_s32(&S.go, 1u, w);
+                }
+            }
             // per-tile row bookkeeping is layer independent
             bool real_t[MT]; int board_t[MT], cell_t[MT];
 #pragma unroll
@@ -1445,12 +1483,12 @@ static int tower_forward_impl(spx_tower* t, const uint64_t* own, const uint64_t*
         SPX_CUDA_T(cudaLaunchKernelEx(&cfg, kern, (const unsigned long long*)own, (const unsigned long long*)opp, needs_eval,
                                       (long long)n, t->n_layers, (const unsigned char*)t->blob, (const float*)(t->blob + t->off_bias), t->head_buf,
                                       t->fused, (const float*)(t->blob + t->off_polw), (const float*)(t->blob + t->off_polb), (const float*)(t->blob + t->off_b1),
-                                      (const float*)(t->blob + t->off_w2), (const float*)(t->blob + t->off_b2), policy, value, spx::EngineDev{}, 1));
+                                      (const float*)(t->blob + t->off_w2), (const float*)(t->blob + t->off_b2), policy, value, spx::EngineDev{}, 1, -1LL));
     } else {
         const int grid = (int)(groups < t->sm_count ? groups : t->sm_count);
         tower_kernel<1><<<grid, NUM_THREADS, sizeof(SmemT<1>), st>>>((const unsigned long long*)own, (const unsigned long long*)opp, needs_eval, n,
                                                             t->n_layers, t->blob, (const float*)(t->blob + t->off_bias), t->head_buf,
-                                                            0, nullptr, nullptr, nullptr, nullptr, nullptr, policy, value, spx::EngineDev{}, 1);
+                                                            0, nullptr, nullptr, nullptr, nullptr, nullptr, policy, value, spx::EngineDev{}, 1, -1LL);
     }
     spx::count_launch();
     SPX_CUDA_T(cudaGetLastError());
@@ -1475,8 +1513,11 @@ int spx_debug_tick_trace(long long* host_out) { return (int)cudaMemcpyFromSymbol
 int spx_debug_trace(long long* host_out) { return (int)cudaMemcpyFromSymbol(host_out, spx::tower::g_trace, sizeof(long long) * (64 * 16 + 3 * 160)); }
 #endif
 
-/* n_ticks ticks (spx_advance + network evaluation each) in ONE launch: see tower_kernel<.., ENGINE = true> */
-int spx_tick_fused(spx_engine* e, spx_tower* t, int32_t n_ticks, float* policy, float* value, void* stream) {
+/* n_ticks ticks (spx_advance + network evaluation each) in ONE launch: see tower_kernel<.., ENGINE = true>.
+   balanced = 0: every game gets exactly n_ticks ticks (the launch lasts as long as its slowest SM pair);
+   balanced = 1: work-conserving -- the launch holds n_ticks x (units of 14 games) network passes and every SM pair draws its next
+   tick from that budget when it gets there, so pairs whose games search longer run fewer ticks and nobody waits. */
+static int tick_fused_impl(spx_engine* e, spx_tower* t, int32_t n_ticks, float* policy, float* value, void* stream, int balanced) {
     if (!e || !t || !policy || !value) return spx::set_err(SPX_E_ARG, "spx_tick_fused: null argument%s", "");
     if (n_ticks <= 0) return 0;
     if (t->ncta != 2 || !t->fused) return spx::set_err(SPX_E_STATE, "spx_tick_fused: needs the SM-pair tower with fused heads%s", "");
@@ -1493,16 +1534,28 @@ int spx_tick_fused(spx_engine* e, spx_tower* t, int32_t n_ticks, float* policy, 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    long long pass_budget = -1;
+    if (balanced && n_ticks > 1) {   // the budget beyond every cluster's first tick; the ticket counter lives next to the tick counter
+        pass_budget = (long long)(n_ticks - 1) * pairs;
+        SPX_CUDA_T(cudaMemsetAsync(e->d.ticks + 1, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    }
     auto kern = t->f16 ? (t->game == SPX_GAME_TICTACTOE ? tower_kernel<2, SPX_GAME_TICTACTOE, true, true> : tower_kernel<2, SPX_GAME_CONNECT4, true, true>)
                        : (t->game == SPX_GAME_TICTACTOE ? tower_kernel<2, SPX_GAME_TICTACTOE, true> : tower_kernel<2, SPX_GAME_CONNECT4, true>);
     SPX_CUDA_T(cudaLaunchKernelEx(&cfg, kern, (const unsigned long long*)e->d.leaf_own, (const unsigned long long*)e->d.leaf_opp,
                                   (const unsigned char*)e->d.needs_eval, n, t->n_layers, (const unsigned char*)t->blob,
                                   (const float*)(t->blob + t->off_bias), t->head_buf, 1, (const float*)(t->blob + t->off_polw),
                                   (const float*)(t->blob + t->off_polb), (const float*)(t->blob + t->off_b1), (const float*)(t->blob + t->off_w2),
-                                  (const float*)(t->blob + t->off_b2), policy, value, e->d, (int)n_ticks));
+                                  (const float*)(t->blob + t->off_b2), policy, value, e->d, (int)n_ticks, pass_budget));
     spx::count_launch();
     SPX_CUDA_T(cudaGetLastError());
     return 0;
+}
+
+int spx_tick_fused(spx_engine* e, spx_tower* t, int32_t n_ticks, float* policy, float* value, void* stream) {
+    return tick_fused_impl(e, t, n_ticks, policy, value, stream, 0);
+}
+int spx_tick_fused_balanced(spx_engine* e, spx_tower* t, int32_t n_ticks, float* policy, float* value, void* stream) {
+    return tick_fused_impl(e, t, n_ticks, policy, value, stream, 1);
 }
 
 int spx_tower_forward(spx_tower* t, const uint64_t* own, const uint64_t* opp, const uint8_t* needs_eval, int64_t n,

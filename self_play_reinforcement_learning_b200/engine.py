@@ -176,13 +176,19 @@ class SelfPlayEngine:
         else:
             self.evaluator(self, events=net_events)
 
-    def run_ticks(self, n, fused=True, chunk=256):
+    def run_ticks(self, n, fused=True, chunk=400, balanced=None):
         """n ticks.  With the native tower the whole loop runs as persistent launches of `chunk` ticks (spx_tick_fused: the
-        network CTAs also advance their games); any other evaluator, or fused=False, launches advance + evaluation per tick."""
+        network CTAs also advance their games); any other evaluator, or fused=False, launches advance + evaluation per tick.
+        balanced: launches are work-conserving (spx_tick_fused_balanced: SM pairs draw their ticks from the launch's budget, a
+        game gets `chunk` ticks per launch on average instead of exactly; games themselves do not depend on it).  Default: on
+        for launches of at least 16 ticks (SPX_TICK_BALANCE=0 switches it off); callers that count ticks per game pass False."""
         fn = getattr(self.evaluator, "fused_ticks", None) if (fused and self.search_threads == 1) else None
+        if balanced is None:
+            balanced = os.environ.get("SPX_TICK_BALANCE", "1") != "0"
         done = 0
         while fn is not None and done < n:
-            if not fn(self, min(chunk, n - done)):
+            k = min(chunk, n - done)
+            if not fn(self, k, balanced=bool(balanced) and k >= 16):
                 break
             done += min(chunk, n - done)
             self._first = False

@@ -402,12 +402,14 @@ class TowerEvaluator:
     def __call__(self, engine, events=None):
         self.tower.forward_bits(engine.leaf_own, engine.leaf_opp, engine.needs_eval, engine.policy, engine.value, events)
 
-    def fused_ticks(self, engine, n):
-        """n whole ticks (advance + evaluation) in one persistent launch (spx_tick_fused); False if this tower cannot."""
+    def fused_ticks(self, engine, n, balanced=False):
+        """n whole ticks (advance + evaluation) in one persistent launch (spx_tick_fused; balanced: the work-conserving form
+        spx_tick_fused_balanced, n ticks per game ON AVERAGE); False if this tower cannot."""
         if not (self.tower.ncta == 2 and self.tower.fused_heads) or os.environ.get("SPX_FUSED_TICK", "1") == "0":
             return False
-        check(lib().spx_tick_fused(engine._h, self.tower._h, int(n), engine.policy.data_ptr(), engine.value.data_ptr(),
-                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)), "spx_tick_fused")
+        fn = lib().spx_tick_fused_balanced if balanced else lib().spx_tick_fused
+        check(fn(engine._h, self.tower._h, int(n), engine.policy.data_ptr(), engine.value.data_ptr(),
+                 C.c_void_p(torch.cuda.current_stream().cuda_stream)), "spx_tick_fused")
         return True
 
 

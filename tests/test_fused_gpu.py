@@ -15,21 +15,21 @@ GAME_COUNTERS = ("sims", "leaf_evals", "terminal_sims", "path_len_sum", "moves",
                  "records_dropped")
 
 
-def _finish(e, fused, chunk, plan=()):
+def _finish(e, fused, chunk, plan=(), balanced=None):
     for n, f in plan:
-        e.run_ticks(n, fused=f, chunk=chunk)
+        e.run_ticks(n, fused=f, chunk=chunk, balanced=balanced)
     for _ in range(100000):
         if e.all_idle():
             break
-        e.run_ticks(150, fused=fused, chunk=chunk)
+        e.run_ticks(150, fused=fused, chunk=chunk, balanced=balanced)
     assert e.all_idle()
 
 
-def _run(net, game, n_games, sims, fused, games_target, chunk, plan=(), **kw):
+def _run(net, game, n_games, sims, fused, games_target, chunk, plan=(), balanced=None, **kw):
     from self_play_reinforcement_learning_b200.selfplay import BatchedSelfPlay
     sp = BatchedSelfPlay(net, game=game, n_games=n_games, sims=sims, net="tower", seed=3, games_target=games_target, move_log=True, **kw)
     e = sp.engine
-    _finish(e, fused, chunk, plan)
+    _finish(e, fused, chunk, plan, balanced)
     torch.cuda.synchronize()
     recs, res = e.drain_records(), e.drain_results()
     out = dict(counters=e.counters(), recs=np.sort(recs, order=["game_index", "tree", "ply"]), res=np.sort(res, order=["game_index"]),
@@ -57,6 +57,21 @@ def test_fused_games_equal_separate_launches(game, n_games, sims, target):
     b = _run(net, game, n_games, sims, True, target, 97)
     c = _run(net, game, n_games, sims, True, target, 1)          # one tick per launch: every hand-over crosses a launch boundary
     assert a["counters"]["errors"] == 0 and a["counters"]["games_finished"] == target and len(a["res"]) == target
+    _same(a, b)
+    _same(a, c)
+
+
+@pytest.mark.parametrize("n_games,sims,target,blocks", [(50, 40, 120, 2), (1100, 12, 1100, 1), (2300, 12, 2300, 1)])
+def test_exact_and_work_conserving_launches_play_the_same_games(n_games, sims, target, blocks):
+    """spx_tick_fused (every game exactly n ticks per launch) and spx_tick_fused_balanced (SM pairs draw their ticks from the
+    launch's budget of passes: the default of run_ticks for launches of >= 16 ticks) in fast mode, mixed and shadow-all mode."""
+    from self_play_reinforcement_learning_b200 import nets
+    torch.manual_seed(7)
+    net = nets.ResidualTower(7, 6, 7, num_blocks=blocks).eval()
+    a = _run(net, 0, n_games, sims, True, target, 40, balanced=False)
+    b = _run(net, 0, n_games, sims, True, target, 40, balanced=True)
+    c = _run(net, 0, n_games, sims, True, target, 17, balanced=True)
+    assert a["counters"]["games_finished"] == target and a["counters"]["errors"] == 0
     _same(a, b)
     _same(a, c)
 
