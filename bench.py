@@ -533,7 +533,7 @@ def main():
                 "vs_baseline": None,
                 "dtype": ("f16" if getattr(getattr(ev, "tower", None), "f16", False) else "bf16") if args.net == "tower" else ("bf16" if args.net == "torch" else "f64"),
                 "data": "synthetic", "config": workload, "positions_per_sec": moves_all / (ms / 1e3), "leaf_evals_per_sec": evals_all / (ms / 1e3),
-                "mean_select_path_len": path, "fused_tick_kernel": bool(fused_tick_ms), "e2e": e2e, "gpu_launches": int(launches1 - launches0), "clocks": clocks,
+                "mean_select_path_len": path, "fused_tick_kernel": bool(fused_tick_ms), "fused_launches": (f"work-conserving (spx_tick_fused_balanced), {args.fused_chunk} ticks per launch: a step is ticks_per_step x ceil(games / 14) network passes, a game gets ticks_per_step ticks on average" if fused_tick_ms and os.environ.get("SPX_TICK_BALANCE", "1") != "0" else None), "e2e": e2e, "gpu_launches": int(launches1 - launches0), "clocks": clocks,
                 "roofline": roof, "search_roofline": search, "env_roofline": env_roof, "config4_head_to_head": config4, "train_step": train_leg, "config5_epoch": config5, "cpu_baseline": cpu}
         print(json.dumps(line), file=json_out, flush=True)
     if world > 1:

@@ -26,7 +26,7 @@ proc = subprocess.Popen(["nvidia-smi", "--id=0", "--query-gpu=clocks.sm,power.dr
 threading.Thread(target=lambda: [lines.append(l) for l in proc.stdout], daemon=True).start()
 N = 3200
 for rep in range(2):
-    for balanced, chunk in ((False, 100), (True, 100), (False, 400), (True, 400), (True, 800)):
+    for balanced, chunk in (((True, 400),) if len(sys.argv) > 2 else ((False, 100), (True, 100), (False, 400), (True, 400), (True, 800))):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         lines.clear()
