@@ -79,7 +79,11 @@ typedef struct spx_config {
                                 * sequential search; K in 2..16 = K search_node tasks in flight per tree with virtual loss and
                                 * per-child locks, under the cooperative round-robin schedule.  The leaf batch
                                 * then has n_games * K slots (slot of worker k of game g = g * K + k).                  */
-    int32_t reserved1;
+    int32_t eval_cache_log2;   /* 0: off.  n in [6, 20]: every game slot keeps a direct-mapped table of 2^n evaluations
+                                * {position, network id, weights version} -> (policy, value) and the fused tick kernel answers
+                                * repeated requests from it instead of the network.  The network is a pure function whose output
+                                * does not depend on batch position, so games, records and statistics are unchanged bit for bit;
+                                * only spx_counters.leaf_evals drops and cache_hits rises.  64 B per entry.   */
 } spx_config;
 
 /* One Move record (mcts.py:17,282-289 + :230): state in the tree's own frame, tree_probs, q, and
@@ -126,6 +130,7 @@ typedef struct spx_counters {
     uint64_t ticks;
     uint64_t records_dropped; /* ring overflow (host drained too rarely)               */
     uint64_t errors;          /* node-pool overflow etc.; must stay 0                  */
+    uint64_t cache_hits;      /* evaluations answered by the evaluation cache (eval_cache_log2) */
 } spx_counters;
 
 const char* spx_last_error(void);

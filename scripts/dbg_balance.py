@@ -15,7 +15,7 @@ from self_play_reinforcement_learning_b200.selfplay import BatchedSelfPlay  # no
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 torch.manual_seed(0)
 net = nets.ResidualTower(7, 6, 7, num_blocks=20).eval()
-sp = BatchedSelfPlay(net, game=0, n_games=G, sims=800, net="tower", seed=0)
+sp = BatchedSelfPlay(net, game=0, n_games=G, sims=800, net="tower", seed=0, eval_cache=int(os.environ.get("SPX_EVAL_CACHE", "0")))
 e = sp.engine
 e.stagger()
 e.run_ticks(1600, chunk=100)
@@ -41,5 +41,5 @@ for rep in range(2):
         mhz = sorted(float(l.split(",")[0]) for l in lines if "," in l)
         print(f"games {G} balanced {int(balanced)} chunk {chunk}: {ms / N:.4f} ms/tick, {(c1['sims'] - c0['sims']) / ms / 1e3:.4f} M sims/s, "
               f"{(c1['leaf_evals'] - c0['leaf_evals']) / ms / 1e3:.4f} M leaf evals/s, leaves/tick {(c1['leaf_evals'] - c0['leaf_evals']) / N:.1f}, "
-              f"errors {c1['errors']}, SM clock {mhz[len(mhz) // 2] if mhz else None}", flush=True)
+              f"cache hits/tick {(c1['cache_hits'] - c0['cache_hits']) / N:.1f}, sims/tick {(c1['sims'] - c0['sims']) / N:.1f}, errors {c1['errors']}, SM clock {mhz[len(mhz) // 2] if mhz else None}", flush=True)
 proc.terminate()

@@ -22,7 +22,7 @@ class Config(C.Structure):
                 ("move_log", C.c_int32), ("two_nets", C.c_int32), ("opponent_kind", C.c_int32), ("reserved0", C.c_int32),
                 ("alpha", C.c_double), ("seed", C.c_uint64),
                 ("slot_offset", C.c_int64), ("slot_stride", C.c_int64), ("games_target", C.c_int64),
-                ("record_capacity", C.c_int64), ("result_capacity", C.c_int64), ("search_threads", C.c_int32), ("reserved1", C.c_int32)]
+                ("record_capacity", C.c_int64), ("result_capacity", C.c_int64), ("search_threads", C.c_int32), ("eval_cache_log2", C.c_int32)]
 
 
 class Record(C.Structure):
@@ -44,7 +44,7 @@ class MoveLog(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("sims", "leaf_evals", "terminal_sims", "path_len_sum", "moves",
-                                          "games_finished", "nodes_allocated", "ticks", "records_dropped", "errors")]
+                                          "games_finished", "nodes_allocated", "ticks", "records_dropped", "errors", "cache_hits")]
 
 
 # every symbol include/spx.h declares (checked by tests/test_abi.py)

@@ -50,8 +50,9 @@ struct alignas(16) GameState {
     u64 game_index; int root_vl[2];                                              //  96  root_vl: MCNode.virtual_loss of the two roots (threaded search)
     TreeState tree[2];                                                           // 112
     u64 cnt_sims, cnt_evals, cnt_term, cnt_path, cnt_moves, cnt_games, cnt_nodes, cnt_err;   // 176 (updated with RED.ADD)
+    u64 cnt_hits, pad2;                                                          // 240  evaluations answered by the slot's evaluation cache
 };
-static_assert(sizeof(TreeState) == 32 && sizeof(GameState) == 240, "GameState layout");
+static_assert(sizeof(TreeState) == 32 && sizeof(GameState) == 256, "GameState layout");
 
 // One worker thread of the threaded search (MCTreeSearch(thread_count = K), mcts.py:328-331): idle, or blocked in the network
 // call of the child (parent, action) it expands -- whose lock it holds -- with its select path in wpaths[g][k][].
@@ -83,6 +84,11 @@ struct EngineDev {
     unsigned long long* ticks;
     int* ext_action;       // [G] external opponent's next move (>= 0) or -1 (opponent_kind == SPX_OPP_EXTERNAL)
     int* own_action;       // [G][2]: {number of moves the policy (tree 0) has played this game, its latest action}
+    // evaluation cache (cfg.eval_cache_log2 > 0; set per launch by spx_tick_fused, null everywhere else): per slot a direct-mapped
+    // table of 64-byte entries {own, opp (net frame) | tag, value, policy[0..1] | policy[2..5] | policy[6..8], 0}
+    uint4* ecache;         // [G][1 << ecache_log2][4]
+    unsigned ecache_log2;
+    unsigned ecache_tag;   // weights version << 8 | 1 (the network id goes into bits 1..7): entries of other weights never match
 };
 
 }  // namespace spx
@@ -91,6 +97,7 @@ struct spx_engine {
     spx::EngineDev d;
     int device;
     int64_t bytes;
+    uint4* ecache;         // the evaluation cache's tables (cfg.eval_cache_log2 > 0), handed to the fused tick kernel per launch
 };
 
 namespace spx {
@@ -455,6 +462,53 @@ __device__ __noinline__ bool search_round_threaded(const EngineDev& E, Ctx<GAME>
     return waiting == 0 && sims_started >= cfg.sims;
 }
 
+// ------------------------------------------------------------------------------------------------ evaluation cache
+// The network is a pure function of (weights, position) and its output is bitwise independent of batch position, so an
+// evaluation of a position the slot has evaluated before (the two trees of a game search overlapping subtrees, Connect4 move
+// orders transpose, every game on the slot starts from the same opening: 46-52 % of all requests at 800 sims/move,
+// scripts/dbg_transpositions.py) can be answered from a table without changing a single bit of the game.  One warp owns a slot at
+// any time, so the table needs no atomics; it is read and written through L2 (.cg) only.
+__device__ __forceinline__ unsigned ecache_slot(const EngineDev& E, u64 own, u64 opp, int net) {
+    u64 h = (own * 0x9E3779B97F4A7C15ULL) ^ (opp * 0xC2B2AE3D27D4EB4FULL) ^ (u64)(net * 0x632BE5AB);
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ULL; h ^= h >> 32;
+    return (unsigned)h & ((1u << E.ecache_log2) - 1u);
+}
+__device__ __forceinline__ uint4* ecache_entry(const EngineDev& E, int g, unsigned slot) {
+    return E.ecache + ((((size_t)g << E.ecache_log2) + slot) << 2);
+}
+// all 32 lanes; true = hit: p_out = this lane's prior (lane < A), v_out = the value
+template <int A>
+__device__ __forceinline__ bool ecache_lookup(const EngineDev& E, int g, int lane, u64 own, u64 opp, int net, float& p_out, float& v_out) {
+    const uint4* ent = ecache_entry(E, g, ecache_slot(E, own, opp, net));
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < 4) w = __ldcg(ent + lane);
+    const unsigned tag = E.ecache_tag | ((unsigned)net << 1);
+    bool ok = true;
+    if (lane == 0) ok = w.x == (unsigned)own && w.y == (unsigned)(own >> 32) && w.z == (unsigned)opp && w.w == (unsigned)(opp >> 32);
+    if (lane == 1) ok = w.x == tag;
+    if ((__ballot_sync(0xffffffffu, ok) & 3u) != 3u) return false;
+    v_out = __uint_as_float(__shfl_sync(0xffffffffu, w.y, 1));
+    const int f = 6 + (lane < A ? lane : 0), src = f >> 2, comp = f & 3;   // float f of the entry = policy[lane]
+    const unsigned x = __shfl_sync(0xffffffffu, w.x, src), y = __shfl_sync(0xffffffffu, w.y, src);
+    const unsigned z = __shfl_sync(0xffffffffu, w.z, src), q = __shfl_sync(0xffffffffu, w.w, src);
+    p_out = lane < A ? __uint_as_float(comp == 0 ? x : comp == 1 ? y : comp == 2 ? z : q) : 0.f;
+    return true;
+}
+// all 32 lanes: my_p = this lane's prior as the network returned it
+template <int A>
+__device__ __forceinline__ void ecache_insert(const EngineDev& E, int g, int lane, u64 own, u64 opp, int net, float my_p, float v) {
+    uint4* ent = ecache_entry(E, g, ecache_slot(E, own, opp, net));
+    unsigned vals[4];
+#pragma unroll
+    for (int cidx = 0; cidx < 4; ++cidx) {
+        const int f = 4 * (lane & 3) + cidx;
+        const unsigned pv = __shfl_sync(0xffffffffu, __float_as_uint(my_p), (f - 6) & 31);
+        vals[cidx] = f == 0 ? (unsigned)own : f == 1 ? (unsigned)(own >> 32) : f == 2 ? (unsigned)opp : f == 3 ? (unsigned)(opp >> 32)
+                   : f == 4 ? (E.ecache_tag | ((unsigned)net << 1)) : f == 5 ? __float_as_uint(v) : (f - 6 < A ? pv : 0u);
+    }
+    if (lane < 4) __stcg(ent + lane, make_uint4(vals[0], vals[1], vals[2], vals[3]));
+}
+
 enum { ADV_EMITTED = 1, ADV_IDLE = 2, ADV_PARKED = 4 };   // advance_game's result; 0 = the sim budget ran out before a leaf came up
 
 // ------------------------------------------------------------------------------------------------ one game, one tick
@@ -468,7 +522,7 @@ enum { ADV_EMITTED = 1, ADV_IDLE = 2, ADV_PARKED = 4 };   // advance_game's resu
 // Registers: only what the select loop needs stays live through the function (phase words, game index, ONE tree's TreeState,
 // this lane's noise); the pending-evaluation words, the env boards, the other tree and the counters live in the slot's
 // GameState and are read / written (lane 0; counters with RED.ADD) where the state machine touches them.
-template <int GAME, bool THREADED = false>
+template <int GAME, bool THREADED = false, bool CACHE = false>
 __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, const int lane, const AdvPre& pre, const float my_p,
                                             const float v_in, int budget, const bool defer_leaf, const bool count_tick,
                                             u64& out_own, u64& out_opp, const float* __restrict__ policy_in = nullptr,
@@ -515,16 +569,30 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
     auto count = [&](u64* counter, const int by) { if (lane == 0 && by) atomicAdd((ull*)counter, (ull)by); };   // RED.ADD: nothing to wait for
     bool emitted = false, parked = false, consumed = false;
     int out_net = 0;
-    // the evaluation the slot will be waiting for when it emits (written to the slot in part 3)
-    int e_kind = PK_NONE, e_tree = 0, e_parent = 0, e_action = 0, e_depth = 0, e_pplayer = 0;
-    u64 e_own = 0, e_opp = 0;
+    // The evaluation in hand: first the one the slot asked for on the previous tick (outputs my_p / v_in from the network), later
+    // every request the evaluation cache answers on the spot; consumed at the top of the loop below.  When the slot emits, the
+    // same variables describe the evaluation it will be waiting for (written to the slot in part 3).
+    int e_kind = pre.c.x, e_tree = pre.c.y, e_parent = pre.c.z, e_action = pre.c.w, e_depth = pre.d.x, e_pplayer = pre.d.y;
+    u64 e_own = pre.pend.x, e_opp = pre.pend.y;
+    unsigned cp0 = pre.p0, cp1 = pre.p1;     // this lane's entries of that evaluation's select path
+    float cur_p = my_p, cur_v = v_in;
+    bool from_net = true;
+    const bool use_cache = CACHE && !THREADED && E.ecache != nullptr;   // CACHE: only the fused tick kernel's instance carries the code
+    if (THREADED && e_kind == PK_THREADS) { consumed = true; e_kind = PK_NONE; }   // the workers consume theirs inside the search round below
 
-    // ---- 1. consume the evaluation this slot asked for on the previous tick
-    if (THREADED && pre.c.x == PK_THREADS) consumed = true;   // the workers consume theirs inside the search round below
-    else if (pre.c.x != PK_NONE) {
-        const int pend_kind = pre.c.x, T = pre.c.y, pend_parent = pre.c.z, pend_action = pre.c.w, pend_depth = pre.d.x;
+    // ---- run the state machine until the next network request: 1. consume the evaluation in hand, 2. go on
+    while (!emitted) {
+      if (e_kind != PK_NONE) {
+        const int pend_kind = e_kind, T = e_tree, pend_parent = e_parent, pend_action = e_action, pend_depth = e_depth;
+        const float my_p = cur_p, v_in = cur_v;
         consumed = true;
+        e_kind = PK_NONE;
         use(T);
+        if (use_cache && from_net) {   // remember what the network said about this position (net frame: mcts.py:316, modules.py:109-112)
+            const bool root = pend_kind == PK_ROOT;
+            ecache_insert<A>(E, g, lane, root ? 0ULL : (e_pplayer > 0 ? e_own : e_opp), root ? 0ULL : (e_pplayer > 0 ? e_opp : e_own),
+                             cfg.two_nets ? T : 0, my_p, v_in);
+        }
         if (pend_kind == PK_ROOT) {  // MCTreeSearch.reset (mcts.py:166-174); root.v is never read
             int player = (T == 0) ? (swap ? -1 : 1) : (swap ? 1 : -1);  // selfplayworker.py:175-176
             ts.node_count = 0;
@@ -537,8 +605,8 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
             else { mover_tree = swap ? 1 : 0; phase = PH_SEARCH; sims_done = -1; /* -1: search not begun */ }
         } else {
             // _expand_node's network branch (mcts.py:316-320) + backup (:361 / :207)
-            const int pplayer = pre.d.y;
-            int idx = alloc_node<GAME>(c, ts, pre.pend.x, pre.pend.y, -pplayer, my_p);
+            const int pplayer = e_pplayer;
+            int idx = alloc_node<GAME>(c, ts, e_own, e_opp, -pplayer, my_p);
             if (idx < 0) { count(&gp->cnt_err, 1); phase = PH_IDLE; }
             else {
                 count(&gp->cnt_nodes, 1);
@@ -546,8 +614,8 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
                 double v = __dmul_rn((double)v_in, (double)pplayer);  // modules.py:112 value*player
                 unsigned p0 = 0, p1 = 0;
                 if (pend_kind == PK_EXPAND) {
-                    if (lane < pend_depth) p0 = pre.p0;
-                    if (lane + 32 < pend_depth) p1 = pre.p1;
+                    if (lane < pend_depth) p0 = cp0;
+                    if (lane + 32 < pend_depth) p1 = cp1;
                 } else if (lane == 0) p0 = ((unsigned)pend_parent << 4) | (unsigned)pend_action;
                 __syncwarp();
                 backup_path<GAME>(c, p0, p1, pend_depth, v, ts);
@@ -560,14 +628,12 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
                 }
             }
         }
-    }
-
-    // ---- 2. run the state machine until the next network request
-    while (!emitted) {
+      }
         if (phase == PH_IDLE) break;
         if (phase == PH_RESET) {
             out_own = 0; out_opp = 0; out_net = cfg.two_nets ? sub_tree : 0;
             e_kind = PK_ROOT; e_tree = sub_tree;
+            if (use_cache && ecache_lookup<A>(E, g, lane, 0ULL, 0ULL, out_net, cur_p, cur_v)) { from_net = false; out_own = 0; out_opp = 0; out_net = 0; count(&gp->cnt_hits, 1); continue; }
             emitted = true;
             break;
         }
@@ -795,6 +861,10 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
             if (lane + 32 < depth) pp[lane + 32] = p1;
             e_kind = PK_EXPAND; e_tree = T; e_parent = node; e_action = act; e_depth = depth;
             e_pplayer = player; e_own = c_own; e_opp = c_opp;
+            if (use_cache && ecache_lookup<A>(E, g, lane, out_own, out_opp, out_net, cur_p, cur_v)) {
+                from_net = false; cp0 = p0; cp1 = p1; out_own = 0; out_opp = 0; out_net = 0; count(&gp->cnt_hits, 1);
+                continue;   // consumed at the top of the loop: create_children, backup, the next simulation
+            }
             emitted = true;
             break;
         }
@@ -840,7 +910,11 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
                     ts.root = ch >= 0 ? ch : -1;
                 }
             }
-            if (wait_net) { emitted = true; break; }
+            if (wait_net) {
+                if (use_cache && ecache_lookup<A>(E, g, lane, out_own, out_opp, out_net, cur_p, cur_v)) { from_net = false; out_own = 0; out_opp = 0; out_net = 0; count(&gp->cnt_hits, 1); continue; }
+                emitted = true;
+                break;
+            }
             if (T == 0 && !cfg.opponent_kind) sub_tree = 1; else phase = PH_ENVSTEP;
             continue;
         }

@@ -112,19 +112,20 @@ __global__ void root_stats_kernel(EngineDev E, int tree, int* n, double* w, int*
 }
 
 __global__ void counters_kernel(EngineDev E, spx_counters* out) {
-    __shared__ unsigned long long acc[8];
-    if (threadIdx.x < 8) acc[threadIdx.x] = 0;
+    __shared__ unsigned long long acc[9];
+    if (threadIdx.x < 9) acc[threadIdx.x] = 0;
     __syncthreads();
     for (int g = threadIdx.x; g < E.cfg.n_games; g += blockDim.x) {
         const GameState& s = E.games[g];
         atomicAdd(&acc[0], s.cnt_sims); atomicAdd(&acc[1], s.cnt_evals); atomicAdd(&acc[2], s.cnt_term); atomicAdd(&acc[3], s.cnt_path);
         atomicAdd(&acc[4], s.cnt_moves); atomicAdd(&acc[5], s.cnt_games); atomicAdd(&acc[6], s.cnt_nodes); atomicAdd(&acc[7], s.cnt_err);
+        atomicAdd(&acc[8], s.cnt_hits);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         out->sims = acc[0]; out->leaf_evals = acc[1]; out->terminal_sims = acc[2]; out->path_len_sum = acc[3];
         out->moves = acc[4]; out->games_finished = acc[5]; out->nodes_allocated = acc[6]; out->errors = acc[7];
-        out->ticks = *E.ticks; out->records_dropped = *E.rec_dropped;
+        out->ticks = *E.ticks; out->records_dropped = *E.rec_dropped; out->cache_hits = acc[8];
     }
 }
 
@@ -471,6 +472,11 @@ int spx_create(const spx_config* cfg, spx_engine** out) {
     }
     SPX_ALLOC(d.ext_action, int, G);
     SPX_ALLOC(d.own_action, int, 2 * G);
+    if (cfg->eval_cache_log2) {   // per slot a direct-mapped table of 64-byte entries (spx_advance.cuh: evaluation cache)
+        if (cfg->eval_cache_log2 < 6 || cfg->eval_cache_log2 > 20) return set_err(SPX_E_ARG, "spx_create: eval_cache_log2 must be 0 (off) or in [6, 20]%s", "");
+        if (d.K > 1) return set_err(SPX_E_ARG, "spx_create: the evaluation cache serves the sequential search (search_threads <= 1)%s", "");
+        SPX_ALLOC(e->ecache, uint4, (G << cfg->eval_cache_log2) * 4);
+    }
 #undef SPX_ALLOC
     e->bytes = bytes;
     *out = e;
@@ -481,7 +487,7 @@ int spx_destroy(spx_engine* e) {
     if (!e) return 0;
     EngineDev& d = e->d;
     void* ptrs[] = {d.games, d.pool, d.paths, d.noise, d.temp_rec, d.mlog, d.rec_ring, d.res_ring, d.rec_count, d.res_count,
-                    d.rec_dropped, d.ticks, d.leaf_own, d.leaf_opp, d.needs_eval, d.net_id, d.ext_action, d.own_action, d.workers, d.wpaths, d.vlpool};
+                    d.rec_dropped, d.ticks, d.leaf_own, d.leaf_opp, d.needs_eval, d.net_id, d.ext_action, d.own_action, d.workers, d.wpaths, d.vlpool, e->ecache};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete e;
     return 0;

@@ -29,6 +29,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -479,7 +480,7 @@ __device__ __noinline__ int engine_step(const spx::EngineDev& E, const int g, co
     const int lane = threadIdx.x & 31;
     const spx::AdvPre pre = spx::advance_prefetch<GAME>(E, g, lane);
     unsigned long long own, opp;
-    const int flags = spx::advance_game<GAME>(E, g, lane, pre, my_p, v_in, budget, defer_leaf != 0, false, own, opp);
+    const int flags = spx::advance_game<GAME, false, true>(E, g, lane, pre, my_p, v_in, budget, defer_leaf != 0, false, own, opp);
     if (leaf2 && lane == 0) { leaf2[0] = own; leaf2[1] = opp; }
     return flags;
 }
@@ -1349,6 +1350,7 @@ struct spx_tower {
     float* head_buf;        // [capacity][64*42] fp32 head-conv activations
     long long capacity;
     int sm_count;
+    unsigned version;       // unique per spx_tower_load of any tower: the tag of the engines' evaluation-cache entries
 };
 
 using namespace spx::tower;
@@ -1452,6 +1454,8 @@ int spx_tower_load(spx_tower* t, const void* dev_blob, int64_t bytes, void* stre
     if (!t || !dev_blob) return spx::set_err(SPX_E_ARG, "spx_tower_load: null argument%s", "");
     if ((size_t)bytes != t->blob_bytes) return spx::set_err(SPX_E_ARG, "spx_tower_load: blob size mismatch%s", "");
     SPX_CUDA_T(cudaMemcpyAsync(t->blob, dev_blob, t->blob_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    static std::atomic<unsigned> g_version{0};
+    t->version = ++g_version;   // new weights: cached evaluations of older versions never match again
     return 0;
 }
 
@@ -1534,6 +1538,10 @@ static int tick_fused_impl(spx_engine* e, spx_tower* t, int32_t n_ticks, float* 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    spx::EngineDev d = e->d;
+    d.ecache = e->ecache;   // the evaluation cache (null = off) answers repeated requests inside the fused kernel only
+    d.ecache_log2 = (unsigned)e->d.cfg.eval_cache_log2;
+    d.ecache_tag = (t->version << 8) | 1u;
     long long pass_budget = -1;
     if (balanced && n_ticks > 1) {   // the budget beyond every cluster's first tick; the ticket counter lives next to the tick counter
         pass_budget = (long long)(n_ticks - 1) * pairs;
@@ -1545,7 +1553,7 @@ static int tick_fused_impl(spx_engine* e, spx_tower* t, int32_t n_ticks, float* 
                                   (const unsigned char*)e->d.needs_eval, n, t->n_layers, (const unsigned char*)t->blob,
                                   (const float*)(t->blob + t->off_bias), t->head_buf, 1, (const float*)(t->blob + t->off_polw),
                                   (const float*)(t->blob + t->off_polb), (const float*)(t->blob + t->off_b1), (const float*)(t->blob + t->off_w2),
-                                  (const float*)(t->blob + t->off_b2), policy, value, e->d, (int)n_ticks, pass_budget));
+                                  (const float*)(t->blob + t->off_b2), policy, value, d, (int)n_ticks, pass_budget));
     spx::count_launch();
     SPX_CUDA_T(cudaGetLastError());
     return 0;

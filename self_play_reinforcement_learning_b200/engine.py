@@ -63,10 +63,13 @@ class SelfPlayEngine:
     def __init__(self, game, n_games, sims, evaluator, *, evaluate=False, strong_play=False, alpha=1.0, seed=0,
                  tie_mode=1, noise_mode=2, emit_records=True, max_sims_per_tick=8, nodes_per_tree=0, move_log=False,
                  two_nets=False, opponent_kind=0, slot_offset=0, slot_stride=None, games_target=None, record_capacity=None,
-                 result_capacity=None, search_threads=1):
+                 result_capacity=None, search_threads=1, eval_cache=0):
         """search_threads: MCTreeSearch(thread_count=K) behind an InferenceProxy (mcts.py:132,328-331; the reference's default is 4):
         K search_node tasks in flight per tree with virtual loss and per-child locks, under the cooperative round-robin
-        schedule.  1 = the sequential search.  With K > 1 the leaf batch has n_games * K rows."""
+        schedule.  1 = the sequential search.  With K > 1 the leaf batch has n_games * K rows.
+        eval_cache: 0 / False = off; True = 4096 entries per game slot; n >= 6 = 2**n entries (64 B each).  The fused tick kernel
+        then answers requests for positions the slot has evaluated before (same weights) from the table instead of the
+        network -- about half of all requests at 800 sims/move -- without changing the games."""
         if not torch.cuda.is_available():
             raise _lib.SpxError("SelfPlayEngine needs a CUDA device (B200); there is no CPU fallback")
         self.game, self.n_games, self.sims = game, int(n_games), int(sims)
@@ -79,6 +82,7 @@ class SelfPlayEngine:
         cfg.move_log, cfg.two_nets, cfg.alpha, cfg.seed = int(move_log), int(two_nets), float(alpha), int(seed)
         cfg.opponent_kind = int(opponent_kind)
         cfg.search_threads = int(search_threads)
+        cfg.eval_cache_log2 = 12 if eval_cache is True else int(eval_cache or 0)
         self.search_threads = max(1, int(search_threads))
         self.n_leaves = int(n_games) * self.search_threads
         cfg.reserved0 = int(os.environ.get("SPX_DBG_FLAGS", "0"), 0)   # timing experiments only (csrc/spx_tower.cu)

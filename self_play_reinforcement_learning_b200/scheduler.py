@@ -115,7 +115,7 @@ class SelfPlayScheduler:
                  evaluation_games=150, games_per_gpu=1024, memory_size=200000, batch_size=128, lr=0.01, momentum=0.9,
                  weight_decay=1e-4, updates_per_epoch=100, alpha=1.0, seed=0, net="tower", evaluation_opponent=None,
                  replay="device", max_memory_size=None, memory_step=0, deduplicate=False, save_dir=None, save_memory=True,
-                 lr_patience=15, amp=None, trainer="auto", search_threads=1):
+                 lr_patience=15, amp=None, trainer="auto", search_threads=1, eval_cache=0):
         """replay: "device" (records stay in HBM: DeviceReplay) or "host" (reference-style Memory of Move tuples).
         max_memory_size / memory_step: UpdateWorker's staggered buffer growth (updateworker.py:107-109).
         save_dir: as in the reference (self_play_parallel.py:56,263-267): every epoch rank 0 writes
@@ -163,6 +163,7 @@ class SelfPlayScheduler:
         self.trainer_kind = "device" if (trainer == "device" or (trainer == "auto" and can)) else "torch"
         self._trainer, self._momentum, self._weight_decay = None, momentum, weight_decay
         self.search_threads = int(search_threads)
+        self.eval_cache = eval_cache       # SelfPlayEngine(eval_cache=...): repeated positions are not re-evaluated (same games, fewer network passes)
         self.start_time = datetime.datetime.now().isoformat()                      # self_play_parallel.py:86
         self.games_played = 0
         self.history = []
@@ -176,7 +177,7 @@ class SelfPlayScheduler:
                              evaluation_network=self.evaluation_network if evaluate else None, evaluate=evaluate, update=update,
                              alpha=self.alpha, seed=self.seed + 7919 * generation, rank=self.rank, world=self.world,
                              games_target=n_games_total, opponent=self.evaluation_opponent if evaluate else None,
-                             search_threads=self.search_threads)
+                             search_threads=self.search_threads, eval_cache=self.eval_cache)
         device_replay = update and self.replay_kind == "device"
         if device_replay and self.memory is None:
             self.memory = DeviceReplay(sp.game, self._memory_size, self.max_memory_size, seed=self.seed)

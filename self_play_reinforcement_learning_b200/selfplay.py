@@ -56,14 +56,15 @@ class BatchedSelfPlay:
     def __init__(self, network, game=None, env=None, n_games=1024, sims=800, net="tower", evaluation_network=None,
                  evaluate=False, update=True, alpha=1.0, strong_play=False, seed=0, rank=0, world=1, games_target=None,
                  max_sims_per_tick=8, noise_mode=2, tie_mode=1, move_log=False, net_dtype=torch.bfloat16, opponent=None,
-                 search_threads=1):
+                 search_threads=1, eval_cache=0):
         """network / evaluation_network: nn.Module (ResidualTower for the native tower; any board net for net='torch').
         env: a reference env class/instance (mapped by variant_string) or ``game`` id.  iterations == sims.
         opponent: None (MCTS self-play / evaluation network), "lookahead" or "random": the reference's hard-coded
         evaluation opponents (general/hardcoded_players.py; the default evaluation_policy_container of main.py:66).
         search_threads: MCTreeSearch(thread_count=K) (mcts.py:132; the reference's default is 4 behind its InferenceProxy): K
         simulations in flight per tree with virtual loss -- a move then takes iterations / K ticks, which is what fills the GPU
-        when an epoch has fewer games than leaf slots (the reference's 750-1500 games); 1 = the sequential search."""
+        when an epoch has fewer games than leaf slots (the reference's 750-1500 games); 1 = the sequential search.
+        eval_cache: the engine's per-slot evaluation cache (SelfPlayEngine; native tower, one network, sequential search)."""
         self.opponent_kind = {None: 0, "mcts": 0, "lookahead": 1, "random": 2}[opponent]
         self.game = game_id_of(env if env is not None else game)
         self.network, self.evaluation_network = network, evaluation_network
@@ -83,7 +84,8 @@ class BatchedSelfPlay:
                                      seed=seed, tie_mode=tie_mode, noise_mode=noise_mode, emit_records=update, two_nets=two,
                                      max_sims_per_tick=max_sims_per_tick, move_log=move_log, opponent_kind=self.opponent_kind,
                                      slot_offset=rank * n_games,
-                                     slot_stride=world * n_games, games_target=games_target, search_threads=search_threads)
+                                     slot_stride=world * n_games, games_target=games_target, search_threads=search_threads,
+                                     eval_cache=eval_cache if (net == "tower" and not two and search_threads <= 1) else 0)
         self._pinned = None
 
     # ------------------------------------------------------------------ weights

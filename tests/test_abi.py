@@ -34,8 +34,8 @@ def test_library_builds_and_exports_header_symbols():
 def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Record) == 80 and C.sizeof(_lib.Result) == 16
     assert C.sizeof(_lib.MoveLog) == 4 * 4 + 8 + 9 * 4 + 4 + 9 * 8 * 2
-    assert C.sizeof(_lib.Counters) == 80
-    assert C.sizeof(_lib.Config) == 14 * 4 + 8 + 8 + 5 * 8 + 2 * 4     # ... + search_threads, reserved1
+    assert C.sizeof(_lib.Counters) == 88     # ... + cache_hits
+    assert C.sizeof(_lib.Config) == 14 * 4 + 8 + 8 + 5 * 8 + 2 * 4     # ... + search_threads, eval_cache_log2
 
 
 def test_no_device_means_loud_failure():

@@ -118,3 +118,52 @@ def test_fused_ticks_other_engine_modes(kw):
     b = _run(net, 0, 20, 30, True, 40, 41, **kw)
     assert a["counters"]["games_finished"] == 40 and a["counters"]["errors"] == 0
     _same(a, b)
+
+
+@pytest.mark.parametrize("game,n_games,sims,target,blocks,kw", [
+    (0, 50, 60, 150, 2, {}),                                             # fast mode, three games per slot (cross-game reuse of the openings)
+    (1, 23, 40, 69, 2, {}),                                              # TicTacToe: 9 priors per entry
+    (0, 1100, 12, 2200, 1, {}),                                          # mixed fast / shadow-all mode
+    (0, 30, 50, 60, 1, dict(opponent="lookahead", evaluate=True, update=False)),
+    (0, 20, 40, 40, 1, dict(strong_play=True, alpha=0.15)),
+])
+def test_evaluation_cache_plays_the_same_games_with_fewer_network_evaluations(game, n_games, sims, target, blocks, kw):
+    """spx_config.eval_cache_log2: requests for positions the slot has evaluated before are answered from its table.  The network
+    is a pure function with batch-position-independent output, so everything but the number of network evaluations is identical."""
+    from self_play_reinforcement_learning_b200 import nets
+    torch.manual_seed(11)
+    net = (nets.ResidualTower(7, 6, 7, num_blocks=blocks) if game == 0 else nets.ResidualTower(3, 3, 9, num_blocks=blocks)).eval()
+    a = _run(net, game, n_games, sims, True, target, 40, **kw)
+    b = _run(net, game, n_games, sims, True, target, 40, eval_cache=True, **kw)
+    c = _run(net, game, n_games, sims, True, target, 23, eval_cache=6, balanced=False, **kw)   # 64 entries: constant eviction
+    assert a["counters"]["games_finished"] == target and a["counters"]["errors"] == 0 and a["counters"]["cache_hits"] == 0
+    for x in (b, c):
+        assert x["counters"]["cache_hits"] > 0
+        assert x["counters"]["leaf_evals"] + x["counters"]["cache_hits"] == a["counters"]["leaf_evals"]
+        x["counters"]["leaf_evals"] = a["counters"]["leaf_evals"]
+        _same(a, x)
+    assert b["counters"]["cache_hits"] > c["counters"]["cache_hits"]
+    assert b["counters"]["cache_hits"] > 0.1 * a["counters"]["leaf_evals"]   # 18 % at 12 sims per move, about half at 800
+
+
+def test_evaluation_cache_is_keyed_by_the_weights_version():
+    """New weights (spx_tower_load) must never be answered with evaluations of the old ones: play with net A, load net B into the
+    same tower, and the games that follow equal an engine that only ever saw net B."""
+    from self_play_reinforcement_learning_b200 import nets
+    from self_play_reinforcement_learning_b200.selfplay import BatchedSelfPlay
+    torch.manual_seed(12)
+    net_a = nets.ResidualTower(7, 6, 7, num_blocks=1).eval()
+    net_b = nets.ResidualTower(7, 6, 7, num_blocks=1).eval()
+    outs = []
+    for first in (net_a, net_b):
+        sp = BatchedSelfPlay(first, game=0, n_games=12, sims=40, net="tower", seed=3, games_target=24, eval_cache=True)
+        e = sp.engine
+        if first is net_a:   # fill the tables with net A's evaluations, then start over with net B's weights
+            e.run_ticks(400, chunk=50)
+            sp.load_weights(net_b)
+            e.reset()
+            e.drain_records(); e.drain_results()
+        _finish(e, True, 50)
+        outs.append((np.sort(e.drain_records(), order=["game_index", "tree", "ply"]).tobytes(), np.sort(e.drain_results(), order=["game_index"]).tobytes()))
+        sp.close()
+    assert outs[0] == outs[1]
