@@ -494,6 +494,9 @@ def main():
     if rank == 0 and world == 1 and args.net == "tower" and not args.no_aux_rooflines and not args.no_config4:
         sp.close()
         config4 = _config4_leg(torch, nets, BatchedSelfPlay, args.blocks)
+    cache_leg = None
+    if rank == 0 and world == 1 and args.net == "tower" and fused and not args.no_aux_rooflines and not args.no_config4:
+        cache_leg = _eval_cache_leg(torch, nets, BatchedSelfPlay, args.blocks, args.games, args.sims, args.fused_chunk, value)
     train_leg = None
     if rank == 0 and world == 1 and args.net == "tower" and not args.no_aux_rooflines and not args.no_config4:
         train_leg = _train_leg(torch, nets, args.blocks)
@@ -534,7 +537,7 @@ def main():
                 "dtype": ("f16" if getattr(getattr(ev, "tower", None), "f16", False) else "bf16") if args.net == "tower" else ("bf16" if args.net == "torch" else "f64"),
                 "data": "synthetic", "config": workload, "positions_per_sec": moves_all / (ms / 1e3), "leaf_evals_per_sec": evals_all / (ms / 1e3),
                 "mean_select_path_len": path, "fused_tick_kernel": bool(fused_tick_ms), "fused_launches": (f"work-conserving (spx_tick_fused_balanced), {args.fused_chunk} ticks per launch: a step is ticks_per_step x ceil(games / 14) network passes, a game gets ticks_per_step ticks on average" if fused_tick_ms and os.environ.get("SPX_TICK_BALANCE", "1") != "0" else None), "e2e": e2e, "gpu_launches": int(launches1 - launches0), "clocks": clocks,
-                "roofline": roof, "search_roofline": search, "env_roofline": env_roof, "config4_head_to_head": config4, "train_step": train_leg, "config5_epoch": config5, "cpu_baseline": cpu}
+                "roofline": roof, "search_roofline": search, "env_roofline": env_roof, "config4_head_to_head": config4, "eval_cache": cache_leg, "train_step": train_leg, "config5_epoch": config5, "cpu_baseline": cpu}
         print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -621,6 +624,40 @@ def _config4_leg(torch, nets, BatchedSelfPlay, blocks, games=4096, sims=400, tic
            "sims_per_s": (c1["sims"] - c0["sims"]) / (ms / 1e3), "moves_per_s": (c1["moves"] - c0["moves"]) / (ms / 1e3),
            "games_per_s": (c1["games_finished"] - c0["games_finished"]) / (ms / 1e3), "ms_per_tick": ms / ticks,
            "leaf_evals_per_tick": (c1["leaf_evals"] - c0["leaf_evals"]) / ticks}
+    sp.close()
+    return out
+
+
+def _eval_cache_leg(torch, nets, BatchedSelfPlay, blocks, games, sims, chunk, headline_sims_per_s, ticks=2400):
+    """The headline workload once more with the engine's evaluation cache switched on (spx_config.eval_cache_log2 = 12: 4096 entries
+    per game slot): requests for positions a slot has evaluated before are answered from its table inside the fused tick kernel.
+    NOT the headline: `value` and `e2e` run one network evaluation per non-terminal simulation, like the reference.  The games are
+    identical either way (tests/test_fused_gpu.py); only the number of network passes per move drops."""
+    torch.manual_seed(0)
+    net = nets.ResidualTower(7, 6, 7, num_blocks=blocks).eval()
+    sp = BatchedSelfPlay(net, game=0, n_games=games, sims=sims, net="tower", seed=0, eval_cache=12)
+    e = sp.engine
+    e.stagger()
+    e.run_ticks(2 * sims, chunk=chunk)
+    e.drain_records(); e.drain_results()
+    torch.cuda.synchronize()
+    c0 = e.counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    done = 0
+    while done < ticks:     # rings drained like the headline loop does between steps
+        e.run_ticks(min(sims, ticks - done), chunk=chunk)
+        done += min(sims, ticks - done)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    c1 = e.counters()
+    d = {k: c1[k] - c0[k] for k in ("sims", "leaf_evals", "cache_hits", "moves")}
+    out = {"workload": f"the headline workload ({games} games, {sims} sims/move, ResidualTower-{blocks}) with eval_cache_log2 = 12 (4096 entries of 64 B per game slot); "
+                       "NOT the headline: value / e2e evaluate every non-terminal simulation with the network",
+           "sims_per_s": d["sims"] / (ms / 1e3), "leaf_evals_per_s": d["leaf_evals"] / (ms / 1e3), "positions_per_s": d["moves"] / (ms / 1e3),
+           "hit_rate": d["cache_hits"] / max(1, d["cache_hits"] + d["leaf_evals"]), "ms_per_tick": ms / ticks, "ticks": ticks,
+           "speedup_vs_value": d["sims"] / (ms / 1e3) / headline_sims_per_s, "errors": c1["errors"], "records_dropped": c1["records_dropped"]}
     sp.close()
     return out
 
