@@ -733,8 +733,8 @@ def _config5_leg(torch, nets, blocks, sims, games=1024):
     # simulations in flight per tree) makes a move take 200 ticks of 752 leaves instead of 800 ticks of 188.
     from self_play_reinforcement_learning_b200.selfplay import BatchedSelfPlay
     small = {}
-    for K in (1, 4):
-        sp = BatchedSelfPlay(net, game=0, n_games=188, sims=sims, net="tower", seed=5, games_target=188, search_threads=K)
+    for K, cache in ((1, 0), (4, 0), (1, 12)):   # (1, 12): the sequential search with the evaluation cache: the same games in fewer passes
+        sp = BatchedSelfPlay(net, game=0, n_games=188, sims=sims, net="tower", seed=5, games_target=188, search_threads=K, eval_cache=cache)
         torch.cuda.synchronize()
         t0 = time.time()
         while True:
@@ -743,7 +743,7 @@ def _config5_leg(torch, nets, blocks, sims, games=1024):
             if sp.engine.all_idle():
                 break
         torch.cuda.synchronize()
-        small[f"thread_count_{K}"] = time.time() - t0
+        small[f"thread_count_{K}" + ("_eval_cache" if cache else "")] = time.time() - t0
         sp.close()
     out["self_play_188_games_seconds"] = small
     out["self_play_188_games_speedup_with_4_threads"] = small["thread_count_1"] / small["thread_count_4"]

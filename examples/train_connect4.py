@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--amp", action="store_true", help="with --trainer torch: bf16 autocast for the SGD steps")
     ap.add_argument("--trainer", default="auto", choices=["auto", "device", "torch"], help="device: the native SGD step (csrc/spx_train.cu)")
     ap.add_argument("--threads", type=int, default=1, help="thread_count of the searches (the reference's default behind its InferenceProxy is 4)")
+    ap.add_argument("--eval-cache", action="store_true", help="per-slot evaluation cache inside the fused tick kernel: the same games in about half the network passes (DESIGN.md 3.9)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -46,7 +47,7 @@ def main():
     sched = SelfPlayScheduler(net, 0, iterations=args.iterations, epoch_length=args.epoch_length, initial_games=args.initial_games,
                               evaluation_games=args.evaluation_games, games_per_gpu=args.games_per_gpu, save_dir=args.save_dir,
                               save_memory=not args.no_save_memory, amp=torch.bfloat16 if args.amp else None, trainer=args.trainer,
-                              search_threads=args.threads)
+                              search_threads=args.threads, eval_cache=args.eval_cache)
     t0 = time.time()
     hist = sched.train_model(num_epochs=args.epochs, resume_model=args.resume, resume_memory=args.resume)
     if sched.rank == 0:
