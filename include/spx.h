@@ -80,8 +80,8 @@ typedef struct spx_config {
                                 * per-child locks, under the cooperative round-robin schedule.  The leaf batch
                                 * then has n_games * K slots (slot of worker k of game g = g * K + k).                  */
     int32_t eval_cache_log2;   /* 0: off.  n in [6, 20]: every game slot keeps a direct-mapped table of 2^n evaluations
-                                * {position, network id, weights version} -> (policy, value) and the fused tick kernel answers
-                                * repeated requests from it instead of the network.  The network is a pure function whose output
+                                * {position, network id, weights version} -> (policy, value) and the search answers repeated
+                                * requests from it instead of the network (spx_tick_fused; spx_advance after spx_set_eval_cache_versions).  The network is a pure function whose output
                                 * does not depend on batch position, so games, records and statistics are unchanged bit for bit;
                                 * only spx_counters.leaf_evals drops and cache_hits rises.  64 B per entry.   */
 } spx_config;
@@ -193,6 +193,11 @@ int spx_restart(spx_engine* e, int64_t slot_offset, int64_t games_target, void* 
 /* change the simulations per move (MCTreeSearch.iterations, mcts.py:131) for all following launches; at most the value
  * the engine was created with (the node pool is sized for it).  Searches in progress run on to the new count. */
 int spx_set_sims(spx_engine* e, int32_t sims);
+/* Evaluation cache with separate launches (spx_advance + a network forward per tick): tell the engine which weights produce
+ * the policy / value arrays the next spx_advance calls consume -- version0 for network 0, version1 for network 1 (two_nets),
+ * e.g. spx_tower_version(); 0 = unknown (the default): spx_advance runs without the cache.  Call again after every weight
+ * refresh (inference_worker.py:68-73).  spx_tick_fused reads the version from its tower and needs no call. */
+int spx_set_eval_cache_versions(spx_engine* e, uint32_t version0, uint32_t version1);
 /* SPX_OPP_EXTERNAL: deliver the opposing player's moves, dev i32[n_games] (-1 = none for that slot).  Replaces
  * opposing_policy(s) + policy.play_action(a, -player) in SelfPlayer.get_and_play_moves (selfplayworker.py:206-224). */
 int spx_set_external_actions(spx_engine* e, const int32_t* actions, void* stream);
@@ -221,6 +226,9 @@ int spx_tower_fused_heads(spx_tower* t);
  * torch.cuda.amp.autocast at inference_worker.py:117), 0: bf16 (SPX_TOWER_DTYPE=bf16 at spx_tower_create).  It is the element
  * type spx_tower_load expects the weight stream in. */
 int spx_tower_f16(spx_tower* t);
+/* a number unique to the weights this tower holds (drawn from a process-wide counter by every spx_tower_load): the tag of the
+ * engines' evaluation-cache entries (spx_config.eval_cache_log2) */
+uint32_t spx_tower_version(spx_tower* t);
 int spx_tower_load(spx_tower* t, const void* dev_blob, int64_t bytes, void* stream);
 /* own/opp: dev u64[n] bitboards in the NET frame; needs_eval: dev u8[n] or NULL (all); policy dev f32[n,A]
  * (softmax), value dev f32[n] (tanh).  Rows whose needs_eval is 0 may be left untouched. */

@@ -88,7 +88,7 @@ struct EngineDev {
     // table of 64-byte entries {own, opp (net frame) | tag, value, policy[0..1] | policy[2..5] | policy[6..8], 0}
     uint4* ecache;         // [G][1 << ecache_log2][4]
     unsigned ecache_log2;
-    unsigned ecache_tag;   // weights version << 8 | 1 (the network id goes into bits 1..7): entries of other weights never match
+    unsigned ecache_tag[2];   // per network id: weights version << 8 | id << 1 | 1: entries of other weights never match
 };
 
 }  // namespace spx
@@ -97,7 +97,8 @@ struct spx_engine {
     spx::EngineDev d;
     int device;
     int64_t bytes;
-    uint4* ecache;         // the evaluation cache's tables (cfg.eval_cache_log2 > 0), handed to the fused tick kernel per launch
+    uint4* ecache;         // the evaluation cache's tables (cfg.eval_cache_log2 > 0), handed to the kernels per launch
+    unsigned cache_ver[2]; // spx_set_eval_cache_versions: the weights versions behind spx_advance's policy / value inputs (0 = unknown: no cache)
 };
 
 namespace spx {
@@ -482,7 +483,7 @@ __device__ __forceinline__ bool ecache_lookup(const EngineDev& E, int g, int lan
     const uint4* ent = ecache_entry(E, g, ecache_slot(E, own, opp, net));
     uint4 w = make_uint4(0u, 0u, 0u, 0u);
     if (lane < 4) w = __ldcg(ent + lane);
-    const unsigned tag = E.ecache_tag | ((unsigned)net << 1);
+    const unsigned tag = E.ecache_tag[net & 1];
     bool ok = true;
     if (lane == 0) ok = w.x == (unsigned)own && w.y == (unsigned)(own >> 32) && w.z == (unsigned)opp && w.w == (unsigned)(opp >> 32);
     if (lane == 1) ok = w.x == tag;
@@ -504,7 +505,7 @@ __device__ __forceinline__ void ecache_insert(const EngineDev& E, int g, int lan
         const int f = 4 * (lane & 3) + cidx;
         const unsigned pv = __shfl_sync(0xffffffffu, __float_as_uint(my_p), (f - 6) & 31);
         vals[cidx] = f == 0 ? (unsigned)own : f == 1 ? (unsigned)(own >> 32) : f == 2 ? (unsigned)opp : f == 3 ? (unsigned)(opp >> 32)
-                   : f == 4 ? (E.ecache_tag | ((unsigned)net << 1)) : f == 5 ? __float_as_uint(v) : (f - 6 < A ? pv : 0u);
+                   : f == 4 ? E.ecache_tag[net & 1] : f == 5 ? __float_as_uint(v) : (f - 6 < A ? pv : 0u);
     }
     if (lane < 4) __stcg(ent + lane, make_uint4(vals[0], vals[1], vals[2], vals[3]));
 }

@@ -62,6 +62,19 @@ __global__ void __launch_bounds__(128, SPX_ADV_MINB) advance_kernel(EngineDev E,
     advance_game<GAME>(E, g, lane, pre, my_p, v, E.cfg.max_sims_per_tick, false, g == 0, own, opp);
 }
 
+// the same tick with the evaluation cache: E.ecache / E.ecache_tag are set by spx_advance for this launch
+template <int GAME>
+__global__ void __launch_bounds__(128, 3) advance_kernel_cached(EngineDev E, const float* __restrict__ policy_in, const float* __restrict__ value_in) {
+    const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (g >= E.cfg.n_games) return;
+    const int lane = threadIdx.x & 31;
+    const AdvPre pre = advance_prefetch<GAME>(E, g, lane);
+    const float my_p = (policy_in && lane < Rules<GAME>::A) ? policy_in[(size_t)g * Rules<GAME>::A + lane] : 0.f;
+    const float v = value_in ? value_in[g] : 0.f;
+    u64 own, opp;
+    advance_game<GAME, false, true>(E, g, lane, pre, my_p, v, E.cfg.max_sims_per_tick, false, g == 0, own, opp);
+}
+
 // the same tick for an engine created with search_threads = K > 1 (leaf slot of worker k of game g = g * K + k)
 template <int GAME>
 __global__ void __launch_bounds__(128, 2) advance_kernel_threaded(EngineDev E, const float* __restrict__ policy_in, const float* __restrict__ value_in) {
@@ -513,10 +526,26 @@ int spx_advance(spx_engine* e, const float* policy, const float* value, void* st
     if (e->d.K > 1) {   // threaded search: K leaf slots per game
         if (e->d.cfg.game == SPX_GAME_CONNECT4) advance_kernel_threaded<SPX_GAME_CONNECT4><<<grid, block, 0, (cudaStream_t)stream>>>(e->d, policy, value);
         else advance_kernel_threaded<SPX_GAME_TICTACTOE><<<grid, block, 0, (cudaStream_t)stream>>>(e->d, policy, value);
+    } else if (e->ecache && e->cache_ver[0] && (!e->d.cfg.two_nets || e->cache_ver[1])) {
+        // evaluation cache: the caller has said which weights versions its policy / value inputs come from
+        EngineDev d = e->d;
+        d.ecache = e->ecache;
+        d.ecache_log2 = (unsigned)d.cfg.eval_cache_log2;
+        d.ecache_tag[0] = (e->cache_ver[0] << 8) | 1u;
+        d.ecache_tag[1] = (e->cache_ver[1] << 8) | 3u;
+        if (d.cfg.game == SPX_GAME_CONNECT4) advance_kernel_cached<SPX_GAME_CONNECT4><<<grid, block, 0, (cudaStream_t)stream>>>(d, policy, value);
+        else advance_kernel_cached<SPX_GAME_TICTACTOE><<<grid, block, 0, (cudaStream_t)stream>>>(d, policy, value);
     } else if (e->d.cfg.game == SPX_GAME_CONNECT4) advance_kernel<SPX_GAME_CONNECT4><<<grid, block, 0, (cudaStream_t)stream>>>(e->d, policy, value);
     else advance_kernel<SPX_GAME_TICTACTOE><<<grid, block, 0, (cudaStream_t)stream>>>(e->d, policy, value);
     count_launch();
     SPX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int spx_set_eval_cache_versions(spx_engine* e, uint32_t version0, uint32_t version1) {
+    if (!e) return set_err(SPX_E_ARG, "spx_set_eval_cache_versions: null engine%s", "");
+    e->cache_ver[0] = version0 & 0xFFFFFFu;
+    e->cache_ver[1] = version1 & 0xFFFFFFu;
     return 0;
 }
 

@@ -1438,6 +1438,7 @@ int spx_tower_ncta(spx_tower* t) { return t ? t->ncta : 0; }
 /* 1: the conv trunk and the fused value layer compute in fp16 (default), 0: bf16 -- the type spx_tower_load expects the weight
  * stream in (nets.pack_tower_blob(dtype=...)) */
 int spx_tower_f16(spx_tower* t) { return t ? t->f16 : 0; }
+uint32_t spx_tower_version(spx_tower* t) { return t ? t->version : 0u; }
 /* 1 when the fully connected heads run inside the tower kernel (SM-pair kernel, default), 0 when heads_kernel follows it */
 int spx_tower_fused_heads(spx_tower* t) { return t ? t->fused : 0; }
 
@@ -1541,7 +1542,8 @@ static int tick_fused_impl(spx_engine* e, spx_tower* t, int32_t n_ticks, float* 
     spx::EngineDev d = e->d;
     d.ecache = e->ecache;   // the evaluation cache (null = off) answers repeated requests inside the fused kernel only
     d.ecache_log2 = (unsigned)e->d.cfg.eval_cache_log2;
-    d.ecache_tag = (t->version << 8) | 1u;
+    d.ecache_tag[0] = (t->version << 8) | 1u;
+    d.ecache_tag[1] = 0u;
     long long pass_budget = -1;
     if (balanced && n_ticks > 1) {   // the budget beyond every cluster's first tick; the ticket counter lives next to the tick counter
         pass_budget = (long long)(n_ticks - 1) * pairs;

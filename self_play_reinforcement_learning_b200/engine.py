@@ -164,6 +164,12 @@ class SelfPlayEngine:
     def advance(self, events=None):
         """spx_advance only (consume last outputs, fill the leaf batch).  ``events``: optional pair of
         torch.cuda.Event recorded right before/after the launch on the launching stream."""
+        if self.cfg.eval_cache_log2:   # the evaluation cache needs to know which weights the outputs it is about to consume came from
+            vers = getattr(self.evaluator, "cache_versions", None)
+            vers = tuple(vers()) if vers else (0, 0)
+            if vers != getattr(self, "_cache_vers", None):
+                check(lib().spx_set_eval_cache_versions(self._h, vers[0], vers[1]), "spx_set_eval_cache_versions")
+                self._cache_vers = vers
         p = None if self._first else self.policy.data_ptr()
         v = None if self._first else self.value.data_ptr()
         if events is None:

@@ -402,6 +402,10 @@ class TowerEvaluator:
     def __call__(self, engine, events=None):
         self.tower.forward_bits(engine.leaf_own, engine.leaf_opp, engine.needs_eval, engine.policy, engine.value, events)
 
+    def cache_versions(self):
+        """Weights versions behind the outputs this evaluator writes (network 0, network 1): the engine's evaluation-cache tags."""
+        return (int(lib().spx_tower_version(self.tower._h)), 0)
+
     def fused_ticks(self, engine, n, balanced=False):
         """n whole ticks (advance + evaluation) in one persistent launch (spx_tick_fused; balanced: the work-conserving form
         spx_tick_fused_balanced, n ticks per game ON AVERAGE); False if this tower cannot."""
@@ -432,6 +436,9 @@ class TwoTowerEvaluator:
 
     def load(self, module_or_blob, which=0):
         self.towers[which].load(module_or_blob)
+
+    def cache_versions(self):
+        return tuple(int(lib().spx_tower_version(t._h)) for t in self.towers)
 
     def __call__(self, engine, events=None):
         n = engine.n_leaves

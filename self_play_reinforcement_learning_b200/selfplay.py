@@ -85,7 +85,7 @@ class BatchedSelfPlay:
                                      max_sims_per_tick=max_sims_per_tick, move_log=move_log, opponent_kind=self.opponent_kind,
                                      slot_offset=rank * n_games,
                                      slot_stride=world * n_games, games_target=games_target, search_threads=search_threads,
-                                     eval_cache=eval_cache if (net == "tower" and not two and search_threads <= 1) else 0)
+                                     eval_cache=eval_cache if (net == "tower" and search_threads <= 1) else 0)
         self._pinned = None
 
     # ------------------------------------------------------------------ weights

@@ -167,3 +167,28 @@ def test_evaluation_cache_is_keyed_by_the_weights_version():
         outs.append((np.sort(e.drain_records(), order=["game_index", "tree", "ply"]).tobytes(), np.sort(e.drain_results(), order=["game_index"]).tobytes()))
         sp.close()
     assert outs[0] == outs[1]
+
+
+def test_evaluation_cache_with_separate_launches_and_with_two_networks():
+    """spx_advance + a forward per tick (spx_set_eval_cache_versions tells the engine whose outputs it consumes), and head-to-head
+    evaluation with two native towers (entries are keyed by network id + weights version: a position evaluated by network 0
+    must not answer network 1)."""
+    from self_play_reinforcement_learning_b200 import nets
+    torch.manual_seed(13)
+    net = nets.ResidualTower(7, 6, 7, num_blocks=1).eval()
+    other = nets.ResidualTower(7, 6, 7, num_blocks=1).eval()
+    a = _run(net, 0, 40, 50, False, 80, 64)
+    b = _run(net, 0, 40, 50, False, 80, 64, eval_cache=True)
+    c = _run(net, 0, 40, 50, True, 80, 64, plan=[(90, True), (60, False), (40, True)], eval_cache=10)   # fused and separate launches share the table
+    for x in (b, c):
+        assert x["counters"]["cache_hits"] > 0.1 * a["counters"]["leaf_evals"]
+        assert x["counters"]["leaf_evals"] + x["counters"]["cache_hits"] == a["counters"]["leaf_evals"]
+        x["counters"]["leaf_evals"] = a["counters"]["leaf_evals"]
+        _same(a, x)
+    kw = dict(evaluation_network=other, evaluate=True, update=False)
+    a = _run(net, 0, 40, 50, False, 80, 64, **kw)
+    b = _run(net, 0, 40, 50, False, 80, 64, eval_cache=True, **kw)
+    assert b["counters"]["cache_hits"] > 0.05 * a["counters"]["leaf_evals"]
+    assert b["counters"]["leaf_evals"] + b["counters"]["cache_hits"] == a["counters"]["leaf_evals"]
+    b["counters"]["leaf_evals"] = a["counters"]["leaf_evals"]
+    _same(a, b)
