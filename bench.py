@@ -601,14 +601,14 @@ def _check_collectives(dist, parallel, blob_dev, rank, world, local_rank):
     return {"broadcast_checksum_equal_on_all_ranks": True, "gathered_records_equal_local_replay": True, "ranks": world}
 
 
-def _config4_leg(torch, nets, BatchedSelfPlay, blocks, games=4096, sims=400, ticks=600):
+def _config4_leg(torch, nets, BatchedSelfPlay, blocks, games=4096, sims=400, ticks=600, eval_cache=0):
     """BASELINE configs[3]: elo.py head-to-head evaluation, two random-init ResidualTower nets, 4096 games, 400 sims/move
     (evaluate mode, no records), both towers native; leaves are partitioned by owning network on the device."""
     torch.manual_seed(0)
     a = nets.ResidualTower(7, 6, 7, num_blocks=blocks).eval()
     torch.manual_seed(1)
     b = nets.ResidualTower(7, 6, 7, num_blocks=blocks).eval()
-    sp = BatchedSelfPlay(a, game=0, n_games=games, sims=sims, net="tower", evaluation_network=b, evaluate=True, update=False, seed=0)
+    sp = BatchedSelfPlay(a, game=0, n_games=games, sims=sims, net="tower", evaluation_network=b, evaluate=True, update=False, seed=0, eval_cache=eval_cache)
     sp.engine.stagger()
     sp.engine.run_ticks(sims)
     torch.cuda.synchronize()
@@ -625,6 +625,11 @@ def _config4_leg(torch, nets, BatchedSelfPlay, blocks, games=4096, sims=400, tic
            "games_per_s": (c1["games_finished"] - c0["games_finished"]) / (ms / 1e3), "ms_per_tick": ms / ticks,
            "leaf_evals_per_tick": (c1["leaf_evals"] - c0["leaf_evals"]) / ticks}
     sp.close()
+    if eval_cache:
+        out["hit_rate"] = (c1["cache_hits"] - c0["cache_hits"]) / max(1, c1["cache_hits"] - c0["cache_hits"] + c1["leaf_evals"] - c0["leaf_evals"])
+    else:   # the same games with the evaluation cache: per-network entries, separate launches
+        w = _config4_leg(torch, nets, BatchedSelfPlay, blocks, games, sims, ticks, eval_cache=12)
+        out["with_eval_cache"] = {k: w[k] for k in ("sims_per_s", "moves_per_s", "ms_per_tick", "leaf_evals_per_tick", "hit_rate")}
     return out
 
 
