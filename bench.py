@@ -730,7 +730,7 @@ def _config5_leg(torch, nets, blocks, sims, games=1024):
     wall = time.time() - t0
     sec = h["seconds"]
     out = {"workload": f"{games} initial + {games} self-play games ({sims} sims/move), 100 SGD steps of batch 128 (native step), weight refresh, "
-                       "128 evaluation games vs OneStepLookahead; one GPU", "seconds": sec, "wall_s_incl_initial_games": wall,
+                       "128 evaluation games vs OneStepLookahead; one GPU; SelfPlayScheduler defaults (evaluation cache on: DESIGN.md 3.9)", "seconds": sec, "wall_s_incl_initial_games": wall,
            "records_in_memory": h["memory"], "loss": h["loss"], "evaluation_reward": h["evaluation_reward"], "trainer": s.trainer_kind,
            "self_play_games_per_s": games / sec["self_play"]}
     # the reference's own epoch size on 8 GPUs is 1500 / 8 = 188 games per GPU: far fewer games than leaf slots, so the phase is

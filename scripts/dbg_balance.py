@@ -15,7 +15,7 @@ from self_play_reinforcement_learning_b200.selfplay import BatchedSelfPlay  # no
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 torch.manual_seed(0)
 net = nets.ResidualTower(7, 6, 7, num_blocks=20).eval()
-sp = BatchedSelfPlay(net, game=0, n_games=G, sims=800, net="tower", seed=0, eval_cache=int(os.environ.get("SPX_EVAL_CACHE", "0")))
+sp = BatchedSelfPlay(net, game=0, n_games=G, sims=800, net="tower", seed=0, eval_cache=int(os.environ.get("SPX_EVAL_CACHE", "0")), max_sims_per_tick=int(os.environ.get("SPX_MAX_SIMS", "8")))
 e = sp.engine
 e.stagger()
 e.run_ticks(1600, chunk=100)

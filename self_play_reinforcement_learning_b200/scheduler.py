@@ -115,7 +115,7 @@ class SelfPlayScheduler:
                  evaluation_games=150, games_per_gpu=1024, memory_size=200000, batch_size=128, lr=0.01, momentum=0.9,
                  weight_decay=1e-4, updates_per_epoch=100, alpha=1.0, seed=0, net="tower", evaluation_opponent=None,
                  replay="device", max_memory_size=None, memory_step=0, deduplicate=False, save_dir=None, save_memory=True,
-                 lr_patience=15, amp=None, trainer="auto", search_threads=1, eval_cache=0):
+                 lr_patience=15, amp=None, trainer="auto", search_threads=1, eval_cache=True):
         """replay: "device" (records stay in HBM: DeviceReplay) or "host" (reference-style Memory of Move tuples).
         max_memory_size / memory_step: UpdateWorker's staggered buffer growth (updateworker.py:107-109).
         save_dir: as in the reference (self_play_parallel.py:56,263-267): every epoch rank 0 writes
@@ -126,6 +126,9 @@ class SelfPlayScheduler:
         ``save_memory=False`` keeps only the model checkpoints.)
         search_threads: thread_count of the policies' MCTreeSearch (mcts.py:132: 4 in the reference, behind its InferenceProxy): K
         simulations in flight per tree with virtual loss, a move takes iterations / K ticks (BatchedSelfPlay); 1 = sequential.
+        eval_cache: the engine's per-slot evaluation cache (SelfPlayEngine(eval_cache=...)): positions a game slot has
+        already sent to the same weights are not evaluated again -- the same games bit for bit in about half the network passes.
+        On by default here (every epoch builds fresh engines after the weight refresh); False switches it off.
         trainer: "device" = the native SGD step (train.DeviceTrainer: TF32 / bf16 tensor-core convolutions, fp32 master weights,
         momentum buffers on the device), "torch" = PyTorch autograd with torch.optim.SGD, "auto" = "device" whenever the network
         is one it is built for and the replay memory is on the device.

@@ -55,7 +55,7 @@ def results_to_dicts(results):
 class BatchedSelfPlay:
     def __init__(self, network, game=None, env=None, n_games=1024, sims=800, net="tower", evaluation_network=None,
                  evaluate=False, update=True, alpha=1.0, strong_play=False, seed=0, rank=0, world=1, games_target=None,
-                 max_sims_per_tick=8, noise_mode=2, tie_mode=1, move_log=False, net_dtype=torch.bfloat16, opponent=None,
+                 max_sims_per_tick=None, noise_mode=2, tie_mode=1, move_log=False, net_dtype=torch.bfloat16, opponent=None,
                  search_threads=1, eval_cache=0):
         """network / evaluation_network: nn.Module (ResidualTower for the native tower; any board net for net='torch').
         env: a reference env class/instance (mapped by variant_string) or ``game`` id.  iterations == sims.
@@ -80,6 +80,8 @@ class BatchedSelfPlay:
         else:
             raise ValueError(net)
         self.net_kind = net
+        if max_sims_per_tick is None:   # simulations a slot may run between two evaluations (terminal re-visits, cache hits): measured optimum
+            max_sims_per_tick = 16 if eval_cache else 8
         self.engine = SelfPlayEngine(self.game, n_games, sims, self.evaluator, evaluate=evaluate, strong_play=strong_play, alpha=alpha,
                                      seed=seed, tie_mode=tie_mode, noise_mode=noise_mode, emit_records=update, two_nets=two,
                                      max_sims_per_tick=max_sims_per_tick, move_log=move_log, opponent_kind=self.opponent_kind,
