@@ -3,7 +3,7 @@
 * configs[1]: 1024 concurrent games x 800 sims/move, ResidualTower-20, the fused tick kernel (spx_tick_fused): one launch per tick
   with every network output of 64 sampled slots logged on the device, their first TWO games replayed through the C oracle
   (records, results, per-move root statistics bit for bit: "visit counts bit-exact given identical network outputs"); then the
-  same 2048 games again with 100 ticks per launch -> identical records and results for ALL games.
+  same 2048 games again with 100 ticks per launch, and once more with the evaluation cache -> identical records and results for ALL games.
 * configs[2] shard: 2048 games on one GPU (two board-group units per SM pair), same check on 32 sampled slots.
 * configs[3]: 4096 head-to-head games x 400 sims, evaluate mode, two different native towers.
 * the same three shapes with the hash network run to completion against oracle_episode (no logging needed): a 32-bit index bug
@@ -86,6 +86,18 @@ def test_fused_tower20_800_sims_full_size_replays_in_oracle(n_games, games_per_s
     assert recs2.tobytes() == recs1.tobytes() and res2.tobytes() == res1.tobytes()
     for k in ("sims", "leaf_evals", "terminal_sims", "path_len_sum", "moves", "games_finished", "nodes_allocated", "errors"):
         assert c1[k] == c2[k], k
+    # ... and with the evaluation cache (spx_config.eval_cache_log2 = 12): about half of the requests answered from the slots'
+    # tables, every record and result of every game still identical
+    e = SelfPlayEngine(game=0, n_games=n_games, sims=sims, evaluator=nets.TowerEvaluator(net), seed=seed, noise_mode=1,
+                       games_target=total, eval_cache=True, max_sims_per_tick=16)
+    e.set_noise_table(table)
+    recs3, res3 = _play_all(e, 100)
+    c3 = e.check_overflow()
+    e.close()
+    assert recs3.tobytes() == recs1.tobytes() and res3.tobytes() == res1.tobytes()
+    for k in ("sims", "terminal_sims", "path_len_sum", "moves", "games_finished", "nodes_allocated", "errors"):
+        assert c1[k] == c3[k], k
+    assert c3["leaf_evals"] + c3["cache_hits"] == c1["leaf_evals"] and c3["cache_hits"] > 0.35 * c1["leaf_evals"]
 
 
 def test_config4_4096_games_400_sims_two_towers_evaluate_mode():
