@@ -193,6 +193,12 @@ int spx_restart(spx_engine* e, int64_t slot_offset, int64_t games_target, void* 
 /* change the simulations per move (MCTreeSearch.iterations, mcts.py:131) for all following launches; at most the value
  * the engine was created with (the node pool is sized for it).  Searches in progress run on to the new count. */
 int spx_set_sims(spx_engine* e, int32_t sims);
+/* Test hook: the fused tick kernel's shadow warp does the fp64 PUCT arithmetic (mcts.py:59-84: q = w / n, u = 4 p sqrt(N + 1) /
+ * (1 + n), score = player q + u + 1e-6 noise) on the integer pipe, because FP64 instructions next to running tcgen05 MMAs slow
+ * the tensor pipe down (csrc/spx_softf64.cuh).  This runs every such operation against the FP64 instruction on n
+ * pseudo-random operand sets and returns the number of differing results per operation in mismatches_out[8]
+ * (mul, add, div by integer, sqrt of integer, f32 -> f64, uniform from 53 bits, comparisons, scaling / negation): all must be 0. */
+int spx_softf64_selftest(uint64_t n, uint64_t seed, uint64_t* mismatches_out, void* stream);
 /* Evaluation cache with separate launches (spx_advance + a network forward per tick): tell the engine which weights produce
  * the policy / value arrays the next spx_advance calls consume -- version0 for network 0, version1 for network 1 (two_nets),
  * e.g. spx_tower_version(); 0 = unknown (the default): spx_advance runs without the cache.  Call again after every weight

@@ -52,7 +52,7 @@ EXPORTS = ["spx_last_error", "spx_version", "spx_launch_count", "spx_env_step", 
            "spx_hashnet_forward", "spx_create", "spx_destroy", "spx_reset", "spx_set_noise_table", "spx_advance",
            "spx_leaf_batch", "spx_root_stats", "spx_drain_records", "spx_drain_results", "spx_read_move_log",
            "spx_counters_read", "spx_all_idle", "spx_device_bytes", "spx_pending_tree", "spx_tower_blob_bytes",
-           "spx_tower_create", "spx_tower_destroy", "spx_tower_ncta", "spx_tower_fused_heads", "spx_tower_f16", "spx_tower_version", "spx_set_eval_cache_versions", "spx_tower_load", "spx_tower_forward", "spx_tower_forward_timed", "spx_partition_leaves", "spx_scatter_outputs", "spx_tttnet_blob_floats", "spx_tttnet_create", "spx_tttnet_destroy",
+           "spx_tower_create", "spx_tower_destroy", "spx_tower_ncta", "spx_tower_fused_heads", "spx_tower_f16", "spx_tower_version", "spx_set_eval_cache_versions", "spx_softf64_selftest", "spx_tower_load", "spx_tower_forward", "spx_tower_forward_timed", "spx_partition_leaves", "spx_scatter_outputs", "spx_tttnet_blob_floats", "spx_tttnet_create", "spx_tttnet_destroy",
            "spx_tttnet_load", "spx_tttnet_forward",
            "spx_advance_timed", "spx_restart", "spx_set_sims", "spx_set_external_actions", "spx_slot_status", "spx_event_create", "spx_event_destroy", "spx_event_elapsed_ms",
            "spx_replay_create", "spx_replay_destroy", "spx_replay_size", "spx_replay_max_size", "spx_replay_change_size", "spx_replay_reset",
@@ -106,6 +106,7 @@ def lib():
         L.spx_tower_version.argtypes = [vp]
         L.spx_tower_version.restype = C.c_uint32
         L.spx_set_eval_cache_versions.argtypes = [vp, C.c_uint32, C.c_uint32]
+        L.spx_softf64_selftest.argtypes = [C.c_uint64, C.c_uint64, vp, vp]
         L.spx_tower_load.argtypes = [vp, vp, i64, vp]
         L.spx_tower_forward.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
         L.spx_tower_forward_timed.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "spx_common.cuh"
+#include "spx_softf64.cuh"
 
 namespace spx {
 
@@ -88,6 +89,7 @@ struct EngineDev {
     // table of 64-byte entries {own, opp (net frame) | tag, value, policy[0..1] | policy[2..5] | policy[6..8], 0}
     uint4* ecache;         // [G][1 << ecache_log2][4]
     unsigned ecache_log2;
+    const double* sqrt_table;   // [sf::SQRT_TABLE] correctly rounded sqrt(m), for the integer-pipe arithmetic of the fused kernel's shadow warp
     unsigned ecache_tag[2];   // per network id: weights version << 8 | id << 1 | 1: entries of other weights never match
 };
 
@@ -205,14 +207,14 @@ template <int GAME> struct Ctx {
 
 // terminal value v = r (already multiplied by the mover) or the strong_play formula (mcts.py:305-313)
 __device__ __forceinline__ double terminal_value(int strong, int r_signed, u64 parent_own, u64 parent_opp) {
-    if (!strong) return (double)r_signed;
+    if (!strong) return r_signed > 0 ? 1.0 : (r_signed < 0 ? -1.0 : 0.0);   // (double)r_signed without a conversion instruction
     int num_steps = __popcll(parent_own | parent_opp) + 1;
     return __dmul_rn(__dsub_rn(1.18, __ddiv_rn((double)(9 * num_steps), 350.0)), (double)r_signed);
 }
 
 // w += v; n += 1 on every edge of the path and on the root itself (MCNode.backup, mcts.py:94-98;
 // ancestors above the current root are never read again so they are skipped).
-template <int GAME>
+template <int GAME, bool SOFT = false>
 __device__ __forceinline__ void backup_path(const Ctx<GAME>& c, unsigned p0, unsigned p1, int depth, double v, TreeState& ts) {
     typedef NodeLayout<GAME> L;
 #pragma unroll
@@ -225,11 +227,11 @@ __device__ __forceinline__ void backup_path(const Ctx<GAME>& c, unsigned p0, uns
             int* pn = (int*)(nd + L::OFF_N) + a;
             double* pw = (double*)(nd + L::OFF_W) + a;
             *pn = *pn + 1;
-            *pw = __dadd_rn(*pw, v);
+            *pw = FP<SOFT>::add(*pw, v);
         }
     }
     ts.root_n += 1;
-    ts.root_w = __dadd_rn(ts.root_w, v);
+    ts.root_w = FP<SOFT>::add(ts.root_w, v);
 }
 
 // create_children (mcts.py:103-107) for a freshly evaluated position + link from its parent edge
@@ -523,7 +525,8 @@ enum { ADV_EMITTED = 1, ADV_IDLE = 2, ADV_PARKED = 4 };   // advance_game's resu
 // Registers: only what the select loop needs stays live through the function (phase words, game index, ONE tree's TreeState,
 // this lane's noise); the pending-evaluation words, the env boards, the other tree and the counters live in the slot's
 // GameState and are read / written (lane 0; counters with RED.ADD) where the state machine touches them.
-template <int GAME, bool THREADED = false, bool CACHE = false>
+// SOFT: the PUCT / backup arithmetic runs on the integer pipe (spx_softf64.cuh: same bits, no FP64 instruction next to the MMAs)
+template <int GAME, bool THREADED = false, bool CACHE = false, bool SOFT = false>
 __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, const int lane, const AdvPre& pre, const float my_p,
                                             const float v_in, int budget, const bool defer_leaf, const bool count_tick,
                                             u64& out_own, u64& out_opp, const float* __restrict__ policy_in = nullptr,
@@ -531,6 +534,7 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
     typedef Rules<GAME> R;
     typedef NodeLayout<GAME> L;
     typedef unsigned long long ull;
+    typedef FP<SOFT> F;
     constexpr int A = R::A;
     Ctx<GAME> c(E, g, lane);
     GameState* gp = E.games + g;
@@ -567,7 +571,11 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
         }
         c.use_tree(T);
     };
+#ifdef SPX_DBG_NO_COUNT   // timing experiment: no per-slot counters
+    auto count = [&](u64*, const int) { };
+#else
     auto count = [&](u64* counter, const int by) { if (lane == 0 && by) atomicAdd((ull*)counter, (ull)by); };   // RED.ADD: nothing to wait for
+#endif
     bool emitted = false, parked = false, consumed = false;
     int out_net = 0;
     // The evaluation in hand: first the one the slot asked for on the previous tick (outputs my_p / v_in from the network), later
@@ -612,14 +620,14 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
             else {
                 count(&gp->cnt_nodes, 1);
                 if (lane == 0) ((int*)(c.node(pend_parent) + L::OFF_CHILD))[pend_action] = idx;
-                double v = __dmul_rn((double)v_in, (double)pplayer);  // modules.py:112 value*player
+                double v = F::signed_by(F::from_f32(v_in), pplayer);  // modules.py:112 value*player
                 unsigned p0 = 0, p1 = 0;
                 if (pend_kind == PK_EXPAND) {
                     if (lane < pend_depth) p0 = cp0;
                     if (lane + 32 < pend_depth) p1 = cp1;
                 } else if (lane == 0) p0 = ((unsigned)pend_parent << 4) | (unsigned)pend_action;
                 __syncwarp();
-                backup_path<GAME>(c, p0, p1, pend_depth, v, ts);
+                backup_path<GAME, SOFT>(c, p0, p1, pend_depth, v, ts);
                 __syncwarp();
                 if (pend_kind == PK_EXPAND) sims_done += 1;
                 else {  // _set_root(node) (mcts.py:209)
@@ -797,22 +805,24 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
                 }
                 // everything that does not depend on this node's statistics is computed while its loads are in flight:
                 // sqrt(N + 1) (N came with the parent edge) and the tie-break noise of this (sim, depth, lane)
-                const double sqrt_n = __dsqrt_rn((double)(N + 1));
-                const double tie = cfg.tie_mode ? __dmul_rn(0.000001, rng_uniform_from(tie_pre, (unsigned)sims_done, (unsigned)depth, (u64)lane)) : 0.0;
+                const double sqrt_n = F::sqrt_int(N + 1, E.sqrt_table);
+                const double tie = cfg.tie_mode ? F::mul(0.000001, F::from_u53(rng_uniform_bits(tie_pre, (unsigned)sims_done, (unsigned)depth, (u64)lane))) : 0.0;
                 if (lane < A) {
                     if (ch >= 0) {   // pull every expanded child towards the SM while the scores are computed (the next level is one of them)
                         const char* cn = c.node(ch);
+#ifndef SPX_DBG_NO_PREFETCH
                         asm volatile(SPX_PREFETCH " [%0];" ::"l"(cn));
                         asm volatile(SPX_PREFETCH " [%0];" ::"l"(cn + 128));
+#endif
                     }
                     if ((meta >> lane) & 1u) {
-                        const double q = n ? __ddiv_rn(w, (double)n) : 0.0;                               // :59-62 (vl = 0)
-                        double p_eff = (double)p;
-                        if (depth == 0) p_eff = __dadd_rn(__dmul_rn(my_noise, 0.25), __dmul_rn((double)p, 0.75));  // :64-69
-                        const double u = __ddiv_rn(__dmul_rn(__dmul_rn(4.0, p_eff), sqrt_n), (double)(1 + n));   // :71-78
-                        score = __dadd_rn(__dmul_rn((double)player, q), u);                               // :80-84
+                        const double q = n ? F::div_int(w, n) : 0.0;                                      // :59-62 (vl = 0)
+                        double p_eff = F::from_f32(p);
+                        if (depth == 0) p_eff = F::add(F::quarter(my_noise), F::mul(p_eff, 0.75));        // :64-69
+                        const double u = F::div_int(F::mul(F::times4(p_eff), sqrt_n), 1 + n);             // :71-78
+                        score = F::add(F::signed_by(q, player), u);                                       // :80-84
                     } else score = -10000000000.0;                                                        // :346-348
-                    if (cfg.tie_mode) score = __dadd_rn(score, tie);
+                    if (cfg.tie_mode) score = F::add(score, tie);
                 }
                 // np.argmax: first maximum wins (A <= 8: three butterfly rounds over 8 lanes suffice)
                 int best = lane;
@@ -821,7 +831,7 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
                 for (int off = (A <= 8 ? 4 : 8); off > 0; off >>= 1) {
                     double os = __shfl_xor_sync(0xffffffffu, bs, off);
                     int ob = __shfl_xor_sync(0xffffffffu, best, off);
-                    if (os > bs || (os == bs && ob < best)) { bs = os; best = ob; }
+                    if (F::gt(os, bs) || (F::eq(os, bs) && ob < best)) { bs = os; best = ob; }
                 }
                 best = __shfl_sync(0xffffffffu, best, 0);
                 child = __shfl_sync(0xffffffffu, ch, best);
@@ -847,7 +857,7 @@ __device__ __forceinline__ int advance_game(const EngineDev& E, const int g, con
                     ((int*)(c.node(node) + L::OFF_CHILD))[act] = r ? CHILD_TERM_WIN : CHILD_TERM_DRAW;
                 const double v = terminal_value(cfg.strong_play, r * player, par_own, par_opp);
                 __syncwarp();
-                backup_path<GAME>(c, p0, p1, depth, v, ts);
+                backup_path<GAME, SOFT>(c, p0, p1, depth, v, ts);
                 __syncwarp();
                 sims_done += 1;
                 count(&gp->cnt_term, 1);

@@ -34,6 +34,12 @@ __host__ __device__ __forceinline__ double rng_uniform_from(u64 prefix, uint32_t
     h = sm64(h ^ idx);
     return (double)(h >> 11) * (1.0 / 9007199254740992.0);
 }
+// the same draw as its 53-bit integer k: the uniform is k * 2^-53
+__host__ __device__ __forceinline__ u64 rng_uniform_bits(u64 prefix, uint32_t sim, uint32_t depth, u64 idx) {
+    u64 h = sm64(prefix ^ ((u64)sim | ((u64)depth << 32)));
+    h = sm64(h ^ idx);
+    return h >> 11;
+}
 
 // ------------------------------------------------------------------------------------------------
 template <int GAME> struct Rules;

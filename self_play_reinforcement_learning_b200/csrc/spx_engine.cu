@@ -89,6 +89,49 @@ __global__ void __launch_bounds__(128, 2) advance_kernel_threaded(EngineDev E, c
     advance_game<GAME, true>(E, g, lane, pre, my_p, v, E.cfg.max_sims_per_tick, false, g == 0, own, opp, policy_in, value_in);
 }
 
+__global__ void sqrt_table_kernel(double* t) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < sf::SQRT_TABLE) t[i] = __dsqrt_rn((double)i);
+}
+
+// spx_softf64_selftest: the integer-pipe arithmetic of spx_softf64.cuh against the FP64 instructions, op by op, on operand pairs drawn
+// from a counter stream (exponents kept close so that sums cancel and round, mantissas full random; every 16th pair is a special:
+// zeros, equal magnitudes, powers of two, the largest / smallest mantissas)
+__global__ void softf64_selftest_kernel(unsigned long long n, unsigned long long seed, unsigned long long* mism, const double* table) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long bad[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u64 h0 = sm64(seed ^ (i * 4 + 0)), h1 = sm64(seed ^ (i * 4 + 1)), h2 = sm64(seed ^ (i * 4 + 2)), h3 = sm64(seed ^ (i * 4 + 3));
+        const int ea = 1023 - 40 + (int)(h2 % 80), eb = ea - 70 + (int)((h2 >> 8) % 140);
+        u64 xa = (h0 & 0x800FFFFFFFFFFFFFULL) | ((u64)ea << 52), xb = (h1 & 0x800FFFFFFFFFFFFFULL) | ((u64)eb << 52);
+        if ((i & 15) == 0) {
+            const int kind = (int)((i >> 4) % 7);
+            if (kind == 0) xa &= sf::SIGN;                                   // +-0 and something
+            if (kind == 1) { xa &= sf::SIGN; xb &= sf::SIGN; }               // +-0 and +-0
+            if (kind == 2) xb = xa ^ sf::SIGN;                               // x + (-x)
+            if (kind == 3) xa &= ~sf::MASK52;                                // a power of two
+            if (kind == 4) xa |= sf::MASK52;                                 // all-ones mantissa
+            if (kind == 5) { xb = (xb & ~(0x7FFULL << 52)) | ((u64)(ea - 1 + (int)(h3 & 3)) << 52); xb ^= ((xa ^ xb) & sf::SIGN) ^ sf::SIGN; }   // near-cancellation
+            if (kind == 6) { xa = (xa & ~sf::MASK52) | (h0 & 0x7); xb = (xb & ~sf::MASK52) | (h1 & 0x3); }                                       // short mantissas: exact ties
+        }
+        const double a = sf::dbl(xa), b = sf::dbl(xb);
+        if (sf::bits(sf::mul(a, b)) != sf::bits(__dmul_rn(a, b))) bad[0]++;
+        if (sf::bits(sf::add(a, b)) != sf::bits(__dadd_rn(a, b))) bad[1]++;
+        const unsigned k = (h3 & 1) ? (unsigned)(1 + (h3 >> 8) % 70000) : (unsigned)(1 + ((h3 >> 8) & 0x7FFFFFFE) % 0x7FFFFFFEu);
+        if (sf::bits(sf::div_u32(a, k)) != sf::bits(__ddiv_rn(a, (double)k))) bad[2]++;
+        const unsigned m = (unsigned)(h3 >> 40) % (2 * sf::SQRT_TABLE);
+        if (sf::bits(sf::sqrt_u32(m, table)) != sf::bits(__dsqrt_rn((double)m))) bad[3]++;
+        const float f = __uint_as_float((unsigned)h3 & ((i & 31) == 1 ? 0x807FFFFFu : 0xFFFFFFFFu));
+        if (f == f && sf::bits(sf::from_f32(f)) != sf::bits((double)f)) bad[4]++;
+        const u64 k53 = (h2 >> 11) >> (h3 % 53);
+        if (sf::bits(sf::from_u53(k53)) != sf::bits((double)k53 * (1.0 / 9007199254740992.0))) bad[5]++;
+        if (sf::gt(a, b) != (a > b) || sf::eq(a, b) != (a == b) || sf::gt(b, a) != (b > a)) bad[6]++;
+        if (sf::bits(sf::mul_pow2(a, 2)) != sf::bits(__dmul_rn(a, 4.0)) || sf::bits(sf::mul_pow2(a, -2)) != sf::bits(__dmul_rn(a, 0.25)) ||
+            sf::bits(sf::neg_if(a, true)) != sf::bits(__dmul_rn(a, -1.0))) bad[7]++;
+    }
+    for (int j = 0; j < 8; ++j) if (bad[j]) atomicAdd(mism + j, bad[j]);
+}
+
 __global__ void reset_kernel(EngineDev E) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= E.cfg.n_games) return;
@@ -485,6 +528,9 @@ int spx_create(const spx_config* cfg, spx_engine** out) {
     }
     SPX_ALLOC(d.ext_action, int, G);
     SPX_ALLOC(d.own_action, int, 2 * G);
+    SPX_ALLOC(d.sqrt_table, double, sf::SQRT_TABLE);
+    sqrt_table_kernel<<<sf::SQRT_TABLE / 256, 256>>>(const_cast<double*>(d.sqrt_table));
+    count_launch();
     if (cfg->eval_cache_log2) {   // per slot a direct-mapped table of 64-byte entries (spx_advance.cuh: evaluation cache)
         if (cfg->eval_cache_log2 < 6 || cfg->eval_cache_log2 > 20) return set_err(SPX_E_ARG, "spx_create: eval_cache_log2 must be 0 (off) or in [6, 20]%s", "");
         if (d.K > 1) return set_err(SPX_E_ARG, "spx_create: the evaluation cache serves the sequential search (search_threads <= 1)%s", "");
@@ -500,7 +546,7 @@ int spx_destroy(spx_engine* e) {
     if (!e) return 0;
     EngineDev& d = e->d;
     void* ptrs[] = {d.games, d.pool, d.paths, d.noise, d.temp_rec, d.mlog, d.rec_ring, d.res_ring, d.rec_count, d.res_count,
-                    d.rec_dropped, d.ticks, d.leaf_own, d.leaf_opp, d.needs_eval, d.net_id, d.ext_action, d.own_action, d.workers, d.wpaths, d.vlpool, e->ecache};
+                    d.rec_dropped, d.ticks, d.leaf_own, d.leaf_opp, d.needs_eval, d.net_id, d.ext_action, d.own_action, d.workers, d.wpaths, d.vlpool, e->ecache, (void*)d.sqrt_table};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete e;
     return 0;
@@ -539,6 +585,24 @@ int spx_advance(spx_engine* e, const float* policy, const float* value, void* st
     else advance_kernel<SPX_GAME_TICTACTOE><<<grid, block, 0, (cudaStream_t)stream>>>(e->d, policy, value);
     count_launch();
     SPX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int spx_softf64_selftest(uint64_t n, uint64_t seed, uint64_t* mismatches_out, void* stream) {
+    if (!mismatches_out) return set_err(SPX_E_ARG, "spx_softf64_selftest: null output%s", "");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* table = nullptr;
+    unsigned long long* mism = nullptr;
+    SPX_CUDA(cudaMalloc((void**)&table, sizeof(double) * sf::SQRT_TABLE));
+    SPX_CUDA(cudaMalloc((void**)&mism, 8 * sizeof(unsigned long long)));
+    SPX_CUDA(cudaMemsetAsync(mism, 0, 8 * sizeof(unsigned long long), st));
+    sqrt_table_kernel<<<sf::SQRT_TABLE / 256, 256, 0, st>>>(table);
+    softf64_selftest_kernel<<<1184, 256, 0, st>>>((unsigned long long)n, (unsigned long long)seed, mism, table);
+    count_launch(); count_launch();
+    SPX_CUDA(cudaGetLastError());
+    SPX_CUDA(cudaMemcpyAsync(mismatches_out, mism, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    SPX_CUDA(cudaStreamSynchronize(st));
+    cudaFree(table); cudaFree(mism);
     return 0;
 }
 

@@ -257,7 +257,7 @@ __device__ __forceinline__ int tap_shift(int tap) { return (tap / 3 - 1) * PAD_S
 //   NCTA == 1 (SPX_TOWER_NCTA=1, fallback): every CTA is on its own (cta_group::1, M=128, 3 x 8 KB ring).
 #ifdef SPX_DBG_TRACE
 __device__ long long g_trace[64 * 16 + 3 * 160];   // + per-CTA {entry, exit, SM id} for the first 160 CTAs
-#define SPX_TRACE(l, k) do { if (blockIdx.x == 0 && (l) < 64) g_trace[(l) * 16 + (k)] = clock64(); } while (0)
+#define SPX_TRACE(l, k) do { if (blockIdx.x == 0 && (l) < 64 && trace_on) g_trace[(l) * 16 + (k)] = clock64(); } while (0)
 #define SPX_TRACE_IF(c, l, k) do { if (c) SPX_TRACE(l, k); __syncwarp(); } while (0)
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ long long g_tt[64 * 12];   // fused tick kernel: globaltimer (ns) of 12 points of passes 20..83, CTA 0, first epilogue thread
@@ -474,13 +474,18 @@ __device__ __forceinline__ void issue_first_tap_skewed(SmemT<2>& S, int taps, un
 // budget for its select loop (inlined into the epilogue code it competed with ~25 kernel-level values and ptxas spilled 60
 // registers across it); the caller saves what it keeps live around the call, once per simulation.  The leaf goes straight to
 // the two shared-memory words the network phase reads.
-template <int GAME>
+// SOFT: the instance the shadow warp calls -- it searches while the tensor pipe runs, and FP64 instructions next to tcgen05 MMAs
+// slow them down, so its arithmetic runs on the integer pipe (spx_softf64.cuh)
+#ifndef SPX_SHADOW_SOFT
+#define SPX_SHADOW_SOFT true   // -DSPX_SHADOW_SOFT=false: the shadow warp on the FP64 pipe (timing experiments)
+#endif
+template <int GAME, bool SOFT>
 __device__ __noinline__ int engine_step(const spx::EngineDev& E, const int g, const float my_p, const float v_in, const int budget,
                                         const int defer_leaf, unsigned long long* leaf2) {
     const int lane = threadIdx.x & 31;
     const spx::AdvPre pre = spx::advance_prefetch<GAME>(E, g, lane);
     unsigned long long own, opp;
-    const int flags = spx::advance_game<GAME, false, true>(E, g, lane, pre, my_p, v_in, budget, defer_leaf != 0, false, own, opp);
+    const int flags = spx::advance_game<GAME, false, true, SOFT>(E, g, lane, pre, my_p, v_in, budget, defer_leaf != 0, false, own, opp);
     if (leaf2 && lane == 0) { leaf2[0] = own; leaf2[1] = opp; }
     return flags;
 }
@@ -513,6 +518,8 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
     const unsigned crank = NCTA == 2 ? cluster_ctarank() : 0u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long n_groups = (n_boards + NB - 1) / NB;
+    const bool trace_on = true;   // (-DSPX_DBG_TRACE) the fused tick kernel traces the layers of ONE mid-launch pass, see the unit loop
+    (void)trace_on;
     if (tid == 0) SPX_TRACE(62, 0);
 #ifdef SPX_DBG_TRACE
     if (tid == 0 && blockIdx.x < 160) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); g_trace[1024 + 3 * blockIdx.x] = (long long)globaltimer_ns(); g_trace[1024 + 3 * blockIdx.x + 2] = smid; }
@@ -610,14 +617,49 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                     defer = true;       // the running pass does not evaluate this leaf: it waits for the next one
                 }
                 if (run && shadow_all && (E.cfg.reserved0 & 1)) run = false;   // timing experiment (SPX_DBG_FLAGS=1): no search, the same leaves again
+#ifdef SPX_DBG_TRACE
+                if (shadow_all && (E.cfg.reserved0 & 1) && (E.cfg.reserved0 & 0xFF8) && gb < n_boards) {
+                    // synthetic interference instead of the search (about 12 us per game slot): which resource does a busy warp take
+                    // from the tensor pipe?  8: dependent fp64 math, 16: dependent integer math, 32: dependent L2 loads
+                    const long long t_end = clock64() + 20000;
+                    double xd = 1.0 + lane;
+                    unsigned xi = lane + 1;
+                    const char* pool = E.pool + (size_t)gb * 2 * (size_t)E.nodes_per_tree * 160;
+                    unsigned off = lane * 32;
+                    while (clock64() < t_end) {
+                        if (E.cfg.reserved0 & 8) { for (int i = 0; i < 32; ++i) xd = __ddiv_rn(__dadd_rn(xd, 1.5), __dsqrt_rn(__dadd_rn(xd, 2.0))); }
+                        if (E.cfg.reserved0 & 64) { for (int i = 0; i < 64; ++i) xd = __dadd_rn(xd, 1.5); }
+                        if (E.cfg.reserved0 & 128) { for (int i = 0; i < 64; ++i) xd = __dmul_rn(xd, 1.0000001); }
+                        if (E.cfg.reserved0 & 256) { for (int i = 0; i < 64; ++i) xd = __fma_rn(xd, 1.0000001, 0.25); }
+                        if (E.cfg.reserved0 & 512) { for (int i = 0; i < 16; ++i) xd = __dadd_rn(__dmul_rn(xd, 1.0000001), (double)(float)xi); for (int i = 0; i < 200; ++i) xi = xi * 1664525u + 1013904223u; }
+                        if (E.cfg.reserved0 & 1024) {   // 64 KB of straight-line integer code: instruction-cache footprint
+#pragma unroll 4096
+                            for (int i = 0; i < 4096; ++i) xi = xi * (1664525u + 2u * (unsigned)i) + 1013904223u;
+                        }
+                        if (E.cfg.reserved0 & 2048) {   // 64-bit integer multiplies, shuffles, votes: what the integer-pipe arithmetic is made of
+                            u64 z = xi | ((u64)xi << 32);
+                            for (int i = 0; i < 64; ++i) { z = __umul64hi(z | 1ULL, 0x9E3779B97F4A7C15ULL) + z * 3ULL; z ^= __shfl_xor_sync(0xffffffffu, z, 1); z += __clzll((long long)z); }
+                            xi = (unsigned)z ^ (unsigned)__ballot_sync(0xffffffffu, z & 1);
+                        }
+                        if (E.cfg.reserved0 & 16) { for (int i = 0; i < 256; ++i) xi = xi * 1664525u + 1013904223u; }
+                        if (E.cfg.reserved0 & 32) { for (int i = 0; i < 8; ++i) off = (off * 1664525u + 1013904223u + (unsigned)__ldcg((const int*)(pool + (off & 0xFFFE0)))) ; }
+                    }
+                    if (xd == 0.123 || xi == 77u || off == 0x12345u) E.leaf_own[gb] = 1;   // keep the loops alive
+                }
+#endif
+                if (run && shadow_all && (E.cfg.reserved0 & 2) && crank == 0) run = false;   // timing experiment (SPX_DBG_FLAGS=2): only the peer CTA searches
+                if (run && shadow_all && (E.cfg.reserved0 & 4) && crank == 1) run = false;   // timing experiment (SPX_DBG_FLAGS=4): only the leader CTA searches
                 if (run) {
-                    const int flags = engine_step<GAME>(E, (int)gb, sp, sv, budget, defer ? 1 : 0, nullptr);
+                    const int flags = engine_step<GAME, SPX_SHADOW_SOFT>(E, (int)gb, sp, sv, budget, defer ? 1 : 0, nullptr);
                     if (!shadow_all && flags) {   // a leaf, or nothing more to do: back to the epilogue warp (0 = budget used up: go on later)
                         __threadfence();
                         if (lane == 0) st_volatile_s32(&S.slot_status[j], FS_DONE);
                     }
                 }
                 __syncwarp();
+#ifdef SPX_DBG_SHADOW_SLEEP   // timing experiment: the shadow warp's work spread out in time
+                __nanosleep(SPX_DBG_SHADOW_SLEEP);
+#endif
                 if (++j == NB) {
                     j = 0;
                     if (shadow_all) { __threadfence(); if (lane == 0) st_volatile_s32(&S.searches_done, p + 1); ++p; }
@@ -640,6 +682,9 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
         const long long grp = NCTA * unit + crank;
         const int pass = tick * U + ui;
         (void)pass;
+#ifdef SPX_DBG_TRACE
+        const bool trace_on = !ENGINE || pass == 30;   // a pass in the middle of the launch: the shadow warp is searching next to it
+#endif
         // cluster-uniform skip when none of the boards of this unit asked for an evaluation (plain forward only: the fused tick
         // kernel always evaluates -- agreeing on a skip would cost a cluster round trip per tick)
         bool any = ENGINE || needs == nullptr;
@@ -857,7 +902,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                             } else
                             if (st == FS_FAST) {
                                 const int fast_budget = (E.cfg.reserved0 >> 8) & 0xFF ? (E.cfg.reserved0 >> 8) & 0xFF : E.cfg.max_sims_per_tick;   // measured: 1 loses 5 % of the leaves, 8 costs 3 us more than 1
-                                const int flags = engine_step<GAME>(E, (int)gbw, my_p, v_next, fast_budget, 0, &S.leaf2[ew][0]);
+                                const int flags = engine_step<GAME, false>(E, (int)gbw, my_p, v_next, fast_budget, 0, &S.leaf2[ew][0]);
                                 emitted = flags & spx::ADV_EMITTED;
                                 if (!flags) { __threadfence(); st = FS_TODO; }   // no leaf yet and not idle: the shadow warp goes on with it
                                 if (lane == 0) st_volatile_s32(&S.slot_status[ew], st);
