@@ -122,7 +122,7 @@ class Elo:
         target = num_games + (num_games & 1)
         G = min(self.n_games_per_gpu, target)
         kw = dict(env=self.model_database.env, n_games=G, sims=self.iterations, evaluate=True, update=False, games_target=target,
-                  seed=self.seed + 104729 * self._comparisons)
+                  seed=self.seed + 104729 * self._comparisons, eval_cache=True)   # same games, fewer network passes
         if isinstance(b, str):
             sp = BatchedSelfPlay(a, net=self.net, opponent=b, **kw)
         else:

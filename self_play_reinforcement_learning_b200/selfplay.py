@@ -166,6 +166,7 @@ def run_tasks(network, env, tasks, result_queue=None, memory_queue=None, task_qu
     target = 2 * max(n_swap, n_plain)                 # even indices: swap_sides False, odd: True
     G = n_games or min(1024, max(2, target + (target & 1)))
     G += G & 1
+    kw.setdefault("eval_cache", True)   # same games, fewer network passes
     sp = BatchedSelfPlay(network, env=env, n_games=G, sims=iterations, net=net, evaluation_network=evaluation_network if evaluate else None,
                          evaluate=evaluate, update=update, alpha=alpha, strong_play=strong_play, seed=seed, games_target=target, **kw)
     moves_all, results_all = [], []
