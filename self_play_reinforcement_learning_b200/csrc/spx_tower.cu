@@ -476,6 +476,9 @@ __device__ __forceinline__ void issue_first_tap_skewed(SmemT<2>& S, int taps, un
 // the two shared-memory words the network phase reads.
 // SOFT: the instance the shadow warp calls -- it searches while the tensor pipe runs, and FP64 instructions next to tcgen05 MMAs
 // slow them down, so its arithmetic runs on the integer pipe (spx_softf64.cuh)
+#ifndef SPX_FAST_SOFT
+#define SPX_FAST_SOFT false    // the epilogue warps' searches between two passes (tensor pipe idle): FP64 instructions (-DSPX_FAST_SOFT=true: integer pipe)
+#endif
 #ifndef SPX_SHADOW_SOFT
 #define SPX_SHADOW_SOFT true   // -DSPX_SHADOW_SOFT=false: the shadow warp on the FP64 pipe (timing experiments)
 #endif
@@ -902,7 +905,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                             } else
                             if (st == FS_FAST) {
                                 const int fast_budget = (E.cfg.reserved0 >> 8) & 0xFF ? (E.cfg.reserved0 >> 8) & 0xFF : E.cfg.max_sims_per_tick;   // measured: 1 loses 5 % of the leaves, 8 costs 3 us more than 1
-                                const int flags = engine_step<GAME, false>(E, (int)gbw, my_p, v_next, fast_budget, 0, &S.leaf2[ew][0]);
+                                const int flags = engine_step<GAME, SPX_FAST_SOFT>(E, (int)gbw, my_p, v_next, fast_budget, 0, &S.leaf2[ew][0]);
                                 emitted = flags & spx::ADV_EMITTED;
                                 if (!flags) { __threadfence(); st = FS_TODO; }   // no leaf yet and not idle: the shadow warp goes on with it
                                 if (lane == 0) st_volatile_s32(&S.slot_status[ew], st);
