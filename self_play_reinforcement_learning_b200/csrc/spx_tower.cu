@@ -279,7 +279,7 @@ template <int NCTA> struct SmemT {
     unsigned long long xbar;            // "the peer CTA's halves of my boards' hidden-layer sums have landed" (st.async complete_tx)
     float xval[8];
     int slot_status[8];                 // FS_* per board slot (fast mode)
-    int quit, passes_done, searches_done;
+    int quit, passes_done, searches_done[2];   // searches_done[k]: jobs finished by shadow warp k (shadow-all mode)
     int go;                             // ENGINE: ticks known to exist | GO_FINAL (no more after those), see "work-conserving launches"
     unsigned char need[8];
     alignas(16) float bias[NCTA == 1 ? 3 : 1][NCTA == 1 ? CH : 4];   // single-CTA kernel only: staged fp32 bias, read as float4
@@ -584,23 +584,28 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
         if (tid < 8) { S.slot_status[tid] = FS_FAST; S.need[tid] = 0; }
         // work-conserving launches (pass_budget >= 0, spx_tick_fused_balanced): tick 0 exists for every cluster; whether tick t + 1
         // exists is decided at the start of tick t by a ticket drawn from the launch's budget of passes (E.ticks[1]), see below
-        if (tid == 0) { S.quit = 0; S.passes_done = 0; S.searches_done = 0; S.go = U == 0 ? GO_FINAL : pass_budget >= 0 ? 1 : (n_ticks | GO_FINAL); }
+        if (tid == 0) { S.quit = 0; S.passes_done = 0; S.searches_done[0] = 0; S.searches_done[1] = 0; S.go = U == 0 ? GO_FINAL : pass_budget >= 0 ? 1 : (n_ticks | GO_FINAL); }
         __syncthreads();
-        if (warp == 3) {
-            // ===================== shadow warp: simulations that need no network evaluation of the running pass
-            int p = 0, j = 0;
+        // Shadow-all mode has a second shadow warp: the warp of this CTA that has no role in the tick loop (the leader's relay warp,
+        // the peer's issuer warp) takes games 4..6 of every job, warp 3 games 0..3 -- with the evaluation cache a unit's seven
+        // searches in a row only just fitted under one pass of the other unit (two units per SM pair).
+        const int sw = warp == 3 ? 0 : ((shadow_all && NCTA == 2 && warp == (crank == 0 ? 2 : 1)) ? 1 : -1);
+        if (sw >= 0) {
+            // ===================== shadow warp(s): simulations that need no network evaluation of the running pass
+            const int j0 = (shadow_all && sw == 1) ? 4 : 0, j1 = (shadow_all && sw == 0) ? 4 : NB;
+            int p = 0, j = j0;
             for (;;) {
                 long long gb = 0;
                 bool run = false, defer = false;
                 int budget = 0;
                 float sp = 0.f, sv = 0.f;
                 if (shadow_all) {
-                    if (j == 0 && p % U == 0) {   // first job of tick p / U: does that tick exist?
+                    if (j == j0 && p % U == 0) {   // first job of tick p / U: does that tick exist?
                         int w;
                         for (;;) { w = ld_flag_uniform(&S.go); if (p / U < (w & (GO_FINAL - 1)) || (w & GO_FINAL)) break; __nanosleep(200); }
                         if (p / U >= (w & (GO_FINAL - 1))) break;
                     }
-                    if (j == 0) {   // job p = the leaves of pass p: needs the outputs of the same unit's previous pass (p - U)
+                    if (j == j0) {   // job p = the leaves of pass p: needs the outputs of the same unit's previous pass (p - U)
                         while (ld_flag_uniform(&S.passes_done) < p - U + 1) __nanosleep(200);
                         __threadfence();
                     }
@@ -663,9 +668,9 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
 #ifdef SPX_DBG_SHADOW_SLEEP   // timing experiment: the shadow warp's work spread out in time
                 __nanosleep(SPX_DBG_SHADOW_SLEEP);
 #endif
-                if (++j == NB) {
-                    j = 0;
-                    if (shadow_all) { __threadfence(); if (lane == 0) st_volatile_s32(&S.searches_done, p + 1); ++p; }
+                if (++j == j1) {
+                    j = j0;
+                    if (shadow_all) { __threadfence(); if (lane == 0) st_volatile_s32(&S.searches_done[sw], p + 1); ++p; }
                     else __nanosleep(300);
                 }
             }
@@ -916,7 +921,7 @@ tower_kernel(const unsigned long long* __restrict__ own_g, const unsigned long l
                     }
                 } else if (et < NB) {
                     // ---- shadow-all mode: the shadow warp has produced this pass's leaves (job == pass)
-                    while (ld_volatile_s32(&S.searches_done) < pass + 1) __nanosleep(100);
+                    while (ld_volatile_s32(&S.searches_done[0]) < pass + 1 || ld_volatile_s32(&S.searches_done[1]) < pass + 1) __nanosleep(100);
                     __threadfence();
                     const long long gb = grp * NB + et;
                     const bool ok = gb < n_boards;
